@@ -1,0 +1,29 @@
+// common.cuh — launch helpers shared by every kernel file in libfsb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define FSB_API extern "C" __attribute__((visibility("default")))
+
+// Every C-ABI entry point returns a cudaError_t-compatible int (0 = success) and
+// never throws.  FSB_E_ARG is our own code for an argument the kernels refuse.
+#define FSB_E_ARG 10001
+
+#define FSB_LAUNCH_CHECK()                         \
+    do {                                           \
+        cudaError_t e__ = cudaGetLastError();      \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+#define FSB_CUDA(x)                                \
+    do {                                           \
+        cudaError_t e__ = (x);                     \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+static inline int fsb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+static inline size_t fsb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#define FSB_NUM_SMS 148  // B200

@@ -1,0 +1,319 @@
+// project_sh.cu — fused EWA projection + SH colour + tile count (forward) and its backward.
+//
+// Replaces gsplat 1.0.0's fully_fused_projection_{fwd,bwd}, compute_sh_{fwd,bwd} and the first
+// pass of isect_tiles (SURVEY.md §2b stages P1, P2, I1-count, P3), reached from
+// /root/reference/dn_splatter/dn_model.py:570-591.
+//
+// HBM-bound streaming kernels: one thread per (camera, Gaussian) forward, one thread per Gaussian
+// looping over cameras backward (so the cross-camera sum is a register accumulation, no atomics).
+#include "common.cuh"
+#include "fs_math.cuh"
+
+namespace {
+
+__device__ __forceinline__ fs::Camera load_camera(const float* __restrict__ viewmats, const float* __restrict__ Ks,
+                                                  int c) {
+    fs::Camera cam;
+    const float* V = viewmats + (size_t)c * 16;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cam.V[i] = __ldg(V + i);
+    const float* K = Ks + (size_t)c * 9;
+    cam.fx = __ldg(K + 0);
+    cam.cx = __ldg(K + 2);
+    cam.fy = __ldg(K + 4);
+    cam.cy = __ldg(K + 5);
+    return cam;
+}
+
+__device__ __forceinline__ int tile_count(float mx, float my, int radius, int tile_size, int tile_w, int tile_h,
+                                          int legacy_bbox, int* x0, int* y0, int* x1, int* y1) {
+    float ts = (float)tile_size;
+    float tr = (float)radius / ts;
+    float tx = mx / ts, ty = my / ts;
+    int ax, ay, bx, by;
+    if (legacy_bbox) {
+        // gsplat 0.1.x map_gaussian_to_intersects: (int) truncation, +1 on the max side
+        ax = (int)(tx - tr); ay = (int)(ty - tr);
+        bx = (int)(tx + tr + 1.f); by = (int)(ty + tr + 1.f);
+    } else {
+        ax = (int)floorf(tx - tr); ay = (int)floorf(ty - tr);
+        bx = (int)ceilf(tx + tr); by = (int)ceilf(ty + tr);
+    }
+    ax = min(max(0, ax), tile_w); ay = min(max(0, ay), tile_h);
+    bx = min(max(0, bx), tile_w); by = min(max(0, by), tile_h);
+    *x0 = ax; *y0 = ay; *x1 = bx; *y1 = by;
+    return (by - ay) * (bx - ax);
+}
+
+__global__ void __launch_bounds__(256)
+project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float* __restrict__ quats,
+                      const float* __restrict__ scales, const float* __restrict__ viewmats,
+                      const float* __restrict__ Ks, int width, int height, float eps2d, float near_plane,
+                      float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h, int sh_degree,
+                      int K, const float* __restrict__ coeffs, const float* __restrict__ campos, int color_stride,
+                      int depth_channel, int32_t* __restrict__ radii, float* __restrict__ means2d,
+                      float* __restrict__ depths, float* __restrict__ conics, float* __restrict__ comps,
+                      float* __restrict__ colors, int32_t* __restrict__ tiles_per_gauss) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)C * N) return;
+    int c = (int)(idx / N);
+    int n = (int)(idx - (int64_t)c * N);
+    fs::Camera cam = load_camera(viewmats, Ks, c);
+    float px = means[3 * (size_t)n + 0], py = means[3 * (size_t)n + 1], pz = means[3 * (size_t)n + 2];
+    float4 q = reinterpret_cast<const float4*>(quats)[n];
+    float sx = scales[3 * (size_t)n + 0], sy = scales[3 * (size_t)n + 1], sz = scales[3 * (size_t)n + 2];
+    fs::ProjFwd o = fs::project_fwd(cam, px, py, pz, q.x, q.y, q.z, q.w, sx, sy, sz, width, height, eps2d,
+                                    near_plane, far_plane, radius_clip);
+    radii[idx] = o.radius;
+    reinterpret_cast<float2*>(means2d)[idx] = make_float2(o.mx, o.my);
+    depths[idx] = o.depth;
+    conics[3 * idx + 0] = o.ca;
+    conics[3 * idx + 1] = o.cb;
+    conics[3 * idx + 2] = o.cc;
+    if (comps) comps[idx] = o.comp;
+    int cnt = 0;
+    if (o.radius > 0) {
+        int x0, y0, x1, y1;
+        cnt = tile_count(o.mx, o.my, o.radius, tile_size, tile_w, tile_h, 0, &x0, &y0, &x1, &y1);
+    }
+    tiles_per_gauss[idx] = cnt;
+    if (colors) {
+        float* out = colors + (size_t)idx * color_stride;
+        float r = 0.f, g = 0.f, b = 0.f;
+        if (o.radius > 0 && sh_degree >= 0) {
+            float dx = px - __ldg(campos + 3 * c + 0);
+            float dy = py - __ldg(campos + 3 * c + 1);
+            float dz = pz - __ldg(campos + 3 * c + 2);
+            float inorm = fs::inv_sqrt(dx * dx + dy * dy + dz * dz);
+            float basis[16];
+            fs::sh_basis(sh_degree, dx * inorm, dy * inorm, dz * inorm, basis);
+            int nb = (sh_degree + 1) * (sh_degree + 1);
+            const float* cf = coeffs + (size_t)n * K * 3;
+#pragma unroll 4
+            for (int k = 0; k < nb; ++k) {
+                r += basis[k] * cf[3 * k + 0];
+                g += basis[k] * cf[3 * k + 1];
+                b += basis[k] * cf[3 * k + 2];
+            }
+            // host-side clamp_min(colors + 0.5, 0) of rendering.rasterization, fused here
+            r = fmaxf(r + 0.5f, 0.f);
+            g = fmaxf(g + 0.5f, 0.f);
+            b = fmaxf(b + 0.5f, 0.f);
+        } else if (sh_degree >= 0) {
+            // masked-out entries are 0 from spherical_harmonics, then +0.5 by the host clamp
+            r = g = b = 0.5f;
+        }
+        if (sh_degree >= 0) {
+            out[0] = r; out[1] = g; out[2] = b;
+        }
+        if (depth_channel >= 0) out[depth_channel] = o.depth;
+    }
+}
+
+// block-wide sum of `v` (blockDim.x == 256), result valid in thread 0
+__device__ __forceinline__ float block_sum_256(float v, float* smem8) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) smem8[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r += smem8[i];
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float* __restrict__ quats,
+                      const float* __restrict__ scales, const float* __restrict__ viewmats,
+                      const float* __restrict__ Ks, int width, int height, float eps2d, int sh_degree, int K,
+                      const float* __restrict__ coeffs, const float* __restrict__ campos, int color_stride,
+                      int depth_channel, const int32_t* __restrict__ radii, const float* __restrict__ v_means2d,
+                      const float* __restrict__ v_depths, const float* __restrict__ v_conics,
+                      const float* __restrict__ v_comps, const float* __restrict__ v_colors,
+                      float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
+                      float* __restrict__ v_coeffs, float* __restrict__ v_viewmats, float* __restrict__ v_campos) {
+    __shared__ float red[8];
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = n < N;
+    float px = 0, py = 0, pz = 0, sx = 1, sy = 1, sz = 1;
+    float4 q = make_float4(1, 0, 0, 0);
+    if (live) {
+        px = means[3 * (size_t)n + 0]; py = means[3 * (size_t)n + 1]; pz = means[3 * (size_t)n + 2];
+        q = reinterpret_cast<const float4*>(quats)[n];
+        sx = scales[3 * (size_t)n + 0]; sy = scales[3 * (size_t)n + 1]; sz = scales[3 * (size_t)n + 2];
+    }
+    float am[3] = {0, 0, 0}, aq[4] = {0, 0, 0, 0}, as[3] = {0, 0, 0};
+    int nb = sh_degree >= 0 ? (sh_degree + 1) * (sh_degree + 1) : 0;
+    bool any_sh = false;
+    for (int c = 0; c < C; ++c) {
+        size_t idx = (size_t)c * N + n;
+        bool vis = live && radii[idx] > 0;
+        float vRv[9], vtv[3], vcp[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 9; ++i) vRv[i] = 0.f;
+        vtv[0] = vtv[1] = vtv[2] = 0.f;
+        if (vis) {
+            fs::Camera cam = load_camera(viewmats, Ks, c);
+            float2 vm = reinterpret_cast<const float2*>(v_means2d)[idx];
+            float vd = v_depths ? v_depths[idx] : 0.f;
+            float vca = v_conics[3 * idx + 0], vcb = v_conics[3 * idx + 1], vcc = v_conics[3 * idx + 2];
+            float vcomp = v_comps ? v_comps[idx] : 0.f;
+            const float* vc = v_colors ? v_colors + idx * color_stride : nullptr;
+            if (vc && depth_channel >= 0) vd += vc[depth_channel];
+            float gm[3], gq[4], gs[3];
+            fs::project_bwd(cam, px, py, pz, q.x, q.y, q.z, q.w, sx, sy, sz, width, height, eps2d, vm.x, vm.y, vd,
+                            vca, vcb, vcc, vcomp, gm, gq, gs, v_viewmats ? vRv : nullptr, v_viewmats ? vtv : nullptr);
+            if (vc && sh_degree >= 0) {
+                float dx = px - __ldg(campos + 3 * c + 0);
+                float dy = py - __ldg(campos + 3 * c + 1);
+                float dz = pz - __ldg(campos + 3 * c + 2);
+                float inorm = fs::inv_sqrt(dx * dx + dy * dy + dz * dz);
+                float ux = dx * inorm, uy = dy * inorm, uz = dz * inorm;
+                float basis[16];
+                fs::sh_basis(sh_degree, ux, uy, uz, basis);
+                const float* cf = coeffs + (size_t)n * K * 3;
+                float r = 0.f, g = 0.f, b = 0.f;
+                for (int k = 0; k < nb; ++k) {
+                    r += basis[k] * cf[3 * k + 0];
+                    g += basis[k] * cf[3 * k + 1];
+                    b += basis[k] * cf[3 * k + 2];
+                }
+                // clamp_min(x + 0.5, 0): gradient passes where x + 0.5 >= 0
+                float vr = (r + 0.5f >= 0.f) ? vc[0] : 0.f;
+                float vg = (g + 0.5f >= 0.f) ? vc[1] : 0.f;
+                float vb = (b + 0.5f >= 0.f) ? vc[2] : 0.f;
+                float* vcf = v_coeffs + (size_t)n * K * 3;
+                if (C == 1) {
+                    for (int k = 0; k < nb; ++k) {
+                        vcf[3 * k + 0] = basis[k] * vr;
+                        vcf[3 * k + 1] = basis[k] * vg;
+                        vcf[3 * k + 2] = basis[k] * vb;
+                    }
+                } else {
+                    for (int k = 0; k < nb; ++k) {
+                        float o0 = any_sh ? vcf[3 * k + 0] : 0.f, o1 = any_sh ? vcf[3 * k + 1] : 0.f,
+                              o2 = any_sh ? vcf[3 * k + 2] : 0.f;
+                        vcf[3 * k + 0] = o0 + basis[k] * vr;
+                        vcf[3 * k + 1] = o1 + basis[k] * vg;
+                        vcf[3 * k + 2] = o2 + basis[k] * vb;
+                    }
+                }
+                any_sh = true;
+                if (sh_degree >= 1) {
+                    float bx[16], by[16], bz[16];
+                    fs::sh_basis_grad(sh_degree, ux, uy, uz, bx, by, bz);
+                    float gx = 0.f, gy = 0.f, gz = 0.f;
+                    for (int k = 1; k < nb; ++k) {
+                        float w = cf[3 * k + 0] * vr + cf[3 * k + 1] * vg + cf[3 * k + 2] * vb;
+                        gx += bx[k] * w; gy += by[k] * w; gz += bz[k] * w;
+                    }
+                    // through u = d / |d|
+                    float dot = gx * ux + gy * uy + gz * uz;
+                    float vdx = (gx - dot * ux) * inorm, vdy = (gy - dot * uy) * inorm, vdz = (gz - dot * uz) * inorm;
+                    gm[0] += vdx; gm[1] += vdy; gm[2] += vdz;
+                    vcp[0] = -vdx; vcp[1] = -vdy; vcp[2] = -vdz;
+                }
+            }
+            am[0] += gm[0]; am[1] += gm[1]; am[2] += gm[2];
+            aq[0] += gq[0]; aq[1] += gq[1]; aq[2] += gq[2]; aq[3] += gq[3];
+            as[0] += gs[0]; as[1] += gs[1]; as[2] += gs[2];
+        }
+        if (v_viewmats) {  // uniform branch: every thread of the block takes part in the reductions
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                float s = block_sum_256(vRv[i], red);
+                if (threadIdx.x == 0 && s != 0.f) atomicAdd(v_viewmats + (size_t)c * 16 + (i / 3) * 4 + (i % 3), s);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float s = block_sum_256(vtv[i], red);
+                if (threadIdx.x == 0 && s != 0.f) atomicAdd(v_viewmats + (size_t)c * 16 + i * 4 + 3, s);
+            }
+        }
+        if (v_campos) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float s = block_sum_256(vcp[i], red);
+                if (threadIdx.x == 0 && s != 0.f) atomicAdd(v_campos + (size_t)c * 3 + i, s);
+            }
+        }
+    }
+    if (!live) return;
+    v_means[3 * (size_t)n + 0] = am[0]; v_means[3 * (size_t)n + 1] = am[1]; v_means[3 * (size_t)n + 2] = am[2];
+    reinterpret_cast<float4*>(v_quats)[n] = make_float4(aq[0], aq[1], aq[2], aq[3]);
+    v_scales[3 * (size_t)n + 0] = as[0]; v_scales[3 * (size_t)n + 1] = as[1]; v_scales[3 * (size_t)n + 2] = as[2];
+    if (v_coeffs) {
+        float* vcf = v_coeffs + (size_t)n * K * 3;
+        int start = any_sh ? nb : 0;  // bases above the active degree (or everything, if never visible) get zero
+        for (int k = start * 3; k < K * 3; ++k) vcf[k] = 0.f;
+    }
+}
+
+// stand-alone tile count for callers that bring their own xys/radii (legacy rasterize_gaussians)
+__global__ void __launch_bounds__(256)
+isect_count_kernel(int64_t M, const float* __restrict__ means2d, const int32_t* __restrict__ radii, int tile_size,
+                   int tile_w, int tile_h, int legacy_bbox, int32_t* __restrict__ tiles_per_gauss) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M) return;
+    int r = radii[idx];
+    int cnt = 0;
+    if (r > 0) {
+        float2 m = reinterpret_cast<const float2*>(means2d)[idx];
+        int x0, y0, x1, y1;
+        cnt = tile_count(m.x, m.y, r, tile_size, tile_w, tile_h, legacy_bbox, &x0, &y0, &x1, &y1);
+    }
+    tiles_per_gauss[idx] = cnt;
+}
+
+}  // namespace
+
+FSB_API int fsb_project_sh_fwd(int C, int N, const float* means, const float* quats, const float* scales,
+                               const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                               float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w,
+                               int tile_h, int sh_degree, int K, const float* coeffs, const float* campos,
+                               int color_stride, int depth_channel, int32_t* radii, float* means2d, float* depths,
+                               float* conics, float* comps, float* colors, int32_t* tiles_per_gauss, void* stream) {
+    if (C <= 0 || N < 0 || sh_degree > 3 || tile_size <= 0) return FSB_E_ARG;
+    if (sh_degree >= 0 && (!coeffs || !campos || !colors || (sh_degree + 1) * (sh_degree + 1) > K)) return FSB_E_ARG;
+    if (colors && (color_stride < 3 || depth_channel >= color_stride)) return FSB_E_ARG;
+    if (N == 0) return 0;
+    int64_t total = (int64_t)C * N;
+    project_sh_fwd_kernel<<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+        tile_w, tile_h, sh_degree, K, coeffs, campos, color_stride, depth_channel, radii, means2d, depths, conics,
+        comps, colors, tiles_per_gauss);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+FSB_API int fsb_project_sh_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                               const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                               int sh_degree, int K, const float* coeffs, const float* campos, int color_stride,
+                               int depth_channel, const int32_t* radii, const float* v_means2d, const float* v_depths,
+                               const float* v_conics, const float* v_comps, const float* v_colors, float* v_means,
+                               float* v_quats, float* v_scales, float* v_coeffs, float* v_viewmats, float* v_campos,
+                               void* stream) {
+    if (C <= 0 || N < 0 || sh_degree > 3) return FSB_E_ARG;
+    if (sh_degree >= 0 && v_colors && (!coeffs || !campos || !v_coeffs)) return FSB_E_ARG;
+    if (N == 0) return 0;
+    project_sh_bwd_kernel<<<fsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
+        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, coeffs, campos, color_stride,
+        depth_channel, radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_means, v_quats, v_scales, v_coeffs,
+        v_viewmats, v_campos);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+FSB_API int fsb_isect_count(int64_t M, const float* means2d, const int32_t* radii, int tile_size, int tile_w,
+                            int tile_h, int legacy_bbox, int32_t* tiles_per_gauss, void* stream) {
+    if (M < 0 || tile_size <= 0) return FSB_E_ARG;
+    if (M == 0) return 0;
+    isect_count_kernel<<<fsb_div_up(M, 256), 256, 0, (cudaStream_t)stream>>>(M, means2d, radii, tile_size, tile_w,
+                                                                           tile_h, legacy_bbox, tiles_per_gauss);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}

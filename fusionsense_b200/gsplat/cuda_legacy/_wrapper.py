@@ -1,0 +1,123 @@
+"""`gsplat.cuda_legacy._wrapper` stand-in: `rasterize_gaussians` (gsplat 0.1.x API) and `num_sh_bases`.
+
+DN-Splatter renders its per-pixel normals through this entry point
+(/root/reference/dn_splatter/dn_model.py:644-653); semantics restated in SURVEY.md Appendix A.6.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ... import ops
+
+# Binning (sorted intersection lists) of the most recent `rasterization()` call, so that the normals pass
+# that DN-Splatter issues right after it on the SAME xys / depths / radii does not bin and sort again.
+_LAST_BINNING: dict = {}
+
+
+def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int, height: int, tile_size: int,
+                     n_isects: int, flatten_ids: Tensor, isect_offsets: Tensor) -> None:
+    """Called by `rasterization()` (single-camera case only)."""
+    _LAST_BINNING.clear()
+    if radii.shape[0] != 1:
+        return
+    _LAST_BINNING.update(
+        key=(means2d.data_ptr(), depths.data_ptr(), radii.data_ptr(), means2d._version, depths._version,
+             radii._version, radii.shape[1], width, height, tile_size),
+        n_isects=n_isects, flatten_ids=flatten_ids, isect_offsets=isect_offsets,
+    )
+
+
+def num_sh_bases(degree: int) -> int:
+    """Number of SH bases for `degree` (call sites: dn_model.py:205,1191)."""
+    if degree == 0:
+        return 1
+    if degree == 1:
+        return 4
+    if degree == 2:
+        return 9
+    if degree == 3:
+        return 16
+    return 25
+
+
+def rasterize_gaussians(
+    xys: Tensor,  # [N, 2]
+    depths: Tensor,  # [N] (or [N, 1])
+    radii: Tensor,  # [N] int32
+    conics: Tensor,  # [N, 3]
+    num_tiles_hit: Tensor,  # [N] int32  (re-derived inside: see SURVEY.md A.6 caveat)
+    colors: Tensor,  # [N, D]
+    opacity: Tensor,  # [N, 1]
+    img_height: int,
+    img_width: int,
+    block_width: int,
+    background: Optional[Tensor] = None,
+    return_alpha: Optional[bool] = False,
+) -> Tensor:
+    """Depth-sorted alpha compositing of 2-D Gaussians (gsplat 0.1.x `rasterize_gaussians`).
+
+    Returns `out_img [H, W, D]` (and `out_alpha [H, W]` when `return_alpha`).  `background=None` means ones.
+    Differentiable w.r.t. xys, conics, colors, opacity.
+    """
+    assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
+    if not xys.is_cuda:
+        raise RuntimeError("fusionsense_b200.gsplat.rasterize_gaussians needs CUDA tensors (no CPU fallback)")
+    if colors.dtype == torch.uint8:
+        colors = colors.float() / 255
+    if background is not None:
+        assert background.shape[0] == colors.shape[-1], f"incorrect shape of background color tensor, expected shape {colors.shape[-1]}"
+    else:
+        background = torch.ones(colors.shape[-1], dtype=torch.float32, device=colors.device)
+    if xys.ndimension() != 2 or xys.size(1) != 2:
+        raise ValueError("xys must have dimensions (N, 2)")
+    if colors.ndimension() != 2:
+        raise ValueError("colors must have dimensions (N, D)")
+
+    N, D = colors.shape
+    W, H, ts = int(img_width), int(img_height), int(block_width)
+    tile_w, tile_h = math.ceil(W / ts), math.ceil(H / ts)
+    depths1 = depths.reshape(-1)
+    radii1 = radii.reshape(-1).to(torch.int32)
+
+    with torch.no_grad():
+        xys_c = xys.detach().float().contiguous()
+        dep_c = depths1.detach().float().contiguous()
+        rad_c = radii1.contiguous()
+        legacy_counts = ops.isect_count(xys_c[None], rad_c[None], ts, tile_w, tile_h, legacy_bbox=True)
+        cached = _LAST_BINNING if _LAST_BINNING.get("key") == (
+            xys_c.data_ptr(), dep_c.data_ptr(), rad_c.data_ptr(), xys._version, depths._version, radii._version,
+            N, W, H, ts) else None
+        offsets, n_isects = ops.isect_scan(legacy_counts)
+        if cached is not None and cached["n_isects"] == n_isects:
+            # legacy bbox is a superset of the 1.0 bbox per Gaussian, so equal totals <=> identical tile sets,
+            # and the keys (tile << 32 | depth bits) are the same: the sorted lists can be shared.
+            flatten_ids, isect_offsets = cached["flatten_ids"], cached["isect_offsets"]
+        elif n_isects > 0:
+            ids, flat = ops.isect_emit(xys_c[None], rad_c[None], dep_c[None], offsets, n_isects, 1, N, ts, tile_w,
+                                       tile_h, legacy_bbox=True)
+            ids, flatten_ids = ops.radix_sort_pairs(ids, flat, 32 + ops.tile_bits_for(tile_w * tile_h) + 1)
+            isect_offsets = ops.isect_offsets(ids, 1, tile_w, tile_h)
+        else:
+            flatten_ids = isect_offsets = None
+
+    if n_isects < 1:
+        out_img = torch.ones(H, W, D, device=xys.device) * background
+        out_alpha = torch.zeros(H, W, device=xys.device)
+    else:
+        Dp = ops.supported_channels(D)
+        cols, bg = colors, background
+        if Dp != D:
+            cols = torch.cat([cols, cols.new_zeros(N, Dp - D)], dim=-1)
+            bg = torch.cat([bg, bg.new_zeros(Dp - D)], dim=-1)
+        out, alpha = ops.RasterizeToPixels.apply(xys[None], conics[None], cols[None], opacity.reshape(1, N),
+                                                 bg[None], None, W, H, ts, isect_offsets, flatten_ids, bool(xys.requires_grad),
+                                                 False)
+        out_img = out[0, ..., :D] if Dp != D else out[0]
+        out_alpha = alpha[0, ..., 0]
+    if return_alpha:
+        return out_img, out_alpha
+    return out_img

@@ -1,0 +1,179 @@
+"""Drop-in for `gsplat.rendering` (gsplat==1.0.0) backed by libfsb200's sm_100a kernels.
+
+Only what FusionSense / DN-Splatter and nerfstudio 1.1.3's splatfacto reach is provided:
+`rasterization()` with the exact gsplat 1.0.0 signature, defaults, return tuple and meta keys
+(reference call site: /root/reference/dn_splatter/dn_model.py:570-591; semantics restated in
+SURVEY.md Appendix A.1).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from .. import ops
+from .cuda_legacy._wrapper import remember_binning
+
+
+def rasterization(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]
+    scales: Tensor,  # [N, 3]
+    opacities: Tensor,  # [N]
+    colors: Tensor,  # [(C,) N, D] or [(C,) N, K, 3]
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: Literal["RGB", "D", "ED", "RGB+D", "RGB+ED"] = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: Literal["classic", "antialiased"] = "classic",
+    channel_chunk: int = 32,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Rasterize 3D Gaussians to `[C, H, W, D]` images; see gsplat 1.0.0 `rasterization` for the contract.
+
+    Differences from upstream, all deliberate: (1) culled Gaussians have zeroed (not uninitialised)
+    `means2d / depths / conics`; (2) `packed=True` and `sparse_grad=True` change gsplat's meta layout to a
+    flattened nnz form that neither DN-Splatter nor splatfacto use — they are refused loudly instead of being
+    emulated; (3) there is no CPU path.
+    """
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert opacities.shape == (N,), opacities.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    assert render_mode in ["RGB", "D", "ED", "RGB+D", "RGB+ED"], render_mode
+    assert rasterize_mode in ["classic", "antialiased"], rasterize_mode
+    if not means.is_cuda:
+        raise RuntimeError("fusionsense_b200.gsplat.rasterization needs CUDA tensors (no CPU fallback)")
+    if packed or sparse_grad:
+        raise NotImplementedError(
+            "fusionsense_b200's rasterization implements the unpacked layout (packed=False, sparse_grad=False) that "
+            "DN-Splatter (dn_model.py:580,586) and splatfacto use"
+        )
+
+    if sh_degree is None:
+        assert (colors.dim() == 2 and colors.shape[0] == N) or (
+            colors.dim() == 3 and colors.shape[:2] == (C, N)
+        ), colors.shape
+    else:
+        assert (colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3) or (
+            colors.dim() == 4 and colors.shape[:2] == (C, N) and colors.shape[3] == 3
+        ), colors.shape
+        assert (sh_degree + 1) ** 2 <= colors.shape[-2], colors.shape
+        if colors.dim() == 4:
+            raise NotImplementedError("per-camera SH coefficients [C,N,K,3] are not used by the reference")
+
+    want_depth = render_mode in ["RGB+D", "RGB+ED", "D", "ED"]
+    only_depth = render_mode in ["D", "ED"]
+    ed_normalize = render_mode in ["ED", "RGB+ED"]
+    use_sh = sh_degree is not None and not only_depth
+    calc_comp = rasterize_mode == "antialiased"
+
+    # colour evaluation fused with the projection when SH is on
+    if use_sh:
+        campos = torch.linalg.inv(viewmats)[:, :3, 3]
+        color_stride = 4 if want_depth else 3
+        depth_channel = 3 if want_depth else -1
+        coeffs = colors
+    else:
+        campos, coeffs, color_stride, depth_channel = None, None, 0, -1
+
+    radii, means2d, depths, conics, comps, sh_colors, tiles_per_gauss = ops.ProjectSH.apply(
+        means, quats, scales, coeffs, viewmats, Ks, campos, width, height, eps2d, near_plane, far_plane,
+        radius_clip, tile_size, sh_degree if use_sh else None, color_stride, depth_channel, calc_comp)
+
+    opac = opacities[None].expand(C, N)
+    if comps is not None:
+        opac = opac * comps
+    opac = opac.contiguous()
+
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+    with torch.no_grad():
+        _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(
+            means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss)
+        remember_binning(means2d, depths, radii, width, height, tile_size, flatten_ids.numel(), flatten_ids,
+                         isect_offsets)
+
+    if use_sh:
+        ras_colors = sh_colors  # [C, N, 3 or 4], depth already in channel 3
+    elif only_depth:
+        ras_colors = depths[..., None]
+    else:
+        ras_colors = colors if colors.dim() == 3 else colors[None].expand(C, N, colors.shape[-1])
+        if want_depth:
+            ras_colors = torch.cat([ras_colors, depths[..., None]], dim=-1)
+    ras_colors = ras_colors.contiguous()
+
+    D = ras_colors.shape[-1]
+    if backgrounds is not None:
+        assert backgrounds.shape == (C, D), backgrounds.shape
+
+    def _raster(cols, bgs, ed):
+        d = cols.shape[-1]
+        dp = ops.supported_channels(d)
+        if dp != d:
+            cols = torch.cat([cols, cols.new_zeros(*cols.shape[:-1], dp - d)], dim=-1)
+            if bgs is not None:
+                bgs = torch.cat([bgs, bgs.new_zeros(C, dp - d)], dim=-1)
+            # the ED channel must stay last for the fused normalisation; fall back to doing it outside
+            fused_ed = False
+        else:
+            fused_ed = ed
+        out, alpha = ops.RasterizeToPixels.apply(means2d, conics, cols, opac, bgs, None, width, height, tile_size,
+                                                 isect_offsets, flatten_ids, absgrad, fused_ed)
+        if dp != d:
+            out = out[..., :d]
+        if ed and not fused_ed:
+            out = torch.cat([out[..., :-1], out[..., -1:] / alpha.clamp(min=1e-10)], dim=-1)
+        return out, alpha
+
+    if D > channel_chunk:
+        n_chunks = (D + channel_chunk - 1) // channel_chunk
+        outs, render_alphas = [], None
+        for i in range(n_chunks):
+            lo, hi = i * channel_chunk, min((i + 1) * channel_chunk, D)
+            bgs = backgrounds[..., lo:hi] if backgrounds is not None else None
+            o, a = _raster(ras_colors[..., lo:hi].contiguous(), bgs, ed_normalize and hi == D)
+            outs.append(o)
+            render_alphas = a
+        render_colors = torch.cat(outs, dim=-1)
+    else:
+        render_colors, render_alphas = _raster(ras_colors, backgrounds, ed_normalize)
+
+    meta = {
+        "camera_ids": None,
+        "gaussian_ids": None,
+        "radii": radii,
+        "means2d": means2d,
+        "depths": depths,
+        "conics": conics,
+        "opacities": opac,
+        "tile_width": tile_width,
+        "tile_height": tile_height,
+        "tiles_per_gauss": tiles_per_gauss,
+        "isect_ids": isect_ids,
+        "flatten_ids": flatten_ids,
+        "isect_offsets": isect_offsets,
+        "width": width,
+        "height": height,
+        "tile_size": tile_size,
+        "n_cameras": C,
+    }
+    return render_colors, render_alphas, meta

@@ -1,0 +1,273 @@
+"""Torch-facing wrappers of the libfsb200 C-ABI: raw stage calls and the autograd Functions.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); all arithmetic of the render
+path runs in the hand-written sm_100a kernels.  There is no CPU path: every function requires CUDA
+tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ._abi import check, lib, ptr
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("fusionsense_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# raw stage calls
+# ---------------------------------------------------------------------------------------------
+def project_sh_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+                   tile_size, sh_degree, coeffs, campos, color_stride, depth_channel, calc_comp):
+    _req_cuda(means, quats, scales, viewmats, Ks)
+    C, N = viewmats.shape[0], means.shape[0]
+    dev = means.device
+    tile_w, tile_h = math.ceil(width / tile_size), math.ceil(height / tile_size)
+    radii = torch.empty((C, N), dtype=torch.int32, device=dev)
+    means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+    depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+    conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+    comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_comp else None
+    colors = torch.empty((C, N, color_stride), dtype=torch.float32, device=dev) if color_stride > 0 else None
+    tiles = torch.empty((C, N), dtype=torch.int32, device=dev)
+    K = coeffs.shape[1] if coeffs is not None else 0
+    check(lib.fsb_project_sh_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height,
+                                 eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w, tile_h,
+                                 -1 if sh_degree is None else sh_degree, K, ptr(coeffs), ptr(campos), color_stride,
+                                 depth_channel, ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps),
+                                 ptr(colors), ptr(tiles), _stream()), "fsb_project_sh_fwd")
+    return radii, means2d, depths, conics, comps, colors, tiles
+
+
+def isect_count(means2d: Tensor, radii: Tensor, tile_size: int, tile_w: int, tile_h: int, legacy_bbox: bool):
+    _req_cuda(means2d, radii)
+    M = radii.numel()
+    tiles = torch.empty(radii.shape, dtype=torch.int32, device=radii.device)
+    check(lib.fsb_isect_count(M, ptr(means2d), ptr(radii), tile_size, tile_w, tile_h, int(legacy_bbox), ptr(tiles),
+                              _stream()), "fsb_isect_count")
+    return tiles
+
+
+def isect_scan(counts: Tensor) -> Tuple[Tensor, int]:
+    """Exclusive int64 offsets of `counts` and the total (one 8-byte D2H read, like gsplat's)."""
+    M = counts.numel()
+    dev = counts.device
+    offsets = torch.empty((M,), dtype=torch.int64, device=dev)
+    total = torch.empty((1,), dtype=torch.int64, device=dev)
+    ws_bytes = lib.fsb_isect_scan_workspace(M)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    check(lib.fsb_isect_scan(M, ptr(counts), ptr(offsets), ptr(total), ptr(ws), ws_bytes, _stream()),
+          "fsb_isect_scan")
+    return offsets, int(total.item())
+
+
+def tile_bits_for(n_tiles: int) -> int:
+    return int(n_tiles).bit_length()
+
+
+def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox):
+    dev = means2d.device
+    ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
+    flat = torch.empty((n_isects,), dtype=torch.int32, device=dev)
+    tb = tile_bits_for(tile_w * tile_h)
+    check(lib.fsb_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h, tb,
+                             int(legacy_bbox), ptr(ids), ptr(flat), _stream()), "fsb_isect_emit")
+    return ids, flat
+
+
+def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tensor, Tensor]:
+    """Stable sort of (int64 keys, int32 vals) on key bits [0, end_bit). Inputs are clobbered."""
+    _req_cuda(keys, vals)
+    n = keys.numel()
+    if n == 0:
+        return keys, vals
+    dev = keys.device
+    keys_b = torch.empty_like(keys)
+    vals_b = torch.empty_like(vals)
+    ws_bytes = lib.fsb_radix_sort_workspace(n, end_bit)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    in_b = ctypes.c_int(0)
+    check(lib.fsb_radix_sort_pairs(n, end_bit, ptr(keys), ptr(vals), ptr(keys_b), ptr(vals_b), ptr(ws), ws_bytes,
+                                   ctypes.addressof(in_b), _stream()), "fsb_radix_sort_pairs")
+    return (keys_b, vals_b) if in_b.value else (keys, vals)
+
+
+def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int) -> Tensor:
+    n_tiles = tile_w * tile_h
+    offsets = torch.empty((C, tile_h, tile_w), dtype=torch.int32, device=sorted_ids.device)
+    check(lib.fsb_isect_offsets(sorted_ids.numel(), ptr(sorted_ids), C, n_tiles, tile_bits_for(n_tiles),
+                                ptr(offsets), _stream()), "fsb_isect_offsets")
+    return offsets
+
+
+def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gauss=None, legacy_bbox=False,
+                sort=True):
+    """gsplat.isect_tiles + isect_offset_encode in one go (unpacked layout).
+
+    means2d [C,N,2], radii [C,N] int32, depths [C,N] -> tiles_per_gauss [C,N], isect_ids [n_isects] int64 (sorted),
+    flatten_ids [n_isects] int32, isect_offsets [C,th,tw] int32.
+    """
+    _req_cuda(means2d, radii, depths)
+    C, N = radii.shape
+    if tiles_per_gauss is None:
+        tiles_per_gauss = isect_count(means2d, radii, tile_size, tile_w, tile_h, legacy_bbox)
+    offsets, n_isects = isect_scan(tiles_per_gauss)
+    ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox)
+    if sort:
+        end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
+        ids, flat = radix_sort_pairs(ids, flat, end_bit)
+    tile_offsets = isect_offsets(ids, C, tile_w, tile_h)
+    return tiles_per_gauss, ids, flat, tile_offsets
+
+
+def supported_channels(D: int) -> int:
+    return lib.fsb_raster_supported_channels(D)
+
+
+def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
+               flatten_ids, ed_normalize=False):
+    _req_cuda(means2d, conics, colors, opacities)
+    C = isect_offsets_t.shape[0]
+    tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
+    N = means2d.shape[-2]
+    D = colors.shape[-1]
+    dev = means2d.device
+    out = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
+    alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+    last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+    check(lib.fsb_raster_fwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
+                             ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
+                             ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(out), ptr(alphas),
+                             ptr(last_ids), _stream()), "fsb_raster_fwd")
+    return out, alphas, last_ids
+
+
+def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
+               flatten_ids, ed_normalize, render_colors, render_alphas, last_ids, v_render_colors, v_render_alphas,
+               absgrad):
+    C = isect_offsets_t.shape[0]
+    tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
+    N = means2d.shape[-2]
+    D = colors.shape[-1]
+    v_means2d = torch.zeros_like(means2d)
+    v_abs = torch.zeros_like(means2d) if absgrad else None
+    v_conics = torch.zeros_like(conics)
+    v_colors = torch.zeros_like(colors)
+    v_opac = torch.zeros_like(opacities)
+    check(lib.fsb_raster_bwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
+                             ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
+                             ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(render_colors),
+                             ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
+                             ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), _stream()),
+          "fsb_raster_bwd")
+    return v_means2d, v_abs, v_conics, v_colors, v_opac
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------------------------
+class ProjectSH(torch.autograd.Function):
+    """fully_fused_projection (+ spherical_harmonics + clamp_min(+0.5) + tile count) of gsplat 1.0.0."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, coeffs, viewmats, Ks, campos, width, height, eps2d, near_plane,
+                far_plane, radius_clip, tile_size, sh_degree, color_stride, depth_channel, calc_comp):
+        means, quats, scales = _f32c(means), _f32c(quats), _f32c(scales)
+        viewmats, Ks, coeffs, campos = _f32c(viewmats), _f32c(Ks), _f32c(coeffs), _f32c(campos)
+        radii, means2d, depths, conics, comps, colors, tiles = project_sh_fwd(
+            means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+            sh_degree, coeffs, campos, color_stride, depth_channel, calc_comp)
+        ctx.save_for_backward(means, quats, scales, coeffs, viewmats, Ks, campos, radii)
+        ctx.cfg = (width, height, eps2d, sh_degree, color_stride, depth_channel)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii, tiles)
+        return radii, means2d, depths, conics, comps, colors, tiles
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_colors, _v_tiles):
+        means, quats, scales, coeffs, viewmats, Ks, campos, radii = ctx.saved_tensors
+        width, height, eps2d, sh_degree, color_stride, depth_channel = ctx.cfg
+        C, N = radii.shape
+        dev = means.device
+        v_means2d = _f32c(v_means2d) if v_means2d is not None else torch.zeros((C, N, 2), device=dev)
+        v_conics = _f32c(v_conics) if v_conics is not None else torch.zeros((C, N, 3), device=dev)
+        v_depths, v_comps, v_colors = _f32c(v_depths), _f32c(v_comps), _f32c(v_colors)
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        want_sh = coeffs is not None and v_colors is not None and ctx.needs_input_grad[3]
+        v_coeffs = torch.empty_like(coeffs) if want_sh else None
+        want_view = ctx.needs_input_grad[4]
+        v_viewmats = torch.zeros_like(viewmats) if want_view else None
+        want_campos = campos is not None and ctx.needs_input_grad[6] and v_colors is not None
+        v_campos = torch.zeros_like(campos) if want_campos else None
+        K = coeffs.shape[1] if coeffs is not None else 0
+        sh = -1 if (sh_degree is None or v_colors is None) else sh_degree
+        if sh >= 0 and v_coeffs is None:
+            # the kernel writes SH gradients whenever it evaluates SH; give it a scratch target
+            v_coeffs = torch.empty_like(coeffs)
+        check(lib.fsb_project_sh_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height,
+                                     eps2d, sh, K, ptr(coeffs), ptr(campos), color_stride, depth_channel, ptr(radii),
+                                     ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_colors),
+                                     ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_coeffs), ptr(v_viewmats),
+                                     ptr(v_campos), _stream()), "fsb_project_sh_bwd")
+        if coeffs is not None and v_coeffs is None and ctx.needs_input_grad[3]:
+            v_coeffs = torch.zeros_like(coeffs)
+        return (v_means, v_quats, v_scales, v_coeffs if ctx.needs_input_grad[3] else None, v_viewmats, None, v_campos,
+                None, None, None, None, None, None, None, None, None, None, None)
+
+
+class RasterizeToPixels(torch.autograd.Function):
+    """rasterize_to_pixels of gsplat 1.0.0 (optionally with the ED normalisation fused in)."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size,
+                isect_offsets_t, flatten_ids, absgrad, ed_normalize):
+        means2d_c, conics_c = _f32c(means2d), _f32c(conics)
+        colors_c, opac_c, bg_c = _f32c(colors), _f32c(opacities), _f32c(backgrounds)
+        masks_c = masks.contiguous().to(torch.uint8) if masks is not None else None
+        out, alphas, last_ids = raster_fwd(means2d_c, conics_c, colors_c, opac_c, bg_c, masks_c, width, height,
+                                           tile_size, isect_offsets_t, flatten_ids, ed_normalize)
+        ctx.save_for_backward(means2d, conics_c, colors_c, opac_c, bg_c, masks_c, isect_offsets_t, flatten_ids, out,
+                              alphas, last_ids)
+        ctx.cfg = (width, height, tile_size, absgrad, ed_normalize)
+        ctx.set_materialize_grads(False)
+        return out, alphas
+
+    @staticmethod
+    def backward(ctx, v_out, v_alphas):
+        (means2d, conics, colors, opac, bg, masks, isect_offsets_t, flatten_ids, out, alphas,
+         last_ids) = ctx.saved_tensors
+        width, height, tile_size, absgrad, ed_normalize = ctx.cfg
+        v_out = _f32c(v_out) if v_out is not None else torch.zeros_like(out)
+        v_alphas = _f32c(v_alphas) if v_alphas is not None else torch.zeros_like(alphas)
+        v_means2d, v_abs, v_conics, v_colors, v_opac = raster_bwd(
+            _f32c(means2d), conics, colors, opac, bg, masks, width, height, tile_size, isect_offsets_t, flatten_ids,
+            ed_normalize, out, alphas, last_ids, v_out, v_alphas, absgrad)
+        if absgrad:
+            # same contract as gsplat: the tensor handed out as meta["means2d"] gets an .absgrad attribute
+            means2d.absgrad = v_abs
+        v_bg = None
+        if bg is not None and ctx.needs_input_grad[4]:
+            v_bg = (v_out * (1.0 - alphas)).sum(dim=(1, 2))
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None

@@ -1,0 +1,115 @@
+"""Seeded synthetic scenes shaped like FusionSense captures.
+
+Used by tests, bench.py and smoke(); there is no network for real datasets.  Everything is generated on
+the CPU with a fixed seed and then moved to the requested device, so the oracle and the kernels see
+bit-identical inputs.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+SEED_BASE = 20241011
+SH_C0 = 0.28209479177387814
+
+
+def rgb_to_sh(rgb: Tensor) -> Tensor:
+    """nerfstudio `RGB2SH` (used at /root/reference/dn_splatter/dn_model.py:211,1193)."""
+    return (rgb - 0.5) / SH_C0
+
+
+@dataclass
+class Scene:
+    means: Tensor  # [N,3]
+    scales: Tensor  # [N,3] log-scales (DN-Splatter parameterisation, dn_model.py:268-269)
+    quats: Tensor  # [N,4] wxyz, un-normalised
+    opacities: Tensor  # [N,1] logits
+    features_dc: Tensor  # [N,3]
+    features_rest: Tensor  # [N,15,3]
+    viewmats: Tensor  # [M,4,4] world->camera (OpenCV)
+    c2w: Tensor  # [M,4,4]
+    Ks: Tensor  # [M,3,3]
+    width: int
+    height: int
+
+    def to(self, device) -> "Scene":
+        kw = {k: (v.to(device) if isinstance(v, Tensor) else v) for k, v in self.__dict__.items()}
+        return Scene(**kw)
+
+    @property
+    def N(self) -> int:
+        return self.means.shape[0]
+
+
+def look_at_cameras(n_views: int, radius: float, elevation_deg: float = 30.0, dtype=torch.float32):
+    """Ring of OpenCV cameras (x right, y down, z forward) looking at the origin. -> c2w [M,4,4], w2c [M,4,4]."""
+    c2ws = []
+    el = math.radians(elevation_deg)
+    for i in range(n_views):
+        az = 2 * math.pi * i / n_views
+        pos = torch.tensor([radius * math.cos(el) * math.cos(az), radius * math.cos(el) * math.sin(az),
+                            radius * math.sin(el)], dtype=torch.float64)
+        fwd = -pos / pos.norm()
+        up = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64)
+        right = torch.linalg.cross(fwd, up)
+        right = right / right.norm()
+        down = torch.linalg.cross(fwd, right)
+        c2w = torch.eye(4, dtype=torch.float64)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, down, fwd, pos
+        c2ws.append(c2w)
+    c2w = torch.stack(c2ws)
+    w2c = torch.linalg.inv(c2w)
+    return c2w.to(dtype), w2c.to(dtype)
+
+
+def bunny_points(n: int, gen: torch.Generator, scale: float = 1.0) -> Tensor:
+    """Points on a procedural 'bunny': the union of three ellipsoid shells (body, head, ears blob)."""
+    parts = [((0.0, 0.0, 0.0), (0.45, 0.32, 0.30), 0.55), ((0.42, 0.0, 0.28), (0.20, 0.17, 0.17), 0.25),
+             ((0.50, 0.0, 0.55), (0.06, 0.12, 0.22), 0.20)]
+    out = []
+    for k, (ctr, rad, frac) in enumerate(parts):
+        m = n - sum(o.shape[0] for o in out) if k == len(parts) - 1 else int(n * frac)
+        d = torch.randn(m, 3, generator=gen)
+        d = d / d.norm(dim=-1, keepdim=True)
+        out.append(d * torch.tensor(rad) + torch.tensor(ctr))
+    return torch.cat(out) * scale
+
+
+def make_scene(n_gaussians: int, width: int, height: int, n_views: int = 1, cfg_id: int = 1, kind: str = "random",
+               fx: Optional[float] = None, cam_radius: Optional[float] = None, sh_degree: int = 3) -> Scene:
+    """kind='random': means ~ U([-1,1]^3), cameras at radius 2.5.  kind='bunny': RealSense-shaped object scene
+    (object ~0.12 m, cameras at 0.4 m, 20 % background shell) as in BASELINE.json configs[1]."""
+    g = torch.Generator().manual_seed(SEED_BASE + cfg_id)
+    N = n_gaussians
+    if kind == "random":
+        means = torch.rand(N, 3, generator=g) * 2 - 1
+        base = 0.01 * (1e6 / N) ** (1 / 3)
+        cam_radius = 2.5 if cam_radius is None else cam_radius
+    elif kind == "bunny":
+        n_bg = N // 5
+        obj = bunny_points(N - n_bg, g, scale=0.12)
+        d = torch.randn(n_bg, 3, generator=g)
+        bg = d / d.norm(dim=-1, keepdim=True) * 0.9
+        bg[:, 2] = bg[:, 2].abs() * -0.3 - 0.05  # a shallow bowl under the object (table / floor)
+        means = torch.cat([obj, bg])
+        base = 0.0012 * (3e5 / N) ** (1 / 3)
+        cam_radius = 0.4 if cam_radius is None else cam_radius
+    else:
+        raise ValueError(kind)
+    log_s = math.log(base) + 0.3 * torch.randn(N, 3, generator=g)
+    log_s[:, 2] += math.log(0.1)  # surfel-like third axis
+    quats = torch.randn(N, 4, generator=g)
+    opac = 1.5 * torch.randn(N, 1, generator=g)
+    dc = rgb_to_sh(torch.rand(N, 3, generator=g))
+    K = (sh_degree + 1) ** 2
+    rest = 0.05 * torch.randn(N, max(K - 1, 0), 3, generator=g)
+    c2w, w2c = look_at_cameras(n_views, cam_radius)
+    fx = fx if fx is not None else {640: 600.0, 1920: 1400.0, 3840: 2800.0}.get(width, 0.9375 * width)
+    Ks = torch.tensor([[fx, 0, width / 2], [0, fx, height / 2], [0, 0, 1]], dtype=torch.float32)[None].repeat(
+        n_views, 1, 1)
+    return Scene(means.float(), log_s.float(), quats.float(), opac.float(), dc.float(), rest.float(), w2c, c2w, Ks,
+                 width, height)

@@ -1,0 +1,115 @@
+/* fsb200.h — C ABI of libfsb200.so, the B200 (sm_100a) hot path of FusionSense / DN-Splatter.
+ *
+ * Each entry point replaces one stage that the reference reaches through gsplat==1.0.0 /
+ * nerfstudio==1.1.3 / torch (not vendored in the reference tree), or one
+ * first-party function of the reference.  The "replaces" notes cite the reference call site
+ * (paths relative to the reference root) that ends up in that stage.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *  - fp32 row-major contiguous tensors; shapes in brackets; "nullable" pointers may be NULL;
+ *  - the caller owns every buffer including workspaces; nothing here allocates or frees;
+ *  - stream-ordered on `stream` (a cudaStream_t passed as void*), re-entrant, no global state;
+ *  - return value: 0 on success, otherwise a cudaError_t value or FSB_E_ARG (10001) for a refused
+ *    argument; nothing throws across the ABI.
+ */
+#ifndef FSB200_H
+#define FSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSB_E_ARG 10001
+
+/* ------------------------------------------------------------------------------------------------
+ * P1+P2+I1(count): fused EWA projection, SH->RGB and tiles-per-Gaussian.
+ * replaces gsplat fully_fused_projection + spherical_harmonics + clamp_min(+0.5) + isect_tiles pass 1,
+ * called from dn_splatter/dn_model.py:570-591.
+ *   means[N,3] quats[N,4](wxyz) scales[N,3] viewmats[C,4,4] Ks[C,3,3]
+ *   sh_degree -1: no colour evaluation; else coeffs[N,K,3], campos[C,3] (camera centres) and
+ *   colors[C,N,color_stride] must be given: channels 0..2 = max(SH+0.5,0).
+ *   depth_channel >= 0: depths are also written into colors[..., depth_channel] ("RGB+ED").
+ *   outputs: radii[C,N] i32 (0 = culled), means2d[C,N,2], depths[C,N], conics[C,N,3],
+ *   comps[C,N] (nullable), tiles_per_gauss[C,N] i32.  Culled entries are written as zeros. */
+int fsb_project_sh_fwd(int C, int N, const float* means, const float* quats, const float* scales,
+                       const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                       float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w,
+                       int tile_h, int sh_degree, int K, const float* coeffs, const float* campos,
+                       int color_stride, int depth_channel, int32_t* radii, float* means2d, float* depths,
+                       float* conics, float* comps, float* colors, int32_t* tiles_per_gauss, void* stream);
+
+/* P3: backward of the above.  replaces gsplat fully_fused_projection_bwd + compute_sh_bwd
+ * (loss.backward() of dn_splatter/dn_model.py:570-591).
+ *   in : v_means2d[C,N,2] v_depths[C,N](nullable) v_conics[C,N,3] v_comps[C,N](nullable)
+ *        v_colors[C,N,color_stride](nullable; channel depth_channel is added to v_depths)
+ *   out: v_means[N,3] v_quats[N,4] v_scales[N,3] v_coeffs[N,K,3](nullable) — overwritten, summed over cameras;
+ *        v_viewmats[C,4,4], v_campos[C,3] (nullable) — ACCUMULATED (atomicAdd), caller zero-fills. */
+int fsb_project_sh_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                       const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                       int sh_degree, int K, const float* coeffs, const float* campos, int color_stride,
+                       int depth_channel, const int32_t* radii, const float* v_means2d, const float* v_depths,
+                       const float* v_conics, const float* v_comps, const float* v_colors, float* v_means,
+                       float* v_quats, float* v_scales, float* v_coeffs, float* v_viewmats, float* v_campos,
+                       void* stream);
+
+/* I1 (count only) for callers that bring their own 2-D means / radii.
+ * legacy_bbox = 1 selects the gsplat 0.1.x rule ((int) truncation, +1 on the max side) used by
+ * gsplat.rasterize_gaussians (dn_splatter/dn_model.py:644-653); 0 = floor/ceil rule of gsplat 1.0. */
+int fsb_isect_count(int64_t M, const float* means2d, const int32_t* radii, int tile_size, int tile_w,
+                    int tile_h, int legacy_bbox, int32_t* tiles_per_gauss, void* stream);
+
+/* exclusive int64 prefix sum of counts[M] (replaces torch.cumsum inside gsplat isect_tiles);
+ * total_dev receives the grand total (= n_isects), a device scalar the caller copies back. */
+size_t fsb_isect_scan_workspace(int64_t M);
+int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, int64_t* total_dev, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* I1 (emit): isect_ids[n_isects] = (cam << (32+tile_bits)) | (tile << 32) | float_bits(depth),
+ * flatten_ids[n_isects] = cam*N + n.  replaces gsplat isect_tiles pass 2 / map_gaussian_to_intersects. */
+int fsb_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
+                   const int64_t* offsets, int tile_size, int tile_w, int tile_h, int tile_bits,
+                   int legacy_bbox, int64_t* isect_ids, int32_t* flatten_ids, void* stream);
+
+/* I2: stable LSD radix sort of (u64 key, i32 value) pairs on key bits [0, end_bit).
+ * replaces cub::DeviceRadixSort::SortPairs in gsplat isect_tiles and torch.sort in the legacy path.
+ * Buffers A (input, clobbered) and B ping-pong; *result_in_b (host int) = 1 if B holds the result. */
+size_t fsb_radix_sort_workspace(int64_t n, int end_bit);
+int fsb_radix_sort_pairs(int64_t n, int end_bit, uint64_t* keys_a, int32_t* vals_a, uint64_t* keys_b,
+                         int32_t* vals_b, void* workspace, size_t workspace_bytes, int* result_in_b,
+                         void* stream);
+
+/* I3: offsets[C, n_tiles] i32 = first sorted position of each (camera, tile).
+ * replaces gsplat isect_offset_encode / legacy get_tile_bin_edges. */
+int fsb_isect_offsets(int64_t n_isects, const int64_t* sorted_ids, int C, int n_tiles, int tile_bits,
+                      int32_t* offsets, void* stream);
+
+/* R1: tile compositing forward.  replaces gsplat rasterize_to_pixels fwd / legacy rasterize_forward.
+ *   means2d[C*N,2] conics[C*N,3] colors[C*N,D] opacities[C*N] ; backgrounds[C,D] nullable ;
+ *   masks[C*tiles] u8 nullable ; ed_normalize: divide channel D-1 by max(alpha,1e-10) ("ED" modes).
+ *   out_colors[C,H,W,D] out_alphas[C,H,W] last_ids[C,H,W] i32.
+ * D must be one of fsb_raster_supported_channels(); tile_size 8 or 16. */
+int fsb_raster_supported_channels(int D);
+int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
+                   const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
+                   int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
+                   const int32_t* flatten_ids, int ed_normalize, float* out_colors, float* out_alphas,
+                   int32_t* last_ids, void* stream);
+
+/* R2: tile compositing backward.  Gradient outputs are ACCUMULATED; the caller zero-fills them.
+ *   v_means2d_abs nullable (absgrad=True in dn_splatter/dn_model.py:587). */
+int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
+                   const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
+                   int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
+                   const int32_t* flatten_ids, int ed_normalize, const float* render_colors,
+                   const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
+                   const float* v_render_alphas, float* v_means2d_abs, float* v_means2d, float* v_conics,
+                   float* v_colors, float* v_opacities, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB200_H */
