@@ -113,3 +113,74 @@ def make_scene(n_gaussians: int, width: int, height: int, n_views: int = 1, cfg_
         n_views, 1, 1)
     return Scene(means.float(), log_s.float(), quats.float(), opac.float(), dc.float(), rest.float(), w2c, c2w, Ks,
                  width, height)
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic capture on disk in the FusionSense layout — VisualHull input
+# ---------------------------------------------------------------------------------------------
+BUNNY_PARTS = (((0.0, 0.0, 0.0), (0.45, 0.32, 0.30)), ((0.42, 0.0, 0.28), (0.20, 0.17, 0.17)),
+               ((0.50, 0.0, 0.55), (0.06, 0.12, 0.22)))
+
+
+def bunny_silhouettes(c2w, fx: float, fy: float, cx: float, cy: float, width: int, height: int, scale: float = 0.12,
+                      center=(0.0, 0.0, 0.0)):
+    """uint8 0/255 masks [M,H,W]: exact ray / ellipsoid-union intersection of the procedural bunny solid."""
+    import numpy as np
+
+    c2w = np.asarray(c2w, dtype=np.float64)
+    js, is_ = np.meshgrid(np.arange(width) + 0.5, np.arange(height) + 0.5)
+    d_cam = np.stack([(js - cx) / fx, (is_ - cy) / fy, np.ones_like(js)], -1)  # OpenCV camera rays
+    masks = []
+    for m in range(c2w.shape[0]):
+        R, o = c2w[m, :3, :3], c2w[m, :3, 3]
+        d = d_cam @ R.T
+        hit = np.zeros((height, width), bool)
+        for ctr, rad in BUNNY_PARTS:
+            ctr = np.asarray(ctr) * scale + np.asarray(center)
+            rad = np.asarray(rad) * scale
+            oo = (o - ctr) / rad
+            dd = d / rad
+            a = (dd * dd).sum(-1)
+            b = 2 * (dd * oo).sum(-1)
+            c = (oo * oo).sum() - 1.0
+            disc = b * b - 4 * a * c
+            t = (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a)
+            hit |= (disc >= 0) & (t > 0)
+        masks.append(hit.astype(np.uint8) * 255)
+    return np.stack(masks)
+
+
+def write_capture(path, n_views: int = 9, width: int = 640, height: int = 480, fx: float = 600.0,
+                  cam_radius: float = 0.4, object_center=(0.02, -0.01, 0.03), masks=None, c2w=None):
+    """Write transforms.json + images/ + masks/ the way utils/VisualHull.py and utils/readCam.py read them.
+
+    Returns (c2w [M,4,4] float64 numpy, masks uint8 [M,H,W]).
+    """
+    import json
+    import os
+
+    import cv2
+    import numpy as np
+
+    os.makedirs(os.path.join(path, "images"), exist_ok=True)
+    os.makedirs(os.path.join(path, "masks"), exist_ok=True)
+    if c2w is None:
+        c2w_t, _ = look_at_cameras(n_views, cam_radius, elevation_deg=30.0, dtype=torch.float64)
+        c2w = c2w_t.numpy().copy()
+        c2w[:, :3, 3] += np.asarray(object_center)
+    cx, cy = width / 2.0, height / 2.0
+    if masks is None:
+        masks = bunny_silhouettes(c2w, fx, fx, cx, cy, width, height, center=object_center)
+    frames, names = [], []
+    for i in range(c2w.shape[0]):
+        fp = f"images/rgb_{i}.png"
+        names.append(fp)
+        frames.append({"file_path": fp, "transform_matrix": c2w[i].tolist()})
+        rgb = np.repeat(masks[i][..., None], 3, axis=-1)
+        cv2.imwrite(os.path.join(path, fp), rgb)
+        cv2.imwrite(os.path.join(path, "masks", f"rgb_{i}.png"), masks[i])
+    meta = {"fl_x": fx, "fl_y": fx, "cx": cx, "cy": cy, "w": width, "h": height, "frames": frames,
+            "train_filenames": names, "val_filenames": [], "test_filenames": []}
+    with open(os.path.join(path, "transforms.json"), "w") as f:
+        json.dump(meta, f)
+    return c2w, masks

@@ -109,6 +109,26 @@ int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* means2d, 
                    const float* v_render_alphas, float* v_means2d_abs, float* v_means2d, float* v_conics,
                    float* v_colors, float* v_opacities, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Visual hull (voxel carving).  replaces utils/VisualHull.py:149-191 (projection/vote loop, threshold
+ * mask, occupied-voxel extraction) with InitializeVoxels (:15-57) folded into axis-table lookups.
+ * Voxel l = (iz*nx + ix)*ny + iy, zs given in the reference's loop order (descending).
+ *   masks[n_views,H,W] u8 (device), mats_host[n_views,12] f64 (HOST: K @ [R|t] rows), lut[256] f64 (device,
+ *   value/255 as numpy computes it), xs/ys/zs f64 axis tables (device).
+ *   votes[nz*nx*ny] f64 ; max_bits: device u64, zero-filled by the caller, gets bits of max(votes). */
+int fsb_vh_max_views(void);
+int fsb_vh_count_block(void);
+int fsb_vh_votes(int n_views, int H, int W, const uint8_t* masks, const double* mats_host, const double* lut,
+                 const double* xs, int nx, const double* ys, int ny, const double* zs, int nz, double* votes,
+                 uint64_t* max_bits, void* stream);
+/* block_counts[ceil(V / fsb_vh_count_block())] i32 = voxels with votes > iso per block of consecutive voxels */
+int fsb_vh_count(int64_t V, const double* votes, double iso, int32_t* block_counts, void* stream);
+/* order-preserving compaction: points[n_occ,3] f64 (x,y,z) and indices[n_occ] i64 (nullable) in voxel order;
+ * block_offsets = exclusive scan of block_counts (fsb_isect_scan). */
+int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* block_offsets, const double* xs,
+                   int nx, const double* ys, int ny, const double* zs, double* points, int64_t* indices,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
