@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — DN-Splatter train step throughput on B200 (BASELINE.json metric, configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "cfg2"): FusionSense sparse-view DN-Splatter training, 9 views 640x480
+RealSense-shaped synthetic bunny scene, 300k Gaussians, one camera view per GPU per iteration:
+get_outputs (RGB+ED rasterization + legacy normals pass) -> losses -> backward -> Adam -> after_train.
+One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for the definition of every key.
+
+--impl reference: the same step through the CPU oracle (oracle/gsplat_ref.py standing in for gsplat, which is
+not vendored in the reference tree) on the box's host cores, each step a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_GAUSS = 300_000
+WIDTH, HEIGHT = 640, 480
+N_VIEWS = 9
+WORKLOAD = "cfg2: DN-Splatter train step, 9 views 640x480 synthetic bunny, 300k Gaussians, 1 view/GPU/iter"
+METRIC = "dn_splatter_train_iter_per_s"
+UNIT = "iter/s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, idx in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > idx and r[idx].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device, gsplat_module=None, fused=True):
+    import torch
+    from fusionsense_b200.dn_step import DNSplatterStep, DNSplatterStepConfig
+    from fusionsense_b200.synthetic import make_scene
+
+    scene = make_scene(N_GAUSS, WIDTH, HEIGHT, n_views=N_VIEWS, cfg_id=2, kind="bunny")
+    cfg = DNSplatterStepConfig(fused_optimizer=fused)
+    if not fused:
+        cfg.stop_split_at = 0  # the CPU oracle has no absgrad side channel; after_train is skipped there
+    return DNSplatterStep(scene, cfg, device=device, step=3000, gsplat_module=gsplat_module)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: CPU oracle
+# ---------------------------------------------------------------------------------------------
+def cpu_step_seconds(steps: int, warmup: int, sample_tiles_frac: float = 1.0):
+    """Time the oracle-driven train step on the host cores. Returns (seconds per full step, cores, sample text)."""
+    import torch
+    from oracle import gsplat_ref as ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_model("cpu", gsplat_module=ref, fused=False)
+    targets = {0: model.render_targets(0)}
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.train_iteration(0, targets[0])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+    sample = (f"{steps} full train step(s) (RGB+ED pass, normals pass, losses, backward, torch Adam) of the same "
+              f"300k-Gaussian 640x480 scene through oracle/gsplat_ref.py, torch CPU fp32, {cores} threads")
+    return statistics.median(ts), cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    sec, cores, sample = cpu_step_seconds(steps, warmup=min(args.warmup, 1))
+    v = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT,
+                   "note": "gsplat==1.0.0 is not vendored in the reference tree and not installed; the reference's "
+                           "CPU path is its algorithm restated in oracle/ (kind=port)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from fusionsense_b200 import ops
+    from fusionsense_b200._abi import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: fusionsense_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    model = build_model(device)
+    views = list(range(N_VIEWS))
+    dev_targets = {v: model.render_targets(v) for v in views}
+    host_targets = {v: {k: t.cpu().pin_memory() for k, t in d.items()} for v, d in dev_targets.items()}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values())
+
+    params = [model.gauss_params[k] for k in model.config.lrs]
+
+    def allreduce_grads():
+        # one flat NCCL all-reduce over all Gaussian parameter gradients (59 floats per Gaussian)
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        o = 0
+        for p in params:
+            n = p.numel()
+            p.grad = flat[o:o + n].view_as(p)
+            o += n
+
+    def one_step(i, batch):
+        v = (i * world + rank) % N_VIEWS
+        for opt in model.optimizers.values():
+            opt.zero_grad(set_to_none=True)
+        outputs = model.get_outputs(v)
+        loss = model.get_loss_dict(outputs, batch(v))["main_loss"]
+        loss.backward()
+        if world > 1:
+            allreduce_grads()
+        model.optimizers["means"].param_groups[0]["lr"] = model._means_lr()
+        model.optimizer_step()
+        model.after_train()
+        model.step += 1
+        return loss
+
+    def resident(v):
+        return dev_targets[v]
+
+    def from_host(v):
+        return {k: t.to(device, non_blocking=True) for k, t in host_targets[v].items()}
+
+    def timed(n_steps, batch, read_loss):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(n_steps):
+            loss = one_step(i, batch)
+            if read_loss:
+                float(loss)  # device -> host read of the step's result
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # warm-up (also primes the caching allocator); inputs (70 MB of parameters + 70 MB of Adam state + per-step
+    # intersection lists) exceed nothing special, so L2 is flushed between legs by the step's own >126 MB traffic.
+    for i in range(args.warmup):
+        one_step(i, resident)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.fsb_launch_count()
+    with ops.kernel_timer.collect():
+        ms_total = timed(args.steps, resident, read_loss=False)
+        ktimes = ops.kernel_timer.summary()
+    launches = lib.fsb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, from_host, read_loss=True)
+
+    ms_per_step = ms_total / args.steps
+    value = world * 1e3 / ms_per_step
+    e2e_value = world * args.steps * 1e3 / ms_e2e
+
+    # roofline of the dominant kernel: raster backward of the RGB+ED pass (D = 4)
+    from fusionsense_b200.gsplat.cuda_legacy import _wrapper as _legacy
+
+    I = int(_legacy._LAST_BINNING.get("n_isects", 0))  # intersections of the last timed step
+    Nv = int((model.radii > 0).sum().item())
+    P = WIDTH * HEIGHT
+    D = 4
+    bwd_ms = ktimes.get("raster_bwd_D4", (float("nan"), 0))[0]
+    bwd_bytes = I * (28 + 4 * D) + P * (4 * D + 12) + Nv * (32 + 4 * D)
+    peak, peak_src = _peaks()
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms == bwd_ms and bwd_ms > 0 else None
+    roofline = {
+        "kernel": "raster_bwd_kernel<4> (RGB+ED pass)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "kernel_ms": bwd_ms,
+        "n_isects": I, "n_visible": Nv,
+        "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md §8d); the HBM fraction is reported as "
+                "BASELINE.json asks, the pipe utilisation is in profiles/",
+        "kernel_ms_all": {k: round(v[0], 4) for k, v in sorted(ktimes.items())},
+        "raster_fwd_bwd_mpix_per_s": (P / ((ktimes.get("raster_fwd_D4", (0, 0))[0] + bwd_ms) * 1e-3) / 1e6)
+        if bwd_ms == bwd_ms and bwd_ms > 0 else None,
+    }
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT,
+                       "views": N_VIEWS, "views_per_iter_per_gpu": 1, "global_views_per_iter": world,
+                       "l2": "per-step working set (parameters, Adam state, gradients, intersection lists, images: "
+                             ">400 MB touched per step) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "gpu_launches_per_step": launches / args.steps,
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+    line = run_ours(args)
+    if line is None:
+        return
+    if line["n_gpus"] == 1 and not args.no_cpu_baseline:
+        sec, cores, sample = cpu_step_seconds(1, warmup=0)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,7 @@ _CTYPES = {
     "size_t": ctypes.c_size_t,
 }
 
-_DECL_RE = re.compile(r"^\s*(int|size_t|int64_t)\s+(fsb_\w+)\s*\(([^;]*?)\)\s*;", re.M | re.S)
+_DECL_RE = re.compile(r"^\s*(int|size_t|int64_t|uint64_t)\s+(fsb_\w+)\s*\(([^;]*?)\)\s*;", re.M | re.S)
 
 
 def parse_header(path: Path = HEADER):

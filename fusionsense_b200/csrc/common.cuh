@@ -10,10 +10,14 @@
 // never throws.  FSB_E_ARG is our own code for an argument the kernels refuse.
 #define FSB_E_ARG 10001
 
+// number of kernels this library has launched (bench.py reports it as "gpu_launches")
+extern unsigned long long g_fsb_launches;
+
 #define FSB_LAUNCH_CHECK()                         \
     do {                                           \
         cudaError_t e__ = cudaGetLastError();      \
         if (e__ != cudaSuccess) return (int)e__;   \
+        __atomic_fetch_add(&g_fsb_launches, 1ull, __ATOMIC_RELAXED); \
     } while (0)
 
 #define FSB_CUDA(x)                                \

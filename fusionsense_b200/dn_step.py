@@ -1,0 +1,316 @@
+"""The DN-Splatter training iteration, as FusionSense configures it, on top of the B200 kernels.
+
+nerfstudio / torchmetrics are not installed in this image, so `DNSplatterModel` itself cannot be instantiated
+here; this module restates, method by method and with the same names, what one `Trainer.train_iteration`
+executes for the `dn-splatter` method:
+
+  get_outputs      /root/reference/dn_splatter/dn_model.py:469-671   (binary opacities, rasterization RGB+ED,
+                                                                      per-Gaussian normals, legacy normals pass)
+  get_loss_dict    /root/reference/dn_splatter/dn_model.py:673-925 + splatfacto base loss (0.8 L1 + 0.2 (1-SSIM))
+  optimizers       /root/reference/dn_splatter/dn_config.py:36-75    (Adam eps=1e-15, exp-decay on means)
+  after_train      nerfstudio splatfacto: xys_grad_norm / vis_counts / max_2Dsize accumulation
+
+Everything that touches Gaussians or pixels goes through the `gsplat` entry points of this package, exactly the
+calls the reference makes; bench.py and smoke() drive this class.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .losses import SSIM, DepthLoss, DepthLossType, TVLoss
+from .synthetic import Scene
+
+
+@dataclass
+class DNSplatterStepConfig:
+    """Effective FusionSense values (configs/config.py:3-39 over DNSplatterModelConfig, dn_model.py:55-142)."""
+    sh_degree: int = 3
+    sh_degree_interval: int = 1000
+    ssim_lambda: float = 0.2
+    use_depth_loss: bool = True
+    depth_loss_type: DepthLossType = DepthLossType.EdgeAwareLogL1
+    depth_tolerance: float = 0.1
+    sensor_depth_lambda: float = 0.2
+    use_depth_smooth_loss: bool = True
+    smooth_loss_lambda: float = 0.1
+    use_normal_loss: bool = True
+    use_normal_tv_loss: bool = True
+    normal_lambda: float = 0.4
+    two_d_gaussians: bool = True
+    use_binary_opacities: bool = True
+    binary_opacities_threshold: float = 0.9
+    warmup_length: int = 500
+    reset_alpha_every: int = 30
+    refine_every: int = 100
+    stop_split_at: int = 10000
+    background_color: str = "white"
+    rasterize_mode: str = "classic"
+    lrs: Dict[str, float] = field(default_factory=lambda: {
+        "means": 1.6e-4, "features_dc": 0.0025, "features_rest": 0.0025 / 20, "opacities": 0.05, "scales": 0.005,
+        "quats": 0.001})
+    means_lr_final: float = 1.6e-6
+    means_lr_max_steps: int = 30000
+    fused_optimizer: bool = True
+    fused_losses: bool = True  # dn_regularizer_loss instead of the torch loss classes
+    fused_glue: bool = True  # gaussian_normals / densify_stats kernels instead of the inline torch ops
+
+
+class DNSplatterStep:
+    def __init__(self, scene: Scene, config: Optional[DNSplatterStepConfig] = None, device="cuda", step: int = 3000,
+                 gsplat_module=None):
+        """`gsplat_module`: whatever `import gsplat` resolves to for dn_model.py (default: this package's sm_100a
+        implementation).  bench.py's reference arm passes the CPU oracle here, the way the reference would run on
+        an installed gsplat."""
+        self.config = config or DNSplatterStepConfig()
+        self.device = torch.device(device)
+        if gsplat_module is None:
+            from . import gsplat as gsplat_module
+        self._rasterization = gsplat_module.rasterization
+        self._rasterize_gaussians = gsplat_module.rasterize_gaussians
+        self._quat_to_rotmat = gsplat_module.quat_to_rotmat
+        sc = scene.to(self.device)
+        self.scene = sc
+        P = torch.nn.Parameter
+        self.gauss_params = {
+            "means": P(sc.means.clone()), "scales": P(sc.scales.clone()), "quats": P(sc.quats.clone()),
+            "features_dc": P(sc.features_dc.clone()), "features_rest": P(sc.features_rest.clone()),
+            "opacities": P(sc.opacities.clone()),
+        }
+        self.step = step
+        self.training = True
+        self.ssim = SSIM(data_range=1.0, kernel_size=11).to(self.device)
+        self.depth_loss = DepthLoss(self.config.depth_loss_type)
+        self.smooth_loss = DepthLoss(DepthLossType.TV)
+        self.tv_loss = TVLoss()
+        self.background = torch.ones(3, device=self.device)  # background_color = "white" (dn_model.py:141)
+        self.xys_grad_norm = None
+        self.vis_counts = None
+        self.max_2Dsize = None
+        self._build_optimizers()
+
+    # ---- parameters / optimisers ------------------------------------------------------------
+    def __getattr__(self, name):
+        gp = self.__dict__.get("gauss_params")
+        if gp is not None and name in gp:
+            return gp[name]
+        raise AttributeError(name)
+
+    @property
+    def num_points(self) -> int:
+        return self.gauss_params["means"].shape[0]
+
+    def _build_optimizers(self):
+        from .optim import FusedAdam
+
+        cfg = self.config
+        self.optimizers = {}
+        fused = cfg.fused_optimizer and self.device.type == "cuda"
+        for name, lr in cfg.lrs.items():
+            cls = FusedAdam if fused else torch.optim.Adam
+            self.optimizers[name] = cls([self.gauss_params[name]], lr=lr, eps=1e-15)
+        self._fused_optim = fused
+
+    def _means_lr(self) -> float:
+        cfg = self.config
+        t = min(self.step / cfg.means_lr_max_steps, 1.0)
+        return cfg.lrs["means"] * (cfg.means_lr_final / cfg.lrs["means"]) ** t
+
+    # ---- dn_model.py:469-671 ----------------------------------------------------------------
+    def get_outputs(self, cam_idx: int) -> Dict[str, Tensor]:
+        cfg, sc = self.config, self.scene
+        if cfg.use_binary_opacities and self.step > cfg.warmup_length:
+            skip_steps = cfg.reset_alpha_every * cfg.refine_every
+            if not self.step % skip_steps == 0 and self.step % skip_steps not in range(1, 200 + 1):
+                self.opacities.data = torch.where(self.opacities >= cfg.binary_opacities_threshold,
+                                                  torch.ones_like(self.opacities), torch.zeros_like(self.opacities))
+        opacities_crop, means_crop = self.opacities, self.means
+        scales_crop, quats_crop = self.scales, self.quats
+        colors_crop = torch.cat((self.features_dc[:, None, :], self.features_rest), dim=1)
+        BLOCK_WIDTH = 16
+        viewmat = sc.viewmats[cam_idx:cam_idx + 1]
+        K = sc.Ks[cam_idx:cam_idx + 1]
+        c2w = sc.c2w[cam_idx:cam_idx + 1]
+        W, H = sc.width, sc.height
+        self.last_size = (H, W)
+        sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)
+        render, alpha, info = self._rasterization(
+            means=means_crop,
+            quats=quats_crop / quats_crop.norm(dim=-1, keepdim=True),
+            scales=torch.exp(scales_crop),
+            opacities=torch.sigmoid(opacities_crop).squeeze(-1),
+            colors=colors_crop,
+            viewmats=viewmat,
+            Ks=K,
+            width=W,
+            height=H,
+            tile_size=BLOCK_WIDTH,
+            packed=False,
+            near_plane=0.01,
+            far_plane=1e10,
+            render_mode="RGB+ED",
+            sh_degree=sh_degree_to_use,
+            sparse_grad=False,
+            absgrad=True,
+            rasterize_mode=cfg.rasterize_mode,
+        )
+        if self.training and info["means2d"].requires_grad:
+            info["means2d"].retain_grad()
+        self.xys = info["means2d"]
+        self.radii = info["radii"][0]
+        self.depths = info["depths"]
+        self.conics = info["conics"]
+        self.num_tiles_hit = info["tiles_per_gauss"]
+        background = self.background
+        rgb = render[:, ..., :3] + (1 - alpha) * background
+        rgb = torch.clamp(rgb, 0.0, 1.0)
+        depth_im = render[:, ..., 3:4]
+        depth_im = torch.where(alpha > 0, depth_im, depth_im.detach().max()).squeeze(0)
+
+        # per-Gaussian normals (dn_model.py:617-636)
+        if cfg.fused_glue and self.device.type == "cuda":
+            from .gaussians import gaussian_normals
+
+            normals, self.normals_world = gaussian_normals(quats_crop, scales_crop, means_crop, c2w.squeeze(0))
+        else:
+            quats_n = quats_crop / quats_crop.norm(dim=-1, keepdim=True)
+            normals = F.one_hot(torch.argmin(scales_crop, dim=-1), num_classes=3).float()
+            rots = self._quat_to_rotmat(quats_n)
+            normals = torch.bmm(rots, normals[:, :, None]).squeeze(-1)
+            normals = F.normalize(normals, dim=1)
+            viewdirs = -means_crop.detach() + c2w.detach()[..., :3, 3]
+            viewdirs = viewdirs / viewdirs.norm(dim=-1, keepdim=True)
+            dots = (normals * viewdirs).sum(-1)
+            negative_dot_indices = dots < 0
+            normals = torch.where(negative_dot_indices[:, None], -normals, normals)
+            self.normals_world = normals.detach()
+            normals = normals @ c2w.squeeze(0)[:3, :3]
+        xys = self.xys[0, ...].detach()
+        normals_im = self._rasterize_gaussians(xys, self.depths[0, ...], self.radii, self.conics[0, ...],
+                                         self.num_tiles_hit[0, ...], normals, torch.sigmoid(opacities_crop), H, W,
+                                         BLOCK_WIDTH)
+        normals_im = normals_im / normals_im.norm(dim=-1, keepdim=True)
+        normals_im = (normals_im + 1) / 2
+        return {"rgb": rgb.squeeze(0), "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
+                "background": background}
+
+    # ---- splatfacto base loss + dn_model.py:673-925 -----------------------------------------
+    def get_loss_dict(self, outputs, batch) -> Dict[str, Tensor]:
+        cfg = self.config
+        gt_rgb = batch["image"]  # already composited / on device
+        pred_img = outputs["rgb"]
+        fused = cfg.fused_losses and self.device.type == "cuda"
+        simloss = 1 - self.ssim(gt_rgb.permute(2, 0, 1)[None, ...], pred_img.permute(2, 0, 1)[None, ...])
+        if fused:
+            rgb_loss = cfg.ssim_lambda * simloss  # the L1 half rides in the fused kernel below
+        else:
+            Ll1 = torch.abs(gt_rgb - pred_img).mean()
+            rgb_loss = (1 - cfg.ssim_lambda) * Ll1 + cfg.ssim_lambda * simloss
+
+        depth_out = outputs["depth"]
+        sensor_depth_gt = batch["sensor_depth"]
+        if fused:
+            from .losses import dn_regularizer_loss
+
+            reg = dn_regularizer_loss(
+                depth_out, sensor_depth_gt, batch["image"], outputs["normal"], batch["normal"],
+                pred_rgb=pred_img, gt_rgb=gt_rgb, rgb_l1_lambda=1 - cfg.ssim_lambda,
+                depth_tolerance=cfg.depth_tolerance,
+                sensor_depth_lambda=cfg.sensor_depth_lambda if cfg.use_depth_loss else 0.0,
+                smooth_loss_lambda=cfg.smooth_loss_lambda if cfg.use_depth_smooth_loss else 0.0,
+                normal_l1_lambda=cfg.normal_lambda if cfg.use_normal_loss else 0.0,
+                normal_tv_lambda=cfg.normal_lambda if (cfg.use_normal_loss and cfg.use_normal_tv_loss) else 0.0)
+            depth_loss, normal_loss = reg, 0
+        else:
+            gt_img = batch["image"].clamp(min=10 / 255.0)
+            depth_loss = 0
+            if cfg.use_depth_loss and cfg.sensor_depth_lambda > 0.0:
+                valid_gt_mask = sensor_depth_gt > cfg.depth_tolerance
+                depth_loss = depth_loss + cfg.sensor_depth_lambda * self.depth_loss(
+                    depth_out, sensor_depth_gt.float(), gt_img, valid_gt_mask)
+            if cfg.use_depth_smooth_loss:
+                depth_loss = depth_loss + cfg.smooth_loss_lambda * self.smooth_loss(depth_out)
+            normal_loss = 0
+            if cfg.use_normal_loss:
+                pred_normal = outputs["normal"]
+                gt_normal = batch["normal"]
+                normal_loss = normal_loss + torch.abs(gt_normal - pred_normal).mean()
+                if cfg.use_normal_tv_loss:
+                    normal_loss = normal_loss + self.tv_loss(pred_normal)
+        if cfg.two_d_gaussians:
+            normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
+        main_loss = rgb_loss + depth_loss + cfg.normal_lambda * normal_loss
+        return {"main_loss": main_loss, "scale_reg": torch.tensor(0.0, device=self.device)}
+
+    # ---- splatfacto after_train ---------------------------------------------
+    @torch.no_grad()
+    def after_train(self):
+        if self.step >= self.config.stop_split_at:
+            return
+        if self.config.fused_glue and self.device.type == "cuda":
+            from .gaussians import densify_stats
+
+            if self.xys_grad_norm is None:
+                self.xys_grad_norm = torch.zeros(self.num_points, device=self.device, dtype=torch.float32)
+                self.vis_counts = torch.ones(self.num_points, device=self.device, dtype=torch.float32)
+            if self.max_2Dsize is None:
+                self.max_2Dsize = torch.zeros(self.num_points, device=self.device, dtype=torch.float32)
+            densify_stats(self.radii, self.xys.absgrad[0], float(max(self.last_size[0], self.last_size[1])),
+                          self.xys_grad_norm, self.vis_counts, self.max_2Dsize)
+            return
+        visible_mask = (self.radii > 0).flatten()
+        grads = self.xys.absgrad[0][visible_mask].norm(dim=-1)
+        if self.xys_grad_norm is None:
+            self.xys_grad_norm = torch.zeros(self.num_points, device=self.device, dtype=torch.float32)
+            self.vis_counts = torch.ones(self.num_points, device=self.device, dtype=torch.float32)
+        self.vis_counts[visible_mask] += 1
+        self.xys_grad_norm[visible_mask] += grads
+        if self.max_2Dsize is None:
+            self.max_2Dsize = torch.zeros_like(self.radii, dtype=torch.float32)
+        newradii = self.radii.detach()[visible_mask]
+        self.max_2Dsize[visible_mask] = torch.maximum(
+            self.max_2Dsize[visible_mask], newradii / float(max(self.last_size[0], self.last_size[1])))
+
+    # ---- Trainer.train_iteration ------------------------------------------------------------
+    def train_iteration(self, cam_idx: int, batch: Dict[str, Tensor]) -> Tensor:
+        for opt in self.optimizers.values():
+            opt.zero_grad(set_to_none=True)
+        outputs = self.get_outputs(cam_idx)
+        loss_dict = self.get_loss_dict(outputs, batch)
+        loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
+        loss.backward()
+        self.optimizers["means"].param_groups[0]["lr"] = self._means_lr()
+        self.optimizer_step()
+        self.after_train()
+        self.step += 1
+        return loss.detach()
+
+    def optimizer_step(self):
+        """optimizers.optimizer_scaler_step_some: every Gaussian group steps every iteration."""
+        if self._fused_optim:
+            from .optim import fused_step
+
+            fused_step(self.optimizers.values())  # one launch for all six groups
+        else:
+            for opt in self.optimizers.values():
+                opt.step()
+
+    @torch.no_grad()
+    def render_targets(self, cam_idx: int, perturb: float = 0.02, seed: int = 0) -> Dict[str, Tensor]:
+        """Ground truth for a synthetic view: a render of a perturbed copy of the scene."""
+        g = torch.Generator(device="cpu").manual_seed(seed + cam_idx)
+        saved = {k: v.data.clone() for k, v in self.gauss_params.items()}
+        for k, v in self.gauss_params.items():
+            noise = torch.randn(v.shape, generator=g).to(self.device)
+            v.data.add_(perturb * v.data.abs().mean() * noise)
+        ub, self.config.use_binary_opacities, self.training = self.config.use_binary_opacities, False, False
+        out = self.get_outputs(cam_idx)
+        self.config.use_binary_opacities, self.training = ub, True
+        for k, v in self.gauss_params.items():
+            v.data.copy_(saved[k])
+        depth = torch.where(out["accumulation"] > 0.5, out["depth"], torch.zeros_like(out["depth"]))
+        return {"image": out["rgb"].contiguous(), "sensor_depth": depth.contiguous(), "normal": out["normal"].contiguous()}

@@ -20,6 +20,52 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual ABI calls on the launching stream (bench.py's roofline leg).
+
+    Disabled by default (zero overhead); `with ops.kernel_timer.collect(): ...` records (start, end) events
+    around the calls wrapped with `_timed`, `summary()` returns mean milliseconds per name after a sync.
+    """
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def collect(self):
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                timer.enabled, timer.events = True, {}
+                return timer
+
+            def __exit__(self_inner, *exc):
+                timer.enabled = False
+                return False
+
+        return _Ctx()
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(torch.cuda.current_stream())
+        self.events.setdefault(name, []).append((s, e))
+        return e
+
+    @staticmethod
+    def stop(e):
+        if e is not None:
+            e.record(torch.cuda.current_stream())
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (sum(s.elapsed_time(e) for s, e in v) / len(v), len(v)) for k, v in self.events.items()}
+
+
+kernel_timer = KernelTimer()
+
+
 def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -107,8 +153,10 @@ def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tensor, 
     ws_bytes = lib.fsb_radix_sort_workspace(n, end_bit)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     in_b = ctypes.c_int(0)
+    ev = kernel_timer.start("radix_sort")
     check(lib.fsb_radix_sort_pairs(n, end_bit, ptr(keys), ptr(vals), ptr(keys_b), ptr(vals_b), ptr(ws), ws_bytes,
                                    ctypes.addressof(in_b), _stream()), "fsb_radix_sort_pairs")
+    kernel_timer.stop(ev)
     return (keys_b, vals_b) if in_b.value else (keys, vals)
 
 
@@ -155,31 +203,35 @@ def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     out = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
     alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
     last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+    ev = kernel_timer.start(f"raster_fwd_D{D}")
     check(lib.fsb_raster_fwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
                              ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(out), ptr(alphas),
                              ptr(last_ids), _stream()), "fsb_raster_fwd")
+    kernel_timer.stop(ev)
     return out, alphas, last_ids
 
 
 def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
                flatten_ids, ed_normalize, render_colors, render_alphas, last_ids, v_render_colors, v_render_alphas,
-               absgrad):
+               absgrad, need_xy=True):
     C = isect_offsets_t.shape[0]
     tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
     N = means2d.shape[-2]
     D = colors.shape[-1]
-    v_means2d = torch.zeros_like(means2d)
-    v_abs = torch.zeros_like(means2d) if absgrad else None
+    v_means2d = torch.zeros_like(means2d) if need_xy else None
+    v_abs = torch.zeros_like(means2d) if (absgrad and need_xy) else None
     v_conics = torch.zeros_like(conics)
     v_colors = torch.zeros_like(colors)
     v_opac = torch.zeros_like(opacities)
+    ev = kernel_timer.start(f"raster_bwd_D{D}")
     check(lib.fsb_raster_bwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
                              ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(render_colors),
                              ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
                              ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), _stream()),
           "fsb_raster_bwd")
+    kernel_timer.stop(ev)
     return v_means2d, v_abs, v_conics, v_colors, v_opac
 
 
@@ -263,8 +315,8 @@ class RasterizeToPixels(torch.autograd.Function):
         v_alphas = _f32c(v_alphas) if v_alphas is not None else torch.zeros_like(alphas)
         v_means2d, v_abs, v_conics, v_colors, v_opac = raster_bwd(
             _f32c(means2d), conics, colors, opac, bg, masks, width, height, tile_size, isect_offsets_t, flatten_ids,
-            ed_normalize, out, alphas, last_ids, v_out, v_alphas, absgrad)
-        if absgrad:
+            ed_normalize, out, alphas, last_ids, v_out, v_alphas, absgrad, need_xy=ctx.needs_input_grad[0])
+        if absgrad and v_abs is not None:
             # same contract as gsplat: the tensor handed out as meta["means2d"] gets an .absgrad attribute
             means2d.absgrad = v_abs
         v_bg = None

@@ -90,17 +90,25 @@ def make_scene(n_gaussians: int, width: int, height: int, n_views: int = 1, cfg_
         base = 0.01 * (1e6 / N) ** (1 / 3)
         cam_radius = 2.5 if cam_radius is None else cam_radius
     elif kind == "bunny":
-        n_bg = N // 5
-        obj = bunny_points(N - n_bg, g, scale=0.12)
-        d = torch.randn(n_bg, 3, generator=g)
-        bg = d / d.norm(dim=-1, keepdim=True) * 0.9
-        bg[:, 2] = bg[:, 2].abs() * -0.3 - 0.05  # a shallow bowl under the object (table / floor)
-        means = torch.cat([obj, bg])
-        base = 0.0012 * (3e5 / N) ** (1 / 3)
+        # 30 % of the Gaussians on the object, 70 % on the surroundings (table plane + room shell), like a
+        # FusionSense capture where most of the ~300k Gaussians model the background.
+        n_obj = (3 * N) // 10
+        n_floor = (N - n_obj) // 2
+        n_wall = N - n_obj - n_floor
+        obj = bunny_points(n_obj, g, scale=0.12)
+        floor = torch.stack([(torch.rand(n_floor, generator=g) * 2 - 1) * 0.9,
+                             (torch.rand(n_floor, generator=g) * 2 - 1) * 0.9,
+                             torch.full((n_floor,), -0.045)], dim=-1)
+        d = torch.randn(n_wall, 3, generator=g)
+        d[:, 2] = d[:, 2].abs()
+        wall = d / d.norm(dim=-1, keepdim=True) * 0.95
+        means = torch.cat([obj, floor, wall])
+        base = torch.cat([torch.full((n_obj,), 0.0008), torch.full((N - n_obj,), 0.004)]) * (3e5 / N) ** 0.5
         cam_radius = 0.4 if cam_radius is None else cam_radius
     else:
         raise ValueError(kind)
-    log_s = math.log(base) + 0.3 * torch.randn(N, 3, generator=g)
+    base_t = base if isinstance(base, Tensor) else torch.full((N,), float(base))
+    log_s = torch.log(base_t)[:, None] + 0.3 * torch.randn(N, 3, generator=g)
     log_s[:, 2] += math.log(0.1)  # surfel-like third axis
     quats = torch.randn(N, 4, generator=g)
     opac = 1.5 * torch.randn(N, 1, generator=g)

@@ -129,6 +129,58 @@ int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* bl
                    int nx, const double* ys, int ny, const double* zs, double* points, int64_t* indices,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * O1: multi-tensor Adam, one launch for all Gaussian parameter groups.  replaces the torch.optim.Adam.step()
+ * calls for the optimizers of dn_splatter/dn_config.py:36-75 (eps 1e-15, betas (0.9, 0.999), no decay).
+ * Every array argument is a HOST array of length n_tensors (<= fsb_adam_max_tensors()); p/g/m/v hold device
+ * pointers to fp32 tensors of n[i] elements; step[i] = 1-based step count of tensor i for this update. */
+int fsb_adam_max_tensors(void);
+int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                   const int64_t* n, const float* lr, const int64_t* step, float beta1, float beta2, float eps,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DN-Splatter regulariser, fused.  replaces dn_splatter/dn_model.py:722-736 (EdgeAwareLogL1 on sensor depth,
+ * losses.py:177-214), :753-756 (TV on depth, losses.py:269-285), :806 (normal L1), :814-815 (normal TV) and the
+ * RGB L1 term of the base splatfacto loss:
+ *   loss = l_sensor*EALogL1(depth, sensor | sensor > depth_tol, edges of max(edge_rgb, rgb_clamp_min))
+ *        + l_smooth*TV(depth) + l_nl1*mean|gt_normal - pred_normal| + l_ntv*TV(pred_normal)
+ *        + l_rgb*mean|gt_rgb - pred_rgb|
+ * Images are [H,W] / [H,W,3] fp32; a term with weight 0 may have NULL inputs.  loss_out: device scalar.
+ * workspace: fsb_dn_loss_workspace() bytes, filled by fwd and read by bwd (mask counts).
+ * bwd: v_loss is a DEVICE scalar; v_depth / v_normal / v_rgb are nullable and overwritten. */
+size_t fsb_dn_loss_workspace(void);
+int fsb_dn_loss_fwd(int H, int W, const float* depth, const float* sensor, const float* edge_rgb,
+                    const float* pred_normal, const float* gt_normal, const float* pred_rgb, const float* gt_rgb,
+                    float depth_tol, float rgb_clamp_min, float l_sensor, float l_smooth, float l_nl1, float l_ntv,
+                    float l_rgb, void* workspace, float* loss_out, void* stream);
+int fsb_dn_loss_bwd(int H, int W, const float* depth, const float* sensor, const float* edge_rgb,
+                    const float* pred_normal, const float* gt_normal, const float* pred_rgb, const float* gt_rgb,
+                    float depth_tol, float rgb_clamp_min, float l_sensor, float l_smooth, float l_nl1, float l_ntv,
+                    float l_rgb, const void* workspace, const float* v_loss, float* v_depth, float* v_normal,
+                    float* v_rgb, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-Gaussian normals.  replaces dn_splatter/dn_model.py:617-636: one_hot(argmin(scales)) -> R(q) column ->
+ * normalize -> flip towards the camera -> rotate into the camera frame (normals @ c2w[:3,:3]).
+ *   quats[N,4] wxyz (any norm), scales[N,3] (log or linear: only the argmin matters), means[N,3],
+ *   c2w: 3 rows of 4 floats (camera-to-world, row-major).  normals_world[N,3] nullable, normals_cam[N,3].
+ * bwd: v_normals_cam[N,3] -> v_quats[N,4] (overwritten); nothing else is differentiable in the reference. */
+int fsb_gaussian_normals_fwd(int N, const float* quats, const float* scales, const float* means, const float* c2w,
+                             float* normals_world, float* normals_cam, void* stream);
+int fsb_gaussian_normals_bwd(int N, const float* quats, const float* scales, const float* means, const float* c2w,
+                             const float* v_normals_cam, float* v_quats, void* stream);
+
+/* Per-step densification statistics.  replaces nerfstudio splatfacto after_train, whose outputs
+ * dn_splatter/dn_model.py:326-451 (refinement_after) consumes.  For radii[n] > 0:
+ *   vis_counts[n] += 1 ; xys_grad_norm[n] += |grads2d[n]|_2 ; max_2Dsize[n] = max(., radii[n] / max_dim) */
+int fsb_densify_stats(int N, const int32_t* radii, const float* grads2d, float max_dim, float* xys_grad_norm,
+                      float* vis_counts, float* max_2Dsize, void* stream);
+
+/* library bookkeeping: kernels launched by libfsb200 since load (monotone), ABI revision */
+uint64_t fsb_launch_count(void);
+int fsb_abi_version(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,99 @@
+"""CPU: libfsb200.so loads and exports every symbol include/fsb200.h declares (no compute calls: no GPU here),
+the ctypes binding is generated from that header, and the product package has no route into oracle/."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_header_symbols_are_exported():
+    from fusionsense_b200 import _abi, _build
+
+    assert _build.LIB_PATH.exists(), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    protos = _abi.parse_header()
+    assert len(protos) >= 20
+    cdll = ctypes.CDLL(str(_build.LIB_PATH))
+    for name in protos:
+        assert hasattr(cdll, name), f"{name} declared in include/fsb200.h but not exported"
+    # and nothing un-declared leaks out of the library
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_build.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\b(fsb_\w+)\b", out))
+    assert exported == set(protos), exported ^ set(protos)
+
+
+def test_pure_host_entry_points_answer_without_a_gpu():
+    from fusionsense_b200._abi import lib
+
+    assert lib.fsb_abi_version() == 1
+    assert lib.fsb_raster_supported_channels(3) == 3 and lib.fsb_raster_supported_channels(6) == 8
+    assert lib.fsb_raster_supported_channels(33) == -1
+    assert lib.fsb_isect_scan_workspace(5000) == 3 * 8
+    assert lib.fsb_radix_sort_workspace(10000, 44) > 6 * 256 * 4
+    assert lib.fsb_adam_max_tensors() == 8 and lib.fsb_vh_max_views() >= 9
+    # argument validation happens before any CUDA call
+    assert lib.fsb_radix_sort_pairs(-1, 44, None, None, None, None, None, 0, None, None) == 10001
+    assert lib.fsb_raster_fwd(1, 1, 7, 0, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None, 0, None,
+                              None, None, None) == 10001  # D = 7 is not an instantiated channel count
+    assert lib.fsb_raster_fwd(1, 1, 3, 0, None, None, None, None, None, None, 16, 16, 5, 1, 1, None, None, 0, None,
+                              None, None, None) == 10001  # tile_size 5: not whole warps
+
+
+def test_product_package_never_imports_the_oracle():
+    for py in (ROOT / "fusionsense_b200").rglob("*.py"):
+        text = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{py} imports oracle/"
+        assert "oracle." not in re.sub(r'""".*?"""', "", text, flags=re.S).replace("# ", ""), py
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+
+    from fusionsense_b200.gsplat import rasterization, rasterize_gaussians
+
+    n = 4
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rasterization(torch.zeros(n, 3), torch.ones(n, 4), torch.ones(n, 3), torch.ones(n), torch.ones(n, 3),
+                      torch.eye(4)[None], torch.eye(3)[None], 32, 32, packed=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rasterize_gaussians(torch.zeros(n, 2), torch.ones(n), torch.ones(n, dtype=torch.int32), torch.ones(n, 3),
+                            torch.ones(n, dtype=torch.int32), torch.ones(n, 3), torch.ones(n, 1), 32, 32, 16)
+
+
+def test_gsplat_shim_resolves_reference_imports():
+    import sys
+
+    import fusionsense_b200
+
+    saved = {k: v for k, v in sys.modules.items() if k == "gsplat" or k.startswith("gsplat.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        fusionsense_b200.install_gsplat_shim()
+        # the four imports of /root/reference/dn_splatter/dn_model.py:29-35
+        from gsplat.rendering import rasterization  # noqa: F401
+        from gsplat import rasterize_gaussians  # noqa: F401
+        from gsplat.cuda_legacy._torch_impl import quat_to_rotmat
+        from gsplat.cuda_legacy._wrapper import num_sh_bases
+        import inspect
+
+        assert [num_sh_bases(d) for d in range(5)] == [1, 4, 9, 16, 25]
+        sig = inspect.signature(rasterization)
+        assert list(sig.parameters)[:9] == ["means", "quats", "scales", "opacities", "colors", "viewmats", "Ks",
+                                            "width", "height"]
+        d = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect._empty}
+        assert d == dict(near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True,
+                         tile_size=16, backgrounds=None, render_mode="RGB", sparse_grad=False, absgrad=False,
+                         rasterize_mode="classic", channel_chunk=32)
+        import torch
+
+        q = torch.tensor([[2.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 3.0]])
+        R = quat_to_rotmat(q)
+        assert torch.allclose(R[0], torch.eye(3)) and torch.allclose(R[1], torch.diag(torch.tensor([-1.0, -1.0, 1.0])))
+    finally:
+        for k in [k for k in sys.modules if k == "gsplat" or k.startswith("gsplat.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
