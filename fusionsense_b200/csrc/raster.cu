@@ -1,22 +1,30 @@
-// raster.cu — tile rasterisation / alpha compositing, forward and backward.
+// raster.cu — tile rasterisation / alpha compositing, forward and backward, load-balanced by list segments.
 //
 // Replaces gsplat 1.0.0's rasterize_to_pixels_{fwd,bwd}_kernel and the legacy rasterize_forward /
 // rasterize_backward_kernel (Appendix A.5/A.6), reached from
 // /root/reference/dn_splatter/dn_model.py:570-591 (RGB + expected depth, D = 4) and :644-653
 // (normals, D = 3, white background).
 //
-// One CTA per tile (tile_size x tile_size threads, one pixel each; a warp owns a strip of 32/tile_size rows).
-// The tile's depth-sorted list is staged through shared memory in batches of blockDim entries.  While staging,
-// each thread computes for its Gaussian the exact bounding box of the ellipse {alpha >= 1/255} and from it
-// the set of warp strips the Gaussian can touch (an 8-bit mask).  Every warp then walks only the entries
-// whose bit is set (ballot + find-first-set): entries it skips are entries all of its lanes would have
-// rejected with the alpha < 1/255 test, so results are unchanged.  The per-pixel loop is FP32/MUFU bound.
+// Why segments: real scenes give a few tiles depth-sorted lists 50x longer than the median (object
+// silhouettes), and one-CTA-per-tile leaves 148 SMs waiting for the handful that own them (ncu:
+// sm__cycles_active max/avg = 3.4 on the 300k-Gaussian bench scene).  Here every tile's list is cut into
+// segments of SEG entries and the unit of work is one (tile, segment) CTA:
 //
-// Forward: front to back, four list entries evaluated together (independent sigma/exp chains) before the
-// sequential blend; warp and CTA early termination.
-// Backward: back to front replay from last_ids; the 8 + D per-Gaussian partial gradients of a warp are
-// reduced with a transposing butterfly (16 shuffles instead of 5 * (8 + D)) that leaves each total in a
-// different lane, so one warp-wide red.global.add updates all of them.
+//   forward   the CTA stages its segment in shared memory (with an exact per-warp-strip reach mask, see
+//             strip_mask) and composites it.  Per-pixel transmittance is chained from segment to segment
+//             through global memory like a decoupled look-back scan: if the predecessor segment has already
+//             published its state the CTA composites exactly from it; otherwise it composites speculatively
+//             from T = 1, waits, and folds the incoming state in:  C = C_in + T_in * C_loc, T = T_in * T_loc.
+//             Pixels whose reference stop rule (T * (1 - alpha) <= 1e-4) fires inside the segment are
+//             re-walked exactly, so the per-pixel semantics of the sequential algorithm are kept.
+//   backward  needs no chain at all: the forward leaves, per (segment, pixel), the transmittance after the
+//             segment and the colour accumulated through it, so every segment replays independently.
+//
+// Inside a CTA (tile_size x tile_size threads, one pixel each, a warp owns a strip of 32/tile_size rows) warps
+// walk only the entries whose reach mask has their bit (ballot + find-first-set); forward evaluates four
+// entries together for ILP; backward reduces the 8 + D per-Gaussian partials with a transposing butterfly
+// (16 shuffles) that leaves each total in its own lane, so one warp-wide red.global.add updates all of them.
+// The per-pixel loop is FP32/MUFU bound, not HBM bound.
 #include "common.cuh"
 
 namespace {
@@ -25,6 +33,95 @@ constexpr float ALPHA_MAX = 0.999f;
 constexpr float ALPHA_MIN = 1.f / 255.f;
 constexpr float T_MIN = 1e-4f;
 constexpr int MAX_BLOCK = 256;  // tile_size <= 16
+// list entries per work unit; shorter for wide colour vectors so the staged segment stays under 48 KB of smem
+__host__ __device__ constexpr int seg_len(int D) { return D <= 8 ? 512 : (D <= 16 ? 256 : 128); }
+
+struct SegHeader {
+    int total_segs;
+    unsigned ticket;
+    int pad[2];
+};
+
+struct Workspace {
+    SegHeader* hdr;
+    int* flags;          // [max_segs]  0 = not published, 1 = published
+    int32_t* seg_start;  // [n_tiles + 1]
+    int32_t* seg_tile;   // [max_segs]
+    float* chain_T;      // [max_segs, 256]  transmittance after the segment; negative = pixel finished
+    int32_t* chain_last; // [max_segs, 256]  last contributing list position so far
+    float* prefix_C;     // [max_segs, 256, D] colour accumulated through the segment
+};
+
+inline int64_t max_segments(int64_t n_isects, int64_t n_tiles, int D) { return n_isects / seg_len(D) + n_tiles; }
+
+inline size_t ws_bytes(int64_t n_isects, int64_t n_tiles, int D) {
+    int64_t ms = max_segments(n_isects, n_tiles, D);
+    size_t b = 256;                                          // header
+    b += fsb_align_up((size_t)ms * 4, 256);                  // flags
+    b += fsb_align_up((size_t)(n_tiles + 1) * 4, 256);       // seg_start
+    b += fsb_align_up((size_t)ms * 4, 256);                  // seg_tile
+    b += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256) * 2;  // chain_T, chain_last
+    b += fsb_align_up((size_t)ms * MAX_BLOCK * D * 4, 256);  // prefix_C
+    return b;
+}
+
+inline Workspace carve_ws(void* base, int64_t n_isects, int64_t n_tiles, int D, size_t* zero_bytes) {
+    int64_t ms = max_segments(n_isects, n_tiles, D);
+    char* p = (char*)base;
+    Workspace w;
+    w.hdr = (SegHeader*)p; p += 256;
+    w.flags = (int*)p; p += fsb_align_up((size_t)ms * 4, 256);
+    if (zero_bytes) *zero_bytes = (size_t)(p - (char*)base);  // header + flags are zero-filled per launch
+    w.seg_start = (int32_t*)p; p += fsb_align_up((size_t)(n_tiles + 1) * 4, 256);
+    w.seg_tile = (int32_t*)p; p += fsb_align_up((size_t)ms * 4, 256);
+    w.chain_T = (float*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
+    w.chain_last = (int32_t*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
+    w.prefix_C = (float*)p;
+    return w;
+}
+
+// ---- segment table: one block scans ceil(len / SEG) over the tiles -------------------------------------------
+__global__ void __launch_bounds__(1024)
+seg_table_kernel(int n_tiles, int64_t n_isects, int SEG, const int32_t* __restrict__ tile_offsets,
+                 int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_tile, SegHeader* __restrict__ hdr) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + tid;
+        int nseg = 0;
+        if (t < n_tiles) {
+            const int32_t b = tile_offsets[t];
+            const int32_t e = (t == n_tiles - 1) ? (int32_t)n_isects : tile_offsets[t + 1];
+            nseg = max(1, (e - b + SEG - 1) / SEG);
+        }
+        int inc = nseg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+        const int carry = s_carry;
+        const int excl = carry + wbase + inc - nseg;
+        if (t < n_tiles) {
+            seg_start[t] = excl;
+            for (int k = 0; k < nseg; ++k) seg_tile[excl + k] = t;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        seg_start[n_tiles] = s_carry;
+        hdr->total_segs = s_carry;
+    }
+}
 
 struct TileGeom {
     int cam, tile_x, tile_y;
@@ -34,10 +131,10 @@ struct TileGeom {
     bool inside;
 };
 
-__device__ __forceinline__ TileGeom tile_geom(int tile_w, int tile_h, int tile_size, int width, int height) {
+__device__ __forceinline__ TileGeom tile_geom(int64_t tile_lin, int tile_w, int tile_h, int tile_size, int width,
+                                              int height) {
     TileGeom g;
     const int n_tiles = tile_w * tile_h;
-    const int64_t tile_lin = blockIdx.x;
     g.cam = (int)(tile_lin / n_tiles);
     const int tile_id = (int)(tile_lin - (int64_t)g.cam * n_tiles);
     g.tile_y = tile_id / tile_w;
@@ -81,10 +178,11 @@ __device__ __forceinline__ uint32_t strip_mask(float gx, float gy, float opac, f
 
 template <int D>
 struct Stage {
-    int32_t id[MAX_BLOCK];
-    float4 xyo[MAX_BLOCK];  // x, y, opacity, strip mask (as int bits)
-    float4 con[MAX_BLOCK];  // conic a, b, c
-    float col[MAX_BLOCK * D];
+    static constexpr int SEG = seg_len(D);
+    int32_t id[SEG];
+    float4 xyo[SEG];  // x, y, opacity, strip mask (as int bits)
+    float4 con[SEG];  // conic a, b, c
+    float col[SEG * D];
 };
 
 template <int D>
@@ -104,6 +202,68 @@ __device__ __forceinline__ void stage_entry(Stage<D>& s, int slot, int32_t g, co
     for (int k = 0; k < D; ++k) s.col[slot * D + k] = cp[k];
 }
 
+// Front-to-back walk of this warp's entries of the staged segment.
+// EXACT: the reference semantics incl. the stop rule (`done` lanes are frozen).  !EXACT: speculative local pass
+// (no stop rule; `done` only masks pixels outside the image).  `last` = list position of the last blended entry.
+template <int D, bool EXACT>
+__device__ __forceinline__ void walk(const Stage<D>& s, int n, int seg_b, const TileGeom& tg, float& T,
+                                     float (&acc)[D], int32_t& last, bool& done) {
+    bool warp_done = __all_sync(0xffffffffu, done);
+    for (int k0 = 0; k0 < n && !warp_done; k0 += 32) {
+        const int tt = k0 + tg.lane;
+        const uint32_t m = (tt < n) ? (uint32_t)__float_as_int(s.xyo[tt].w) : 0u;
+        uint32_t bits = __ballot_sync(0xffffffffu, (m >> tg.warp) & 1u);
+        while (bits) {
+            int t[4];
+            float alpha[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (bits) {
+                    t[u] = k0 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                } else {
+                    t[u] = -1;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ok[u] = false;
+                alpha[u] = 0.f;
+                if (t[u] >= 0) {
+                    const float4 xyo = s.xyo[t[u]];
+                    const float4 con = s.con[t[u]];
+                    const float dx = xyo.x - tg.px, dy = xyo.y - tg.py;
+                    const float sigma = 0.5f * (con.x * dx * dx + con.z * dy * dy) + con.y * dx * dy;
+                    alpha[u] = fminf(ALPHA_MAX, xyo.z * __expf(-sigma));
+                    ok[u] = !(sigma < 0.f || alpha[u] < ALPHA_MIN);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ok[u] && !done) {
+                    const float next_T = T * (1.f - alpha[u]);
+                    if (EXACT && next_T <= T_MIN) {
+                        done = true;
+                    } else {
+                        const float w = alpha[u] * T;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) acc[k] += s.col[t[u] * D + k] * w;
+                        last = seg_b + t[u];
+                        T = next_T;
+                    }
+                }
+            }
+            if (EXACT && __all_sync(0xffffffffu, done)) {
+                warp_done = true;
+                break;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int ld_flag(const int* p) { return *((volatile const int*)p); }
+
 template <int D>
 __global__ void __launch_bounds__(MAX_BLOCK)
 raster_fwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
@@ -111,116 +271,138 @@ raster_fwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
                   const float* __restrict__ opacities, const float* __restrict__ backgrounds,
                   const uint8_t* __restrict__ masks, int width, int height, int tile_size, int tile_w, int tile_h,
                   const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
-                  int ed_normalize, float* __restrict__ out_colors, float* __restrict__ out_alphas,
+                  int ed_normalize, Workspace ws, float* __restrict__ out_colors, float* __restrict__ out_alphas,
                   int32_t* __restrict__ last_ids) {
+    constexpr int SEG = seg_len(D);
     __shared__ Stage<D> s;
-    const TileGeom tg = tile_geom(tile_w, tile_h, tile_size, width, height);
-    const int64_t tile_lin = blockIdx.x;
-    const int64_t pix = ((int64_t)tg.cam * height + tg.i) * width + tg.j;
-
-    float acc[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) acc[k] = 0.f;
-
-    if (masks != nullptr && !masks[tile_lin]) {
-        if (tg.inside) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) out_colors[pix * D + k] = backgrounds ? backgrounds[tg.cam * D + k] : 0.f;
-            out_alphas[pix] = 0.f;
-            last_ids[pix] = 0;
-        }
-        return;
-    }
+    __shared__ int s_seg, s_ready;
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_seg = (int)atomicAdd(&ws.hdr->ticket, 1u);
+    __syncthreads();
+    const int seg = s_seg;  // dynamic numbering: every predecessor segment has been started before this one
+    if (seg >= ws.hdr->total_segs) return;
+    const int64_t tile_lin = ws.seg_tile[seg];
+    const int k = seg - ws.seg_start[tile_lin];
+    const int nseg = ws.seg_start[tile_lin + 1] - ws.seg_start[tile_lin];
+    const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
+    const int64_t pix = tg.inside ? ((int64_t)tg.cam * height + tg.i) * width + tg.j : 0;
+    const bool masked = (masks != nullptr && !masks[tile_lin]);
 
     const int32_t range_start = tile_offsets[tile_lin];
     const int32_t range_end =
         (tile_lin == (int64_t)C * tile_w * tile_h - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
-    const int num_batches = (range_end - range_start + tg.block_size - 1) / tg.block_size;
+    const int32_t seg_b = range_start + k * SEG;
+    const int n = masked ? 0 : max(0, min(range_end, seg_b + SEG) - seg_b);
 
-    bool done = !tg.inside;
+    if (tg.tr == 0) s_ready = (k == 0) ? 1 : ld_flag(ws.flags + seg - 1);
+    __syncthreads();
+    const bool have_in = (s_ready != 0);
+
     float T = 1.f;
-    int32_t cur_idx = 0;
+    float acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.f;
+    int32_t last = 0;
+    bool done = !tg.inside;
+    const size_t cidx = (size_t)seg * MAX_BLOCK + tg.tr;
 
-    for (int b = 0; b < num_batches; ++b) {
-        if (__syncthreads_count(done) >= tg.block_size) break;
-        const int32_t batch_start = range_start + tg.block_size * b;
-        const int32_t idx = batch_start + tg.tr;
-        if (idx < range_end) stage_entry<D>(s, tg.tr, flatten_ids[idx], means2d, conics, colors, opacities, tg, tile_size);
+    auto load_in = [&](float& Ti, float (&Ci)[D], int32_t& li, bool& di) {
+        while (ld_flag(ws.flags + seg - 1) == 0) {
+        }
+        __threadfence();
+        const size_t pidx = (size_t)(seg - 1) * MAX_BLOCK + tg.tr;
+        const float t_in = __ldcg(ws.chain_T + pidx);
+        li = __ldcg(ws.chain_last + pidx);
+#pragma unroll
+        for (int c = 0; c < D; ++c) Ci[c] = __ldcg(ws.prefix_C + pidx * D + c);
+        di = (t_in < 0.f);
+        Ti = fabsf(t_in);
+    };
+
+    if (have_in) {
+        if (k > 0) {
+            bool d_in;
+            load_in(T, acc, last, d_in);
+            done = done || d_in;
+        }
+        // whole tile already finished (or nothing to add): skip staging
+        if (__syncthreads_count(done) < tg.block_size && n > 0) {
+            for (int e = tg.tr; e < n; e += tg.block_size)
+                stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
+            __syncthreads();
+            walk<D, true>(s, n, seg_b, tg, T, acc, last, done);
+        }
+    } else {
+        // predecessor still running: composite this segment from T = 1, then fold the incoming state in
+        for (int e = tg.tr; e < n; e += tg.block_size)
+            stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
         __syncthreads();
-        const int batch_size = min(tg.block_size, range_end - batch_start);
-        bool warp_done = __all_sync(0xffffffffu, done);
-        for (int k0 = 0; k0 < batch_size && !warp_done; k0 += 32) {
-            const int tt = k0 + tg.lane;
-            const uint32_t m = (tt < batch_size) ? (uint32_t)__float_as_int(s.xyo[tt].w) : 0u;
-            uint32_t bits = __ballot_sync(0xffffffffu, (m >> tg.warp) & 1u);
-            while (bits) {
-                // up to four entries of this warp's strip, evaluated together
-                int t[4];
-                float alpha[4];
-                bool ok[4];
+        float T_loc = 1.f;
+        float C_loc[D];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (bits) {
-                        t[u] = k0 + __ffs(bits) - 1;
-                        bits &= bits - 1;
-                    } else {
-                        t[u] = -1;
-                    }
-                }
+        for (int c = 0; c < D; ++c) C_loc[c] = 0.f;
+        int32_t last_loc = -1;
+        bool outside = !tg.inside;
+        walk<D, false>(s, n, seg_b, tg, T_loc, C_loc, last_loc, outside);
+        bool d_in;
+        load_in(T, acc, last, d_in);
+        done = done || d_in;
+        bool redo = false;
+        if (!done) {
+            if (T * T_loc > T_MIN) {  // the stop rule cannot have fired inside the segment
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    ok[u] = false;
-                    alpha[u] = 0.f;
-                    if (t[u] >= 0) {
-                        const float4 xyo = s.xyo[t[u]];
-                        const float4 con = s.con[t[u]];
-                        const float dx = xyo.x - tg.px, dy = xyo.y - tg.py;
-                        const float sigma = 0.5f * (con.x * dx * dx + con.z * dy * dy) + con.y * dx * dy;
-                        alpha[u] = fminf(ALPHA_MAX, xyo.z * __expf(-sigma));
-                        ok[u] = !(sigma < 0.f || alpha[u] < ALPHA_MIN);
-                    }
-                }
+                for (int c = 0; c < D; ++c) acc[c] += T * C_loc[c];
+                T *= T_loc;
+                if (last_loc >= 0) last = last_loc;
+            } else {
+                redo = true;
+            }
+        }
+        if (__any_sync(0xffffffffu, redo)) {
+            // exact re-walk from the incoming state for the pixels that stop inside this segment
+            bool frozen = !redo;
+            float Tr = T;
+            float Cr[D];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (ok[u] && !done) {
-                        const float next_T = T * (1.f - alpha[u]);
-                        if (next_T <= T_MIN) {
-                            done = true;
-                        } else {
-                            const float w = alpha[u] * T;
+            for (int c = 0; c < D; ++c) Cr[c] = acc[c];
+            int32_t lr = last;
+            walk<D, true>(s, n, seg_b, tg, Tr, Cr, lr, frozen);
+            if (redo) {
+                T = Tr;
+                last = lr;
+                done = frozen;
 #pragma unroll
-                            for (int k = 0; k < D; ++k) acc[k] += s.col[t[u] * D + k] * w;
-                            cur_idx = batch_start + t[u];
-                            T = next_T;
-                        }
-                    }
-                }
-                if (__all_sync(0xffffffffu, done)) {
-                    warp_done = true;
-                    break;
-                }
+                for (int c = 0; c < D; ++c) acc[c] = Cr[c];
             }
         }
     }
 
+    // publish (also consumed by the backward pass)
+    ws.chain_T[cidx] = (done && tg.inside) ? -T : T;
+    ws.chain_last[cidx] = last;
+#pragma unroll
+    for (int c = 0; c < D; ++c) ws.prefix_C[cidx * D + c] = acc[c];
+    if (k < nseg - 1) {
+        __threadfence();
+        __syncthreads();
+        if (tg.tr == 0) *((volatile int*)(ws.flags + seg)) = 1;
+        return;
+    }
     if (tg.inside) {
-        const float alpha_out = 1.f - T;
+        const float alpha_out = masked ? 0.f : 1.f - T;
         out_alphas[pix] = alpha_out;
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            float v = backgrounds ? acc[k] + T * backgrounds[tg.cam * D + k] : acc[k];
-            if (ed_normalize && k == D - 1) v = v / fmaxf(alpha_out, 1e-10f);
-            out_colors[pix * D + k] = v;
+        for (int c = 0; c < D; ++c) {
+            float v = backgrounds ? acc[c] + (1.f - alpha_out) * backgrounds[tg.cam * D + c] : acc[c];
+            if (ed_normalize && c == D - 1) v = v / fmaxf(alpha_out, 1e-10f);
+            out_colors[pix * D + c] = v;
         }
-        last_ids[pix] = cur_idx;
+        last_ids[pix] = last;
     }
 }
 
-// Sum NV (<= 16) per-lane values over the warp so that lane L ends up with the total of value index
+// Sum up to 16 per-lane values over the warp so that lane L ends up with the total of value index
 // slot_of_lane(L); 16 shuffles in all.  v[] is clobbered; the total is returned.
-template <int NV>
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[16], int lane) {
-    static_assert(NV <= 16, "at most 16 values");
     {
         const bool hi = lane & 16;
 #pragma unroll
@@ -261,7 +443,6 @@ __device__ __forceinline__ int slot_of_lane(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-// Generic (D > 8) fallback reduction: plain butterflies.
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -276,66 +457,74 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
                   const float* __restrict__ opacities, const float* __restrict__ backgrounds,
                   const uint8_t* __restrict__ masks, int width, int height, int tile_size, int tile_w, int tile_h,
                   const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
-                  int ed_normalize, const float* __restrict__ render_colors,
+                  int ed_normalize, Workspace ws, const float* __restrict__ render_colors,
                   const float* __restrict__ render_alphas, const int32_t* __restrict__ last_ids,
                   const float* __restrict__ v_render_colors, const float* __restrict__ v_render_alphas,
                   float* __restrict__ v_means2d_abs, float* __restrict__ v_means2d, float* __restrict__ v_conics,
                   float* __restrict__ v_colors, float* __restrict__ v_opacities) {
+    constexpr int SEG = seg_len(D);
     __shared__ Stage<D> s;
-    const TileGeom tg = tile_geom(tile_w, tile_h, tile_size, width, height);
-    const int64_t tile_lin = blockIdx.x;
+    __shared__ int32_t s_wmax[MAX_BLOCK / 32];
+    const int seg = blockIdx.x;
+    if (seg >= ws.hdr->total_segs) return;
+    const int64_t tile_lin = ws.seg_tile[seg];
     if (masks != nullptr && !masks[tile_lin]) return;
+    const int k = seg - ws.seg_start[tile_lin];
+    const int seg_last = ws.seg_start[tile_lin + 1] - 1;
+    const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
     const int64_t pix = tg.inside ? ((int64_t)tg.cam * height + tg.i) * width + tg.j : 0;
 
     const int32_t range_start = tile_offsets[tile_lin];
     const int32_t range_end =
         (tile_lin == (int64_t)C * tile_w * tile_h - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
-    const int num_batches = (range_end - range_start + tg.block_size - 1) / tg.block_size;
-    if (num_batches <= 0) return;
+    const int32_t seg_b = range_start + k * SEG;
+    const int n = max(0, min(range_end, seg_b + SEG) - seg_b);
+    if (n <= 0) return;
 
-    float T_final = 1.f, v_ra = 0.f;
+    int32_t bin_final = -1;
+    if (tg.inside) bin_final = last_ids[pix];
+    int32_t warp_bin_final = bin_final;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
+    if (tg.lane == 0) s_wmax[tg.warp] = warp_bin_final;
+    __syncthreads();
+    int32_t cta_bin_final = -1;
+    for (int w = 0; w < tg.n_warps; ++w) cta_bin_final = max(cta_bin_final, s_wmax[w]);
+    if (cta_bin_final < seg_b) return;  // no pixel of the tile reaches into this segment
+
+    float T_final = 1.f, v_ra = 0.f, T = 1.f;
     float v_rc[D];
     float buffer[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) { v_rc[k] = 0.f; buffer[k] = 0.f; }
-    int32_t bin_final = -1;
+    for (int c = 0; c < D; ++c) { v_rc[c] = 0.f; buffer[c] = 0.f; }
     if (tg.inside) {
         const float alpha_out = render_alphas[pix];
         T_final = 1.f - alpha_out;
         v_ra = v_render_alphas[pix];
 #pragma unroll
-        for (int k = 0; k < D; ++k) v_rc[k] = v_render_colors[pix * D + k];
+        for (int c = 0; c < D; ++c) v_rc[c] = v_render_colors[pix * D + c];
         if (ed_normalize) {
-            // out[D-1] = acc / max(alpha, 1e-10)
             const float den = fmaxf(alpha_out, 1e-10f);
             const float v_ed = v_rc[D - 1];
             v_rc[D - 1] = v_ed / den;
             if (alpha_out >= 1e-10f) v_ra += -v_ed * render_colors[pix * D + D - 1] / den;
         }
-        bin_final = last_ids[pix];
+        // state at the END of this segment, left behind by the forward pass
+        const size_t cidx = (size_t)seg * MAX_BLOCK + tg.tr;
+        const size_t lidx = (size_t)seg_last * MAX_BLOCK + tg.tr;
+        T = fabsf(ws.chain_T[cidx]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) buffer[c] = ws.prefix_C[lidx * D + c] - ws.prefix_C[cidx * D + c];
     }
-    float T = T_final;
     float bg_dot = 0.f;
     if (backgrounds) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) bg_dot += backgrounds[tg.cam * D + k] * v_rc[k];
+        for (int c = 0; c < D; ++c) bg_dot += backgrounds[tg.cam * D + c] * v_rc[c];
     }
-    int32_t warp_bin_final = bin_final;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
-    // deepest list position any pixel of the tile reached: batches entirely behind it are never staged
-    __shared__ int32_t s_wmax[MAX_BLOCK / 32];
-    if (tg.lane == 0) s_wmax[tg.warp] = warp_bin_final;
-    __syncthreads();
-    int32_t cta_bin_final = -1;
-    for (int w = 0; w < tg.n_warps; ++w) cta_bin_final = max(cta_bin_final, s_wmax[w]);
-    if (cta_bin_final < range_start) return;
-    const int b_first = (range_end - 1 - cta_bin_final) / tg.block_size;
     const bool want_xy = (v_means2d != nullptr);
     const bool want_abs = (v_means2d_abs != nullptr);
 
-    // per-lane atomic target for the transposed reduction (D <= 8: 8 + D <= 16 slots)
     constexpr bool kTranspose = (D <= 8);
     const int slot = slot_of_lane(tg.lane);
     float* slot_base = nullptr;
@@ -348,97 +537,96 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
         else if (slot < D + 8) { slot_base = want_abs ? v_means2d_abs + (slot - D - 6) : nullptr; slot_stride = 2; }
     }
 
-    for (int b = b_first; b < num_batches; ++b) {
-        __syncthreads();
-        const int32_t batch_end = range_end - 1 - tg.block_size * b;
-        const int batch_size = min(tg.block_size, batch_end + 1 - range_start);
-        const int32_t idx = batch_end - tg.tr;
-        if (idx >= range_start) stage_entry<D>(s, tg.tr, flatten_ids[idx], means2d, conics, colors, opacities, tg, tile_size);
-        __syncthreads();
-        const int t_first = max(0, batch_end - warp_bin_final);
-        for (int k0 = (t_first & ~31); k0 < batch_size; k0 += 32) {
-            const int tt = k0 + tg.lane;
-            const uint32_t m = (tt < batch_size && tt >= t_first) ? (uint32_t)__float_as_int(s.xyo[tt].w) : 0u;
-            uint32_t bits = __ballot_sync(0xffffffffu, (m >> tg.warp) & 1u);
-            while (bits) {
-                const int t = k0 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                bool valid = tg.inside && (batch_end - t <= bin_final);
-                float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
-                float4 con = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    const float4 xyo = s.xyo[t];
-                    con = s.con[t];
-                    opac = xyo.z;
-                    dx = xyo.x - tg.px; dy = xyo.y - tg.py;
-                    const float sigma = 0.5f * (con.x * dx * dx + con.z * dy * dy) + con.y * dx * dy;
-                    vis = __expf(-sigma);
-                    alpha = fminf(ALPHA_MAX, opac * vis);
-                    if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
-                }
-                if (!__any_sync(0xffffffffu, valid)) continue;
+    // entries behind every pixel's last id are not even staged
+    const int n_used = min(n, cta_bin_final - seg_b + 1);
+    for (int e = tg.tr; e < n_used; e += tg.block_size)
+        stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
+    __syncthreads();
 
-                float v[16];
+    const int t_hi = min(n_used - 1, warp_bin_final - seg_b);  // last entry this warp can need
+    for (int k0 = (t_hi >= 0 ? (t_hi & ~31) : -32); k0 >= 0; k0 -= 32) {
+        const int tt = k0 + tg.lane;
+        const uint32_t m = (tt <= t_hi) ? (uint32_t)__float_as_int(s.xyo[tt].w) : 0u;
+        uint32_t bits = __ballot_sync(0xffffffffu, (m >> tg.warp) & 1u);
+        while (bits) {
+            const int hb = 31 - __clz(bits);
+            const int t = k0 + hb;
+            bits &= ~(1u << hb);
+            bool valid = tg.inside && (seg_b + t <= bin_final);
+            float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
+            float4 con = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float4 xyo = s.xyo[t];
+                con = s.con[t];
+                opac = xyo.z;
+                dx = xyo.x - tg.px; dy = xyo.y - tg.py;
+                const float sigma = 0.5f * (con.x * dx * dx + con.z * dy * dy) + con.y * dx * dy;
+                vis = __expf(-sigma);
+                alpha = fminf(ALPHA_MAX, opac * vis);
+                if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+            }
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            float v[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = 0.f;
-                float v_colD[D > 8 ? D : 1];
-                if (valid) {
-                    const float ra = 1.f / (1.f - alpha);
-                    T *= ra;
-                    const float fac = alpha * T;
-                    float v_alpha = 0.f;
+            for (int c = 0; c < 16; ++c) v[c] = 0.f;
+            float v_colD[D > 8 ? D : 1];
+            if (valid) {
+                const float ra = 1.f / (1.f - alpha);
+                T *= ra;
+                const float fac = alpha * T;
+                float v_alpha = 0.f;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const float ck = s.col[t * D + k];
-                        if constexpr (kTranspose) v[k] = fac * v_rc[k];
-                        else v_colD[k] = fac * v_rc[k];
-                        v_alpha += (ck * T - buffer[k] * ra) * v_rc[k];
-                        buffer[k] += ck * fac;
-                    }
-                    v_alpha += T_final * ra * v_ra;
-                    if (backgrounds) v_alpha += -T_final * ra * bg_dot;
-                    if (opac * vis <= ALPHA_MAX) {
-                        const float v_sigma = -opac * vis * v_alpha;
-                        constexpr int B = kTranspose ? D : 0;
-                        v[B + 0] = 0.5f * v_sigma * dx * dx;
-                        v[B + 1] = v_sigma * dx * dy;
-                        v[B + 2] = 0.5f * v_sigma * dy * dy;
-                        v[B + 3] = vis * v_alpha;
-                        if (want_xy) {
-                            const float gx = v_sigma * (con.x * dx + con.y * dy);
-                            const float gy = v_sigma * (con.y * dx + con.z * dy);
-                            v[B + 4] = gx;
-                            v[B + 5] = gy;
-                            if (want_abs) {
-                                v[B + 6] = fabsf(gx);
-                                v[B + 7] = fabsf(gy);
-                            }
+                for (int c = 0; c < D; ++c) {
+                    const float ck = s.col[t * D + c];
+                    if constexpr (kTranspose) v[c] = fac * v_rc[c];
+                    else v_colD[c] = fac * v_rc[c];
+                    v_alpha += (ck * T - buffer[c] * ra) * v_rc[c];
+                    buffer[c] += ck * fac;
+                }
+                v_alpha += T_final * ra * v_ra;
+                if (backgrounds) v_alpha += -T_final * ra * bg_dot;
+                if (opac * vis <= ALPHA_MAX) {
+                    const float v_sigma = -opac * vis * v_alpha;
+                    constexpr int B = kTranspose ? D : 0;
+                    v[B + 0] = 0.5f * v_sigma * dx * dx;
+                    v[B + 1] = v_sigma * dx * dy;
+                    v[B + 2] = 0.5f * v_sigma * dy * dy;
+                    v[B + 3] = vis * v_alpha;
+                    if (want_xy) {
+                        const float gx = v_sigma * (con.x * dx + con.y * dy);
+                        const float gy = v_sigma * (con.y * dx + con.z * dy);
+                        v[B + 4] = gx;
+                        v[B + 5] = gy;
+                        if (want_abs) {
+                            v[B + 6] = fabsf(gx);
+                            v[B + 7] = fabsf(gy);
                         }
                     }
-                } else if constexpr (!kTranspose) {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) v_colD[k] = 0.f;
                 }
-                const int32_t g = s.id[t];
-                if constexpr (kTranspose) {
-                    const float total = warp_transpose_sum<8 + D>(v, tg.lane);
-                    if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
-                } else {
-                    // wide colour vectors: colours by plain butterflies, the 8 geometric values transposed
+            } else if constexpr (!kTranspose) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const float tot = warp_sum(v_colD[k]);
-                        if (tg.lane == 0) atomicAdd(v_colors + (size_t)g * D + k, tot);
-                    }
-                    const float total = warp_transpose_sum<8>(v, tg.lane);
-                    if (!(tg.lane & 1) && total != 0.f) {
-                        float* p = nullptr;
-                        if (slot < 3) p = v_conics + 3 * (size_t)g + slot;
-                        else if (slot == 3) p = v_opacities + g;
-                        else if (slot < 6) p = want_xy ? v_means2d + 2 * (size_t)g + (slot - 4) : nullptr;
-                        else if (slot < 8) p = want_abs ? v_means2d_abs + 2 * (size_t)g + (slot - 6) : nullptr;
-                        if (p) atomicAdd(p, total);
-                    }
+                for (int c = 0; c < D; ++c) v_colD[c] = 0.f;
+            }
+            const int32_t g = s.id[t];
+            if constexpr (kTranspose) {
+                const float total = warp_transpose_sum(v, tg.lane);
+                if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
+            } else {
+                // wide colour vectors: colours by plain butterflies, the 8 geometric values transposed
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const float tot = warp_sum(v_colD[c]);
+                    if (tg.lane == 0) atomicAdd(v_colors + (size_t)g * D + c, tot);
+                }
+                const float total = warp_transpose_sum(v, tg.lane);
+                if (!(tg.lane & 1) && total != 0.f) {
+                    float* p = nullptr;
+                    if (slot < 3) p = v_conics + 3 * (size_t)g + slot;
+                    else if (slot == 3) p = v_opacities + g;
+                    else if (slot < 6) p = want_xy ? v_means2d + 2 * (size_t)g + (slot - 4) : nullptr;
+                    else if (slot < 8) p = want_abs ? v_means2d_abs + 2 * (size_t)g + (slot - 6) : nullptr;
+                    if (p) atomicAdd(p, total);
                 }
             }
         }
@@ -449,12 +637,19 @@ template <int D>
 int launch_fwd(int C, int N, int64_t n_isects, const float* means2d, const float* conics, const float* colors,
                const float* opacities, const float* backgrounds, const uint8_t* masks, int width, int height,
                int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
-               int ed_normalize, float* out_colors, float* out_alphas, int32_t* last_ids, cudaStream_t st) {
+               int ed_normalize, void* workspace, float* out_colors, float* out_alphas, int32_t* last_ids,
+               cudaStream_t st) {
+    const int64_t n_tiles = (int64_t)C * tile_w * tile_h;
+    size_t zero_bytes = 0;
+    Workspace ws = carve_ws(workspace, n_isects, n_tiles, D, &zero_bytes);
+    FSB_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, st));
+    seg_table_kernel<<<1, 1024, 0, st>>>((int)n_tiles, n_isects, seg_len(D), tile_offsets, ws.seg_start, ws.seg_tile, ws.hdr);
+    FSB_LAUNCH_CHECK();
     dim3 block(tile_size, tile_size);
-    unsigned grid = (unsigned)((int64_t)C * tile_w * tile_h);
+    unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
     raster_fwd_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors, opacities,
                                                  backgrounds, masks, width, height, tile_size, tile_w, tile_h,
-                                                 tile_offsets, flatten_ids, ed_normalize, out_colors, out_alphas,
+                                                 tile_offsets, flatten_ids, ed_normalize, ws, out_colors, out_alphas,
                                                  last_ids);
     FSB_LAUNCH_CHECK();
     return 0;
@@ -464,17 +659,26 @@ template <int D>
 int launch_bwd(int C, int N, int64_t n_isects, const float* means2d, const float* conics, const float* colors,
                const float* opacities, const float* backgrounds, const uint8_t* masks, int width, int height,
                int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
-               int ed_normalize, const float* render_colors, const float* render_alphas, const int32_t* last_ids,
-               const float* v_render_colors, const float* v_render_alphas, float* v_means2d_abs, float* v_means2d,
-               float* v_conics, float* v_colors, float* v_opacities, cudaStream_t st) {
+               int ed_normalize, void* workspace, const float* render_colors, const float* render_alphas,
+               const int32_t* last_ids, const float* v_render_colors, const float* v_render_alphas,
+               float* v_means2d_abs, float* v_means2d, float* v_conics, float* v_colors, float* v_opacities,
+               cudaStream_t st) {
+    const int64_t n_tiles = (int64_t)C * tile_w * tile_h;
+    Workspace ws = carve_ws(workspace, n_isects, n_tiles, D, nullptr);
     dim3 block(tile_size, tile_size);
-    unsigned grid = (unsigned)((int64_t)C * tile_w * tile_h);
+    unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
     raster_bwd_kernel<D><<<grid, block, 0, st>>>(
         C, N, n_isects, (const float2*)means2d, conics, colors, opacities, backgrounds, masks, width, height,
-        tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize, render_colors, render_alphas, last_ids,
-        v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities);
+        tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize, ws, render_colors, render_alphas,
+        last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities);
     FSB_LAUNCH_CHECK();
     return 0;
+}
+
+bool bad_geometry(int C, int tile_size, int64_t n_isects) {
+    // whole warps made of whole rows: tile_size 8 or 16 (the reference uses 16, dn_model.py:547)
+    return C <= 0 || tile_size < 2 || tile_size > 16 || (tile_size * tile_size) % 32 != 0 || 32 % tile_size != 0 ||
+           n_isects < 0 || n_isects > 0x7fffffffLL;
 }
 
 }  // namespace
@@ -500,40 +704,51 @@ FSB_API int fsb_raster_supported_channels(int D) {
     return -1;
 }
 
+// bytes of the per-call workspace: segment table + the per-(segment, pixel) chain state that the forward
+// leaves for the backward (n_tiles = C * tile_w * tile_h)
+FSB_API size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D) {
+    if (n_isects < 0 || n_tiles <= 0 || D <= 0) return 0;
+    return ws_bytes(n_isects, n_tiles, D);
+}
+
 FSB_API int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
                            const float* colors, const float* opacities, const float* backgrounds,
                            const uint8_t* masks, int width, int height, int tile_size, int tile_w, int tile_h,
                            const int32_t* tile_offsets, const int32_t* flatten_ids, int ed_normalize,
-                           float* out_colors, float* out_alphas, int32_t* last_ids, void* stream) {
-    if (C <= 0 || tile_size < 2 || tile_size > 16 || (tile_size * tile_size) % 32 != 0 || 32 % tile_size != 0 ||
-        n_isects < 0 || n_isects > 0x7fffffffLL)
-        return FSB_E_ARG;  // whole warps made of whole rows: tile_size 8 or 16 (the reference uses 16, dn_model.py:547)
+                           void* workspace, size_t workspace_bytes, float* out_colors, float* out_alphas,
+                           int32_t* last_ids, void* stream) {
+    if (bad_geometry(C, tile_size, n_isects)) return FSB_E_ARG;
     if (tile_w <= 0 || tile_h <= 0) return 0;
+    if (!workspace || workspace_bytes < fsb_raster_workspace(n_isects, (int64_t)C * tile_w * tile_h, D))
+        return FSB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     FSB_DISPATCH_D(D, (launch_fwd<DD>(C, N, n_isects, means2d, conics, colors, opacities, backgrounds, masks, width,
                                       height, tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize,
-                                      out_colors, out_alphas, last_ids, st)));
+                                      workspace, out_colors, out_alphas, last_ids, st)));
 }
 
 // Gradient outputs are ACCUMULATED into (atomicAdd); the caller zero-fills them first.
+// `workspace` is the buffer the matching fsb_raster_fwd call filled.
 // v_means2d / v_means2d_abs may be NULL (no gradient wanted for the 2-D means: the legacy normals pass of
 // dn_model.py:638 detaches them); v_means2d_abs requires v_means2d.
 FSB_API int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
                            const float* colors, const float* opacities, const float* backgrounds,
                            const uint8_t* masks, int width, int height, int tile_size, int tile_w, int tile_h,
                            const int32_t* tile_offsets, const int32_t* flatten_ids, int ed_normalize,
-                           const float* render_colors, const float* render_alphas, const int32_t* last_ids,
-                           const float* v_render_colors, const float* v_render_alphas, float* v_means2d_abs,
-                           float* v_means2d, float* v_conics, float* v_colors, float* v_opacities, void* stream) {
-    if (C <= 0 || tile_size < 2 || tile_size > 16 || (tile_size * tile_size) % 32 != 0 || 32 % tile_size != 0 ||
-        n_isects < 0 || n_isects > 0x7fffffffLL)
-        return FSB_E_ARG;
+                           void* workspace, size_t workspace_bytes, const float* render_colors,
+                           const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
+                           const float* v_render_alphas, float* v_means2d_abs, float* v_means2d, float* v_conics,
+                           float* v_colors, float* v_opacities, void* stream) {
+    if (bad_geometry(C, tile_size, n_isects)) return FSB_E_ARG;
     if (ed_normalize && !render_colors) return FSB_E_ARG;
     if (v_means2d_abs && !v_means2d) return FSB_E_ARG;
     if (tile_w <= 0 || tile_h <= 0 || n_isects == 0) return 0;
+    if (!workspace || workspace_bytes < fsb_raster_workspace(n_isects, (int64_t)C * tile_w * tile_h, D))
+        return FSB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     FSB_DISPATCH_D(D, (launch_bwd<DD>(C, N, n_isects, means2d, conics, colors, opacities, backgrounds, masks, width,
                                       height, tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize,
-                                      render_colors, render_alphas, last_ids, v_render_colors, v_render_alphas,
-                                      v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, st)));
+                                      workspace, render_colors, render_alphas, last_ids, v_render_colors,
+                                      v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities,
+                                      st)));
 }

@@ -203,17 +203,19 @@ def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     out = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
     alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
     last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+    ws_bytes = lib.fsb_raster_workspace(flatten_ids.numel(), C * tile_h * tile_w, D)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     ev = kernel_timer.start(f"raster_fwd_D{D}")
     check(lib.fsb_raster_fwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
-                             ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(out), ptr(alphas),
-                             ptr(last_ids), _stream()), "fsb_raster_fwd")
+                             ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(ws), ws_bytes, ptr(out),
+                             ptr(alphas), ptr(last_ids), _stream()), "fsb_raster_fwd")
     kernel_timer.stop(ev)
-    return out, alphas, last_ids
+    return out, alphas, last_ids, ws
 
 
 def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
-               flatten_ids, ed_normalize, render_colors, render_alphas, last_ids, v_render_colors, v_render_alphas,
+               flatten_ids, ed_normalize, ws, render_colors, render_alphas, last_ids, v_render_colors, v_render_alphas,
                absgrad, need_xy=True):
     C = isect_offsets_t.shape[0]
     tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
@@ -227,8 +229,8 @@ def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     ev = kernel_timer.start(f"raster_bwd_D{D}")
     check(lib.fsb_raster_bwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
-                             ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(render_colors),
-                             ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
+                             ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(ws), ws.numel(),
+                             ptr(render_colors), ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
                              ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), _stream()),
           "fsb_raster_bwd")
     kernel_timer.stop(ev)
@@ -298,10 +300,10 @@ class RasterizeToPixels(torch.autograd.Function):
         means2d_c, conics_c = _f32c(means2d), _f32c(conics)
         colors_c, opac_c, bg_c = _f32c(colors), _f32c(opacities), _f32c(backgrounds)
         masks_c = masks.contiguous().to(torch.uint8) if masks is not None else None
-        out, alphas, last_ids = raster_fwd(means2d_c, conics_c, colors_c, opac_c, bg_c, masks_c, width, height,
-                                           tile_size, isect_offsets_t, flatten_ids, ed_normalize)
+        out, alphas, last_ids, ws = raster_fwd(means2d_c, conics_c, colors_c, opac_c, bg_c, masks_c, width, height,
+                                               tile_size, isect_offsets_t, flatten_ids, ed_normalize)
         ctx.save_for_backward(means2d, conics_c, colors_c, opac_c, bg_c, masks_c, isect_offsets_t, flatten_ids, out,
-                              alphas, last_ids)
+                              alphas, last_ids, ws)
         ctx.cfg = (width, height, tile_size, absgrad, ed_normalize)
         ctx.set_materialize_grads(False)
         return out, alphas
@@ -309,13 +311,13 @@ class RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_out, v_alphas):
         (means2d, conics, colors, opac, bg, masks, isect_offsets_t, flatten_ids, out, alphas,
-         last_ids) = ctx.saved_tensors
+         last_ids, ws) = ctx.saved_tensors
         width, height, tile_size, absgrad, ed_normalize = ctx.cfg
         v_out = _f32c(v_out) if v_out is not None else torch.zeros_like(out)
         v_alphas = _f32c(v_alphas) if v_alphas is not None else torch.zeros_like(alphas)
         v_means2d, v_abs, v_conics, v_colors, v_opac = raster_bwd(
             _f32c(means2d), conics, colors, opac, bg, masks, width, height, tile_size, isect_offsets_t, flatten_ids,
-            ed_normalize, out, alphas, last_ids, v_out, v_alphas, absgrad, need_xy=ctx.needs_input_grad[0])
+            ed_normalize, ws, out, alphas, last_ids, v_out, v_alphas, absgrad, need_xy=ctx.needs_input_grad[0])
         if absgrad and v_abs is not None:
             # same contract as gsplat: the tensor handed out as meta["means2d"] gets an .absgrad attribute
             means2d.absgrad = v_abs

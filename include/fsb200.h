@@ -91,23 +91,28 @@ int fsb_isect_offsets(int64_t n_isects, const int64_t* sorted_ids, int C, int n_
  *   means2d[C*N,2] conics[C*N,3] colors[C*N,D] opacities[C*N] ; backgrounds[C,D] nullable ;
  *   masks[C*tiles] u8 nullable ; ed_normalize: divide channel D-1 by max(alpha,1e-10) ("ED" modes).
  *   out_colors[C,H,W,D] out_alphas[C,H,W] last_ids[C,H,W] i32.
+ * Work is split into (tile, list segment) units chained through `workspace` (fsb_raster_workspace() bytes,
+ * n_tiles = C*tile_w*tile_h); the forward leaves per-segment state there that the backward consumes.
  * D must be one of fsb_raster_supported_channels(); tile_size 8 or 16. */
 int fsb_raster_supported_channels(int D);
+size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D);
 int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
                    const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
                    int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
-                   const int32_t* flatten_ids, int ed_normalize, float* out_colors, float* out_alphas,
-                   int32_t* last_ids, void* stream);
+                   const int32_t* flatten_ids, int ed_normalize, void* workspace, size_t workspace_bytes,
+                   float* out_colors, float* out_alphas, int32_t* last_ids, void* stream);
 
 /* R2: tile compositing backward.  Gradient outputs are ACCUMULATED; the caller zero-fills them.
- *   v_means2d_abs nullable (absgrad=True in dn_splatter/dn_model.py:587). */
+ *   workspace: the buffer filled by the matching fsb_raster_fwd call.
+ *   v_means2d_abs nullable (absgrad=True in dn_splatter/dn_model.py:587); v_means2d nullable (2-D means detached,
+ *   dn_model.py:638). */
 int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
                    const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
                    int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
-                   const int32_t* flatten_ids, int ed_normalize, const float* render_colors,
-                   const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
-                   const float* v_render_alphas, float* v_means2d_abs, float* v_means2d, float* v_conics,
-                   float* v_colors, float* v_opacities, void* stream);
+                   const int32_t* flatten_ids, int ed_normalize, void* workspace, size_t workspace_bytes,
+                   const float* render_colors, const float* render_alphas, const int32_t* last_ids,
+                   const float* v_render_colors, const float* v_render_alphas, float* v_means2d_abs,
+                   float* v_means2d, float* v_conics, float* v_colors, float* v_opacities, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Visual hull (voxel carving).  replaces utils/VisualHull.py:149-191 (projection/vote loop, threshold

@@ -117,7 +117,7 @@ def test_radix_sort_pairs_stable(n, end_bit):
     assert torch.equal(v_gpu.cpu(), vals[order])
 
 
-def _raster_inputs(n, W, H, C, D, seed, scale_mult=3.0, bg=False):
+def _raster_inputs(n, W, H, C, D, seed, scale_mult=3.0, bg=False, opac_shift=0.0):
     ops = _ops()
     sc = make_scene(n, W, H, n_views=max(C, 2), cfg_id=seed)
     d, coeffs, scales, (radii, m2, dep, con, comp, cols, tiles) = _project_gpu(sc, W, H, C=C, scale_mult=scale_mult)
@@ -128,32 +128,47 @@ def _raster_inputs(n, W, H, C, D, seed, scale_mult=3.0, bg=False):
         colors = cols
     else:
         colors = torch.rand(C, n, D, generator=g).to(DEV)
-    opac = torch.sigmoid(d.opacities[:, 0])[None].expand(C, n).contiguous()
+    opac = torch.sigmoid(d.opacities[:, 0] + opac_shift)[None].expand(C, n).contiguous()
     bgs = torch.rand(C, D, generator=g).to(DEV) if bg else None
     return m2, con, colors.contiguous(), opac, bgs, offs, flat, g
 
 
-@pytest.mark.parametrize("n,W,H,C,D,bg", [(20000, 640, 480, 1, 4, False), (3000, 200, 150, 2, 3, True),
-                                           (50000, 640, 480, 1, 3, True), (2000, 128, 96, 1, 8, False)])
-def test_raster_forward(n, W, H, C, D, bg):
+# (n, W, H, C, D, bg, scale_mult, opac_shift): the last three rows give every tile a list of several thousand
+# entries, i.e. many chained 512-entry segments, once translucent (no pixel ever stops: pure chaining) and once
+# opaque (the T <= 1e-4 stop rule fires inside later segments: speculative pass + exact re-walk), plus wide colours.
+RASTER_CASES = [(20000, 640, 480, 1, 4, False, 3.0, 0.0), (3000, 200, 150, 2, 3, True, 3.0, 0.0),
+                (50000, 640, 480, 1, 3, True, 3.0, 0.0), (2000, 128, 96, 1, 8, False, 3.0, 0.0),
+                (40000, 128, 96, 1, 4, True, 8.0, -4.0), (40000, 128, 96, 2, 3, True, 8.0, 1.0),
+                (6000, 96, 64, 1, 16, False, 6.0, 0.0)]
+
+
+@pytest.mark.parametrize("n,W,H,C,D,bg,mult,oshift", RASTER_CASES)
+def test_raster_forward(n, W, H, C, D, bg, mult, oshift):
     ops = _ops()
-    m2, con, colors, opac, bgs, offs, flat, _ = _raster_inputs(n, W, H, C, D, seed=11, bg=bg)
-    out, alpha, last = ops.raster_fwd(m2, con, colors, opac, bgs, None, W, H, 16, offs, flat)
+    m2, con, colors, opac, bgs, offs, flat, _ = _raster_inputs(n, W, H, C, D, seed=11, bg=bg, scale_mult=mult,
+                                                               opac_shift=oshift)
+    if mult > 5:
+        lens = torch.diff(torch.cat([offs.reshape(-1).long().cpu(), torch.tensor([flat.numel()])]))
+        assert lens.max() > 3 * 512, "case must span several list segments"
+    out, alpha, last, _ws = ops.raster_fwd(m2, con, colors, opac, bgs, None, W, H, 16, offs, flat)
     o_ref, a_ref, l_ref = ref.rasterize_to_pixels(m2.cpu(), con.cpu(), colors.cpu(), opac.cpu(), W, H, 16, offs.cpu(),
                                                   flat.cpu(), backgrounds=None if bgs is None else bgs.cpu(),
                                                   return_last_ids=True)
-    tag = f"[{n},{W}x{H},C{C},D{D}]"
+    tag = f"[{n},{W}x{H},C{C},D{D},m{mult},o{oshift}]"
     assert alpha.max() > 0.5
     assert_close(out.cpu(), o_ref, "raster.fwd.colors" + tag, tol=1e-4)
     assert_close(alpha.cpu(), a_ref, "raster.fwd.alpha" + tag, tol=1e-4)
     assert (last.cpu() != l_ref).float().mean() < 1e-3
 
 
-@pytest.mark.parametrize("n,W,H,C,D,bg,ed", [(20000, 640, 480, 1, 4, False, True), (3000, 200, 150, 2, 3, True, False),
-                                              (2000, 128, 96, 1, 8, False, False)])
-def test_raster_backward(n, W, H, C, D, bg, ed):
+@pytest.mark.parametrize("n,W,H,C,D,bg,ed,mult,oshift", [
+    (20000, 640, 480, 1, 4, False, True, 3.0, 0.0), (3000, 200, 150, 2, 3, True, False, 3.0, 0.0),
+    (2000, 128, 96, 1, 8, False, False, 3.0, 0.0), (40000, 128, 96, 1, 4, True, True, 8.0, -4.0),
+    (40000, 128, 96, 1, 3, True, False, 8.0, 1.0), (6000, 96, 64, 1, 16, False, False, 6.0, 0.0)])
+def test_raster_backward(n, W, H, C, D, bg, ed, mult, oshift):
     ops = _ops()
-    m2, con, colors, opac, bgs, offs, flat, g = _raster_inputs(n, W, H, C, D, seed=12, bg=bg)
+    m2, con, colors, opac, bgs, offs, flat, g = _raster_inputs(n, W, H, C, D, seed=12, bg=bg, scale_mult=mult,
+                                                               opac_shift=oshift)
     v_out = torch.randn(C, H, W, D, generator=g)
     v_alpha = torch.randn(C, H, W, 1, generator=g)
     ins = [t.detach().clone().requires_grad_(True) for t in (m2, con, colors, opac)]
@@ -166,7 +181,7 @@ def test_raster_backward(n, W, H, C, D, bg, ed):
     if ed:
         o_ref = torch.cat([o_ref[..., :-1], o_ref[..., -1:] / a_ref.clamp(min=1e-10)], dim=-1)
     (o_ref * v_out.double()).sum().add((a_ref * v_alpha.double()).sum()).backward()
-    tag = f"[{n},{W}x{H},C{C},D{D},ed{int(ed)}]"
+    tag = f"[{n},{W}x{H},C{C},D{D},ed{int(ed)},m{mult},o{oshift}]"
     assert_close(out.cpu(), o_ref, "raster.bwd.fwd_colors" + tag, tol=1e-4)
     for name, a, b in zip(("means2d", "conics", "colors", "opacities"), ins, rins):
         assert_close(a.grad.cpu(), b.grad, f"raster.bwd.v_{name}" + tag, tol=1e-4, outlier_frac=2e-3)

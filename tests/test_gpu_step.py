@@ -34,7 +34,7 @@ def test_fused_step_matches_torch_restatement():
     for k in fused.gauss_params:
         assert_close(fused.gauss_params[k].grad, plain.gauss_params[k].grad, f"step.grad.{k}", tol=1e-4,
                      outlier_frac=2e-3)
-    assert torch.equal(fused.normals_world, plain.normals_world)
+    assert_close(fused.normals_world, plain.normals_world, "step.normals_world", tol=1e-6, outlier_frac=1e-5)
     # optimiser + densification statistics
     for m in (fused, plain):
         m.optimizers["means"].param_groups[0]["lr"] = m._means_lr()
