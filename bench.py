@@ -230,9 +230,14 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.fsb_launch_count()
+    profiling = os.environ.get("FSB_PROFILE") == "1"  # ncu --profile-from-start off: capture the timed steps only
+    if profiling:
+        torch.cuda.profiler.start()
     with ops.kernel_timer.collect():
         ms_total = timed(args.steps, resident, read_loss=False)
         ktimes = ops.kernel_timer.summary()
+    if profiling:
+        torch.cuda.profiler.stop()
     launches = lib.fsb_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(args.steps, from_host, read_loss=True)

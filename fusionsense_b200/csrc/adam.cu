@@ -28,16 +28,18 @@ constexpr int ADAM_THREADS = 256;
 constexpr int ADAM_VEC = 4;
 constexpr int ADAM_PER_BLOCK = ADAM_THREADS * ADAM_VEC * 4;  // 4096 elements per CTA
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps,
-                                         float step_size, float bc2_sqrt) {
-    m = m + (g - m) * (1.f - b1);
-    v = v * b2 + (1.f - b2) * g * g;
+// omb1 / omb2 = 1 - beta computed in double on the host and rounded once, like torch's Python floats
+// (1.f - 0.999f is 4.7e-5 off 0.001f, which shows up in exp_avg_sq after a few steps).
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float omb1, float b2, float omb2,
+                                         float eps, float step_size, float bc2_sqrt) {
+    m = m + (g - m) * omb1;
+    v = v * b2 + omb2 * g * g;
     float denom = sqrtf(v) / bc2_sqrt + eps;
     p = p - step_size * (m / denom);
 }
 
 __global__ void __launch_bounds__(ADAM_THREADS)
-adam_multi_kernel(FsbAdamArgs a, int n_tensors, float b1, float b2, float eps) {
+adam_multi_kernel(FsbAdamArgs a, int n_tensors, float omb1, float b2, float omb2, float eps) {
     int t = 0;
 #pragma unroll
     for (int i = 1; i < FSB_ADAM_MAX_TENSORS; ++i)
@@ -59,17 +61,17 @@ adam_multi_kernel(FsbAdamArgs a, int n_tensors, float b1, float b2, float eps) {
             float4 G = *reinterpret_cast<const float4*>(g + i);
             float4 M = *reinterpret_cast<float4*>(m + i);
             float4 V = *reinterpret_cast<float4*>(v + i);
-            adam_one(P.x, G.x, M.x, V.x, b1, b2, eps, ss, bc2s);
-            adam_one(P.y, G.y, M.y, V.y, b1, b2, eps, ss, bc2s);
-            adam_one(P.z, G.z, M.z, V.z, b1, b2, eps, ss, bc2s);
-            adam_one(P.w, G.w, M.w, V.w, b1, b2, eps, ss, bc2s);
+            adam_one(P.x, G.x, M.x, V.x, omb1, b2, omb2, eps, ss, bc2s);
+            adam_one(P.y, G.y, M.y, V.y, omb1, b2, omb2, eps, ss, bc2s);
+            adam_one(P.z, G.z, M.z, V.z, omb1, b2, omb2, eps, ss, bc2s);
+            adam_one(P.w, G.w, M.w, V.w, omb1, b2, omb2, eps, ss, bc2s);
             *reinterpret_cast<float4*>(p + i) = P;
             *reinterpret_cast<float4*>(m + i) = M;
             *reinterpret_cast<float4*>(v + i) = V;
         } else {
             for (int k = 0; k < ADAM_VEC && i + k < n; ++k) {
                 float P = p[i + k], M = m[i + k], V = v[i + k];
-                adam_one(P, g[i + k], M, V, b1, b2, eps, ss, bc2s);
+                adam_one(P, g[i + k], M, V, omb1, b2, omb2, eps, ss, bc2s);
                 p[i + k] = P; m[i + k] = M; v[i + k] = V;
             }
         }
@@ -83,8 +85,8 @@ FSB_API int fsb_adam_max_tensors(void) { return FSB_ADAM_MAX_TENSORS; }
 // All array arguments are HOST arrays of length n_tensors; the pointers inside p/g/m/v are device pointers.
 // step[i] is the 1-based step count of tensor i AFTER this update (torch's state["step"] post-increment).
 FSB_API int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
-                           const int64_t* n, const float* lr, const int64_t* step, float beta1, float beta2,
-                           float eps, void* stream) {
+                           const int64_t* n, const double* lr, const int64_t* step, double beta1, double beta2,
+                           double eps, void* stream) {
     if (n_tensors <= 0 || n_tensors > FSB_ADAM_MAX_TENSORS) return FSB_E_ARG;
     FsbAdamArgs a;
     int blocks = 0;
@@ -94,9 +96,9 @@ FSB_API int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g
         a.block_start[i] = blocks;
         blocks += (int)((n[i] + ADAM_PER_BLOCK - 1) / ADAM_PER_BLOCK);
         // bias corrections in double like Python's floats in torch.optim.Adam, then rounded once
-        double bc1 = 1.0 - pow((double)beta1, (double)step[i]);
-        double bc2 = 1.0 - pow((double)beta2, (double)step[i]);
-        a.step_size[i] = (float)((double)lr[i] / bc1);
+        double bc1 = 1.0 - pow(beta1, (double)step[i]);
+        double bc2 = 1.0 - pow(beta2, (double)step[i]);
+        a.step_size[i] = (float)(lr[i] / bc1);
         a.bc2_sqrt[i] = (float)sqrt(bc2);
         a.inv_bc2_sqrt[i] = (float)(1.0 / sqrt(bc2));
     }
@@ -107,7 +109,8 @@ FSB_API int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g
         a.step_size[i] = 0.f; a.bc2_sqrt[i] = 1.f; a.inv_bc2_sqrt[i] = 1.f;
     }
     if (blocks == 0) return 0;
-    adam_multi_kernel<<<blocks, ADAM_THREADS, 0, (cudaStream_t)stream>>>(a, n_tensors, beta1, beta2, eps);
+    adam_multi_kernel<<<blocks, ADAM_THREADS, 0, (cudaStream_t)stream>>>(
+        a, n_tensors, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -32,7 +32,7 @@ def _launch(entries, beta1, beta2, eps):
         m = VP(*[e[2].data_ptr() for e in chunk])
         v = VP(*[e[3].data_ptr() for e in chunk])
         numel = (ctypes.c_int64 * n)(*[e[0].numel() for e in chunk])
-        lr = (ctypes.c_float * n)(*[float(e[4]) for e in chunk])
+        lr = (ctypes.c_double * n)(*[float(e[4]) for e in chunk])
         step = (ctypes.c_int64 * n)(*[int(e[5]) for e in chunk])
         check(lib.fsb_adam_multi(n, ctypes.addressof(p), ctypes.addressof(g), ctypes.addressof(m),
                                  ctypes.addressof(v), ctypes.addressof(numel), ctypes.addressof(lr),

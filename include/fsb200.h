@@ -141,7 +141,7 @@ int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* bl
  * pointers to fp32 tensors of n[i] elements; step[i] = 1-based step count of tensor i for this update. */
 int fsb_adam_max_tensors(void);
 int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
-                   const int64_t* n, const float* lr, const int64_t* step, float beta1, float beta2, float eps,
+                   const int64_t* n, const double* lr, const int64_t* step, double beta1, double beta2, double eps,
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
