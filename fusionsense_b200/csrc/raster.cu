@@ -6,19 +6,26 @@
 // (normals, D = 3, white background).
 //
 // Why segments: real scenes give a few tiles depth-sorted lists 50x longer than the median (object
-// silhouettes), and one-CTA-per-tile leaves 148 SMs waiting for the handful that own them (ncu:
-// sm__cycles_active max/avg = 3.4 on the 300k-Gaussian bench scene).  Here every tile's list is cut into
-// segments of SEG entries and the unit of work is one (tile, segment) CTA:
+// silhouettes: on the 300k-Gaussian bench scene the median tile holds 108 entries, the 99th percentile 5171,
+// the longest 7589), and one-CTA-per-tile leaves 148 SMs waiting for the handful that own them.  Every tile's
+// list is cut into segments of SEG entries and the unit of work is one (tile, segment) CTA.  Compositing is an
+// associative scan over (C, T) pairs — (C1, T1) o (C2, T2) = (C1 + T1 C2, T1 T2) — so:
 //
-//   forward   the CTA stages its segment in shared memory (with an exact per-warp-strip reach mask, see
-//             strip_mask) and composites it.  Per-pixel transmittance is chained from segment to segment
-//             through global memory like a decoupled look-back scan: if the predecessor segment has already
-//             published its state the CTA composites exactly from it; otherwise it composites speculatively
-//             from T = 1, waits, and folds the incoming state in:  C = C_in + T_in * C_loc, T = T_in * T_loc.
-//             Pixels whose reference stop rule (T * (1 - alpha) <= 1e-4) fires inside the segment are
-//             re-walked exactly, so the per-pixel semantics of the sequential algorithm are kept.
-//   backward  needs no chain at all: the forward leaves, per (segment, pixel), the transmittance after the
-//             segment and the colour accumulated through it, so every segment replays independently.
+//   forward A   raster_seg_kernel: every segment composites its entries from T = 1 with the reference's own
+//               per-pixel rules (alpha test, stop when T (1 - alpha) <= 1e-4).  A pixel that stops locally would
+//               also stop when started from any T_in <= 1, so its state is flagged "saturated" (negative T).
+//               Tiles with a single segment (97 % of them) are finished here.
+//   forward B   raster_fold_kernel: one CTA per multi-segment tile folds the segment states in order,
+//               C += T C_loc, T *= T_loc — pure arithmetic.  Where the stop rule fires inside a segment
+//               (T T_loc <= 1e-4 or the segment saturated locally) the pixel is marked for stage C.
+//   forward C   raster_stop_kernel: the marked pixels re-walk that one segment exactly from their incoming
+//               state, so the sequential per-pixel semantics (stop position, last id) are kept.  Every pixel
+//               stops at most once, so all re-walks are independent and run in parallel.
+//               No CTA ever waits for another one (round-1 ncu of a chained look-back version: half of all
+//               warp samples sat in the flag spin loop; of a fold-with-inline-re-walk version: 310 us on the
+//               critical path of the longest tile).
+//   backward    needs no chain at all: the forward leaves, per (segment, pixel), the transmittance after the
+//               segment and the colour accumulated through it, so every segment replays independently.
 //
 // Inside a CTA (tile_size x tile_size threads, one pixel each, a warp owns a strip of 32/tile_size rows) warps
 // walk only the entries whose reach mask has their bit (ballot + find-first-set); forward evaluates four
@@ -38,17 +45,17 @@ __host__ __device__ constexpr int seg_len(int D) { return D <= 8 ? 512 : (D <= 1
 
 struct SegHeader {
     int total_segs;
-    unsigned ticket;
-    int pad[2];
+    int pad[3];
 };
 
+// chain_T / chain_last / prefix_C hold the segment-LOCAL state after raster_seg_kernel and the chained state
+// (what the backward reads) once raster_combine_kernel has folded the tile.
 struct Workspace {
     SegHeader* hdr;
-    int* flags;          // [max_segs]  0 = not published, 1 = published
     int32_t* seg_start;  // [n_tiles + 1]
     int32_t* seg_tile;   // [max_segs]
     float* chain_T;      // [max_segs, 256]  transmittance after the segment; negative = pixel finished
-    int32_t* chain_last; // [max_segs, 256]  last contributing list position so far
+    int32_t* chain_last; // [max_segs, 256]  last contributing list position so far (-1: none in a local state)
     float* prefix_C;     // [max_segs, 256, D] colour accumulated through the segment
 };
 
@@ -57,7 +64,6 @@ inline int64_t max_segments(int64_t n_isects, int64_t n_tiles, int D) { return n
 inline size_t ws_bytes(int64_t n_isects, int64_t n_tiles, int D) {
     int64_t ms = max_segments(n_isects, n_tiles, D);
     size_t b = 256;                                          // header
-    b += fsb_align_up((size_t)ms * 4, 256);                  // flags
     b += fsb_align_up((size_t)(n_tiles + 1) * 4, 256);       // seg_start
     b += fsb_align_up((size_t)ms * 4, 256);                  // seg_tile
     b += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256) * 2;  // chain_T, chain_last
@@ -65,13 +71,11 @@ inline size_t ws_bytes(int64_t n_isects, int64_t n_tiles, int D) {
     return b;
 }
 
-inline Workspace carve_ws(void* base, int64_t n_isects, int64_t n_tiles, int D, size_t* zero_bytes) {
+inline Workspace carve_ws(void* base, int64_t n_isects, int64_t n_tiles, int D) {
     int64_t ms = max_segments(n_isects, n_tiles, D);
     char* p = (char*)base;
     Workspace w;
     w.hdr = (SegHeader*)p; p += 256;
-    w.flags = (int*)p; p += fsb_align_up((size_t)ms * 4, 256);
-    if (zero_bytes) *zero_bytes = (size_t)(p - (char*)base);  // header + flags are zero-filled per launch
     w.seg_start = (int32_t*)p; p += fsb_align_up((size_t)(n_tiles + 1) * 4, 256);
     w.seg_tile = (int32_t*)p; p += fsb_align_up((size_t)ms * 4, 256);
     w.chain_T = (float*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
@@ -202,10 +206,10 @@ __device__ __forceinline__ void stage_entry(Stage<D>& s, int slot, int32_t g, co
     for (int k = 0; k < D; ++k) s.col[slot * D + k] = cp[k];
 }
 
-// Front-to-back walk of this warp's entries of the staged segment.
-// EXACT: the reference semantics incl. the stop rule (`done` lanes are frozen).  !EXACT: speculative local pass
-// (no stop rule; `done` only masks pixels outside the image).  `last` = list position of the last blended entry.
-template <int D, bool EXACT>
+// Front-to-back walk of this warp's entries of the staged segment with the reference's per-pixel rules:
+// skip when sigma < 0 or alpha < 1/255, stop (entry NOT blended, pixel `done`) when T (1 - alpha) <= 1e-4.
+// `done` lanes are frozen.  `last` = list position of the last blended entry.
+template <int D>
 __device__ __forceinline__ void walk(const Stage<D>& s, int n, int seg_b, const TileGeom& tg, float& T,
                                      float (&acc)[D], int32_t& last, bool& done) {
     bool warp_done = __all_sync(0xffffffffu, done);
@@ -243,7 +247,7 @@ __device__ __forceinline__ void walk(const Stage<D>& s, int n, int seg_b, const 
             for (int u = 0; u < 4; ++u) {
                 if (ok[u] && !done) {
                     const float next_T = T * (1.f - alpha[u]);
-                    if (EXACT && next_T <= T_MIN) {
+                    if (next_T <= T_MIN) {
                         done = true;
                     } else {
                         const float w = alpha[u] * T;
@@ -254,7 +258,7 @@ __device__ __forceinline__ void walk(const Stage<D>& s, int n, int seg_b, const 
                     }
                 }
             }
-            if (EXACT && __all_sync(0xffffffffu, done)) {
+            if (__all_sync(0xffffffffu, done)) {
                 warp_done = true;
                 break;
             }
@@ -262,142 +266,197 @@ __device__ __forceinline__ void walk(const Stage<D>& s, int n, int seg_b, const 
     }
 }
 
-__device__ __forceinline__ int ld_flag(const int* p) { return *((volatile const int*)p); }
+struct FwdOut {
+    const float* backgrounds;
+    int ed_normalize;
+    float* out_colors;
+    float* out_alphas;
+    int32_t* last_ids;
+};
 
 template <int D>
-__global__ void __launch_bounds__(MAX_BLOCK)
-raster_fwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
-                  const float* __restrict__ conics, const float* __restrict__ colors,
-                  const float* __restrict__ opacities, const float* __restrict__ backgrounds,
-                  const uint8_t* __restrict__ masks, int width, int height, int tile_size, int tile_w, int tile_h,
-                  const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
-                  int ed_normalize, Workspace ws, float* __restrict__ out_colors, float* __restrict__ out_alphas,
-                  int32_t* __restrict__ last_ids) {
+__device__ __forceinline__ void write_pixel(const FwdOut& o, const TileGeom& tg, int64_t pix, bool masked, float T,
+                                            const float (&acc)[D], int32_t last) {
+    const float alpha_out = masked ? 0.f : 1.f - T;
+    o.out_alphas[pix] = alpha_out;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        float v = o.backgrounds ? acc[c] + (1.f - alpha_out) * o.backgrounds[tg.cam * D + c] : acc[c];
+        if (o.ed_normalize && c == D - 1) v = v / fmaxf(alpha_out, 1e-10f);
+        o.out_colors[pix * D + c] = v;
+    }
+    o.last_ids[pix] = last;
+}
+
+struct SegGeom {
+    int64_t tile_lin;
+    int k, nseg, n;
+    int32_t seg_b;
+    bool masked;
+};
+
+template <int D>
+__device__ __forceinline__ SegGeom seg_geom(const Workspace& ws, int seg, int64_t tile_lin, int64_t n_cam_tiles,
+                                            int64_t n_isects, const int32_t* __restrict__ tile_offsets,
+                                            const uint8_t* __restrict__ masks) {
     constexpr int SEG = seg_len(D);
-    __shared__ Stage<D> s;
-    __shared__ int s_seg, s_ready;
-    if (threadIdx.x == 0 && threadIdx.y == 0) s_seg = (int)atomicAdd(&ws.hdr->ticket, 1u);
-    __syncthreads();
-    const int seg = s_seg;  // dynamic numbering: every predecessor segment has been started before this one
-    if (seg >= ws.hdr->total_segs) return;
-    const int64_t tile_lin = ws.seg_tile[seg];
-    const int k = seg - ws.seg_start[tile_lin];
-    const int nseg = ws.seg_start[tile_lin + 1] - ws.seg_start[tile_lin];
-    const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
-    const int64_t pix = tg.inside ? ((int64_t)tg.cam * height + tg.i) * width + tg.j : 0;
-    const bool masked = (masks != nullptr && !masks[tile_lin]);
-
+    SegGeom g;
+    g.tile_lin = tile_lin;
+    const int s0 = ws.seg_start[tile_lin];
+    g.k = seg - s0;
+    g.nseg = ws.seg_start[tile_lin + 1] - s0;
+    g.masked = (masks != nullptr && !masks[tile_lin]);
     const int32_t range_start = tile_offsets[tile_lin];
-    const int32_t range_end =
-        (tile_lin == (int64_t)C * tile_w * tile_h - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
-    const int32_t seg_b = range_start + k * SEG;
-    const int n = masked ? 0 : max(0, min(range_end, seg_b + SEG) - seg_b);
+    const int32_t range_end = (tile_lin == n_cam_tiles - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
+    g.seg_b = range_start + g.k * SEG;
+    g.n = g.masked ? 0 : max(0, min(range_end, g.seg_b + SEG) - g.seg_b);
+    return g;
+}
 
-    if (tg.tr == 0) s_ready = (k == 0) ? 1 : ld_flag(ws.flags + seg - 1);
+// forward A: every (tile, segment) composites its own entries from T = 1.
+template <int D>
+__global__ void __launch_bounds__(MAX_BLOCK)
+raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
+                  const float* __restrict__ conics, const float* __restrict__ colors,
+                  const float* __restrict__ opacities, const uint8_t* __restrict__ masks, int width, int height,
+                  int tile_size, int tile_w, int tile_h, const int32_t* __restrict__ tile_offsets,
+                  const int32_t* __restrict__ flatten_ids, Workspace ws, FwdOut o) {
+    __shared__ Stage<D> s;
+    const int seg = blockIdx.x;
+    if (seg >= ws.hdr->total_segs) return;
+    const SegGeom sg = seg_geom<D>(ws, seg, ws.seg_tile[seg], (int64_t)C * tile_w * tile_h, n_isects, tile_offsets,
+                                   masks);
+    const TileGeom tg = tile_geom(sg.tile_lin, tile_w, tile_h, tile_size, width, height);
+
+    for (int e = tg.tr; e < sg.n; e += tg.block_size)
+        stage_entry<D>(s, e, flatten_ids[sg.seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
     __syncthreads();
-    const bool have_in = (s_ready != 0);
 
     float T = 1.f;
     float acc[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) acc[c] = 0.f;
-    int32_t last = 0;
+    int32_t last = (sg.k == 0) ? 0 : -1;
     bool done = !tg.inside;
+    walk<D>(s, sg.n, sg.seg_b, tg, T, acc, last, done);
+
     const size_t cidx = (size_t)seg * MAX_BLOCK + tg.tr;
-
-    auto load_in = [&](float& Ti, float (&Ci)[D], int32_t& li, bool& di) {
-        while (ld_flag(ws.flags + seg - 1) == 0) {
-        }
-        __threadfence();
-        const size_t pidx = (size_t)(seg - 1) * MAX_BLOCK + tg.tr;
-        const float t_in = __ldcg(ws.chain_T + pidx);
-        li = __ldcg(ws.chain_last + pidx);
-#pragma unroll
-        for (int c = 0; c < D; ++c) Ci[c] = __ldcg(ws.prefix_C + pidx * D + c);
-        di = (t_in < 0.f);
-        Ti = fabsf(t_in);
-    };
-
-    if (have_in) {
-        if (k > 0) {
-            bool d_in;
-            load_in(T, acc, last, d_in);
-            done = done || d_in;
-        }
-        // whole tile already finished (or nothing to add): skip staging
-        if (__syncthreads_count(done) < tg.block_size && n > 0) {
-            for (int e = tg.tr; e < n; e += tg.block_size)
-                stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
-            __syncthreads();
-            walk<D, true>(s, n, seg_b, tg, T, acc, last, done);
-        }
-    } else {
-        // predecessor still running: composite this segment from T = 1, then fold the incoming state in
-        for (int e = tg.tr; e < n; e += tg.block_size)
-            stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
-        __syncthreads();
-        float T_loc = 1.f;
-        float C_loc[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) C_loc[c] = 0.f;
-        int32_t last_loc = -1;
-        bool outside = !tg.inside;
-        walk<D, false>(s, n, seg_b, tg, T_loc, C_loc, last_loc, outside);
-        bool d_in;
-        load_in(T, acc, last, d_in);
-        done = done || d_in;
-        bool redo = false;
-        if (!done) {
-            if (T * T_loc > T_MIN) {  // the stop rule cannot have fired inside the segment
-#pragma unroll
-                for (int c = 0; c < D; ++c) acc[c] += T * C_loc[c];
-                T *= T_loc;
-                if (last_loc >= 0) last = last_loc;
-            } else {
-                redo = true;
-            }
-        }
-        if (__any_sync(0xffffffffu, redo)) {
-            // exact re-walk from the incoming state for the pixels that stop inside this segment
-            bool frozen = !redo;
-            float Tr = T;
-            float Cr[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) Cr[c] = acc[c];
-            int32_t lr = last;
-            walk<D, true>(s, n, seg_b, tg, Tr, Cr, lr, frozen);
-            if (redo) {
-                T = Tr;
-                last = lr;
-                done = frozen;
-#pragma unroll
-                for (int c = 0; c < D; ++c) acc[c] = Cr[c];
-            }
-        }
-    }
-
-    // publish (also consumed by the backward pass)
     ws.chain_T[cidx] = (done && tg.inside) ? -T : T;
     ws.chain_last[cidx] = last;
 #pragma unroll
     for (int c = 0; c < D; ++c) ws.prefix_C[cidx * D + c] = acc[c];
-    if (k < nseg - 1) {
-        __threadfence();
-        __syncthreads();
-        if (tg.tr == 0) *((volatile int*)(ws.flags + seg)) = 1;
-        return;
+    if (sg.nseg == 1 && tg.inside) {
+        const int64_t pix = ((int64_t)tg.cam * height + tg.i) * width + tg.j;
+        write_pixel<D>(o, tg, pix, sg.masked, T, acc, last);
     }
-    if (tg.inside) {
-        const float alpha_out = masked ? 0.f : 1.f - T;
-        out_alphas[pix] = alpha_out;
+}
+
+constexpr int32_t STOP_MARK = INT32_MIN;  // chain_last value: "this pixel's stop rule fires inside this segment"
+
+// forward B: fold the segment states of every multi-segment tile in list order (pure arithmetic, no list walk).
+// Overwrites the local states with the chained ones; a pixel whose stop rule fires inside segment k gets
+// chain_last[k] = STOP_MARK and is finished by raster_stop_kernel.
+template <int D>
+__global__ void __launch_bounds__(MAX_BLOCK)
+raster_fold_kernel(int C, int width, int height, int tile_size, int tile_w, int tile_h,
+                   const uint8_t* __restrict__ masks, Workspace ws, FwdOut o) {
+    const int64_t tile_lin = blockIdx.x;
+    const int seg0 = ws.seg_start[tile_lin];
+    const int nseg = ws.seg_start[tile_lin + 1] - seg0;
+    if (nseg <= 1) return;
+    const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
+    size_t cidx = (size_t)seg0 * MAX_BLOCK + tg.tr;
+    const float t0 = ws.chain_T[cidx];
+    float T = fabsf(t0);
+    bool done = (t0 < 0.f) || !tg.inside;
+    bool pending = false;  // stop segment found, result still to be produced by raster_stop_kernel
+    int32_t last = ws.chain_last[cidx];
+    float acc[D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-            float v = backgrounds ? acc[c] + (1.f - alpha_out) * backgrounds[tg.cam * D + c] : acc[c];
-            if (ed_normalize && c == D - 1) v = v / fmaxf(alpha_out, 1e-10f);
-            out_colors[pix * D + c] = v;
+    for (int c = 0; c < D; ++c) acc[c] = ws.prefix_C[cidx * D + c];
+    for (int k = 1; k < nseg; ++k) {
+        if (__syncthreads_count(done) == tg.block_size) break;
+        if (done) continue;
+        cidx = (size_t)(seg0 + k) * MAX_BLOCK + tg.tr;
+        const float tl = ws.chain_T[cidx];
+        const float Tl = fabsf(tl);
+        if (!(tl < 0.f) && T * Tl > T_MIN) {  // the stop rule cannot have fired inside this segment
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                acc[c] += T * ws.prefix_C[cidx * D + c];
+                ws.prefix_C[cidx * D + c] = acc[c];
+            }
+            T *= Tl;
+            ws.chain_T[cidx] = T;
+            const int32_t ll = ws.chain_last[cidx];
+            if (ll >= 0) last = ll;
+            ws.chain_last[cidx] = last;
+        } else {
+            ws.chain_last[cidx] = STOP_MARK;
+            done = true;
+            pending = true;
         }
-        last_ids[pix] = last;
     }
+    if (pending) return;
+    // the backward takes the tile total from the last segment's slot
+    const size_t lidx = (size_t)(seg0 + nseg - 1) * MAX_BLOCK + tg.tr;
+#pragma unroll
+    for (int c = 0; c < D; ++c) ws.prefix_C[lidx * D + c] = acc[c];
+    if (tg.inside) {
+        const bool masked = (masks != nullptr && !masks[tile_lin]);
+        const int64_t pix = ((int64_t)tg.cam * height + tg.i) * width + tg.j;
+        write_pixel<D>(o, tg, pix, masked, T, acc, last);
+    }
+}
+
+// forward C: the pixels whose stop rule fires inside this segment re-walk it exactly from their incoming
+// (chained) state, which keeps the sequential semantics: stop position, last id, nothing blended after it.
+template <int D>
+__global__ void __launch_bounds__(MAX_BLOCK)
+raster_stop_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
+                   const float* __restrict__ conics, const float* __restrict__ colors,
+                   const float* __restrict__ opacities, const uint8_t* __restrict__ masks, int width, int height,
+                   int tile_size, int tile_w, int tile_h, const int32_t* __restrict__ tile_offsets,
+                   const int32_t* __restrict__ flatten_ids, Workspace ws, FwdOut o) {
+    __shared__ Stage<D> s;
+    const int seg = blockIdx.x;
+    if (seg >= ws.hdr->total_segs) return;
+    const int64_t tile_lin = ws.seg_tile[seg];
+    if (seg == ws.seg_start[tile_lin]) return;  // first segments are exact already
+    const int tr = threadIdx.y * blockDim.x + threadIdx.x;
+    const size_t cidx = (size_t)seg * MAX_BLOCK + tr;
+    const bool redo = (ws.chain_last[cidx] == STOP_MARK);
+    if (!__syncthreads_or(redo)) return;
+    const SegGeom sg = seg_geom<D>(ws, seg, tile_lin, (int64_t)C * tile_w * tile_h, n_isects, tile_offsets, masks);
+    const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
+    for (int e = tg.tr; e < sg.n; e += tg.block_size)
+        stage_entry<D>(s, e, flatten_ids[sg.seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
+    __syncthreads();
+    float T = 1.f;
+    float acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.f;
+    int32_t last = 0;
+    const size_t pidx = cidx - MAX_BLOCK;  // chained state after the previous segment
+    if (redo) {
+        T = fabsf(ws.chain_T[pidx]);
+        last = ws.chain_last[pidx];
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = ws.prefix_C[pidx * D + c];
+    }
+    bool frozen = !redo;
+    walk<D>(s, sg.n, sg.seg_b, tg, T, acc, last, frozen);
+    if (!redo) return;
+    ws.chain_T[cidx] = -T;
+    ws.chain_last[cidx] = last;
+    const size_t lidx = (size_t)(ws.seg_start[tile_lin + 1] - 1) * MAX_BLOCK + tr;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        ws.prefix_C[cidx * D + c] = acc[c];
+        ws.prefix_C[lidx * D + c] = acc[c];
+    }
+    const int64_t pix = ((int64_t)tg.cam * height + tg.i) * width + tg.j;
+    write_pixel<D>(o, tg, pix, sg.masked, T, acc, last);
 }
 
 // Sum up to 16 per-lane values over the warp so that lane L ends up with the total of value index
@@ -640,18 +699,25 @@ int launch_fwd(int C, int N, int64_t n_isects, const float* means2d, const float
                int ed_normalize, void* workspace, float* out_colors, float* out_alphas, int32_t* last_ids,
                cudaStream_t st) {
     const int64_t n_tiles = (int64_t)C * tile_w * tile_h;
-    size_t zero_bytes = 0;
-    Workspace ws = carve_ws(workspace, n_isects, n_tiles, D, &zero_bytes);
-    FSB_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, st));
+    Workspace ws = carve_ws(workspace, n_isects, n_tiles, D);
     seg_table_kernel<<<1, 1024, 0, st>>>((int)n_tiles, n_isects, seg_len(D), tile_offsets, ws.seg_start, ws.seg_tile, ws.hdr);
     FSB_LAUNCH_CHECK();
     dim3 block(tile_size, tile_size);
+    FwdOut o{backgrounds, ed_normalize, out_colors, out_alphas, last_ids};
     unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
-    raster_fwd_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors, opacities,
-                                                 backgrounds, masks, width, height, tile_size, tile_w, tile_h,
-                                                 tile_offsets, flatten_ids, ed_normalize, ws, out_colors, out_alphas,
-                                                 last_ids);
+    raster_seg_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors, opacities,
+                                                 masks, width, height, tile_size, tile_w, tile_h, tile_offsets,
+                                                 flatten_ids, ws, o);
     FSB_LAUNCH_CHECK();
+    if (n_isects > seg_len(D)) {  // otherwise no tile can hold more than one segment
+        raster_fold_kernel<D><<<(unsigned)n_tiles, block, 0, st>>>(C, width, height, tile_size, tile_w, tile_h, masks,
+                                                                   ws, o);
+        FSB_LAUNCH_CHECK();
+        raster_stop_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors,
+                                                      opacities, masks, width, height, tile_size, tile_w, tile_h,
+                                                      tile_offsets, flatten_ids, ws, o);
+        FSB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -664,7 +730,7 @@ int launch_bwd(int C, int N, int64_t n_isects, const float* means2d, const float
                float* v_means2d_abs, float* v_means2d, float* v_conics, float* v_colors, float* v_opacities,
                cudaStream_t st) {
     const int64_t n_tiles = (int64_t)C * tile_w * tile_h;
-    Workspace ws = carve_ws(workspace, n_isects, n_tiles, D, nullptr);
+    Workspace ws = carve_ws(workspace, n_isects, n_tiles, D);
     dim3 block(tile_size, tile_size);
     unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
     raster_bwd_kernel<D><<<grid, block, 0, st>>>(

@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-from .losses import SSIM, DepthLoss, DepthLossType, TVLoss
+from .losses import SSIM, DepthLoss, DepthLossType, FusedSSIM, TVLoss
 from .synthetic import Scene
 
 
@@ -83,7 +83,10 @@ class DNSplatterStep:
         }
         self.step = step
         self.training = True
-        self.ssim = SSIM(data_range=1.0, kernel_size=11).to(self.device)
+        if self.config.fused_losses and self.device.type == "cuda":
+            self.ssim = FusedSSIM(data_range=1.0, kernel_size=11)
+        else:
+            self.ssim = SSIM(data_range=1.0, kernel_size=11).to(self.device)
         self.depth_loss = DepthLoss(self.config.depth_loss_type)
         self.smooth_loss = DepthLoss(DepthLossType.TV)
         self.tv_loss = TVLoss()

@@ -121,7 +121,8 @@ class DepthLoss(nn.Module):
 
 # ---------------------------------------------------------------------------------------------
 # SSIM as torchmetrics' StructuralSimilarityIndexMeasure computes it (gaussian 11x11, sigma 1.5,
-# reflect padding, border crop, mean) — stays in torch: SURVEY.md §8a row a11.
+# reflect padding, border crop, mean).  Plain-torch restatement: the checker of FusedSSIM below and what the CPU
+# reference arm runs; the CUDA product path uses FusedSSIM.
 # ---------------------------------------------------------------------------------------------
 class SSIM(nn.Module):
     def __init__(self, data_range: float = 1.0, kernel_size: int = 11, sigma: float = 1.5, k1=0.01, k2=0.03):
@@ -146,6 +147,87 @@ class SSIM(nn.Module):
         s_p, s_t, s_pt = e_pp - mu_pp, e_tt - mu_tt, e_pt - mu_pt
         ssim = ((2 * mu_pt + c1) * (2 * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_p + s_t + c2))
         return ssim[..., pad:-pad, pad:-pad].reshape(ssim.shape[0], -1).mean(-1).mean()
+
+
+class _FusedSSIMFn(torch.autograd.Function):
+    """ssim(x, y) with the gradient taken w.r.t. x (SSIM is symmetric, the caller orders the arguments)."""
+
+    @staticmethod
+    def forward(ctx, x, y, taps, data_range, k1, k2):
+        from ._abi import check, lib, ptr
+        from .ops import _f32c, _stream
+
+        if not (x.is_cuda and y.is_cuda):
+            raise RuntimeError("FusedSSIM needs CUDA tensors (no CPU fallback)")
+        x, y = _f32c(x), _f32c(y)
+        H, W, C = x.shape
+        need = ctx.needs_input_grad[0]
+        dev = x.device
+        ws = torch.empty((lib.fsb_ssim_workspace(),), dtype=torch.uint8, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        maps = torch.empty((3, H - 10, W - 10, C), dtype=torch.float32, device=dev) if need else None
+        d = [maps[i] for i in range(3)] if need else [None] * 3
+        check(lib.fsb_ssim_fwd(H, W, C, ptr(x), ptr(y), data_range, k1, k2, taps, ptr(ws), ptr(out), ptr(d[0]),
+                               ptr(d[1]), ptr(d[2]), _stream()), "fsb_ssim_fwd")
+        if need:
+            ctx.save_for_backward(x, y, maps)
+        ctx.cfg = (taps, data_range, k1, k2)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_out):
+        from ._abi import check, lib, ptr
+        from .ops import _stream
+
+        x, y, maps = ctx.saved_tensors
+        taps, data_range, k1, k2 = ctx.cfg
+        H, W, C = x.shape
+        v_x = torch.empty_like(x)
+        v_out = v_out.contiguous().float()
+        check(lib.fsb_ssim_bwd(H, W, C, ptr(x), ptr(y), data_range, k1, k2, taps, ptr(maps[0]), ptr(maps[1]),
+                               ptr(maps[2]), ptr(v_out), ptr(v_x), _stream()), "fsb_ssim_bwd")
+        return v_x, None, None, None, None, None
+
+
+class FusedSSIM(nn.Module):
+    """Drop-in for the `self.ssim` object of dn_model.py:244 on libfsb200's kernels (csrc/ssim.cu).
+
+    Called like torchmetrics: `ssim(preds[B,C,H,W], target[B,C,H,W]) -> scalar` with B == 1 (one camera per step,
+    dn_model.py:487); also accepts [H,W,C] images directly, which skips the permute copies.  One launch forward,
+    one backward, against ~45 torch launches each way.
+    """
+
+    def __init__(self, data_range: float = 1.0, kernel_size: int = 11, sigma: float = 1.5, k1=0.01, k2=0.03):
+        super().__init__()
+        import ctypes
+
+        if kernel_size != 11:
+            raise ValueError("FusedSSIM implements the reference's setting only: kernel_size=11")
+        self.data_range, self.k1, self.k2 = float(data_range), float(k1), float(k2)
+        dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1.0)
+        g = torch.exp(-((dist / sigma) ** 2) / 2)
+        g = g / g.sum()
+        self._taps_arr = (ctypes.c_float * kernel_size)(*[float(v) for v in g])
+        self._taps = ctypes.addressof(self._taps_arr)
+
+    @staticmethod
+    def _hwc(t: Tensor) -> Tensor:
+        if t.dim() == 4:
+            if t.shape[0] != 1:
+                raise ValueError("FusedSSIM handles one image per call (the reference trains one camera per step)")
+            return t[0].permute(1, 2, 0)  # a view; contiguous again when it came from an [H,W,C] image
+        return t
+
+    def forward(self, preds: Tensor, target: Tensor) -> Tensor:
+        p, t = self._hwc(preds), self._hwc(target)
+        if t.requires_grad and not p.requires_grad:
+            return _FusedSSIMFn.apply(t, p, self._taps, self.data_range, self.k1, self.k2)
+        if p.requires_grad and t.requires_grad:
+            # both sides differentiable: two symmetric evaluations, each carrying one gradient
+            a = _FusedSSIMFn.apply(p, t.detach(), self._taps, self.data_range, self.k1, self.k2)
+            b = _FusedSSIMFn.apply(t, p.detach(), self._taps, self.data_range, self.k1, self.k2)
+            return a + (b - b.detach())
+        return _FusedSSIMFn.apply(p, t, self._taps, self.data_range, self.k1, self.k2)
 
 
 # ---------------------------------------------------------------------------------------------

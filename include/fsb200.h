@@ -135,6 +135,23 @@ int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* bl
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SSIM of the base splatfacto loss: `1 - self.ssim(gt, pred)` with torchmetrics
+ * StructuralSimilarityIndexMeasure(data_range=1.0, kernel_size=11, sigma=1.5) — dn_splatter/dn_model.py:244,
+ * reached through super().get_loss_dict at dn_model.py:683.  Mean over the (H-10)x(W-10) interior (torchmetrics
+ * crops the reflect-padded border) and the channels.  x, y: [H,W,C] fp32, C <= 4; taps: HOST array of
+ * fsb_ssim_taps() normalised gaussian weights; workspace: fsb_ssim_workspace() bytes.
+ * fwd: ssim_out = device scalar; d_mu/d_xx/d_xy [(H-10),(W-10),C] (nullable, all or none) = partials w.r.t. the
+ * window moments of x, consumed by bwd.  bwd: v_out = DEVICE scalar dL/dssim, v_x[H,W,C] overwritten. */
+int fsb_ssim_taps(void);
+size_t fsb_ssim_workspace(void);
+int fsb_ssim_fwd(int H, int W, int C, const float* x, const float* y, float data_range, float k1, float k2,
+                 const float* taps, void* workspace, float* ssim_out, float* d_mu, float* d_xx, float* d_xy,
+                 void* stream);
+int fsb_ssim_bwd(int H, int W, int C, const float* x, const float* y, float data_range, float k1, float k2,
+                 const float* taps, const float* d_mu, const float* d_xx, const float* d_xy, const float* v_out,
+                 float* v_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * O1: multi-tensor Adam, one launch for all Gaussian parameter groups.  replaces the torch.optim.Adam.step()
  * calls for the optimizers of dn_splatter/dn_config.py:36-75 (eps 1e-15, betas (0.9, 0.999), no decay).
  * Every array argument is a HOST array of length n_tensors (<= fsb_adam_max_tensors()); p/g/m/v hold device
