@@ -25,6 +25,30 @@ __device__ __forceinline__ fs::Camera load_camera(const float* __restrict__ view
     return cam;
 }
 
+// camera centre = -R^-1 t of the (affine) view matrix; what rendering.rasterization takes from
+// torch.linalg.inv(viewmats)[:, :3, 3].  Used when the caller passes campos = NULL (13 tiny LU launches saved).
+__device__ __forceinline__ void camera_centre(const fs::Camera& cam, const float* __restrict__ campos, int c,
+                                              float* o) {
+    if (campos) {
+        o[0] = __ldg(campos + 3 * c + 0); o[1] = __ldg(campos + 3 * c + 1); o[2] = __ldg(campos + 3 * c + 2);
+        return;
+    }
+    const float* V = cam.V;  // row-major 3x4
+    const float r00 = V[0], r01 = V[1], r02 = V[2], t0 = V[3];
+    const float r10 = V[4], r11 = V[5], r12 = V[6], t1 = V[7];
+    const float r20 = V[8], r21 = V[9], r22 = V[10], t2 = V[11];
+    const float c00 = r11 * r22 - r12 * r21, c01 = r12 * r20 - r10 * r22, c02 = r10 * r21 - r11 * r20;
+    const float det = r00 * c00 + r01 * c01 + r02 * c02;
+    const float id = 1.f / det;
+    // inverse = adjugate / det; row i of the inverse dotted with t
+    const float i00 = c00, i01 = r02 * r21 - r01 * r22, i02 = r01 * r12 - r02 * r11;
+    const float i10 = c01, i11 = r00 * r22 - r02 * r20, i12 = r02 * r10 - r00 * r12;
+    const float i20 = c02, i21 = r01 * r20 - r00 * r21, i22 = r00 * r11 - r01 * r10;
+    o[0] = -(i00 * t0 + i01 * t1 + i02 * t2) * id;
+    o[1] = -(i10 * t0 + i11 * t1 + i12 * t2) * id;
+    o[2] = -(i20 * t0 + i21 * t1 + i22 * t2) * id;
+}
+
 __device__ __forceinline__ int tile_count(float mx, float my, int radius, int tile_size, int tile_w, int tile_h,
                                           int legacy_bbox, int* x0, int* y0, int* x1, int* y1) {
     float ts = (float)tile_size;
@@ -53,7 +77,8 @@ project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float
                       int K, const float* __restrict__ coeffs, const float* __restrict__ campos, int color_stride,
                       int depth_channel, int32_t* __restrict__ radii, float* __restrict__ means2d,
                       float* __restrict__ depths, float* __restrict__ conics, float* __restrict__ comps,
-                      float* __restrict__ colors, int32_t* __restrict__ tiles_per_gauss) {
+                      float* __restrict__ colors, int32_t* __restrict__ tiles_per_gauss,
+                      unsigned long long* __restrict__ legacy_extra) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)C * N) return;
     int c = (int)(idx / N);
@@ -75,15 +100,21 @@ project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float
     if (o.radius > 0) {
         int x0, y0, x1, y1;
         cnt = tile_count(o.mx, o.my, o.radius, tile_size, tile_w, tile_h, 0, &x0, &y0, &x1, &y1);
+        if (legacy_extra) {
+            // tiles the gsplat 0.1.x bbox rule would add (it differs only when (x + r) / tile_size rounds to an
+            // integer: ~1 Gaussian per frame); zero means the legacy normals pass can share these sorted lists
+            const int lc = tile_count(o.mx, o.my, o.radius, tile_size, tile_w, tile_h, 1, &x0, &y0, &x1, &y1);
+            if (lc != cnt) atomicAdd(legacy_extra, (unsigned long long)(lc > cnt ? lc - cnt : cnt - lc));
+        }
     }
     tiles_per_gauss[idx] = cnt;
     if (colors) {
         float* out = colors + (size_t)idx * color_stride;
         float r = 0.f, g = 0.f, b = 0.f;
         if (o.radius > 0 && sh_degree >= 0) {
-            float dx = px - __ldg(campos + 3 * c + 0);
-            float dy = py - __ldg(campos + 3 * c + 1);
-            float dz = pz - __ldg(campos + 3 * c + 2);
+            float cc[3];
+            camera_centre(cam, campos, c, cc);
+            float dx = px - cc[0], dy = py - cc[1], dz = pz - cc[2];
             float inorm = fs::inv_sqrt(dx * dx + dy * dy + dz * dz);
             float basis[16];
             fs::sh_basis(sh_degree, dx * inorm, dy * inorm, dz * inorm, basis);
@@ -168,9 +199,9 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
             fs::project_bwd(cam, px, py, pz, q.x, q.y, q.z, q.w, sx, sy, sz, width, height, eps2d, vm.x, vm.y, vd,
                             vca, vcb, vcc, vcomp, gm, gq, gs, v_viewmats ? vRv : nullptr, v_viewmats ? vtv : nullptr);
             if (vc && sh_degree >= 0) {
-                float dx = px - __ldg(campos + 3 * c + 0);
-                float dy = py - __ldg(campos + 3 * c + 1);
-                float dz = pz - __ldg(campos + 3 * c + 2);
+                float cc[3];
+                camera_centre(cam, campos, c, cc);
+                float dx = px - cc[0], dy = py - cc[1], dz = pz - cc[2];
                 float inorm = fs::inv_sqrt(dx * dx + dy * dy + dz * dz);
                 float ux = dx * inorm, uy = dy * inorm, uz = dz * inorm;
                 float basis[16];
@@ -276,16 +307,17 @@ FSB_API int fsb_project_sh_fwd(int C, int N, const float* means, const float* qu
                                float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w,
                                int tile_h, int sh_degree, int K, const float* coeffs, const float* campos,
                                int color_stride, int depth_channel, int32_t* radii, float* means2d, float* depths,
-                               float* conics, float* comps, float* colors, int32_t* tiles_per_gauss, void* stream) {
+                               float* conics, float* comps, float* colors, int32_t* tiles_per_gauss,
+                               int64_t* legacy_extra, void* stream) {
     if (C <= 0 || N < 0 || sh_degree > 3 || tile_size <= 0) return FSB_E_ARG;
-    if (sh_degree >= 0 && (!coeffs || !campos || !colors || (sh_degree + 1) * (sh_degree + 1) > K)) return FSB_E_ARG;
+    if (sh_degree >= 0 && (!coeffs || !colors || (sh_degree + 1) * (sh_degree + 1) > K)) return FSB_E_ARG;
     if (colors && (color_stride < 3 || depth_channel >= color_stride)) return FSB_E_ARG;
     if (N == 0) return 0;
     int64_t total = (int64_t)C * N;
     project_sh_fwd_kernel<<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
         tile_w, tile_h, sh_degree, K, coeffs, campos, color_stride, depth_channel, radii, means2d, depths, conics,
-        comps, colors, tiles_per_gauss);
+        comps, colors, tiles_per_gauss, (unsigned long long*)legacy_extra);
     FSB_LAUNCH_CHECK();
     return 0;
 }
@@ -298,7 +330,8 @@ FSB_API int fsb_project_sh_bwd(int C, int N, const float* means, const float* qu
                                float* v_quats, float* v_scales, float* v_coeffs, float* v_viewmats, float* v_campos,
                                void* stream) {
     if (C <= 0 || N < 0 || sh_degree > 3) return FSB_E_ARG;
-    if (sh_degree >= 0 && v_colors && (!coeffs || !campos || !v_coeffs)) return FSB_E_ARG;
+    if (sh_degree >= 0 && v_colors && (!coeffs || !v_coeffs)) return FSB_E_ARG;
+    if (v_campos && !campos) return FSB_E_ARG;
     if (N == 0) return 0;
     project_sh_bwd_kernel<<<fsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, coeffs, campos, color_stride,

@@ -19,15 +19,19 @@ _LAST_BINNING: dict = {}
 
 
 def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int, height: int, tile_size: int,
-                     n_isects: int, flatten_ids: Tensor, isect_offsets: Tensor) -> None:
-    """Called by `rasterization()` (single-camera case only)."""
+                     n_isects: int, flatten_ids: Tensor, isect_offsets: Tensor,
+                     legacy_extra: Optional[int] = None) -> None:
+    """Called by `rasterization()` (single-camera case only).
+
+    `legacy_extra`: number of tiles by which the 0.1.x bbox rule differs from the 1.0 rule on these Gaussians,
+    counted by the projection kernel and read back together with n_isects; None = not counted."""
     _LAST_BINNING.clear()
     if radii.shape[0] != 1:
         return
     _LAST_BINNING.update(
         key=(means2d.data_ptr(), depths.data_ptr(), radii.data_ptr(), means2d._version, depths._version,
              radii._version, radii.shape[1], width, height, tile_size),
-        n_isects=n_isects, flatten_ids=flatten_ids, isect_offsets=isect_offsets,
+        n_isects=n_isects, flatten_ids=flatten_ids, isect_offsets=isect_offsets, legacy_extra=legacy_extra,
     )
 
 
@@ -87,12 +91,22 @@ def rasterize_gaussians(
         xys_c = xys.detach().float().contiguous()
         dep_c = depths1.detach().float().contiguous()
         rad_c = radii1.contiguous()
-        legacy_counts = ops.isect_count(xys_c[None], rad_c[None], ts, tile_w, tile_h, legacy_bbox=True)
         cached = _LAST_BINNING if _LAST_BINNING.get("key") == (
             xys_c.data_ptr(), dep_c.data_ptr(), rad_c.data_ptr(), xys._version, depths._version, radii._version,
             N, W, H, ts) else None
-        offsets, n_isects = ops.isect_scan(legacy_counts)
-        if cached is not None and cached["n_isects"] == n_isects:
+        if cached is not None and cached.get("legacy_extra") == 0:
+            # same xys / depths / radii as the rasterization() call just before, and its projection kernel found
+            # the 0.1.x bbox of every Gaussian equal to the 1.0 one: identical tile sets, identical keys
+            # (tile << 32 | depth bits) -> the sorted lists are shared; no binning, no sort, no host sync.
+            n_isects = cached["n_isects"]
+            flatten_ids, isect_offsets = cached["flatten_ids"], cached["isect_offsets"]
+            offsets = None
+        else:
+            legacy_counts = ops.isect_count(xys_c[None], rad_c[None], ts, tile_w, tile_h, legacy_bbox=True)
+            offsets, n_isects = ops.isect_scan(legacy_counts)
+        if offsets is None:
+            pass
+        elif cached is not None and cached["n_isects"] == n_isects:
             # legacy bbox is a superset of the 1.0 bbox per Gaussian, so equal totals <=> identical tile sets,
             # and the keys (tile << 32 | depth bits) are the same: the sorted lists can be shared.
             flatten_ids, isect_offsets = cached["flatten_ids"], cached["isect_offsets"]

@@ -87,16 +87,20 @@ def rasterization(
 
     # colour evaluation fused with the projection when SH is on
     if use_sh:
-        campos = torch.linalg.inv(viewmats)[:, :3, 3]
+        # camera centres: evaluated inside the kernel (-R^-1 t) unless a gradient has to reach the view matrices
+        campos = torch.linalg.inv(viewmats)[:, :3, 3] if viewmats.requires_grad else None
         color_stride = 4 if want_depth else 3
         depth_channel = 3 if want_depth else -1
         coeffs = colors
     else:
         campos, coeffs, color_stride, depth_channel = None, None, 0, -1
 
+    # totals[0] <- n_isects (scan), totals[1] <- tiles by which the legacy 0.1.x bbox rule would differ; one D2H read
+    totals = torch.zeros(2, dtype=torch.int64, device=means.device)
     radii, means2d, depths, conics, comps, sh_colors, tiles_per_gauss = ops.ProjectSH.apply(
         means, quats, scales, coeffs, viewmats, Ks, campos, width, height, eps2d, near_plane, far_plane,
-        radius_clip, tile_size, sh_degree if use_sh else None, color_stride, depth_channel, calc_comp)
+        radius_clip, tile_size, sh_degree if use_sh else None, color_stride, depth_channel, calc_comp,
+        totals[1:] if C == 1 else None)
 
     opac = opacities[None].expand(C, N)
     if comps is not None:
@@ -107,9 +111,10 @@ def rasterization(
     tile_height = math.ceil(height / float(tile_size))
     with torch.no_grad():
         _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(
-            means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss)
+            means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
+            totals=totals)
         remember_binning(means2d, depths, radii, width, height, tile_size, flatten_ids.numel(), flatten_ids,
-                         isect_offsets)
+                         isect_offsets, legacy_extra=totals.host[1] if C == 1 else None)
 
     if use_sh:
         ras_colors = sh_colors  # [C, N, 3 or 4], depth already in channel 3

@@ -84,7 +84,7 @@ def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
 # raw stage calls
 # ---------------------------------------------------------------------------------------------
 def project_sh_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-                   tile_size, sh_degree, coeffs, campos, color_stride, depth_channel, calc_comp):
+                   tile_size, sh_degree, coeffs, campos, color_stride, depth_channel, calc_comp, legacy_extra=None):
     _req_cuda(means, quats, scales, viewmats, Ks)
     C, N = viewmats.shape[0], means.shape[0]
     dev = means.device
@@ -101,7 +101,7 @@ def project_sh_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, nea
                                  eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w, tile_h,
                                  -1 if sh_degree is None else sh_degree, K, ptr(coeffs), ptr(campos), color_stride,
                                  depth_channel, ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps),
-                                 ptr(colors), ptr(tiles), _stream()), "fsb_project_sh_fwd")
+                                 ptr(colors), ptr(tiles), ptr(legacy_extra), _stream()), "fsb_project_sh_fwd")
     return radii, means2d, depths, conics, comps, colors, tiles
 
 
@@ -114,16 +114,22 @@ def isect_count(means2d: Tensor, radii: Tensor, tile_size: int, tile_w: int, til
     return tiles
 
 
-def isect_scan(counts: Tensor) -> Tuple[Tensor, int]:
-    """Exclusive int64 offsets of `counts` and the total (one 8-byte D2H read, like gsplat's)."""
+def isect_scan(counts: Tensor, totals: Optional[Tensor] = None):
+    """Exclusive int64 offsets of `counts` and the total (one small D2H read, like gsplat's).
+
+    `totals`: optional int64 device tensor whose element 0 receives the total; the whole tensor comes back in the
+    same read (rasterization() keeps the legacy-bbox mismatch counter in element 1), and the return value is then
+    (offsets, list_of_ints)."""
     M = counts.numel()
     dev = counts.device
     offsets = torch.empty((M,), dtype=torch.int64, device=dev)
-    total = torch.empty((1,), dtype=torch.int64, device=dev)
+    total = totals if totals is not None else torch.empty((1,), dtype=torch.int64, device=dev)
     ws_bytes = lib.fsb_isect_scan_workspace(M)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     check(lib.fsb_isect_scan(M, ptr(counts), ptr(offsets), ptr(total), ptr(ws), ws_bytes, _stream()),
           "fsb_isect_scan")
+    if totals is not None:
+        return offsets, [int(v) for v in total.tolist()]
     return offsets, int(total.item())
 
 
@@ -169,7 +175,7 @@ def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int) -> Tenso
 
 
 def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gauss=None, legacy_bbox=False,
-                sort=True):
+                sort=True, totals=None):
     """gsplat.isect_tiles + isect_offset_encode in one go (unpacked layout).
 
     means2d [C,N,2], radii [C,N] int32, depths [C,N] -> tiles_per_gauss [C,N], isect_ids [n_isects] int64 (sorted),
@@ -179,7 +185,10 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
     C, N = radii.shape
     if tiles_per_gauss is None:
         tiles_per_gauss = isect_count(means2d, radii, tile_size, tile_w, tile_h, legacy_bbox)
-    offsets, n_isects = isect_scan(tiles_per_gauss)
+    offsets, n_isects = isect_scan(tiles_per_gauss, totals)
+    if totals is not None:
+        totals.host = n_isects  # the values that came back with the one D2H read
+        n_isects = n_isects[0]
     ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox)
     if sort:
         end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
@@ -221,11 +230,16 @@ def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
     N = means2d.shape[-2]
     D = colors.shape[-1]
-    v_means2d = torch.zeros_like(means2d) if need_xy else None
-    v_abs = torch.zeros_like(means2d) if (absgrad and need_xy) else None
-    v_conics = torch.zeros_like(conics)
-    v_colors = torch.zeros_like(colors)
-    v_opac = torch.zeros_like(opacities)
+    # one zero-filled allocation (one fill launch) carved into the five accumulation targets
+    CN = means2d.shape[0] * N
+    sizes = [2 * CN if need_xy else 0, 2 * CN if (absgrad and need_xy) else 0, 3 * CN, D * CN, CN]
+    flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=means2d.device)
+    parts = torch.split(flat, sizes)
+    v_means2d = parts[0].view(means2d.shape) if need_xy else None
+    v_abs = parts[1].view(means2d.shape) if (absgrad and need_xy) else None
+    v_conics = parts[2].view(conics.shape)
+    v_colors = parts[3].view(colors.shape)
+    v_opac = parts[4].view(opacities.shape)
     ev = kernel_timer.start(f"raster_bwd_D{D}")
     check(lib.fsb_raster_bwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
@@ -245,12 +259,13 @@ class ProjectSH(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means, quats, scales, coeffs, viewmats, Ks, campos, width, height, eps2d, near_plane,
-                far_plane, radius_clip, tile_size, sh_degree, color_stride, depth_channel, calc_comp):
+                far_plane, radius_clip, tile_size, sh_degree, color_stride, depth_channel, calc_comp,
+                legacy_extra=None):
         means, quats, scales = _f32c(means), _f32c(quats), _f32c(scales)
         viewmats, Ks, coeffs, campos = _f32c(viewmats), _f32c(Ks), _f32c(coeffs), _f32c(campos)
         radii, means2d, depths, conics, comps, colors, tiles = project_sh_fwd(
             means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
-            sh_degree, coeffs, campos, color_stride, depth_channel, calc_comp)
+            sh_degree, coeffs, campos, color_stride, depth_channel, calc_comp, legacy_extra)
         ctx.save_for_backward(means, quats, scales, coeffs, viewmats, Ks, campos, radii)
         ctx.cfg = (width, height, eps2d, sh_degree, color_stride, depth_channel)
         ctx.set_materialize_grads(False)
@@ -288,7 +303,7 @@ class ProjectSH(torch.autograd.Function):
         if coeffs is not None and v_coeffs is None and ctx.needs_input_grad[3]:
             v_coeffs = torch.zeros_like(coeffs)
         return (v_means, v_quats, v_scales, v_coeffs if ctx.needs_input_grad[3] else None, v_viewmats, None, v_campos,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class RasterizeToPixels(torch.autograd.Function):

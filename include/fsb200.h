@@ -30,17 +30,22 @@ extern "C" {
  * replaces gsplat fully_fused_projection + spherical_harmonics + clamp_min(+0.5) + isect_tiles pass 1,
  * called from dn_splatter/dn_model.py:570-591.
  *   means[N,3] quats[N,4](wxyz) scales[N,3] viewmats[C,4,4] Ks[C,3,3]
- *   sh_degree -1: no colour evaluation; else coeffs[N,K,3], campos[C,3] (camera centres) and
- *   colors[C,N,color_stride] must be given: channels 0..2 = max(SH+0.5,0).
+ *   sh_degree -1: no colour evaluation; else coeffs[N,K,3] and colors[C,N,color_stride] must be given:
+ *   channels 0..2 = max(SH+0.5,0).  campos[C,3] = camera centres (torch.linalg.inv(viewmats)[:, :3, 3]); nullable:
+ *   NULL means -R^-1 t is evaluated inside the kernel.
  *   depth_channel >= 0: depths are also written into colors[..., depth_channel] ("RGB+ED").
  *   outputs: radii[C,N] i32 (0 = culled), means2d[C,N,2], depths[C,N], conics[C,N,3],
- *   comps[C,N] (nullable), tiles_per_gauss[C,N] i32.  Culled entries are written as zeros. */
+ *   comps[C,N] (nullable), tiles_per_gauss[C,N] i32.  Culled entries are written as zeros.
+ *   legacy_extra (nullable, i64, caller zero-fills): ACCUMULATES the number of tiles by which the gsplat 0.1.x
+ *   bbox rule (fsb_isect_count legacy_bbox=1) differs from tiles_per_gauss; 0 means the legacy normals pass
+ *   (dn_model.py:644-653) bins to exactly the same sorted lists. */
 int fsb_project_sh_fwd(int C, int N, const float* means, const float* quats, const float* scales,
                        const float* viewmats, const float* Ks, int width, int height, float eps2d,
                        float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w,
                        int tile_h, int sh_degree, int K, const float* coeffs, const float* campos,
                        int color_stride, int depth_channel, int32_t* radii, float* means2d, float* depths,
-                       float* conics, float* comps, float* colors, int32_t* tiles_per_gauss, void* stream);
+                       float* conics, float* comps, float* colors, int32_t* tiles_per_gauss,
+                       int64_t* legacy_extra, void* stream);
 
 /* P3: backward of the above.  replaces gsplat fully_fused_projection_bwd + compute_sh_bwd
  * (loss.backward() of dn_splatter/dn_model.py:570-591).
