@@ -141,23 +141,30 @@ project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float
     }
 }
 
-// block-wide sum of `v` (blockDim.x == 256), result valid in thread 0
-__device__ __forceinline__ float block_sum_256(float v, float* smem8) {
+constexpr int PB_THREADS = 128;           // backward block size
+constexpr int PB_WARPS = PB_THREADS / 32;
+constexpr int SH_ROW_MAX = 48;            // K * 3 floats of SH coefficients per Gaussian staged through smem (K <= 16)
+
+// block-wide sum of `v` (blockDim.x == PB_THREADS), result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* smem) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     __syncthreads();
-    if (l == 0) smem8[w] = v;
+    if (l == 0) smem[w] = v;
     __syncthreads();
     float r = 0.f;
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r += smem8[i];
+        for (int i = 0; i < PB_WARPS; ++i) r += smem[i];
     }
     return r;
 }
 
-__global__ void __launch_bounds__(256)
+// One thread per Gaussian, looping over cameras.  The SH rows (192 B per Gaussian at K = 16) are the bulk of the
+// traffic; a thread-per-row access pattern touches 32 sectors per request, so each warp moves its 32 rows
+// through a shared-memory tile with row-contiguous (coalesced) global loads and stores.
+__global__ void __launch_bounds__(PB_THREADS)
 project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float* __restrict__ quats,
                       const float* __restrict__ scales, const float* __restrict__ viewmats,
                       const float* __restrict__ Ks, int width, int height, float eps2d, int sh_degree, int K,
@@ -167,9 +174,16 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                       const float* __restrict__ v_comps, const float* __restrict__ v_colors,
                       float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
                       float* __restrict__ v_coeffs, float* __restrict__ v_viewmats, float* __restrict__ v_campos) {
-    __shared__ float red[8];
+    __shared__ float red[PB_WARPS];
+    __shared__ float tiles[PB_WARPS][32][SH_ROW_MAX + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float (*tile)[SH_ROW_MAX + 1] = tiles[warp];
     int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n0 = n - lane;  // first Gaussian of this warp
     bool live = n < N;
+    const int L = K * 3;
+    const bool do_sh = (sh_degree >= 0 && v_colors != nullptr && v_coeffs != nullptr);
+    const bool staged = do_sh && L <= SH_ROW_MAX;  // rows go through the tile
     float px = 0, py = 0, pz = 0, sx = 1, sy = 1, sz = 1;
     float4 q = make_float4(1, 0, 0, 0);
     if (live) {
@@ -180,9 +194,25 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
     float am[3] = {0, 0, 0}, aq[4] = {0, 0, 0, 0}, as[3] = {0, 0, 0};
     int nb = sh_degree >= 0 ? (sh_degree + 1) * (sh_degree + 1) : 0;
     bool any_sh = false;
+    // gradient rows accumulate in the tile (staged) across cameras; with one camera the tile first carries the
+    // coefficients themselves (coalesced load), with several they are read straight from global memory
+    const bool coeffs_in_tile = staged && C == 1;
+    if (staged && !coeffs_in_tile) {
+        for (int k = 0; k < L; ++k) tile[lane][k] = 0.f;
+    }
     for (int c = 0; c < C; ++c) {
         size_t idx = (size_t)c * N + n;
         bool vis = live && radii[idx] > 0;
+        if (coeffs_in_tile) {
+            const unsigned vmask = __ballot_sync(0xffffffffu, vis);
+            for (int r = 0; r < 32; ++r) {
+                if (!((vmask >> r) & 1u)) continue;
+                const float* row = coeffs + (size_t)(n0 + r) * L;
+                if (lane < L) tile[r][lane] = row[lane];
+                if (lane + 32 < L) tile[r][lane + 32] = row[lane + 32];
+            }
+            __syncwarp();
+        }
         float vRv[9], vtv[3], vcp[3] = {0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 9; ++i) vRv[i] = 0.f;
@@ -206,7 +236,7 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 float ux = dx * inorm, uy = dy * inorm, uz = dz * inorm;
                 float basis[16];
                 fs::sh_basis(sh_degree, ux, uy, uz, basis);
-                const float* cf = coeffs + (size_t)n * K * 3;
+                const float* cf = coeffs_in_tile ? &tile[lane][0] : coeffs + (size_t)n * L;
                 float r = 0.f, g = 0.f, b = 0.f;
                 for (int k = 0; k < nb; ++k) {
                     r += basis[k] * cf[3 * k + 0];
@@ -217,31 +247,46 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 float vr = (r + 0.5f >= 0.f) ? vc[0] : 0.f;
                 float vg = (g + 0.5f >= 0.f) ? vc[1] : 0.f;
                 float vb = (b + 0.5f >= 0.f) ? vc[2] : 0.f;
-                float* vcf = v_coeffs + (size_t)n * K * 3;
-                if (C == 1) {
-                    for (int k = 0; k < nb; ++k) {
-                        vcf[3 * k + 0] = basis[k] * vr;
-                        vcf[3 * k + 1] = basis[k] * vg;
-                        vcf[3 * k + 2] = basis[k] * vb;
-                    }
-                } else {
-                    for (int k = 0; k < nb; ++k) {
-                        float o0 = any_sh ? vcf[3 * k + 0] : 0.f, o1 = any_sh ? vcf[3 * k + 1] : 0.f,
-                              o2 = any_sh ? vcf[3 * k + 2] : 0.f;
-                        vcf[3 * k + 0] = o0 + basis[k] * vr;
-                        vcf[3 * k + 1] = o1 + basis[k] * vg;
-                        vcf[3 * k + 2] = o2 + basis[k] * vb;
-                    }
-                }
-                any_sh = true;
+                float gx = 0.f, gy = 0.f, gz = 0.f;
                 if (sh_degree >= 1) {
                     float bx[16], by[16], bz[16];
                     fs::sh_basis_grad(sh_degree, ux, uy, uz, bx, by, bz);
-                    float gx = 0.f, gy = 0.f, gz = 0.f;
                     for (int k = 1; k < nb; ++k) {
                         float w = cf[3 * k + 0] * vr + cf[3 * k + 1] * vg + cf[3 * k + 2] * vb;
                         gx += bx[k] * w; gy += by[k] * w; gz += bz[k] * w;
                     }
+                }
+                // the coefficients of this row are not needed any more: the tile row now takes the gradient
+                if (do_sh) {
+                    if (staged) {
+                        float* vrow = &tile[lane][0];
+                        if (coeffs_in_tile) {
+                            for (int k = 0; k < nb; ++k) {
+                                vrow[3 * k + 0] = basis[k] * vr;
+                                vrow[3 * k + 1] = basis[k] * vg;
+                                vrow[3 * k + 2] = basis[k] * vb;
+                            }
+                            for (int k = nb * 3; k < L; ++k) vrow[k] = 0.f;
+                        } else {
+                            for (int k = 0; k < nb; ++k) {
+                                vrow[3 * k + 0] += basis[k] * vr;
+                                vrow[3 * k + 1] += basis[k] * vg;
+                                vrow[3 * k + 2] += basis[k] * vb;
+                            }
+                        }
+                    } else {
+                        float* vcf = v_coeffs + (size_t)n * L;
+                        for (int k = 0; k < nb; ++k) {
+                            float o0 = any_sh ? vcf[3 * k + 0] : 0.f, o1 = any_sh ? vcf[3 * k + 1] : 0.f,
+                                  o2 = any_sh ? vcf[3 * k + 2] : 0.f;
+                            vcf[3 * k + 0] = o0 + basis[k] * vr;
+                            vcf[3 * k + 1] = o1 + basis[k] * vg;
+                            vcf[3 * k + 2] = o2 + basis[k] * vb;
+                        }
+                    }
+                }
+                any_sh = true;
+                if (sh_degree >= 1) {
                     // through u = d / |d|
                     float dot = gx * ux + gy * uy + gz * uz;
                     float vdx = (gx - dot * ux) * inorm, vdy = (gy - dot * uy) * inorm, vdz = (gz - dot * uz) * inorm;
@@ -256,32 +301,46 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
         if (v_viewmats) {  // uniform branch: every thread of the block takes part in the reductions
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
-                float s = block_sum_256(vRv[i], red);
+                float s = block_sum(vRv[i], red);
                 if (threadIdx.x == 0 && s != 0.f) atomicAdd(v_viewmats + (size_t)c * 16 + (i / 3) * 4 + (i % 3), s);
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                float s = block_sum_256(vtv[i], red);
+                float s = block_sum(vtv[i], red);
                 if (threadIdx.x == 0 && s != 0.f) atomicAdd(v_viewmats + (size_t)c * 16 + i * 4 + 3, s);
             }
         }
         if (v_campos) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                float s = block_sum_256(vcp[i], red);
+                float s = block_sum(vcp[i], red);
                 if (threadIdx.x == 0 && s != 0.f) atomicAdd(v_campos + (size_t)c * 3 + i, s);
             }
+        }
+    }
+    if (v_coeffs) {
+        if (staged) {
+            // rows of Gaussians that were never visible (or hold stale coefficients) are zero
+            if (!any_sh) {
+                for (int k = 0; k < L; ++k) tile[lane][k] = 0.f;
+            }
+            __syncwarp();
+            const int rows = min(32, N - n0);
+            for (int r = 0; r < rows; ++r) {
+                float* row = v_coeffs + (size_t)(n0 + r) * L;
+                if (lane < L) row[lane] = tile[r][lane];
+                if (lane + 32 < L) row[lane + 32] = tile[r][lane + 32];
+            }
+        } else if (live) {
+            float* vcf = v_coeffs + (size_t)n * L;
+            int start = any_sh ? nb : 0;  // bases above the active degree (or everything, if never visible) get zero
+            for (int k = start * 3; k < L; ++k) vcf[k] = 0.f;
         }
     }
     if (!live) return;
     v_means[3 * (size_t)n + 0] = am[0]; v_means[3 * (size_t)n + 1] = am[1]; v_means[3 * (size_t)n + 2] = am[2];
     reinterpret_cast<float4*>(v_quats)[n] = make_float4(aq[0], aq[1], aq[2], aq[3]);
     v_scales[3 * (size_t)n + 0] = as[0]; v_scales[3 * (size_t)n + 1] = as[1]; v_scales[3 * (size_t)n + 2] = as[2];
-    if (v_coeffs) {
-        float* vcf = v_coeffs + (size_t)n * K * 3;
-        int start = any_sh ? nb : 0;  // bases above the active degree (or everything, if never visible) get zero
-        for (int k = start * 3; k < K * 3; ++k) vcf[k] = 0.f;
-    }
 }
 
 // stand-alone tile count for callers that bring their own xys/radii (legacy rasterize_gaussians)
@@ -333,7 +392,7 @@ FSB_API int fsb_project_sh_bwd(int C, int N, const float* means, const float* qu
     if (sh_degree >= 0 && v_colors && (!coeffs || !v_coeffs)) return FSB_E_ARG;
     if (v_campos && !campos) return FSB_E_ARG;
     if (N == 0) return 0;
-    project_sh_bwd_kernel<<<fsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
+    project_sh_bwd_kernel<<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, coeffs, campos, color_stride,
         depth_channel, radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_means, v_quats, v_scales, v_coeffs,
         v_viewmats, v_campos);

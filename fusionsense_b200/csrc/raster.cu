@@ -36,6 +36,13 @@
 
 namespace {
 
+// 1 / x to 1 ulp (MUFU.RCP): the reference kernels are built with fast-math and divide the same way
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 constexpr float ALPHA_MAX = 0.999f;
 constexpr float ALPHA_MIN = 1.f / 255.f;
 constexpr float T_MIN = 1e-4f;
@@ -459,47 +466,47 @@ raster_stop_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ me
     write_pixel<D>(o, tg, pix, sg.masked, T, acc, last);
 }
 
-// Sum up to 16 per-lane values over the warp so that lane L ends up with the total of value index
-// slot_of_lane(L); 16 shuffles in all.  v[] is clobbered; the total is returned.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[16], int lane) {
-    {
-        const bool hi = lane & 16;
+// Reduce-scatter of N per-lane values over the warp: a butterfly that halves the live values at every stage
+// (lanes with the stage bit set keep the upper half, the others the lower half), so lane L ends up with the
+// warp total of value index slot_of_lane<N>(L).  ceil(N/2) + ceil(N/4) + ... shuffles in all (13 for N = 12,
+// 9 for N = 7) against 5 N for plain butterflies.  v[] is clobbered; the lane's total is returned.
+template <int N, int XOR>
+struct Bfly {
+    template <int NV>
+    static __device__ __forceinline__ float run(float (&v)[NV], int lane) {
+        constexpr int H = (N + 1) / 2;
+        const bool hi = lane & XOR;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? v[i] : v[i + 8];
-            const float keep = hi ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int i = 0; i < H; ++i) {
+            const float lo_v = v[i];
+            const float hi_v = (H + i < N) ? v[H + i] : 0.f;
+            const float send = hi ? lo_v : hi_v;
+            const float keep = hi ? hi_v : lo_v;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, XOR);
         }
+        return Bfly<H, XOR / 2>::run(v, lane);
     }
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? v[i] : v[i + 4];
-            const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = hi ? v[i] : v[i + 2];
-            const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    {
-        const bool hi = lane & 2;
-        const float send = hi ? v[0] : v[1];
-        const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+};
+template <int N>
+struct Bfly<N, 0> {
+    template <int NV>
+    static __device__ __forceinline__ float run(float (&v)[NV], int) { return v[0]; }
+};
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
+    return Bfly<N, 16>::run(v, lane);
 }
-// value index held by lane L after warp_transpose_sum
+// value index held by lane L after warp_transpose_sum<N>, or -1 if the lane holds none
+template <int N>
 __device__ __forceinline__ int slot_of_lane(int lane) {
-    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    int base = 0, n = N, nt = N;  // n: values this lane's group really holds; nt: the stage width (uniform)
+#pragma unroll
+    for (int x = 16; x > 0; x >>= 1) {
+        const int h = (nt + 1) / 2;
+        if (lane & x) { base += h; n -= h; } else { n = min(n, h); }
+        nt = h;
+    }
+    return n >= 1 ? base : -1;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -509,7 +516,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Slots of the packed gradient vector: [0, D) colours, then conic a b c, opacity, xy, |xy|.
-template <int D>
+// XYMODE: 0 = no gradient for the 2-D means (the normals pass detaches them), 1 = xy, 2 = xy and |xy| (absgrad).
+template <int D, int XYMODE>
 __global__ void __launch_bounds__(MAX_BLOCK)
 raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
                   const float* __restrict__ conics, const float* __restrict__ colors,
@@ -581,19 +589,21 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
 #pragma unroll
         for (int c = 0; c < D; ++c) bg_dot += backgrounds[tg.cam * D + c] * v_rc[c];
     }
-    const bool want_xy = (v_means2d != nullptr);
-    const bool want_abs = (v_means2d_abs != nullptr);
-
+    constexpr bool want_xy = (XYMODE >= 1);
+    constexpr bool want_abs = (XYMODE >= 2);
     constexpr bool kTranspose = (D <= 8);
-    const int slot = slot_of_lane(tg.lane);
+    constexpr int NG = 4 + 2 * XYMODE;             // conic a b c, opacity (, xy (, |xy|))
+    constexpr int NV = kTranspose ? D + NG : NG;   // values reduced by the transposing butterfly
+    constexpr int B = kTranspose ? D : 0;          // first geometric slot
+    const int slot = slot_of_lane<NV>(tg.lane);
     float* slot_base = nullptr;
     int slot_stride = 0;
-    if (kTranspose && !(tg.lane & 1)) {
-        if (slot < D) { slot_base = v_colors + slot; slot_stride = D; }
-        else if (slot < D + 3) { slot_base = v_conics + (slot - D); slot_stride = 3; }
-        else if (slot == D + 3) { slot_base = v_opacities; slot_stride = 1; }
-        else if (slot < D + 6) { slot_base = want_xy ? v_means2d + (slot - D - 4) : nullptr; slot_stride = 2; }
-        else if (slot < D + 8) { slot_base = want_abs ? v_means2d_abs + (slot - D - 6) : nullptr; slot_stride = 2; }
+    if (slot >= 0) {
+        if (slot < B) { slot_base = v_colors + slot; slot_stride = D; }
+        else if (slot < B + 3) { slot_base = v_conics + (slot - B); slot_stride = 3; }
+        else if (slot == B + 3) { slot_base = v_opacities; slot_stride = 1; }
+        else if (slot < B + 6) { slot_base = v_means2d + (slot - B - 4); slot_stride = 2; }
+        else { slot_base = v_means2d_abs + (slot - B - 6); slot_stride = 2; }
     }
 
     // entries behind every pixel's last id are not even staged
@@ -626,12 +636,12 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
             }
             if (!__any_sync(0xffffffffu, valid)) continue;
 
-            float v[16];
+            float v[NV];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = 0.f;
+            for (int c = 0; c < NV; ++c) v[c] = 0.f;
             float v_colD[D > 8 ? D : 1];
             if (valid) {
-                const float ra = 1.f / (1.f - alpha);
+                const float ra = fast_rcp(1.f - alpha);
                 T *= ra;
                 const float fac = alpha * T;
                 float v_alpha = 0.f;
@@ -647,17 +657,16 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
                 if (backgrounds) v_alpha += -T_final * ra * bg_dot;
                 if (opac * vis <= ALPHA_MAX) {
                     const float v_sigma = -opac * vis * v_alpha;
-                    constexpr int B = kTranspose ? D : 0;
                     v[B + 0] = 0.5f * v_sigma * dx * dx;
                     v[B + 1] = v_sigma * dx * dy;
                     v[B + 2] = 0.5f * v_sigma * dy * dy;
                     v[B + 3] = vis * v_alpha;
-                    if (want_xy) {
+                    if constexpr (want_xy) {
                         const float gx = v_sigma * (con.x * dx + con.y * dy);
                         const float gy = v_sigma * (con.y * dx + con.z * dy);
                         v[B + 4] = gx;
                         v[B + 5] = gy;
-                        if (want_abs) {
+                        if constexpr (want_abs) {
                             v[B + 6] = fabsf(gx);
                             v[B + 7] = fabsf(gy);
                         }
@@ -679,14 +688,7 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
                     if (tg.lane == 0) atomicAdd(v_colors + (size_t)g * D + c, tot);
                 }
                 const float total = warp_transpose_sum(v, tg.lane);
-                if (!(tg.lane & 1) && total != 0.f) {
-                    float* p = nullptr;
-                    if (slot < 3) p = v_conics + 3 * (size_t)g + slot;
-                    else if (slot == 3) p = v_opacities + g;
-                    else if (slot < 6) p = want_xy ? v_means2d + 2 * (size_t)g + (slot - 4) : nullptr;
-                    else if (slot < 8) p = want_abs ? v_means2d_abs + 2 * (size_t)g + (slot - 6) : nullptr;
-                    if (p) atomicAdd(p, total);
-                }
+                if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
             }
         }
     }
@@ -733,10 +735,15 @@ int launch_bwd(int C, int N, int64_t n_isects, const float* means2d, const float
     Workspace ws = carve_ws(workspace, n_isects, n_tiles, D);
     dim3 block(tile_size, tile_size);
     unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
-    raster_bwd_kernel<D><<<grid, block, 0, st>>>(
-        C, N, n_isects, (const float2*)means2d, conics, colors, opacities, backgrounds, masks, width, height,
-        tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize, ws, render_colors, render_alphas,
-        last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities);
+#define FSB_BWD_LAUNCH(MODE)                                                                                       \
+    raster_bwd_kernel<D, MODE><<<grid, block, 0, st>>>(                                                             \
+        C, N, n_isects, (const float2*)means2d, conics, colors, opacities, backgrounds, masks, width, height,       \
+        tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize, ws, render_colors, render_alphas,       \
+        last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities)
+    if (v_means2d_abs) FSB_BWD_LAUNCH(2);
+    else if (v_means2d) FSB_BWD_LAUNCH(1);
+    else FSB_BWD_LAUNCH(0);
+#undef FSB_BWD_LAUNCH
     FSB_LAUNCH_CHECK();
     return 0;
 }

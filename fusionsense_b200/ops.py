@@ -17,7 +17,12 @@ from ._abi import check, lib, ptr
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream on the current device (the cheap private accessor when this
+    torch has it: torch.cuda.current_stream() builds a Stream object, ~10x slower, and runs ~20 times per step)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:  # pragma: no cover
+        return torch.cuda.current_stream().cuda_stream
 
 
 class KernelTimer:

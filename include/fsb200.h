@@ -140,6 +140,18 @@ int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* bl
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a16: visual-hull pruning without the distance matrix.  replaces torch.cdist(means[close], hull).min(-1) and
+ * the threshold mask of dn_splatter/dn_model.py:1254-1269 (every refine_every steps).
+ *   fsb_hull_min_dist: pts[N,3], hull[V,3], center[3] (device, nullable: no radius filter), r_close;
+ *     min_dist[N] = distance to the nearest hull point for points within r_close of center, +inf otherwise.
+ *     stop_below > 0 lets a point stop once a hull point is closer than that (result then an upper bound).
+ *   fsb_hull_prune_mask: mask[N] u8 = (lo < min_dist <= hi) && !protect[n]  (protect u8, nullable). */
+int fsb_hull_min_dist(int N, const float* pts, int V, const float* hull, const float* center, float r_close,
+                      float stop_below, float* min_dist, void* stream);
+int fsb_hull_prune_mask(int N, const float* min_dist, float lo, float hi, const uint8_t* protect, uint8_t* mask,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SSIM of the base splatfacto loss: `1 - self.ssim(gt, pred)` with torchmetrics
  * StructuralSimilarityIndexMeasure(data_range=1.0, kernel_size=11, sigma=1.5) — dn_splatter/dn_model.py:244,
  * reached through super().get_loss_dict at dn_model.py:683.  Mean over the (H-10)x(W-10) interior (torchmetrics
