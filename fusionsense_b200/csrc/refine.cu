@@ -27,20 +27,26 @@ __global__ void __launch_bounds__(RF_THREADS)
 refine_classify_kernel(int N, const float* __restrict__ xys_grad_norm, const float* __restrict__ vis_counts,
                        const float* __restrict__ max_2Dsize, const float* __restrict__ scales, float half_max_dim,
                        float densify_grad_thresh, float densify_size_thresh, float split_screen_size,
-                       const uint8_t* __restrict__ add_mask, uint8_t* __restrict__ action,
+                       float size_fac, const uint8_t* __restrict__ add_mask, uint8_t* __restrict__ action,
                        int32_t* __restrict__ split_flag, int32_t* __restrict__ dup_flag) {
     const int n = blockIdx.x * RF_THREADS + threadIdx.x;
     if (n >= N) return;
     // avg_grad_norm = (xys_grad_norm / vis_counts) * 0.5 * max(H, W)
     const float avg = (xys_grad_norm[n] / vis_counts[n]) * 0.5f * half_max_dim;
     const bool high = avg > densify_grad_thresh;
-    const float smax = fmaxf(fmaxf(expf(scales[3 * (size_t)n]), expf(scales[3 * (size_t)n + 1])),
-                             expf(scales[3 * (size_t)n + 2]));
+    const float e0 = expf(scales[3 * (size_t)n]), e1 = expf(scales[3 * (size_t)n + 1]),
+                e2 = expf(scales[3 * (size_t)n + 2]);
+    const float smax = fmaxf(fmaxf(e0, e1), e2);
     bool split = smax > densify_size_thresh;
     if (split_screen_size > 0.f && max_2Dsize) split = split || (max_2Dsize[n] > split_screen_size);
     split = split && high;
-    bool dup = (smax <= densify_size_thresh) && high;
-    if (add_mask && add_mask[n]) { split = false; dup = false; }
+    if (add_mask && add_mask[n]) split = false;
+    // `dups` is evaluated AFTER split_gaussians has shrunk the split parents' scales in place (dn_model.py:369-375
+    // over nerfstudio's split_gaussians): a split parent whose shrunk scale fits the threshold is duplicated too
+    float dmax = smax;
+    if (split) dmax = fmaxf(fmaxf(expf(logf(e0 / size_fac)), expf(logf(e1 / size_fac))), expf(logf(e2 / size_fac)));
+    bool dup = (dmax <= densify_size_thresh) && high;
+    if (add_mask && add_mask[n]) dup = false;
     action[n] = (split ? 1 : 0) | (dup ? 2 : 0);
     split_flag[n] = split ? 1 : 0;
     dup_flag[n] = dup ? 1 : 0;
@@ -88,8 +94,8 @@ refine_keep_kernel(int64_t M, int N, int n_split, int n_dup, int samps, const ui
     }
     if (cull_scale_thresh > 0.f) {
         float sx = expf(scales[3 * (size_t)p]), sy = expf(scales[3 * (size_t)p + 1]), sz = expf(scales[3 * (size_t)p + 2]);
-        if (child) {
-            // children carry log(exp(s) / size_fac)
+        if (child || (is_new && action && (action[p] & 1))) {
+            // children (and duplicates of already-shrunk split parents) carry log(exp(s) / size_fac)
             sx = expf(logf(sx / size_fac)); sy = expf(logf(sy / size_fac)); sz = expf(logf(sz / size_fac));
         }
         bool toobig = fmaxf(fmaxf(sx, sy), sz) > cull_scale_thresh;
@@ -115,16 +121,25 @@ refine_gather_kernel(int64_t M, int N, int width, const float* __restrict__ src,
 }
 
 __global__ void __launch_bounds__(RF_THREADS)
-refine_split_fixup_kernel(int64_t n_children, int N, const float* __restrict__ means, const float* __restrict__ scales,
+refine_split_fixup_kernel(int64_t n_new, int64_t n_children, int N, const uint8_t* __restrict__ action,
+                          const float* __restrict__ means, const float* __restrict__ scales,
                           const float* __restrict__ quats, const float* __restrict__ samples,
                           const int32_t* __restrict__ parent, const int32_t* __restrict__ keep,
                           const int64_t* __restrict__ offsets, float size_fac, float* __restrict__ out_means,
                           float* __restrict__ out_scales) {
     const int64_t i = (int64_t)blockIdx.x * RF_THREADS + threadIdx.x;
-    if (i >= n_children) return;
+    if (i >= n_new) return;
     const int64_t j = (int64_t)N + i;
     if (!keep[j]) return;
     const int p = parent[j];
+    if (i >= n_children) {
+        // a duplicate: only the copies of split parents differ from a plain gather (their scales were shrunk)
+        if (!(action[p] & 1)) return;
+        const size_t o = (size_t)offsets[j];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) out_scales[3 * o + r] = logf(expf(scales[3 * (size_t)p + r]) / size_fac);
+        return;
+    }
     const float es0 = expf(scales[3 * (size_t)p]), es1 = expf(scales[3 * (size_t)p + 1]),
                 es2 = expf(scales[3 * (size_t)p + 2]);
     const float s0 = es0 * samples[3 * i], s1 = es1 * samples[3 * i + 1], s2 = es2 * samples[3 * i + 2];
@@ -146,13 +161,14 @@ refine_split_fixup_kernel(int64_t n_children, int N, const float* __restrict__ m
 // split_screen_size <= 0 disables the screen-size test (step >= stop_screen_size_at).
 FSB_API int fsb_refine_classify(int N, const float* xys_grad_norm, const float* vis_counts, const float* max_2Dsize,
                                 const float* scales, float max_dim, float densify_grad_thresh,
-                                float densify_size_thresh, float split_screen_size, const uint8_t* add_mask,
-                                uint8_t* action, int32_t* split_flag, int32_t* dup_flag, void* stream) {
+                                float densify_size_thresh, float split_screen_size, float size_fac,
+                                const uint8_t* add_mask, uint8_t* action, int32_t* split_flag, int32_t* dup_flag,
+                                void* stream) {
     if (N < 0) return FSB_E_ARG;
     if (N == 0) return 0;
     refine_classify_kernel<<<fsb_div_up(N, RF_THREADS), RF_THREADS, 0, (cudaStream_t)stream>>>(
         N, xys_grad_norm, vis_counts, max_2Dsize, scales, max_dim, densify_grad_thresh, densify_size_thresh,
-        split_screen_size, add_mask, action, split_flag, dup_flag);
+        split_screen_size, size_fac, add_mask, action, split_flag, dup_flag);
     FSB_LAUNCH_CHECK();
     return 0;
 }
@@ -199,16 +215,19 @@ FSB_API int fsb_refine_gather(int64_t M, int N, int width, const float* src, con
     return 0;
 }
 
-// children rows (candidates N .. N + n_children): out_means / out_scales rows overwritten with the sampled
-// position and the shrunk scale.  samples[n_children, 3] ~ N(0, I) from the caller.
-FSB_API int fsb_refine_split_fixup(int64_t n_children, int N, const float* means, const float* scales,
-                                   const float* quats, const float* samples, const int32_t* parent,
-                                   const int32_t* keep, const int64_t* offsets, float size_fac, float* out_means,
-                                   float* out_scales, void* stream) {
-    if (n_children < 0) return FSB_E_ARG;
-    if (n_children == 0) return 0;
-    refine_split_fixup_kernel<<<fsb_div_up(n_children, RF_THREADS), RF_THREADS, 0, (cudaStream_t)stream>>>(
-        n_children, N, means, scales, quats, samples, parent, keep, offsets, size_fac, out_means, out_scales);
+// new rows (candidates N .. N + n_new; the first n_children of them are split children): children get the sampled
+// position and the shrunk scale, duplicates of split parents the shrunk scale.  samples[n_children, 3] ~ N(0, I)
+// from the caller.
+FSB_API int fsb_refine_split_fixup(int64_t n_new, int64_t n_children, int N, const uint8_t* action,
+                                   const float* means, const float* scales, const float* quats,
+                                   const float* samples, const int32_t* parent, const int32_t* keep,
+                                   const int64_t* offsets, float size_fac, float* out_means, float* out_scales,
+                                   void* stream) {
+    if (n_new < 0 || n_children < 0 || n_children > n_new) return FSB_E_ARG;
+    if (n_new == 0) return 0;
+    refine_split_fixup_kernel<<<fsb_div_up(n_new, RF_THREADS), RF_THREADS, 0, (cudaStream_t)stream>>>(
+        n_new, n_children, N, action, means, scales, quats, samples, parent, keep, offsets, size_fac, out_means,
+        out_scales);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -48,6 +48,16 @@ class DNSplatterStepConfig:
     reset_alpha_every: int = 30
     refine_every: int = 100
     stop_split_at: int = 10000
+    # nerfstudio 1.1.3 SplatfactoModelConfig defaults that refinement reads
+    densify_grad_thresh: float = 0.0008
+    densify_size_thresh: float = 0.01
+    n_split_samples: int = 2
+    cull_alpha_thresh: float = 0.1
+    cull_scale_thresh: float = 0.5
+    cull_screen_size: float = 0.15
+    split_screen_size: float = 0.05
+    stop_screen_size_at: int = 4000
+    continue_cull_post_densification: bool = True
     background_color: str = "white"
     rasterize_mode: str = "classic"
     lrs: Dict[str, float] = field(default_factory=lambda: {
@@ -94,6 +104,9 @@ class DNSplatterStep:
         self.xys_grad_norm = None
         self.vis_counts = None
         self.max_2Dsize = None
+        self.add_mask = None
+        self.num_train_data = sc.viewmats.shape[0]
+        self.last_size = (sc.height, sc.width)
         self._build_optimizers()
 
     # ---- parameters / optimisers ------------------------------------------------------------
@@ -277,6 +290,17 @@ class DNSplatterStep:
         newradii = self.radii.detach()[visible_mask]
         self.max_2Dsize[visible_mask] = torch.maximum(
             self.max_2Dsize[visible_mask], newradii / float(max(self.last_size[0], self.last_size[1])))
+
+    # ---- dn_model.py:326-451 / :1249-1276 (AFTER_TRAIN_ITERATION callbacks, every refine_every steps) ----------
+    def refinement_after(self, samples=None):
+        from .densify import refinement_after
+
+        return refinement_after(self, self.optimizers, self.step, samples=samples)
+
+    def hull_pruning(self, visual_hull: Tensor, scale_factor: float = 1.0):
+        from .densify import hull_pruning
+
+        return hull_pruning(self, self.optimizers, self.step, visual_hull, scale_factor)
 
     # ---- Trainer.train_iteration ------------------------------------------------------------
     def train_iteration(self, cam_idx: int, batch: Dict[str, Tensor]) -> Tensor:

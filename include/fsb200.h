@@ -140,6 +140,41 @@ int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* bl
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a15: densify / prune bookkeeping.  replaces dn_splatter/dn_model.py:326-451 (refinement_after) and the
+ * nerfstudio 1.1.3 helpers it drives (split_gaussians, dup_gaussians, cull_gaussians, dup_in_optim,
+ * remove_from_optim).  The concatenated candidate model has M = N + samps*n_split + n_dup rows:
+ * the N originals, the split children sample-major (.repeat(samps, 1)), the duplicates.
+ *   classify : action[N] u8 (bit0 split, bit1 dup) + 0/1 i32 flags for fsb_isect_scan.  scales = LOG scales.
+ *              max_dim = max(H, W); split_screen_size <= 0 disables that test; max_2Dsize / add_mask nullable.
+ *   index    : split_idcs[n_split], dup_idcs[n_dup] i32 from the exclusive scans of the flags.
+ *   keep     : parent[M] i32, keep[M] i32 = !cull_gaussians(...) evaluated on the candidate row; action nullable
+ *              (cull only); extra_cull[N] u8 nullable; cull_scale_thresh <= 0 / cull_screen_size <= 0 disable
+ *              the too-big tests.
+ *   gather   : out[offsets[j], :] = src[parent[j], :] for kept j (offsets = exclusive scan of keep);
+ *              zero_new = 1 writes zeros for j >= N (Adam moments of new rows).
+ *   split_fixup: over the n_new = samps*n_split + n_dup new rows: kept children get mean = mu + R(q/|q|)(exp(s)*eps)
+ *              and scale = log(exp(s)/size_fac); kept duplicates of split parents the shrunk scale (the reference
+ *              shrinks split parents in place before it evaluates `dups`).  samples[samps*n_split, 3] ~ N(0, I)
+ *              supplied by the caller. */
+int fsb_refine_classify(int N, const float* xys_grad_norm, const float* vis_counts, const float* max_2Dsize,
+                        const float* scales, float max_dim, float densify_grad_thresh, float densify_size_thresh,
+                        float split_screen_size, float size_fac, const uint8_t* add_mask, uint8_t* action,
+                        int32_t* split_flag, int32_t* dup_flag, void* stream);
+int fsb_refine_index(int N, const uint8_t* action, const int64_t* split_rank, const int64_t* dup_rank,
+                     int32_t* split_idcs, int32_t* dup_idcs, void* stream);
+int fsb_refine_keep(int64_t M, int N, int n_split, int n_dup, int samps, const uint8_t* action,
+                    const int32_t* split_idcs, const int32_t* dup_idcs, const float* opacities,
+                    const float* scales, const float* max_2Dsize, float cull_alpha_thresh, float cull_scale_thresh,
+                    float cull_screen_size, float size_fac, const uint8_t* extra_cull, int32_t* parent,
+                    int32_t* keep, void* stream);
+int fsb_refine_gather(int64_t M, int N, int width, const float* src, const int32_t* parent, const int32_t* keep,
+                      const int64_t* offsets, int zero_new, float* out, void* stream);
+int fsb_refine_split_fixup(int64_t n_new, int64_t n_children, int N, const uint8_t* action, const float* means,
+                           const float* scales, const float* quats, const float* samples, const int32_t* parent,
+                           const int32_t* keep, const int64_t* offsets, float size_fac, float* out_means,
+                           float* out_scales, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * a16: visual-hull pruning without the distance matrix.  replaces torch.cdist(means[close], hull).min(-1) and
  * the threshold mask of dn_splatter/dn_model.py:1254-1269 (every refine_every steps).
  *   fsb_hull_min_dist: pts[N,3], hull[V,3], center[3] (device, nullable: no radius filter), r_close;
