@@ -187,89 +187,132 @@ __device__ __forceinline__ uint32_t strip_mask(float gx, float gy, float opac, f
     return m;
 }
 
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// A staged list segment.  The per-entry constants are stored in the form the inner loops consume:
+//   alpha = min(0.999, 2^(p + L)),  p = a' dx^2 + b' dx dy + c' dy^2  (= -log2e * sigma),  L = log2(opacity)
+// so one evaluation is 2 FADD + 6 FMUL/FFMA + 1 FADD + MUFU.EX2 + FMNMX, and "sigma < 0" is "p > 0".
+// Slot SEG is a dummy entry with alpha = 0 that pads the per-warp work lists to a multiple of four.
 template <int D>
 struct Stage {
     static constexpr int SEG = seg_len(D);
+    static constexpr int DP = (D == 3) ? 4 : D;  // colour row stride (one 128-bit load for D = 3 and D = 4)
     int32_t id[SEG];
-    float4 xyo[SEG];  // x, y, opacity, strip mask (as int bits)
-    float4 con[SEG];  // conic a, b, c
-    float col[SEG * D];
+    float4 geo[SEG + 1];  // x, y, log2(opacity), strip mask (as int bits)
+    float4 con[SEG + 1];  // -0.5 log2e a, -log2e b, -0.5 log2e c, 1 / opacity
+    float col[(SEG + 1) * DP];
+    alignas(8) uint16_t wlist[MAX_BLOCK / 32][SEG + 4];  // per warp: the entries whose strip mask has its bit
 };
 
 template <int D>
 __device__ __forceinline__ void stage_entry(Stage<D>& s, int slot, int32_t g, const float2* __restrict__ means2d,
                                             const float* __restrict__ conics, const float* __restrict__ colors,
                                             const float* __restrict__ opacities, const TileGeom& tg, int tile_size) {
+    constexpr int DP = Stage<D>::DP;
     s.id[slot] = g;
     const float2 xy = means2d[g];
     const float o = opacities[g];
     const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
     const uint32_t m = strip_mask(xy.x, xy.y, o, a, b, c, (float)(tg.tile_x * tile_size),
                                   (float)(tg.tile_y * tile_size), tile_size, tg.rows_per_warp, tg.n_warps);
-    s.xyo[slot] = make_float4(xy.x, xy.y, o, __int_as_float((int)m));
-    s.con[slot] = make_float4(a, b, c, 0.f);
+    s.geo[slot] = make_float4(xy.x, xy.y, __log2f(o), __int_as_float((int)m));
+    s.con[slot] = make_float4(-0.5f * LOG2E * a, -LOG2E * b, -0.5f * LOG2E * c, fast_rcp(o));
     const float* cp = colors + (size_t)g * D;
 #pragma unroll
-    for (int k = 0; k < D; ++k) s.col[slot * D + k] = cp[k];
+    for (int k = 0; k < D; ++k) s.col[slot * DP + k] = cp[k];
 }
 
-// Front-to-back walk of this warp's entries of the staged segment with the reference's per-pixel rules:
+// Stage entries [0, n) of the segment that starts at list position seg_b (all threads), then build the per-warp
+// work lists.  Returns the number of entries in this warp's list (it is padded to a multiple of 4 with SEG).
+template <int D>
+__device__ __forceinline__ int stage_segment(Stage<D>& s, int n, int32_t seg_b, const int32_t* __restrict__ flatten_ids,
+                                             const float2* __restrict__ means2d, const float* __restrict__ conics,
+                                             const float* __restrict__ colors, const float* __restrict__ opacities,
+                                             const TileGeom& tg, int tile_size) {
+    constexpr int SEG = Stage<D>::SEG;
+    for (int e = tg.tr; e < n; e += tg.block_size)
+        stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
+    if (tg.tr == 0) {
+        s.geo[SEG] = make_float4(0.f, 0.f, -1000.f, 0.f);  // 2^-1000 = 0: fails the alpha test
+        s.con[SEG] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    uint16_t* wl = s.wlist[tg.warp];
+    int base = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int tt = k0 + tg.lane;
+        const uint32_t m = (tt < n) ? (uint32_t)__float_as_int(s.geo[tt].w) : 0u;
+        const bool bit = (m >> tg.warp) & 1u;
+        const uint32_t bits = __ballot_sync(0xffffffffu, bit);
+        if (bit) wl[base + __popc(bits & ((1u << tg.lane) - 1u))] = (uint16_t)tt;
+        base += __popc(bits);
+    }
+    if (tg.lane < 4) wl[base + tg.lane] = (uint16_t)SEG;
+    __syncwarp();
+    return base;
+}
+
+// alpha of staged entry t at this thread's pixel; `p` receives -log2e * sigma, `au` the unclamped opacity * vis
+__device__ __forceinline__ float eval_alpha(const float4& geo, const float4& con, float px, float py, float& dx,
+                                            float& dy, float& p, float& au) {
+    dx = geo.x - px;
+    dy = geo.y - py;
+    p = fmaf(con.y * dx, dy, fmaf(con.z * dy, dy, con.x * dx * dx));
+    au = fast_ex2(p + geo.z);
+    return fminf(ALPHA_MAX, au);
+}
+
+// Front-to-back walk of this warp's work list with the reference's per-pixel rules:
 // skip when sigma < 0 or alpha < 1/255, stop (entry NOT blended, pixel `done`) when T (1 - alpha) <= 1e-4.
 // `done` lanes are frozen.  `last` = list position of the last blended entry.
 template <int D>
-__device__ __forceinline__ void walk(const Stage<D>& s, int n, int seg_b, const TileGeom& tg, float& T,
+__device__ __forceinline__ void walk(const Stage<D>& s, int cnt, int seg_b, const TileGeom& tg, float& T,
                                      float (&acc)[D], int32_t& last, bool& done) {
-    bool warp_done = __all_sync(0xffffffffu, done);
-    for (int k0 = 0; k0 < n && !warp_done; k0 += 32) {
-        const int tt = k0 + tg.lane;
-        const uint32_t m = (tt < n) ? (uint32_t)__float_as_int(s.xyo[tt].w) : 0u;
-        uint32_t bits = __ballot_sync(0xffffffffu, (m >> tg.warp) & 1u);
-        while (bits) {
-            int t[4];
-            float alpha[4];
-            bool ok[4];
+    constexpr int DP = Stage<D>::DP;
+    if (__all_sync(0xffffffffu, done)) return;
+    const uint16_t* wl = s.wlist[tg.warp];
+    for (int i = 0; i < cnt; i += 4) {
+        const uint2 pk = *reinterpret_cast<const uint2*>(wl + i);
+        const int t[4] = {(int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)(pk.y & 0xffffu), (int)(pk.y >> 16)};
+        float alpha[4];
+        bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (bits) {
-                    t[u] = k0 + __ffs(bits) - 1;
-                    bits &= bits - 1;
+        for (int u = 0; u < 4; ++u) {
+            float dx, dy, p, au;
+            alpha[u] = eval_alpha(s.geo[t[u]], s.con[t[u]], tg.px, tg.py, dx, dy, p, au);
+            ok[u] = (p <= 0.f) && (alpha[u] >= ALPHA_MIN);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ok[u] && !done) {
+                const float next_T = fmaf(-T, alpha[u], T);
+                if (next_T <= T_MIN) {
+                    done = true;
                 } else {
-                    t[u] = -1;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ok[u] = false;
-                alpha[u] = 0.f;
-                if (t[u] >= 0) {
-                    const float4 xyo = s.xyo[t[u]];
-                    const float4 con = s.con[t[u]];
-                    const float dx = xyo.x - tg.px, dy = xyo.y - tg.py;
-                    const float sigma = 0.5f * (con.x * dx * dx + con.z * dy * dy) + con.y * dx * dy;
-                    alpha[u] = fminf(ALPHA_MAX, xyo.z * __expf(-sigma));
-                    ok[u] = !(sigma < 0.f || alpha[u] < ALPHA_MIN);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (ok[u] && !done) {
-                    const float next_T = T * (1.f - alpha[u]);
-                    if (next_T <= T_MIN) {
-                        done = true;
+                    const float w = alpha[u] * T;
+                    const float* cp = s.col + t[u] * DP;
+                    if constexpr (D == 3 || D == 4) {
+                        const float4 c4 = *reinterpret_cast<const float4*>(cp);
+                        acc[0] = fmaf(c4.x, w, acc[0]);
+                        acc[1] = fmaf(c4.y, w, acc[1]);
+                        acc[2] = fmaf(c4.z, w, acc[2]);
+                        if constexpr (D == 4) acc[3] = fmaf(c4.w, w, acc[3]);
                     } else {
-                        const float w = alpha[u] * T;
 #pragma unroll
-                        for (int k = 0; k < D; ++k) acc[k] += s.col[t[u] * D + k] * w;
-                        last = seg_b + t[u];
-                        T = next_T;
+                        for (int k = 0; k < D; ++k) acc[k] = fmaf(cp[k], w, acc[k]);
                     }
+                    last = seg_b + t[u];
+                    T = next_T;
                 }
-            }
-            if (__all_sync(0xffffffffu, done)) {
-                warp_done = true;
-                break;
             }
         }
+        if (__all_sync(0xffffffffu, done)) break;
     }
 }
 
@@ -335,9 +378,7 @@ raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
                                    masks);
     const TileGeom tg = tile_geom(sg.tile_lin, tile_w, tile_h, tile_size, width, height);
 
-    for (int e = tg.tr; e < sg.n; e += tg.block_size)
-        stage_entry<D>(s, e, flatten_ids[sg.seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
-    __syncthreads();
+    const int cnt = stage_segment<D>(s, sg.n, sg.seg_b, flatten_ids, means2d, conics, colors, opacities, tg, tile_size);
 
     float T = 1.f;
     float acc[D];
@@ -345,7 +386,7 @@ raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
     for (int c = 0; c < D; ++c) acc[c] = 0.f;
     int32_t last = (sg.k == 0) ? 0 : -1;
     bool done = !tg.inside;
-    walk<D>(s, sg.n, sg.seg_b, tg, T, acc, last, done);
+    walk<D>(s, cnt, sg.seg_b, tg, T, acc, last, done);
 
     const size_t cidx = (size_t)seg * MAX_BLOCK + tg.tr;
     ws.chain_T[cidx] = (done && tg.inside) ? -T : T;
@@ -436,9 +477,7 @@ raster_stop_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ me
     if (!__syncthreads_or(redo)) return;
     const SegGeom sg = seg_geom<D>(ws, seg, tile_lin, (int64_t)C * tile_w * tile_h, n_isects, tile_offsets, masks);
     const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
-    for (int e = tg.tr; e < sg.n; e += tg.block_size)
-        stage_entry<D>(s, e, flatten_ids[sg.seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
-    __syncthreads();
+    const int cnt = stage_segment<D>(s, sg.n, sg.seg_b, flatten_ids, means2d, conics, colors, opacities, tg, tile_size);
     float T = 1.f;
     float acc[D];
 #pragma unroll
@@ -452,7 +491,7 @@ raster_stop_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ me
         for (int c = 0; c < D; ++c) acc[c] = ws.prefix_C[pidx * D + c];
     }
     bool frozen = !redo;
-    walk<D>(s, sg.n, sg.seg_b, tg, T, acc, last, frozen);
+    walk<D>(s, cnt, sg.seg_b, tg, T, acc, last, frozen);
     if (!redo) return;
     ws.chain_T[cidx] = -T;
     ws.chain_last[cidx] = last;
@@ -608,89 +647,79 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
 
     // entries behind every pixel's last id are not even staged
     const int n_used = min(n, cta_bin_final - seg_b + 1);
-    for (int e = tg.tr; e < n_used; e += tg.block_size)
-        stage_entry<D>(s, e, flatten_ids[seg_b + e], means2d, conics, colors, opacities, tg, tile_size);
-    __syncthreads();
+    const int cnt = stage_segment<D>(s, n_used, seg_b, flatten_ids, means2d, conics, colors, opacities, tg, tile_size);
+    constexpr int DP = Stage<D>::DP;
+    const uint16_t* wl = s.wlist[tg.warp];
+    const bool opac_slot = (slot == B + 3);
 
-    const int t_hi = min(n_used - 1, warp_bin_final - seg_b);  // last entry this warp can need
-    for (int k0 = (t_hi >= 0 ? (t_hi & ~31) : -32); k0 >= 0; k0 -= 32) {
-        const int tt = k0 + tg.lane;
-        const uint32_t m = (tt <= t_hi) ? (uint32_t)__float_as_int(s.xyo[tt].w) : 0u;
-        uint32_t bits = __ballot_sync(0xffffffffu, (m >> tg.warp) & 1u);
-        while (bits) {
-            const int hb = 31 - __clz(bits);
-            const int t = k0 + hb;
-            bits &= ~(1u << hb);
-            bool valid = tg.inside && (seg_b + t <= bin_final);
-            float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
-            float4 con = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                const float4 xyo = s.xyo[t];
-                con = s.con[t];
-                opac = xyo.z;
-                dx = xyo.x - tg.px; dy = xyo.y - tg.py;
-                const float sigma = 0.5f * (con.x * dx * dx + con.z * dy * dy) + con.y * dx * dy;
-                vis = __expf(-sigma);
-                alpha = fminf(ALPHA_MAX, opac * vis);
-                if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+    const int t_hi = warp_bin_final - seg_b;  // last entry this warp can need
+    for (int i = cnt - 1; i >= 0; --i) {
+        const int t = wl[i];
+        if (t > t_hi) continue;  // warp-uniform
+        const float4 con = s.con[t];
+        float dx, dy, p, au;
+        const float alpha = eval_alpha(s.geo[t], con, tg.px, tg.py, dx, dy, p, au);
+        const bool valid = tg.inside && (seg_b + t <= bin_final) && (p <= 0.f) && (alpha >= ALPHA_MIN);
+        if (!__any_sync(0xffffffffu, valid)) continue;
+
+        float v[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) v[c] = 0.f;
+        float v_colD[D > 8 ? D : 1];
+        if (valid) {
+            const float ra = fast_rcp(1.f - alpha);
+            T *= ra;
+            const float fac = alpha * T;
+            float v_alpha = 0.f;
+            const float* cp = s.col + t * DP;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float ck = cp[c];
+                if constexpr (kTranspose) v[c] = fac * v_rc[c];
+                else v_colD[c] = fac * v_rc[c];
+                v_alpha += (ck * T - buffer[c] * ra) * v_rc[c];
+                buffer[c] += ck * fac;
             }
-            if (!__any_sync(0xffffffffu, valid)) continue;
-
-            float v[NV];
-#pragma unroll
-            for (int c = 0; c < NV; ++c) v[c] = 0.f;
-            float v_colD[D > 8 ? D : 1];
-            if (valid) {
-                const float ra = fast_rcp(1.f - alpha);
-                T *= ra;
-                const float fac = alpha * T;
-                float v_alpha = 0.f;
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const float ck = s.col[t * D + c];
-                    if constexpr (kTranspose) v[c] = fac * v_rc[c];
-                    else v_colD[c] = fac * v_rc[c];
-                    v_alpha += (ck * T - buffer[c] * ra) * v_rc[c];
-                    buffer[c] += ck * fac;
-                }
-                v_alpha += T_final * ra * v_ra;
-                if (backgrounds) v_alpha += -T_final * ra * bg_dot;
-                if (opac * vis <= ALPHA_MAX) {
-                    const float v_sigma = -opac * vis * v_alpha;
-                    v[B + 0] = 0.5f * v_sigma * dx * dx;
-                    v[B + 1] = v_sigma * dx * dy;
-                    v[B + 2] = 0.5f * v_sigma * dy * dy;
-                    v[B + 3] = vis * v_alpha;
-                    if constexpr (want_xy) {
-                        const float gx = v_sigma * (con.x * dx + con.y * dy);
-                        const float gy = v_sigma * (con.y * dx + con.z * dy);
-                        v[B + 4] = gx;
-                        v[B + 5] = gy;
-                        if constexpr (want_abs) {
-                            v[B + 6] = fabsf(gx);
-                            v[B + 7] = fabsf(gy);
-                        }
+            v_alpha += T_final * ra * v_ra;
+            if (backgrounds) v_alpha += -T_final * ra * bg_dot;
+            if (au <= ALPHA_MAX) {
+                // au = opacity * vis.  v_sigma = -au v_alpha; the opacity gradient vis v_alpha = (au / opacity) v_alpha
+                // is reduced as au v_alpha and divided by the opacity once, by the lane that owns the total.
+                const float nvs = au * v_alpha;
+                const float hs = -0.5f * nvs;
+                v[B + 0] = hs * dx * dx;
+                v[B + 1] = -nvs * dx * dy;
+                v[B + 2] = hs * dy * dy;
+                v[B + 3] = nvs;
+                if constexpr (want_xy) {
+                    // conic a = -2 a' / log2e etc.:  v_sigma (a dx + b dy) = (nvs / log2e) (2 a' dx + b' dy)
+                    const float vk = nvs * (1.f / LOG2E);
+                    const float gx = vk * fmaf(2.f * con.x, dx, con.y * dy);
+                    const float gy = vk * fmaf(2.f * con.z, dy, con.y * dx);
+                    v[B + 4] = gx;
+                    v[B + 5] = gy;
+                    if constexpr (want_abs) {
+                        v[B + 6] = fabsf(gx);
+                        v[B + 7] = fabsf(gy);
                     }
                 }
-            } else if constexpr (!kTranspose) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) v_colD[c] = 0.f;
             }
-            const int32_t g = s.id[t];
-            if constexpr (kTranspose) {
-                const float total = warp_transpose_sum(v, tg.lane);
-                if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
-            } else {
-                // wide colour vectors: colours by plain butterflies, the 8 geometric values transposed
+        } else if constexpr (!kTranspose) {
 #pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const float tot = warp_sum(v_colD[c]);
-                    if (tg.lane == 0) atomicAdd(v_colors + (size_t)g * D + c, tot);
-                }
-                const float total = warp_transpose_sum(v, tg.lane);
-                if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
+            for (int c = 0; c < D; ++c) v_colD[c] = 0.f;
+        }
+        const int32_t g = s.id[t];
+        if constexpr (!kTranspose) {
+            // wide colour vectors: colours by plain butterflies, the geometric values transposed
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float tot = warp_sum(v_colD[c]);
+                if (tg.lane == 0) atomicAdd(v_colors + (size_t)g * D + c, tot);
             }
         }
+        float total = warp_transpose_sum(v, tg.lane);
+        if (opac_slot) total *= con.w;
+        if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
     }
 }
 
