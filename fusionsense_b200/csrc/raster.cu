@@ -64,6 +64,7 @@ struct Workspace {
     float* chain_T;      // [max_segs, 256]  transmittance after the segment; negative = pixel finished
     int32_t* chain_last; // [max_segs, 256]  last contributing list position so far (-1: none in a local state)
     float* prefix_C;     // [max_segs, 256, D] colour accumulated through the segment
+    int32_t* done_k;     // [n_tiles, 8]  per warp strip: the first segment after which all its pixels are finished
 };
 
 inline int64_t max_segments(int64_t n_isects, int64_t n_tiles, int D) { return n_isects / seg_len(D) + n_tiles; }
@@ -75,6 +76,7 @@ inline size_t ws_bytes(int64_t n_isects, int64_t n_tiles, int D) {
     b += fsb_align_up((size_t)ms * 4, 256);                  // seg_tile
     b += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256) * 2;  // chain_T, chain_last
     b += fsb_align_up((size_t)ms * MAX_BLOCK * D * 4, 256);  // prefix_C
+    b += fsb_align_up((size_t)n_tiles * 8 * 4, 256);         // done_k
     return b;
 }
 
@@ -87,7 +89,8 @@ inline Workspace carve_ws(void* base, int64_t n_isects, int64_t n_tiles, int D) 
     w.seg_tile = (int32_t*)p; p += fsb_align_up((size_t)ms * 4, 256);
     w.chain_T = (float*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
     w.chain_last = (int32_t*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
-    w.prefix_C = (float*)p;
+    w.prefix_C = (float*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * D * 4, 256);
+    w.done_k = (int32_t*)p;
     return w;
 }
 
@@ -364,7 +367,12 @@ __device__ __forceinline__ SegGeom seg_geom(const Workspace& ws, int seg, int64_
 }
 
 // forward A: every (tile, segment) composites its own entries from T = 1.
-template <int D>
+// PHASE 0 runs the first segment of every tile (grid = tiles), PHASE 1 all later segments (grid = segments, the
+// first ones exit).  A warp strip whose 32 pixels are all finished after segment k (exactly for k = 0, by the
+// local-saturation argument for k > 0) records k in done_k; a later segment skips that strip: nothing it could
+// composite is ever used.  The kernel boundary makes every first-segment result visible to phase 1, which is
+// where most of the saving is: opaque tiles stop inside their first segment or two.
+template <int D, int PHASE>
 __global__ void __launch_bounds__(MAX_BLOCK)
 raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
                   const float* __restrict__ conics, const float* __restrict__ colors,
@@ -372,13 +380,31 @@ raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
                   int tile_size, int tile_w, int tile_h, const int32_t* __restrict__ tile_offsets,
                   const int32_t* __restrict__ flatten_ids, Workspace ws, FwdOut o) {
     __shared__ Stage<D> s;
-    const int seg = blockIdx.x;
-    if (seg >= ws.hdr->total_segs) return;
-    const SegGeom sg = seg_geom<D>(ws, seg, ws.seg_tile[seg], (int64_t)C * tile_w * tile_h, n_isects, tile_offsets,
-                                   masks);
+    int seg;
+    int64_t tile_lin;
+    if (PHASE == 0) {
+        tile_lin = blockIdx.x;
+        seg = ws.seg_start[tile_lin];
+    } else {
+        seg = blockIdx.x;
+        if (seg >= ws.hdr->total_segs) return;
+        tile_lin = ws.seg_tile[seg];
+        if (seg == ws.seg_start[tile_lin]) return;
+    }
+    const SegGeom sg = seg_geom<D>(ws, seg, tile_lin, (int64_t)C * tile_w * tile_h, n_isects, tile_offsets, masks);
     const TileGeom tg = tile_geom(sg.tile_lin, tile_w, tile_h, tile_size, width, height);
+    int32_t* done_k = ws.done_k + tile_lin * 8 + tg.warp;
+    bool skip = false;
+    if (PHASE == 1) {
+        skip = (*done_k < sg.k);  // written by phase 0 (visible) or, opportunistically, by an earlier segment
+        // a skipped strip leaves no state behind, but its slots must not keep a stale STOP_MARK from an earlier
+        // call that used the same workspace memory (raster_stop_kernel scans chain_last of every later segment)
+        if (skip) ws.chain_last[(size_t)seg * MAX_BLOCK + tg.tr] = -1;
+        if (__syncthreads_and(skip)) return;
+    }
 
     const int cnt = stage_segment<D>(s, sg.n, sg.seg_b, flatten_ids, means2d, conics, colors, opacities, tg, tile_size);
+    if (skip) return;
 
     float T = 1.f;
     float acc[D];
@@ -387,6 +413,7 @@ raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
     int32_t last = (sg.k == 0) ? 0 : -1;
     bool done = !tg.inside;
     walk<D>(s, cnt, sg.seg_b, tg, T, acc, last, done);
+    if (sg.nseg > 1 && __all_sync(0xffffffffu, done) && tg.lane == 0) atomicMin(done_k, sg.k);
 
     const size_t cidx = (size_t)seg * MAX_BLOCK + tg.tr;
     ws.chain_T[cidx] = (done && tg.inside) ? -T : T;
@@ -736,11 +763,17 @@ int launch_fwd(int C, int N, int64_t n_isects, const float* means2d, const float
     dim3 block(tile_size, tile_size);
     FwdOut o{backgrounds, ed_normalize, out_colors, out_alphas, last_ids};
     unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
-    raster_seg_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors, opacities,
-                                                 masks, width, height, tile_size, tile_w, tile_h, tile_offsets,
-                                                 flatten_ids, ws, o);
+    const bool multi = n_isects > seg_len(D);  // otherwise no tile can hold more than one segment
+    if (multi) FSB_CUDA(cudaMemsetAsync(ws.done_k, 0x7f, (size_t)n_tiles * 8 * 4, st));
+    raster_seg_kernel<D, 0><<<(unsigned)n_tiles, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors,
+                                                                 opacities, masks, width, height, tile_size, tile_w,
+                                                                 tile_h, tile_offsets, flatten_ids, ws, o);
     FSB_LAUNCH_CHECK();
-    if (n_isects > seg_len(D)) {  // otherwise no tile can hold more than one segment
+    if (multi) {
+        raster_seg_kernel<D, 1><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors,
+                                                        opacities, masks, width, height, tile_size, tile_w, tile_h,
+                                                        tile_offsets, flatten_ids, ws, o);
+        FSB_LAUNCH_CHECK();
         raster_fold_kernel<D><<<(unsigned)n_tiles, block, 0, st>>>(C, width, height, tile_size, tile_w, tile_h, masks,
                                                                    ws, o);
         FSB_LAUNCH_CHECK();

@@ -167,8 +167,11 @@ class _FusedSSIMFn(torch.autograd.Function):
         out = torch.empty((), dtype=torch.float32, device=dev)
         maps = torch.empty((3, H - 10, W - 10, C), dtype=torch.float32, device=dev) if need else None
         d = [maps[i] for i in range(3)] if need else [None] * 3
+        from .ops import kernel_timer
+        ev = kernel_timer.start("ssim_fwd")
         check(lib.fsb_ssim_fwd(H, W, C, ptr(x), ptr(y), data_range, k1, k2, taps, ptr(ws), ptr(out), ptr(d[0]),
                                ptr(d[1]), ptr(d[2]), _stream()), "fsb_ssim_fwd")
+        kernel_timer.stop(ev)
         if need:
             ctx.save_for_backward(x, y, maps)
         ctx.cfg = (taps, data_range, k1, k2)
@@ -184,8 +187,11 @@ class _FusedSSIMFn(torch.autograd.Function):
         H, W, C = x.shape
         v_x = torch.empty_like(x)
         v_out = v_out.contiguous().float()
+        from .ops import kernel_timer
+        ev = kernel_timer.start("ssim_bwd")
         check(lib.fsb_ssim_bwd(H, W, C, ptr(x), ptr(y), data_range, k1, k2, taps, ptr(maps[0]), ptr(maps[1]),
                                ptr(maps[2]), ptr(v_out), ptr(v_x), _stream()), "fsb_ssim_bwd")
+        kernel_timer.stop(ev)
         return v_x, None, None, None, None, None
 
 

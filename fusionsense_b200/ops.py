@@ -102,11 +102,13 @@ def project_sh_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, nea
     colors = torch.empty((C, N, color_stride), dtype=torch.float32, device=dev) if color_stride > 0 else None
     tiles = torch.empty((C, N), dtype=torch.int32, device=dev)
     K = coeffs.shape[1] if coeffs is not None else 0
+    ev = kernel_timer.start("project_sh_fwd")
     check(lib.fsb_project_sh_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height,
                                  eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w, tile_h,
                                  -1 if sh_degree is None else sh_degree, K, ptr(coeffs), ptr(campos), color_stride,
                                  depth_channel, ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps),
                                  ptr(colors), ptr(tiles), ptr(legacy_extra), _stream()), "fsb_project_sh_fwd")
+    kernel_timer.stop(ev)
     return radii, means2d, depths, conics, comps, colors, tiles
 
 
@@ -147,8 +149,10 @@ def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_
     ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
     flat = torch.empty((n_isects,), dtype=torch.int32, device=dev)
     tb = tile_bits_for(tile_w * tile_h)
+    ev = kernel_timer.start("isect_emit")
     check(lib.fsb_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h, tb,
                              int(legacy_bbox), ptr(ids), ptr(flat), _stream()), "fsb_isect_emit")
+    kernel_timer.stop(ev)
     return ids, flat
 
 
@@ -300,11 +304,13 @@ class ProjectSH(torch.autograd.Function):
         if sh >= 0 and v_coeffs is None:
             # the kernel writes SH gradients whenever it evaluates SH; give it a scratch target
             v_coeffs = torch.empty_like(coeffs)
+        ev = kernel_timer.start("project_sh_bwd")
         check(lib.fsb_project_sh_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height,
                                      eps2d, sh, K, ptr(coeffs), ptr(campos), color_stride, depth_channel, ptr(radii),
                                      ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_colors),
                                      ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_coeffs), ptr(v_viewmats),
                                      ptr(v_campos), _stream()), "fsb_project_sh_bwd")
+        kernel_timer.stop(ev)
         if coeffs is not None and v_coeffs is None and ctx.needs_input_grad[3]:
             v_coeffs = torch.zeros_like(coeffs)
         return (v_means, v_quats, v_scales, v_coeffs if ctx.needs_input_grad[3] else None, v_viewmats, None, v_campos,

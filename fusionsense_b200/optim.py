@@ -17,7 +17,7 @@ from typing import Iterable, List
 import torch
 
 from ._abi import check, lib
-from .ops import _stream
+from .ops import _stream, kernel_timer
 
 
 def _launch(entries, beta1, beta2, eps):
@@ -84,5 +84,7 @@ def fused_step(optimizers: Iterable[FusedAdam]) -> None:
     for opt in optimizers:
         for e in opt._collect():
             buckets.setdefault((e[6], e[7]), []).append(e[:6])
+    ev = kernel_timer.start("adam_multi")
     for (betas, eps), entries in buckets.items():
         _launch(entries, betas[0], betas[1], eps)
+    kernel_timer.stop(ev)

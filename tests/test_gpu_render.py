@@ -161,6 +161,37 @@ def test_raster_forward(n, W, H, C, D, bg, mult, oshift):
     assert (last.cpu() != l_ref).float().mean() < 1e-3
 
 
+@pytest.mark.parametrize("pattern", [0x80000000, 0xFFFFFFFF, 0x7FC00000])
+def test_raster_forward_backward_on_dirty_workspace(pattern):
+    """The per-call workspace comes from torch's caching allocator, i.e. it usually holds the previous call's
+    segment states.  Poison the pool with bit patterns that mean something to the kernels (0x80000000 = the
+    "stop inside this segment" mark / -0.0, all ones = NaN / -1, a quiet NaN) and check the opaque multi-segment
+    case, where later segments skip finished strips and leave their slots unwritten."""
+    ops = _ops()
+    n, W, H, C, D, bg, mult, oshift = (40000, 128, 96, 2, 3, True, 8.0, 1.0)
+    m2, con, colors, opac, bgs, offs, flat, g = _raster_inputs(n, W, H, C, D, seed=11, bg=bg, scale_mult=mult,
+                                                               opac_shift=oshift)
+    o_ref, a_ref = ref.rasterize_to_pixels(m2.cpu(), con.cpu(), colors.cpu(), opac.cpu(), W, H, 16, offs.cpu(),
+                                           flat.cpu(), backgrounds=bgs.cpu())
+    v_out = torch.randn(C, H, W, D, generator=g).to(DEV)
+    grads = []
+    for rep in range(2):
+        torch.cuda.empty_cache()
+        junk = torch.full((64 << 20,), pattern - (1 << 32) if pattern >= (1 << 31) else pattern, dtype=torch.int32,
+                          device=DEV)
+        del junk  # back to the pool, contents intact: the next allocations are carved out of it
+        ins = [t.detach().clone().requires_grad_(True) for t in (m2, con, colors, opac)]
+        out, alpha = ops.RasterizeToPixels.apply(ins[0], ins[1], ins[2], ins[3], bgs, None, W, H, 16, offs, flat,
+                                                 True, False)
+        assert_close(out.cpu(), o_ref, f"raster.dirty{pattern:x}.colors{rep}", tol=1e-4)
+        assert_close(alpha.cpu(), a_ref, f"raster.dirty{pattern:x}.alpha{rep}", tol=1e-4)
+        (out * v_out).sum().backward()
+        grads.append([t.grad.clone() for t in ins])
+    for a, b in zip(*grads):
+        assert torch.isfinite(a).all()
+        assert_close(a, b, f"raster.dirty{pattern:x}.grad_repeat", tol=1e-5, outlier_frac=1e-3)
+
+
 @pytest.mark.parametrize("n,W,H,C,D,bg,ed,mult,oshift", [
     (20000, 640, 480, 1, 4, False, True, 3.0, 0.0), (3000, 200, 150, 2, 3, True, False, 3.0, 0.0),
     (2000, 128, 96, 1, 8, False, False, 3.0, 0.0), (40000, 128, 96, 1, 4, True, True, 8.0, -4.0),
