@@ -41,6 +41,7 @@ class DNSplatterStepConfig:
     use_normal_loss: bool = True
     use_normal_tv_loss: bool = True
     normal_lambda: float = 0.4
+    normal_supervision: str = "mono"  # "mono" (FusionSense: DSINE/omnidata maps) or "depth" (dn_model.py:773-795)
     two_d_gaussians: bool = True
     use_binary_opacities: bool = True
     binary_opacities_threshold: float = 0.9
@@ -68,6 +69,20 @@ class DNSplatterStepConfig:
     fused_optimizer: bool = True
     fused_losses: bool = True  # dn_regularizer_loss instead of the torch loss classes
     fused_glue: bool = True  # gaussian_normals / densify_stats kernels instead of the inline torch ops
+
+
+def _torch_normal_from_depth_image(depths, fx, fy, cx, cy, img_size, c2w, device, smooth=False):
+    """Literal torch form of normal_utils.py:23-46 + camera_utils.py:69-144, used only when the step is driven on
+    the CPU by the reference arm (the CUDA path calls utils/normal_utils.py -> fsb_normal_from_depth)."""
+    W, H = img_size
+    u, v = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+    coords = (torch.stack((u, v), dim=-1) + 0.5).view(-1, 2).float().to(device)
+    d = depths.reshape(-1).float()
+    pts = torch.stack(((coords[:, 0] - cx) * d / fx, (coords[:, 1] - cy) * d / fy, d), dim=-1)
+    pts = (pts @ torch.linalg.inv(c2w[..., :3, :3]) + c2w[..., :3, 3]).view(H, W, 3)
+    n = torch.cross(pts[1:H - 1, 2:W] - pts[1:H - 1, 0:W - 2], pts[0:H - 2, 1:W - 1] - pts[2:H, 1:W - 1], dim=-1)
+    n = F.normalize(n, p=2, dim=-1)
+    return F.pad(n.permute(2, 0, 1), (1, 1, 1, 1), mode="constant").permute(1, 2, 0)
 
 
 class DNSplatterStep:
@@ -153,6 +168,7 @@ class DNSplatterStep:
         c2w = sc.c2w[cam_idx:cam_idx + 1]
         W, H = sc.width, sc.height
         self.last_size = (H, W)
+        self._last_cam = cam_idx
         sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)
         render, alpha, info = self._rasterization(
             means=means_crop,
@@ -229,11 +245,12 @@ class DNSplatterStep:
 
         depth_out = outputs["depth"]
         sensor_depth_gt = batch["sensor_depth"]
+        gt_normal = self._gt_normal(batch, depth_out) if cfg.use_normal_loss else None
         if fused:
             from .losses import dn_regularizer_loss
 
             reg = dn_regularizer_loss(
-                depth_out, sensor_depth_gt, batch["image"], outputs["normal"], batch["normal"],
+                depth_out, sensor_depth_gt, batch["image"], outputs["normal"], gt_normal,
                 pred_rgb=pred_img, gt_rgb=gt_rgb, rgb_l1_lambda=1 - cfg.ssim_lambda,
                 depth_tolerance=cfg.depth_tolerance,
                 sensor_depth_lambda=cfg.sensor_depth_lambda if cfg.use_depth_loss else 0.0,
@@ -253,7 +270,6 @@ class DNSplatterStep:
             normal_loss = 0
             if cfg.use_normal_loss:
                 pred_normal = outputs["normal"]
-                gt_normal = batch["normal"]
                 normal_loss = normal_loss + torch.abs(gt_normal - pred_normal).mean()
                 if cfg.use_normal_tv_loss:
                     normal_loss = normal_loss + self.tv_loss(pred_normal)
@@ -261,6 +277,26 @@ class DNSplatterStep:
             normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
         main_loss = rgb_loss + depth_loss + cfg.normal_lambda * normal_loss
         return {"main_loss": main_loss, "scale_reg": torch.tensor(0.0, device=self.device)}
+
+    def _gt_normal(self, batch, depth_out) -> Tensor:
+        """dn_model.py:770-795: monocular normal maps from the batch, or pseudo normals from the rendered depth."""
+        cfg, sc = self.config, self.scene
+        if "normal" in batch and cfg.normal_supervision == "mono":
+            return batch["normal"]
+        if cfg.normal_supervision == "depth":
+            if self.device.type == "cuda":
+                from .utils.normal_utils import normal_from_depth_image
+            else:
+                normal_from_depth_image = _torch_normal_from_depth_image  # reference arm (oracle-driven, CPU)
+            K = sc.Ks[self._last_cam]
+            gt_normal = normal_from_depth_image(
+                depths=depth_out.detach(), fx=K[0, 0].item(), fy=K[1, 1].item(), cx=K[0, 2].item(), cy=K[1, 2].item(),
+                img_size=(sc.width, sc.height), c2w=torch.eye(4, dtype=torch.float, device=depth_out.device),
+                device=self.device, smooth=False)
+            gt_normal = gt_normal @ torch.diag(torch.tensor([1, -1, -1], device=depth_out.device, dtype=depth_out.dtype))
+            return (1 + gt_normal) / 2
+        raise RuntimeError("normal supervision with monocular normals enabled but the batch holds none "
+                           "(dn_model.py:796-803 quits here)")
 
     # ---- splatfacto after_train (SURVEY.md A.7) ---------------------------------------------
     @torch.no_grad()

@@ -251,6 +251,18 @@ int fsb_gaussian_normals_bwd(int N, const float* quats, const float* scales, con
 int fsb_densify_stats(int N, const int32_t* radii, const float* grads2d, float max_dim, float* xys_grad_norm,
                       float* vis_counts, float* max_2Dsize, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * a13: pseudo ground-truth normals from a depth image.  replaces normal_from_depth_image
+ * (dn_splatter/utils/normal_utils.py:23-46 = get_means3d_backproj, utils/camera_utils.py:92-144, then
+ * pcd_to_normal, normal_utils.py:7-20), called from dn_splatter/dn_model.py:779-789 when
+ * normal_supervision == "depth".
+ *   depth[H,W]: back-projected at pixel centres (u + 0.5 - cx) * d / fx; rot_inv: HOST 3x3 row-major
+ *   inverse of c2w[:3,:3] (nullable = identity), trans: HOST c2w[:3,3] (nullable = 0): world = p @ rot_inv + trans.
+ *   xyz[H,W,3] (nullable): when given, the points are taken from it instead (pcd_to_normal alone).
+ *   normals[H,W,3] = normalize((right - left) x (top - bottom)), the one-pixel border is zero. */
+int fsb_normal_from_depth(int H, int W, const float* depth, const float* xyz, float fx, float fy, float cx,
+                          float cy, const float* rot_inv, const float* trans, float* normals, void* stream);
+
 /* library bookkeeping: kernels launched by libfsb200 since load (monotone), ABI revision */
 uint64_t fsb_launch_count(void);
 int fsb_abi_version(void);
