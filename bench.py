@@ -168,27 +168,40 @@ def run_ours(args):
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values())
 
     params = [model.gauss_params[k] for k in model.config.lrs]
+    graph_mode = args.mode == "graph"
 
-    def allreduce_grads():
-        # one flat NCCL all-reduce over all Gaussian parameter gradients (59 floats per Gaussian)
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
+    def allreduce_grads(ps, overflow=None):
+        # one flat NCCL all-reduce (SUM) over all Gaussian parameter gradients (59 floats per Gaussian) plus the
+        # overflow flag of the static-capacity step; the loss is pre-scaled by 1/world, so the sum is the mean
+        parts = [p.grad.reshape(-1) for p in ps]
+        if overflow is not None:
+            parts.append(overflow.float())
+        flat = torch.cat(parts)
         dist.all_reduce(flat)
-        flat.div_(world)
         o = 0
-        for p in params:
+        for p in ps:
             n = p.numel()
             p.grad = flat[o:o + n].view_as(p)
             o += n
+        if overflow is not None:
+            overflow.copy_(flat[o:o + 1] > 0)
 
-    def one_step(i, batch):
+    runner = None
+    if graph_mode:
+        from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+        runner = GraphedDNSplatterStep(model, dev_targets, grad_sync=allreduce_grads if world > 1 else None,
+                                       loss_scale=1.0 / world)
+
+    def eager_step(i, batch):
         v = (i * world + rank) % N_VIEWS
         for opt in model.optimizers.values():
             opt.zero_grad(set_to_none=True)
         outputs = model.get_outputs(v)
         loss = model.get_loss_dict(outputs, batch(v))["main_loss"]
-        loss.backward()
+        (loss / world if world > 1 else loss).backward()
         if world > 1:
-            allreduce_grads()
+            allreduce_grads(params)
         model.optimizers["means"].param_groups[0]["lr"] = model._means_lr()
         model.optimizer_step()
         model.after_train()
@@ -201,16 +214,29 @@ def run_ours(args):
     def from_host(v):
         return {k: t.to(device, non_blocking=True) for k, t in host_targets[v].items()}
 
-    def timed(n_steps, batch, read_loss):
+    def one_step(i, staged, read_loss):
+        """One training iteration; `staged`: this step's targets come from pinned host memory; `read_loss`: the
+        step's result is read back to the host."""
+        if runner is None:
+            loss = eager_step(i, from_host if staged else resident)
+            if read_loss:
+                float(loss)
+            return
+        v = (i * world + rank) % N_VIEWS
+        if staged:
+            runner.stage(v, host_targets[v])
+        runner.train_iteration(v)
+        if read_loss:
+            runner.poll()  # 32-byte D2H read of [loss, overflow count, n_isects x2]
+
+    def timed(n_steps, staged, read_loss):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(n_steps):
-            loss = one_step(i, batch)
-            if read_loss:
-                float(loss)  # device -> host read of the step's result
+            one_step(i, staged, read_loss)
         e.record()
         if world > 1:
             dist.barrier()
@@ -220,27 +246,47 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # warm-up (also primes the caching allocator); inputs (70 MB of parameters + 70 MB of Adam state + per-step
-    # intersection lists) exceed nothing special, so L2 is flushed between legs by the step's own >126 MB traffic.
+    # warm-up (also primes the caching allocator and, in graph mode, captures the step)
     for i in range(args.warmup):
-        one_step(i, resident)
+        one_step(i, False, False)
     torch.cuda.synchronize()
+    if runner is not None and runner.poll()["new_overflows"]:
+        for i in range(args.warmup):  # capacity grew: capture again before timing
+            one_step(i, False, False)
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = lib.fsb_launch_count()
+    replays0 = runner.replays if runner else 0
     profiling = os.environ.get("FSB_PROFILE") == "1"  # ncu --profile-from-start off: capture the timed steps only
     if profiling:
         torch.cuda.profiler.start()
-    with ops.kernel_timer.collect():
-        ms_total = timed(args.steps, resident, read_loss=False)
-        ktimes = ops.kernel_timer.summary()
+    ms_total = timed(args.steps, False, False)
     if profiling:
         torch.cuda.profiler.stop()
     launches = lib.fsb_launch_count() - launches0
+    graph_info = None
+    if runner is not None:
+        info = runner.poll()
+        if info["new_overflows"]:
+            raise SystemExit(f"bench: {info['new_overflows']} timed step(s) overflowed the intersection capacity; rerun")
+        # replays launch the captured kernels without passing through the library's entry points
+        launches += (runner.replays - replays0) * runner.launches_per_replay
+        graph_info = {"captures": runner.captures, "capacity": runner.capacity, "n_isects": info["n_isects"],
+                      "n_isects_normals": info["n_isects_normals"], "libfsb200_launches_per_replay": runner.launches_per_replay}
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(args.steps, from_host, read_loss=True)
+    ms_e2e = timed(args.steps, True, True)
+    if runner is not None and runner.poll()["overflowed_steps"]:
+        raise SystemExit("bench: a step of the e2e leg overflowed the intersection capacity; rerun")
+
+    # per-kernel CUDA-event times of the same workload: eager launches (a replayed graph offers no place to record
+    # events between its kernels), same kernels, same sizes, same stream, after the timed legs
+    with ops.kernel_timer.collect():
+        for i in range(6):
+            eager_step(i, resident)
+        ktimes = ops.kernel_timer.summary()
 
     ms_per_step = ms_total / args.steps
     value = world * 1e3 / ms_per_step
@@ -277,9 +323,14 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT,
                        "views": N_VIEWS, "views_per_iter_per_gpu": 1, "global_views_per_iter": world,
+                       "execution": ("one CUDA graph replay per iteration (static-capacity intersection lists, "
+                                     "no host sync); every kernel of the eager step runs in every replay"
+                                     if graph_mode else "eager launches"),
+                       "graph": graph_info,
                        "l2": "per-step working set (parameters, Adam state, gradients, intersection lists, images: "
                              ">400 MB touched per step) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 32 if graph_mode else 4},
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks,
@@ -297,6 +348,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the iteration is one CUDA graph replay (default); eager: per-kernel launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -39,7 +39,9 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(ADAM_THREADS)
-adam_multi_kernel(FsbAdamArgs a, int n_tensors, float omb1, float b2, float omb2, float eps) {
+adam_multi_kernel(FsbAdamArgs a, int n_tensors, float omb1, float b2, float omb2, float eps,
+                  const float* __restrict__ hyper_dev, const int32_t* __restrict__ skip_flag) {
+    if (skip_flag != nullptr && *skip_flag != 0) return;
     int t = 0;
 #pragma unroll
     for (int i = 1; i < FSB_ADAM_MAX_TENSORS; ++i)
@@ -50,7 +52,8 @@ adam_multi_kernel(FsbAdamArgs a, int n_tensors, float omb1, float b2, float omb2
     const float* __restrict__ g = a.g[t];
     float* __restrict__ m = a.m[t];
     float* __restrict__ v = a.v[t];
-    const float ss = a.step_size[t], bc2s = a.bc2_sqrt[t];
+    const float ss = hyper_dev ? hyper_dev[t] : a.step_size[t];
+    const float bc2s = hyper_dev ? hyper_dev[FSB_ADAM_MAX_TENSORS + t] : a.bc2_sqrt[t];
     const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -110,7 +113,31 @@ FSB_API int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g
     }
     if (blocks == 0) return 0;
     adam_multi_kernel<<<blocks, ADAM_THREADS, 0, (cudaStream_t)stream>>>(
-        a, n_tensors, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps);
+        a, n_tensors, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, nullptr, nullptr);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+FSB_API int fsb_adam_multi_dev(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                               const int64_t* n, const float* hyper_dev, const int32_t* skip_flag, double beta1,
+                               double beta2, double eps, void* stream) {
+    if (n_tensors <= 0 || n_tensors > FSB_ADAM_MAX_TENSORS || !hyper_dev) return FSB_E_ARG;
+    FsbAdamArgs a;
+    int blocks = 0;
+    for (int i = 0; i < FSB_ADAM_MAX_TENSORS; ++i) {
+        const bool live = i < n_tensors;
+        if (live && n[i] < 0) return FSB_E_ARG;
+        a.p[i] = live ? p[i] : nullptr; a.g[i] = live ? g[i] : nullptr;
+        a.m[i] = live ? m[i] : nullptr; a.v[i] = live ? v[i] : nullptr;
+        a.n[i] = live ? n[i] : 0;
+        a.block_start[i] = blocks;
+        if (live) blocks += (int)((n[i] + ADAM_PER_BLOCK - 1) / ADAM_PER_BLOCK);
+        a.step_size[i] = 0.f; a.bc2_sqrt[i] = 1.f; a.inv_bc2_sqrt[i] = 1.f;
+    }
+    a.block_start[FSB_ADAM_MAX_TENSORS] = blocks;
+    if (blocks == 0) return 0;
+    adam_multi_kernel<<<blocks, ADAM_THREADS, 0, (cudaStream_t)stream>>>(
+        a, n_tensors, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, hyper_dev, skip_flag);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -31,3 +31,13 @@ static inline int fsb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / 
 static inline size_t fsb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 #define FSB_NUM_SMS 148  // B200
+
+// "Static capacity" mode (CUDA-graph capturable, no host read of the intersection count): the host passes the
+// CAPACITY of the list buffers as the count and a device pointer to the true count; kernels use min(true, capacity).
+#ifdef __CUDACC__
+__device__ __forceinline__ int64_t fsb_eff_n(int64_t n_or_cap, const int64_t* __restrict__ n_dev) {
+    if (n_dev == nullptr) return n_or_cap;
+    const int64_t v = *n_dev;
+    return v < n_or_cap ? v : n_or_cap;
+}
+#endif

@@ -84,7 +84,8 @@ normals_bwd_kernel(int N, const float* __restrict__ quats, const float* __restri
 __global__ void __launch_bounds__(256)
 densify_stats_kernel(int N, const int32_t* __restrict__ radii, const float2* __restrict__ grads2d, float max_dim,
                      float* __restrict__ xys_grad_norm, float* __restrict__ vis_counts,
-                     float* __restrict__ max_2Dsize) {
+                     float* __restrict__ max_2Dsize, const int32_t* __restrict__ skip_flag) {
+    if (skip_flag != nullptr && *skip_flag != 0) return;
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     int r = radii[n];
@@ -118,11 +119,11 @@ FSB_API int fsb_gaussian_normals_bwd(int N, const float* quats, const float* sca
 }
 
 FSB_API int fsb_densify_stats(int N, const int32_t* radii, const float* grads2d, float max_dim, float* xys_grad_norm,
-                              float* vis_counts, float* max_2Dsize, void* stream) {
+                              float* vis_counts, float* max_2Dsize, const int32_t* skip_flag, void* stream) {
     if (N < 0 || !(max_dim > 0.f)) return FSB_E_ARG;
     if (N == 0) return 0;
     densify_stats_kernel<<<fsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        N, radii, (const float2*)grads2d, max_dim, xys_grad_norm, vis_counts, max_2Dsize);
+        N, radii, (const float2*)grads2d, max_dim, xys_grad_norm, vis_counts, max_2Dsize, skip_flag);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -98,10 +98,14 @@ scan_apply_kernel(int64_t M, const int32_t* __restrict__ counts, const int64_t* 
 __global__ void __launch_bounds__(256)
 isect_emit_kernel(int C, int N, const float* __restrict__ means2d, const int32_t* __restrict__ radii,
                   const float* __restrict__ depths, const int64_t* __restrict__ offsets, int tile_size, int tile_w,
-                  int tile_h, int tile_bits, int legacy_bbox, int64_t* __restrict__ isect_ids,
+                  int tile_h, int tile_bits, int legacy_bbox, const int64_t* __restrict__ n_dev, int64_t capacity,
+                  int32_t* __restrict__ overflow_flag, int64_t* __restrict__ isect_ids,
                   int32_t* __restrict__ flatten_ids) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)C * N) return;
+    // static-capacity mode: entries past the end of the buffers are dropped and the step is flagged as invalid
+    const int64_t limit = n_dev ? capacity : INT64_MAX;
+    if (idx == 0 && n_dev && overflow_flag && *n_dev > capacity) *overflow_flag = 1;
     int r = radii[idx];
     if (r <= 0) return;
     float2 m = reinterpret_cast<const float2*>(means2d)[idx];
@@ -127,16 +131,19 @@ isect_emit_kernel(int C, int N, const float* __restrict__ means2d, const int32_t
     for (int i = ay; i < by; ++i)
         for (int j = ax; j < bx; ++j) {
             int64_t tile = (int64_t)i * tile_w + j;
-            isect_ids[cur] = cam_part | (tile << 32) | depth_part;
-            flatten_ids[cur] = val;
+            if (cur < limit) {
+                isect_ids[cur] = cam_part | (tile << 32) | depth_part;
+                flatten_ids[cur] = val;
+            }
             ++cur;
         }
 }
 
 // isect_offsets[c, ty, tx] = first sorted position whose (camera, tile) id is >= this one
 __global__ void __launch_bounds__(256)
-isect_offsets_kernel(int64_t n_isects, const int64_t* __restrict__ sorted_ids, int C, int n_tiles, int tile_bits,
-                     int32_t* __restrict__ offsets) {
+isect_offsets_kernel(int64_t n_isects, const int64_t* __restrict__ n_dev, const int64_t* __restrict__ sorted_ids, int C,
+                     int n_tiles, int tile_bits, int32_t* __restrict__ offsets) {
+    n_isects = fsb_eff_n(n_isects, n_dev);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total_tiles = (int64_t)C * n_tiles;
     if (n_isects == 0) {
@@ -191,24 +198,27 @@ FSB_API int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, i
 
 FSB_API int fsb_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
                            const int64_t* offsets, int tile_size, int tile_w, int tile_h, int tile_bits,
-                           int legacy_bbox, int64_t* isect_ids, int32_t* flatten_ids, void* stream) {
+                           int legacy_bbox, const int64_t* n_dev, int64_t capacity, int32_t* overflow_flag,
+                           int64_t* isect_ids, int32_t* flatten_ids, void* stream) {
     if (C <= 0 || N < 0 || tile_size <= 0 || tile_bits < 0 || tile_bits > 30) return FSB_E_ARG;
+    if (n_dev && capacity < 0) return FSB_E_ARG;
     if ((int64_t)C * N > 0x7fffffffLL) return FSB_E_ARG;  // flatten_ids are int32 (same limit as gsplat)
     if (N == 0) return 0;
     int64_t total = (int64_t)C * N;
     isect_emit_kernel<<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        C, N, means2d, radii, depths, offsets, tile_size, tile_w, tile_h, tile_bits, legacy_bbox, isect_ids,
-        flatten_ids);
+        C, N, means2d, radii, depths, offsets, tile_size, tile_w, tile_h, tile_bits, legacy_bbox, n_dev, capacity,
+        overflow_flag, isect_ids, flatten_ids);
     FSB_LAUNCH_CHECK();
     return 0;
 }
 
-FSB_API int fsb_isect_offsets(int64_t n_isects, const int64_t* sorted_ids, int C, int n_tiles, int tile_bits,
-                              int32_t* offsets, void* stream) {
+FSB_API int fsb_isect_offsets(int64_t n_isects, const int64_t* n_dev, const int64_t* sorted_ids, int C, int n_tiles,
+                              int tile_bits, int32_t* offsets, void* stream) {
     if (n_isects < 0 || n_isects > 0x7fffffffLL || C <= 0 || n_tiles <= 0) return FSB_E_ARG;
     int64_t work = n_isects > 0 ? n_isects : (int64_t)C * n_tiles;
-    isect_offsets_kernel<<<fsb_div_up(work, 256), 256, 0, (cudaStream_t)stream>>>(n_isects, sorted_ids, C, n_tiles,
-                                                                                 tile_bits, offsets);
+    if (n_dev && work < (int64_t)C * n_tiles) work = (int64_t)C * n_tiles;  // the true count may be zero
+    isect_offsets_kernel<<<fsb_div_up(work, 256), 256, 0, (cudaStream_t)stream>>>(n_isects, n_dev, sorted_ids, C,
+                                                                                 n_tiles, tile_bits, offsets);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -25,7 +25,9 @@ constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VAL_MASK = ~FLAG_MASK;
 
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(int64_t n, const uint64_t* __restrict__ keys, int passes, uint32_t* __restrict__ hist) {
+radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ keys, int passes,
+                  uint32_t* __restrict__ hist) {
+    n = fsb_eff_n(n, n_dev);
     __shared__ uint32_t sh[MAX_PASSES][RADIX];
     for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += SORT_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
@@ -51,7 +53,8 @@ radix_hist_kernel(int64_t n, const uint64_t* __restrict__ keys, int passes, uint
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-onesweep_pass_kernel(int64_t n, const uint64_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ keys_in,
+                     const int32_t* __restrict__ vals_in,
                      uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ pass_hist, volatile uint32_t* status, uint32_t* tile_counter,
                      int shift) {
@@ -60,10 +63,14 @@ onesweep_pass_kernel(int64_t n, const uint64_t* __restrict__ keys_in, const int3
     __shared__ uint32_t scan_tmp[SORT_WARPS];
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    n = fsb_eff_n(n, n_dev);
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    // static-capacity mode launches tiles for the capacity; a tile past the true count holds nothing and no later
+    // tile exists that would look back at it
+    if ((int64_t)tile * SORT_TILE >= n) return;
     const int64_t tile_base = (int64_t)tile * SORT_TILE + (int64_t)warp * (32 * KPT);
 
     uint64_t key[KPT];
@@ -165,9 +172,10 @@ FSB_API size_t fsb_radix_sort_workspace(int64_t n, int end_bit) {
 
 // Sorts pairs by key bits [0, end_bit).  Buffers A (input, clobbered) and B ping-pong;
 // *result_in_b tells the caller which one holds the sorted pairs (it depends only on end_bit).
-FSB_API int fsb_radix_sort_pairs(int64_t n, int end_bit, uint64_t* keys_a, int32_t* vals_a, uint64_t* keys_b,
-                                 int32_t* vals_b, void* workspace, size_t workspace_bytes, int* result_in_b,
-                                 void* stream) {
+// n_dev (nullable): device pointer to the true count; n is then the capacity (see common.cuh).
+FSB_API int fsb_radix_sort_pairs(int64_t n, const int64_t* n_dev, int end_bit, uint64_t* keys_a, int32_t* vals_a,
+                                 uint64_t* keys_b, int32_t* vals_b, void* workspace, size_t workspace_bytes,
+                                 int* result_in_b, void* stream) {
     if (n < 0 || n >= (1ll << 30) || end_bit < 1 || end_bit > 64) return FSB_E_ARG;
     int passes = sort_num_passes(end_bit);
     if (passes > MAX_PASSES) return FSB_E_ARG;
@@ -181,13 +189,13 @@ FSB_API int fsb_radix_sort_pairs(int64_t n, int end_bit, uint64_t* keys_a, int32
     uint32_t* status = (uint32_t*)((char*)counters + fsb_align_up((size_t)passes * sizeof(uint32_t), 256));
     FSB_CUDA(cudaMemsetAsync(workspace, 0, fsb_radix_sort_workspace(n, end_bit), st));
     int hist_blocks = (int)(tiles < FSB_NUM_SMS * 8 ? tiles : FSB_NUM_SMS * 8);
-    radix_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(n, keys_a, passes, hist);
+    radix_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(n, n_dev, keys_a, passes, hist);
     FSB_LAUNCH_CHECK();
     uint64_t* kin = keys_a; int32_t* vin = vals_a;
     uint64_t* kout = keys_b; int32_t* vout = vals_b;
     for (int p = 0; p < passes; ++p) {
         onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
-            n, kin, vin, kout, vout, hist + (size_t)p * RADIX, status + (size_t)p * tiles * RADIX, counters + p,
+            n, n_dev, kin, vin, kout, vout, hist + (size_t)p * RADIX, status + (size_t)p * tiles * RADIX, counters + p,
             8 * p);
         FSB_LAUNCH_CHECK();
         uint64_t* tk = kin; kin = kout; kout = tk;

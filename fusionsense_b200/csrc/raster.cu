@@ -96,8 +96,10 @@ inline Workspace carve_ws(void* base, int64_t n_isects, int64_t n_tiles, int D) 
 
 // ---- segment table: one block scans ceil(len / SEG) over the tiles -------------------------------------------
 __global__ void __launch_bounds__(1024)
-seg_table_kernel(int n_tiles, int64_t n_isects, int SEG, const int32_t* __restrict__ tile_offsets,
-                 int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_tile, SegHeader* __restrict__ hdr) {
+seg_table_kernel(int n_tiles, int64_t n_isects, const int64_t* __restrict__ n_dev, int SEG,
+                 const int32_t* __restrict__ tile_offsets, int32_t* __restrict__ seg_start,
+                 int32_t* __restrict__ seg_tile, SegHeader* __restrict__ hdr) {
+    n_isects = fsb_eff_n(n_isects, n_dev);
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -374,12 +376,13 @@ __device__ __forceinline__ SegGeom seg_geom(const Workspace& ws, int seg, int64_
 // where most of the saving is: opaque tiles stop inside their first segment or two.
 template <int D, int PHASE>
 __global__ void __launch_bounds__(MAX_BLOCK)
-raster_seg_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
+raster_seg_kernel(int C, int N, int64_t n_isects, const int64_t* __restrict__ n_dev, const float2* __restrict__ means2d,
                   const float* __restrict__ conics, const float* __restrict__ colors,
                   const float* __restrict__ opacities, const uint8_t* __restrict__ masks, int width, int height,
                   int tile_size, int tile_w, int tile_h, const int32_t* __restrict__ tile_offsets,
                   const int32_t* __restrict__ flatten_ids, Workspace ws, FwdOut o) {
     __shared__ Stage<D> s;
+    n_isects = fsb_eff_n(n_isects, n_dev);
     int seg;
     int64_t tile_lin;
     if (PHASE == 0) {
@@ -488,12 +491,13 @@ raster_fold_kernel(int C, int width, int height, int tile_size, int tile_w, int 
 // (chained) state, which keeps the sequential semantics: stop position, last id, nothing blended after it.
 template <int D>
 __global__ void __launch_bounds__(MAX_BLOCK)
-raster_stop_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
+raster_stop_kernel(int C, int N, int64_t n_isects, const int64_t* __restrict__ n_dev, const float2* __restrict__ means2d,
                    const float* __restrict__ conics, const float* __restrict__ colors,
                    const float* __restrict__ opacities, const uint8_t* __restrict__ masks, int width, int height,
                    int tile_size, int tile_w, int tile_h, const int32_t* __restrict__ tile_offsets,
                    const int32_t* __restrict__ flatten_ids, Workspace ws, FwdOut o) {
     __shared__ Stage<D> s;
+    n_isects = fsb_eff_n(n_isects, n_dev);
     const int seg = blockIdx.x;
     if (seg >= ws.hdr->total_segs) return;
     const int64_t tile_lin = ws.seg_tile[seg];
@@ -585,7 +589,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // XYMODE: 0 = no gradient for the 2-D means (the normals pass detaches them), 1 = xy, 2 = xy and |xy| (absgrad).
 template <int D, int XYMODE>
 __global__ void __launch_bounds__(MAX_BLOCK)
-raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ means2d,
+raster_bwd_kernel(int C, int N, int64_t n_isects, const int64_t* __restrict__ n_dev, const float2* __restrict__ means2d,
                   const float* __restrict__ conics, const float* __restrict__ colors,
                   const float* __restrict__ opacities, const float* __restrict__ backgrounds,
                   const uint8_t* __restrict__ masks, int width, int height, int tile_size, int tile_w, int tile_h,
@@ -598,6 +602,7 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
     constexpr int SEG = seg_len(D);
     __shared__ Stage<D> s;
     __shared__ int32_t s_wmax[MAX_BLOCK / 32];
+    n_isects = fsb_eff_n(n_isects, n_dev);
     const int seg = blockIdx.x;
     if (seg >= ws.hdr->total_segs) return;
     const int64_t tile_lin = ws.seg_tile[seg];
@@ -751,33 +756,33 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const float2* __restrict__ mea
 }
 
 template <int D>
-int launch_fwd(int C, int N, int64_t n_isects, const float* means2d, const float* conics, const float* colors,
+int launch_fwd(int C, int N, int64_t n_isects, const int64_t* n_dev, const float* means2d, const float* conics, const float* colors,
                const float* opacities, const float* backgrounds, const uint8_t* masks, int width, int height,
                int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
                int ed_normalize, void* workspace, float* out_colors, float* out_alphas, int32_t* last_ids,
                cudaStream_t st) {
     const int64_t n_tiles = (int64_t)C * tile_w * tile_h;
     Workspace ws = carve_ws(workspace, n_isects, n_tiles, D);
-    seg_table_kernel<<<1, 1024, 0, st>>>((int)n_tiles, n_isects, seg_len(D), tile_offsets, ws.seg_start, ws.seg_tile, ws.hdr);
+    seg_table_kernel<<<1, 1024, 0, st>>>((int)n_tiles, n_isects, n_dev, seg_len(D), tile_offsets, ws.seg_start, ws.seg_tile, ws.hdr);
     FSB_LAUNCH_CHECK();
     dim3 block(tile_size, tile_size);
     FwdOut o{backgrounds, ed_normalize, out_colors, out_alphas, last_ids};
     unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
-    const bool multi = n_isects > seg_len(D);  // otherwise no tile can hold more than one segment
+    const bool multi = n_dev != nullptr || n_isects > seg_len(D);  // otherwise no tile can hold more than one segment
     if (multi) FSB_CUDA(cudaMemsetAsync(ws.done_k, 0x7f, (size_t)n_tiles * 8 * 4, st));
-    raster_seg_kernel<D, 0><<<(unsigned)n_tiles, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors,
+    raster_seg_kernel<D, 0><<<(unsigned)n_tiles, block, 0, st>>>(C, N, n_isects, n_dev, (const float2*)means2d, conics, colors,
                                                                  opacities, masks, width, height, tile_size, tile_w,
                                                                  tile_h, tile_offsets, flatten_ids, ws, o);
     FSB_LAUNCH_CHECK();
     if (multi) {
-        raster_seg_kernel<D, 1><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors,
+        raster_seg_kernel<D, 1><<<grid, block, 0, st>>>(C, N, n_isects, n_dev, (const float2*)means2d, conics, colors,
                                                         opacities, masks, width, height, tile_size, tile_w, tile_h,
                                                         tile_offsets, flatten_ids, ws, o);
         FSB_LAUNCH_CHECK();
         raster_fold_kernel<D><<<(unsigned)n_tiles, block, 0, st>>>(C, width, height, tile_size, tile_w, tile_h, masks,
                                                                    ws, o);
         FSB_LAUNCH_CHECK();
-        raster_stop_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, (const float2*)means2d, conics, colors,
+        raster_stop_kernel<D><<<grid, block, 0, st>>>(C, N, n_isects, n_dev, (const float2*)means2d, conics, colors,
                                                       opacities, masks, width, height, tile_size, tile_w, tile_h,
                                                       tile_offsets, flatten_ids, ws, o);
         FSB_LAUNCH_CHECK();
@@ -786,7 +791,7 @@ int launch_fwd(int C, int N, int64_t n_isects, const float* means2d, const float
 }
 
 template <int D>
-int launch_bwd(int C, int N, int64_t n_isects, const float* means2d, const float* conics, const float* colors,
+int launch_bwd(int C, int N, int64_t n_isects, const int64_t* n_dev, const float* means2d, const float* conics, const float* colors,
                const float* opacities, const float* backgrounds, const uint8_t* masks, int width, int height,
                int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
                int ed_normalize, void* workspace, const float* render_colors, const float* render_alphas,
@@ -799,7 +804,7 @@ int launch_bwd(int C, int N, int64_t n_isects, const float* means2d, const float
     unsigned grid = (unsigned)max_segments(n_isects, n_tiles, D);
 #define FSB_BWD_LAUNCH(MODE)                                                                                       \
     raster_bwd_kernel<D, MODE><<<grid, block, 0, st>>>(                                                             \
-        C, N, n_isects, (const float2*)means2d, conics, colors, opacities, backgrounds, masks, width, height,       \
+        C, N, n_isects, n_dev, (const float2*)means2d, conics, colors, opacities, backgrounds, masks, width, height, \
         tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize, ws, render_colors, render_alphas,       \
         last_ids, v_render_colors, v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities)
     if (v_means2d_abs) FSB_BWD_LAUNCH(2);
@@ -846,7 +851,8 @@ FSB_API size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D) {
     return ws_bytes(n_isects, n_tiles, D);
 }
 
-FSB_API int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
+// n_isects_dev (nullable): static-capacity mode, n_isects is then the capacity of flatten_ids (common.cuh).
+FSB_API int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d, const float* conics,
                            const float* colors, const float* opacities, const float* backgrounds,
                            const uint8_t* masks, int width, int height, int tile_size, int tile_w, int tile_h,
                            const int32_t* tile_offsets, const int32_t* flatten_ids, int ed_normalize,
@@ -857,7 +863,7 @@ FSB_API int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* m
     if (!workspace || workspace_bytes < fsb_raster_workspace(n_isects, (int64_t)C * tile_w * tile_h, D))
         return FSB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    FSB_DISPATCH_D(D, (launch_fwd<DD>(C, N, n_isects, means2d, conics, colors, opacities, backgrounds, masks, width,
+    FSB_DISPATCH_D(D, (launch_fwd<DD>(C, N, n_isects, n_isects_dev, means2d, conics, colors, opacities, backgrounds, masks, width,
                                       height, tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize,
                                       workspace, out_colors, out_alphas, last_ids, st)));
 }
@@ -866,7 +872,7 @@ FSB_API int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* m
 // `workspace` is the buffer the matching fsb_raster_fwd call filled.
 // v_means2d / v_means2d_abs may be NULL (no gradient wanted for the 2-D means: the legacy normals pass of
 // dn_model.py:638 detaches them); v_means2d_abs requires v_means2d.
-FSB_API int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
+FSB_API int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d, const float* conics,
                            const float* colors, const float* opacities, const float* backgrounds,
                            const uint8_t* masks, int width, int height, int tile_size, int tile_w, int tile_h,
                            const int32_t* tile_offsets, const int32_t* flatten_ids, int ed_normalize,
@@ -881,7 +887,7 @@ FSB_API int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* m
     if (!workspace || workspace_bytes < fsb_raster_workspace(n_isects, (int64_t)C * tile_w * tile_h, D))
         return FSB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    FSB_DISPATCH_D(D, (launch_bwd<DD>(C, N, n_isects, means2d, conics, colors, opacities, backgrounds, masks, width,
+    FSB_DISPATCH_D(D, (launch_bwd<DD>(C, N, n_isects, n_isects_dev, means2d, conics, colors, opacities, backgrounds, masks, width,
                                       height, tile_size, tile_w, tile_h, tile_offsets, flatten_ids, ed_normalize,
                                       workspace, render_colors, render_alphas, last_ids, v_render_colors,
                                       v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities,

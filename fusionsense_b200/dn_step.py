@@ -157,15 +157,19 @@ class DNSplatterStep:
         if cfg.use_binary_opacities and self.step > cfg.warmup_length:
             skip_steps = cfg.reset_alpha_every * cfg.refine_every
             if not self.step % skip_steps == 0 and self.step % skip_steps not in range(1, 200 + 1):
-                self.opacities.data = torch.where(self.opacities >= cfg.binary_opacities_threshold,
-                                                  torch.ones_like(self.opacities), torch.zeros_like(self.opacities))
+                # dn_model.py:497-503 assigns where(op >= thr, 1, 0) to .data; in place here (same values), so the
+                # parameter keeps its storage and a captured graph keeps reading the live tensor
+                self.opacities.data.ge_(cfg.binary_opacities_threshold)
         opacities_crop, means_crop = self.opacities, self.means
         scales_crop, quats_crop = self.scales, self.quats
         colors_crop = torch.cat((self.features_dc[:, None, :], self.features_rest), dim=1)
         BLOCK_WIDTH = 16
-        viewmat = sc.viewmats[cam_idx:cam_idx + 1]
-        K = sc.Ks[cam_idx:cam_idx + 1]
-        c2w = sc.c2w[cam_idx:cam_idx + 1]
+        if isinstance(cam_idx, Tensor):  # device index (captured step: the view is chosen at replay time)
+            viewmat, K, c2w = (t.index_select(0, cam_idx) for t in (sc.viewmats, sc.Ks, sc.c2w))
+        else:
+            viewmat = sc.viewmats[cam_idx:cam_idx + 1]
+            K = sc.Ks[cam_idx:cam_idx + 1]
+            c2w = sc.c2w[cam_idx:cam_idx + 1]
         W, H = sc.width, sc.height
         self.last_size = (H, W)
         self._last_cam = cam_idx
@@ -276,7 +280,7 @@ class DNSplatterStep:
         if cfg.two_d_gaussians:
             normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
         main_loss = rgb_loss + depth_loss + cfg.normal_lambda * normal_loss
-        return {"main_loss": main_loss, "scale_reg": torch.tensor(0.0, device=self.device)}
+        return {"main_loss": main_loss, "scale_reg": torch.zeros((), device=self.device)}
 
     def _gt_normal(self, batch, depth_out) -> Tensor:
         """dn_model.py:770-795: monocular normal maps from the batch, or pseudo normals from the rendered depth."""
@@ -288,6 +292,9 @@ class DNSplatterStep:
                 from .utils.normal_utils import normal_from_depth_image
             else:
                 normal_from_depth_image = _torch_normal_from_depth_image  # reference arm (oracle-driven, CPU)
+            if isinstance(self._last_cam, Tensor):
+                raise NotImplementedError("normal_supervision='depth' reads the intrinsics on the host "
+                                          "(dn_model.py:781-784 .item()); not available in a captured step")
             K = sc.Ks[self._last_cam]
             gt_normal = normal_from_depth_image(
                 depths=depth_out.detach(), fx=K[0, 0].item(), fy=K[1, 1].item(), cx=K[0, 2].item(), cy=K[1, 2].item(),
@@ -300,7 +307,7 @@ class DNSplatterStep:
 
     # ---- splatfacto after_train ---------------------------------------------
     @torch.no_grad()
-    def after_train(self):
+    def after_train(self, skip_flag=None):
         if self.step >= self.config.stop_split_at:
             return
         if self.config.fused_glue and self.device.type == "cuda":
@@ -312,7 +319,7 @@ class DNSplatterStep:
             if self.max_2Dsize is None:
                 self.max_2Dsize = torch.zeros(self.num_points, device=self.device, dtype=torch.float32)
             densify_stats(self.radii, self.xys.absgrad[0], float(max(self.last_size[0], self.last_size[1])),
-                          self.xys_grad_norm, self.vis_counts, self.max_2Dsize)
+                          self.xys_grad_norm, self.vis_counts, self.max_2Dsize, skip_flag=skip_flag)
             return
         visible_mask = (self.radii > 0).flatten()
         grads = self.xys.absgrad[0][visible_mask].norm(dim=-1)

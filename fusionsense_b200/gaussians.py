@@ -50,9 +50,10 @@ def gaussian_normals(quats: Tensor, scales: Tensor, means: Tensor, c2w: Tensor) 
 
 @torch.no_grad()
 def densify_stats(radii: Tensor, grads2d: Tensor, max_dim: float, xys_grad_norm: Tensor, vis_counts: Tensor,
-                  max_2Dsize: Tensor) -> None:
+                  max_2Dsize: Tensor, skip_flag: Tensor = None) -> None:
     """In-place: for visible Gaussians (radii > 0) vis_counts += 1, xys_grad_norm += |grads2d|,
-    max_2Dsize = max(max_2Dsize, radii / max_dim).  grads2d: `xys.absgrad[0]` (or `.grad[0]`), [N,2]."""
+    max_2Dsize = max(max_2Dsize, radii / max_dim).  grads2d: `xys.absgrad[0]` (or `.grad[0]`), [N,2].
+    `skip_flag` (device int32[1]): non-zero makes the call a no-op (overflowed step of a captured graph)."""
     _req_cuda(radii, grads2d, xys_grad_norm, vis_counts, max_2Dsize)
     N = radii.numel()
     assert radii.dtype == torch.int32 and radii.is_contiguous()
@@ -60,4 +61,4 @@ def densify_stats(radii: Tensor, grads2d: Tensor, max_dim: float, xys_grad_norm:
     for t in (xys_grad_norm, vis_counts, max_2Dsize):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == N
     check(lib.fsb_densify_stats(N, ptr(radii), ptr(g), float(max_dim), ptr(xys_grad_norm), ptr(vis_counts),
-                                ptr(max_2Dsize), _stream()), "fsb_densify_stats")
+                                ptr(max_2Dsize), ptr(skip_flag), _stream()), "fsb_densify_stats")

@@ -1,0 +1,191 @@
+"""The DN-Splatter training iteration as ONE CUDA graph launch.
+
+At FusionSense's scene sizes (300 k Gaussians, 640x480) the eager iteration is host-bound: ~135 launches per step
+(40 of ours, the rest the torch glue `dn_model.py` issues around the gsplat calls) and one stream synchronisation
+for the intersection count keep the GPU ~45 % busy (profiles/).  The kernels' static-capacity mode
+(include/fsb200.h) removes the synchronisation and fixes the launch sequence, so the whole iteration
+
+    zero_grad -> get_outputs (rasterization RGB+ED, normals, legacy normals pass) -> get_loss_dict -> backward
+    -> Adam (all groups, one launch) -> after_train statistics
+
+is captured once with `torch.cuda.graph` and replayed per step; the per-replay inputs (camera index, Adam step
+sizes) are uploaded with fsb_upload_small.  Nothing is skipped or cached between replays: every kernel of the
+eager step runs in every replay on the live parameters.
+
+Re-capture happens when something the capture froze changes: the number of Gaussians (refinement every
+`refine_every` steps), the active SH degree, the binary-opacity window, the end of densification, or an overflow of
+the intersection capacity (the device then leaves parameters, Adam state and statistics untouched for that step;
+the host notices through `poll()`, grows the capacity and re-runs).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from ._abi import check, lib
+from .dn_step import DNSplatterStep
+from .optim import CapturedAdam
+
+
+class GraphedDNSplatterStep:
+    def __init__(self, model: DNSplatterStep, targets: Dict[int, Dict[str, Tensor]], capacity: Optional[int] = None,
+                 margin: float = 1.3, grad_sync=None, loss_scale: float = 1.0):
+        """`targets[v]` = batch of view v (`image`, `sensor_depth`, `normal`, device tensors).  They are stacked
+        into one resident tensor per key; `stage(v, host_batch)` overwrites a view's slot from host memory.
+        `grad_sync(params, overflow_flag)`: optional hook run inside the captured step between backward and Adam
+        (multi-GPU: the NCCL all-reduce of the parameter gradients and of the overflow flag); `loss_scale`
+        multiplies the loss before backward (1 / world_size keeps the mean over the global camera batch)."""
+        if model.device.type != "cuda":
+            raise RuntimeError("GraphedDNSplatterStep needs a CUDA model (no CPU fallback)")
+        if not model._fused_optim:
+            raise RuntimeError("GraphedDNSplatterStep needs fused_optimizer=True")
+        self.model = model
+        self.device = model.device
+        views = sorted(targets)
+        assert views == list(range(len(views))), "targets must cover views 0..V-1"
+        self.targets = {k: torch.stack([targets[v][k] for v in views]).contiguous() for k in targets[views[0]]}
+        self.margin = float(margin)
+        self.capacity = int(capacity) if capacity else None
+        self.cam = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._cam_host = (ctypes.c_int64 * 1)()
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # [loss, overflowed steps so far, n_isects of the RGB+ED pass, n_isects of the legacy normals pass]
+        self.result = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._overflow_seen = 0
+        self.max_isects_seen = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.signature = None
+        self.adam: Optional[CapturedAdam] = None
+        self.captures = 0
+        self.replays = 0
+        self.grad_sync = grad_sync
+        self.loss_scale = float(loss_scale)
+        self.launches_per_replay = 0  # libfsb200 kernels inside one replay (counted while capturing)
+
+    # ---- what the capture freezes ------------------------------------------------------------
+    def _signature(self):
+        m, cfg = self.model, self.model.config
+        skip_steps = cfg.reset_alpha_every * cfg.refine_every
+        binary = (cfg.use_binary_opacities and m.step > cfg.warmup_length and not m.step % skip_steps == 0
+                  and m.step % skip_steps not in range(1, 200 + 1))
+        return (m.num_points, min(m.step // cfg.sh_degree_interval, cfg.sh_degree), binary,
+                m.step >= cfg.stop_split_at, self.capacity, tuple(id(p) for p in m.gauss_params.values()))
+
+    @torch.no_grad()
+    def _probe_capacity(self) -> int:
+        """Largest intersection count over the training views (legacy bbox rule, the larger of the two), by the
+        eager path with its one host read per view."""
+        m = self.model
+        worst = 0
+        training, m.training = m.training, False
+        try:
+            for v in range(self.targets["image"].shape[0]):
+                m.get_outputs(v)
+                from .gsplat.cuda_legacy import _wrapper as legacy
+
+                worst = max(worst, int(legacy._LAST_BINNING.get("n_isects", 0)))
+        finally:
+            m.training = training
+        return worst
+
+    def _body(self, warmup: bool = False):
+        """One iteration in static-capacity mode on the current stream.  `warmup`: run eagerly before the capture
+        with the skip flag raised, so every lazy initialisation happens outside the graph while parameters, Adam
+        state and statistics stay untouched."""
+        m = self.model
+        for opt in m.optimizers.values():
+            opt.zero_grad(set_to_none=True)
+        if warmup:
+            self.overflow.fill_(1)
+        else:
+            self.overflow.zero_()
+        with ops.static_capacity(self.capacity, self.overflow) as st:
+            outputs = m.get_outputs(self.cam)
+            batch = {k: t.index_select(0, self.cam)[0] for k, t in self.targets.items()}
+            loss_dict = m.get_loss_dict(outputs, batch)
+            loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
+            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+            counts = list(st.counts)
+        if self.grad_sync is not None:
+            self.grad_sync([p for p in m.gauss_params.values() if p.grad is not None], self.overflow)
+        self.adam.launch(skip_flag=self.overflow)
+        m.after_train(skip_flag=self.overflow)
+        if warmup:
+            return
+        with torch.no_grad():
+            self.result[0:1].copy_(loss.detach().reshape(1))
+            self.result[1:2].add_(self.overflow)
+            for i, c in enumerate(counts[:2]):
+                self.result[2 + i:3 + i].copy_(c)
+
+    def capture(self) -> None:
+        m = self.model
+        if self.capacity is None or self.capacity <= 0:
+            seen = self.max_isects_seen or self._probe_capacity()
+            self.capacity = int(seen * self.margin) + 65536
+        if m.xys_grad_norm is None:
+            m.xys_grad_norm = torch.zeros(m.num_points, device=self.device, dtype=torch.float32)
+            m.vis_counts = torch.ones(m.num_points, device=self.device, dtype=torch.float32)
+        if m.max_2Dsize is None:
+            m.max_2Dsize = torch.zeros(m.num_points, device=self.device, dtype=torch.float32)
+        self.adam = CapturedAdam(m.optimizers.values())
+        self.graph = None
+        side = self._side = getattr(self, "_side", None) or torch.cuda.Stream()  # warm-up and capture share it
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._body(warmup=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = lib.fsb_launch_count()
+        with torch.cuda.graph(g, stream=side):
+            self._body()
+        self.launches_per_replay = int(lib.fsb_launch_count() - n0)
+        self.graph = g
+        self.signature = self._signature()
+        self.captures += 1
+
+    # ---- per step ----------------------------------------------------------------------------
+    def train_iteration(self, cam_idx: int) -> Tensor:
+        """One training iteration on view `cam_idx`; returns the device-resident result vector
+        [loss, overflowed steps, n_isects, n_isects (normals pass)] (float64, overwritten by the next call)."""
+        m = self.model
+        if self.graph is None or self.signature != self._signature():
+            self.capture()
+        m.optimizers["means"].param_groups[0]["lr"] = m._means_lr()
+        self.adam.advance()
+        self._cam_host[0] = int(cam_idx)
+        check(lib.fsb_upload_small(self.cam.data_ptr(), ctypes.addressof(self._cam_host), 8, ops._stream()),
+              "fsb_upload_small")
+        self.graph.replay()
+        m.step += 1
+        self.replays += 1
+        return self.result
+
+    def stage(self, cam_idx: int, host_batch: Dict[str, Tensor]) -> int:
+        """Copy a view's targets from (pinned) host memory into its resident slot; returns the bytes moved."""
+        n = 0
+        for k, t in host_batch.items():
+            self.targets[k][cam_idx].copy_(t, non_blocking=True)
+            n += t.numel() * t.element_size()
+        return n
+
+    def poll(self) -> Dict[str, float]:
+        """Read the result vector (one 32-byte D2H copy; synchronises with the last replay) and handle overflowed
+        steps: they changed nothing on the device, so the host counters are rolled back, the capacity grows and the
+        next call re-captures."""
+        loss, overflowed, n0, n1 = self.result.tolist()
+        self.max_isects_seen = max(self.max_isects_seen, int(n0), int(n1))
+        new = int(overflowed) - self._overflow_seen
+        if new > 0:
+            self._overflow_seen = int(overflowed)
+            self.model.step -= new
+            self.adam.rollback(new)
+            self.capacity = int(max(self.capacity * 1.5, self.max_isects_seen * self.margin)) + 65536
+            self.graph = None
+        return {"loss": loss, "overflowed_steps": int(overflowed), "n_isects": int(n0), "n_isects_normals": int(n1),
+                "capacity": self.capacity, "new_overflows": new}

@@ -91,10 +91,18 @@ def rasterize_gaussians(
         xys_c = xys.detach().float().contiguous()
         dep_c = depths1.detach().float().contiguous()
         rad_c = radii1.contiguous()
-        cached = _LAST_BINNING if _LAST_BINNING.get("key") == (
+        static = ops.static_mode()
+        n_dev = None
+        cached = _LAST_BINNING if static is None and _LAST_BINNING.get("key") == (
             xys_c.data_ptr(), dep_c.data_ptr(), rad_c.data_ptr(), xys._version, depths._version, radii._version,
             N, W, H, ts) else None
-        if cached is not None and cached.get("legacy_extra") == 0:
+        if static is not None:
+            # static-capacity mode (CUDA-graph capture): no host read, so whether the 0.1.x bbox rule adds tiles
+            # is not known here; bin with the legacy rule on the device-side count
+            _, _, flatten_ids, isect_offsets = ops.isect_tiles(xys_c[None], rad_c[None], dep_c[None], ts, tile_w,
+                                                               tile_h, legacy_bbox=True)
+            n_dev, n_isects, offsets = flatten_ids.n_dev, static.capacity, None
+        elif cached is not None and cached.get("legacy_extra") == 0:
             # same xys / depths / radii as the rasterization() call just before, and its projection kernel found
             # the 0.1.x bbox of every Gaussian equal to the 1.0 one: identical tile sets, identical keys
             # (tile << 32 | depth bits) -> the sorted lists are shared; no binning, no sort, no host sync.
@@ -129,7 +137,7 @@ def rasterize_gaussians(
             bg = torch.cat([bg, bg.new_zeros(Dp - D)], dim=-1)
         out, alpha = ops.RasterizeToPixels.apply(xys[None], conics[None], cols[None], opacity.reshape(1, N),
                                                  bg[None], None, W, H, ts, isect_offsets, flatten_ids, bool(xys.requires_grad),
-                                                 False)
+                                                 False, n_dev)
         out_img = out[0, ..., :D] if Dp != D else out[0]
         out_alpha = alpha[0, ..., 0]
     if return_alpha:

@@ -113,8 +113,9 @@ def rasterization(
         _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(
             means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
             totals=totals)
+        n_dev = getattr(flatten_ids, "n_dev", None)  # static-capacity mode (ops.static_capacity): count on device
         remember_binning(means2d, depths, radii, width, height, tile_size, flatten_ids.numel(), flatten_ids,
-                         isect_offsets, legacy_extra=totals.host[1] if C == 1 else None)
+                         isect_offsets, legacy_extra=totals.host[1] if (C == 1 and n_dev is None) else None)
 
     if use_sh:
         ras_colors = sh_colors  # [C, N, 3 or 4], depth already in channel 3
@@ -142,7 +143,7 @@ def rasterization(
         else:
             fused_ed = ed
         out, alpha = ops.RasterizeToPixels.apply(means2d, conics, cols, opac, bgs, None, width, height, tile_size,
-                                                 isect_offsets, flatten_ids, absgrad, fused_ed)
+                                                 isect_offsets, flatten_ids, absgrad, fused_ed, n_dev)
         if dp != d:
             out = out[..., :d]
         if ed and not fused_ed:

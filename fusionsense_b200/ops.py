@@ -71,6 +71,42 @@ class KernelTimer:
 kernel_timer = KernelTimer()
 
 
+class StaticCapacity:
+    """Static-capacity mode of the intersection pipeline (include/fsb200.h): list buffers are allocated for
+    `capacity` entries, the true count stays on the device, nothing is read back to the host, and the launch
+    sequence of a whole render + backward is fixed, so a CUDA graph can capture it.  `overflow` is a device int32[1]
+    that fsb_isect_emit raises when a count exceeds the capacity (the step's results are then invalid)."""
+
+    def __init__(self, capacity: int, overflow: Tensor):
+        assert capacity > 0 and overflow.dtype == torch.int32 and overflow.is_cuda
+        self.capacity, self.overflow = int(capacity), overflow
+        self.counts = []  # device int64[1] tensors of the true counts seen in this scope (for reporting)
+
+
+_static: Optional[StaticCapacity] = None
+
+
+def static_mode() -> Optional[StaticCapacity]:
+    return _static
+
+
+class static_capacity:
+    """`with ops.static_capacity(capacity, overflow_flag): ...` — see StaticCapacity."""
+
+    def __init__(self, capacity: int, overflow: Tensor):
+        self.state = StaticCapacity(capacity, overflow)
+
+    def __enter__(self):
+        global _static
+        self.prev, _static = _static, self.state
+        return self.state
+
+    def __exit__(self, *exc):
+        global _static
+        _static = self.prev
+        return False
+
+
 def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -121,7 +157,7 @@ def isect_count(means2d: Tensor, radii: Tensor, tile_size: int, tile_w: int, til
     return tiles
 
 
-def isect_scan(counts: Tensor, totals: Optional[Tensor] = None):
+def isect_scan(counts: Tensor, totals: Optional[Tensor] = None, read_back: bool = True):
     """Exclusive int64 offsets of `counts` and the total (one small D2H read, like gsplat's).
 
     `totals`: optional int64 device tensor whose element 0 receives the total; the whole tensor comes back in the
@@ -135,6 +171,8 @@ def isect_scan(counts: Tensor, totals: Optional[Tensor] = None):
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     check(lib.fsb_isect_scan(M, ptr(counts), ptr(offsets), ptr(total), ptr(ws), ws_bytes, _stream()),
           "fsb_isect_scan")
+    if not read_back:
+        return offsets, None
     if totals is not None:
         return offsets, [int(v) for v in total.tolist()]
     return offsets, int(total.item())
@@ -144,20 +182,24 @@ def tile_bits_for(n_tiles: int) -> int:
     return int(n_tiles).bit_length()
 
 
-def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox):
+def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox, n_dev=None,
+               overflow=None):
+    """`n_dev` (device int64[1]) selects static-capacity mode: `n_isects` is then the capacity of the buffers."""
     dev = means2d.device
     ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
     flat = torch.empty((n_isects,), dtype=torch.int32, device=dev)
     tb = tile_bits_for(tile_w * tile_h)
     ev = kernel_timer.start("isect_emit")
     check(lib.fsb_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h, tb,
-                             int(legacy_bbox), ptr(ids), ptr(flat), _stream()), "fsb_isect_emit")
+                             int(legacy_bbox), ptr(n_dev), n_isects, ptr(overflow), ptr(ids), ptr(flat), _stream()),
+          "fsb_isect_emit")
     kernel_timer.stop(ev)
     return ids, flat
 
 
-def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tensor, Tensor]:
-    """Stable sort of (int64 keys, int32 vals) on key bits [0, end_bit). Inputs are clobbered."""
+def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int, n_dev: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Stable sort of (int64 keys, int32 vals) on key bits [0, end_bit). Inputs are clobbered.
+    `n_dev`: static-capacity mode, only the first min(*n_dev, len) pairs are sorted (the rest is untouched)."""
     _req_cuda(keys, vals)
     n = keys.numel()
     if n == 0:
@@ -169,16 +211,16 @@ def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tensor, 
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     in_b = ctypes.c_int(0)
     ev = kernel_timer.start("radix_sort")
-    check(lib.fsb_radix_sort_pairs(n, end_bit, ptr(keys), ptr(vals), ptr(keys_b), ptr(vals_b), ptr(ws), ws_bytes,
+    check(lib.fsb_radix_sort_pairs(n, ptr(n_dev), end_bit, ptr(keys), ptr(vals), ptr(keys_b), ptr(vals_b), ptr(ws), ws_bytes,
                                    ctypes.addressof(in_b), _stream()), "fsb_radix_sort_pairs")
     kernel_timer.stop(ev)
     return (keys_b, vals_b) if in_b.value else (keys, vals)
 
 
-def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int) -> Tensor:
+def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int, n_dev: Optional[Tensor] = None) -> Tensor:
     n_tiles = tile_w * tile_h
     offsets = torch.empty((C, tile_h, tile_w), dtype=torch.int32, device=sorted_ids.device)
-    check(lib.fsb_isect_offsets(sorted_ids.numel(), ptr(sorted_ids), C, n_tiles, tile_bits_for(n_tiles),
+    check(lib.fsb_isect_offsets(sorted_ids.numel(), ptr(n_dev), ptr(sorted_ids), C, n_tiles, tile_bits_for(n_tiles),
                                 ptr(offsets), _stream()), "fsb_isect_offsets")
     return offsets
 
@@ -194,6 +236,22 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
     C, N = radii.shape
     if tiles_per_gauss is None:
         tiles_per_gauss = isect_count(means2d, radii, tile_size, tile_w, tile_h, legacy_bbox)
+    st = static_mode()
+    if st is not None:
+        # no host read: buffers for the capacity, the true count stays in totals[0] on the device
+        if totals is None:
+            totals = torch.zeros(1, dtype=torch.int64, device=radii.device)
+        offsets, _ = isect_scan(tiles_per_gauss, totals, read_back=False)
+        n_dev = totals[:1]
+        st.counts.append(n_dev)
+        ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h,
+                               legacy_bbox, n_dev=n_dev, overflow=st.overflow)
+        if sort:
+            end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
+            ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=n_dev)
+        tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=n_dev)
+        flat.n_dev = n_dev
+        return tiles_per_gauss, ids, flat, tile_offsets
     offsets, n_isects = isect_scan(tiles_per_gauss, totals)
     if totals is not None:
         totals.host = n_isects  # the values that came back with the one D2H read
@@ -211,7 +269,7 @@ def supported_channels(D: int) -> int:
 
 
 def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
-               flatten_ids, ed_normalize=False):
+               flatten_ids, ed_normalize=False, n_dev=None):
     _req_cuda(means2d, conics, colors, opacities)
     C = isect_offsets_t.shape[0]
     tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
@@ -224,7 +282,7 @@ def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     ws_bytes = lib.fsb_raster_workspace(flatten_ids.numel(), C * tile_h * tile_w, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     ev = kernel_timer.start(f"raster_fwd_D{D}")
-    check(lib.fsb_raster_fwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
+    check(lib.fsb_raster_fwd(C, N, D, flatten_ids.numel(), ptr(n_dev), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
                              ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(ws), ws_bytes, ptr(out),
                              ptr(alphas), ptr(last_ids), _stream()), "fsb_raster_fwd")
@@ -234,7 +292,7 @@ def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
 
 def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
                flatten_ids, ed_normalize, ws, render_colors, render_alphas, last_ids, v_render_colors, v_render_alphas,
-               absgrad, need_xy=True):
+               absgrad, need_xy=True, n_dev=None):
     C = isect_offsets_t.shape[0]
     tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
     N = means2d.shape[-2]
@@ -250,7 +308,7 @@ def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     v_colors = parts[3].view(colors.shape)
     v_opac = parts[4].view(opacities.shape)
     ev = kernel_timer.start(f"raster_bwd_D{D}")
-    check(lib.fsb_raster_bwd(C, N, D, flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
+    check(lib.fsb_raster_bwd(C, N, D, flatten_ids.numel(), ptr(n_dev), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                              ptr(backgrounds), ptr(masks), width, height, tile_size, tile_w, tile_h,
                              ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(ws), ws.numel(),
                              ptr(render_colors), ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
@@ -322,12 +380,13 @@ class RasterizeToPixels(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size,
-                isect_offsets_t, flatten_ids, absgrad, ed_normalize):
+                isect_offsets_t, flatten_ids, absgrad, ed_normalize, n_dev=None):
         means2d_c, conics_c = _f32c(means2d), _f32c(conics)
         colors_c, opac_c, bg_c = _f32c(colors), _f32c(opacities), _f32c(backgrounds)
         masks_c = masks.contiguous().to(torch.uint8) if masks is not None else None
         out, alphas, last_ids, ws = raster_fwd(means2d_c, conics_c, colors_c, opac_c, bg_c, masks_c, width, height,
-                                               tile_size, isect_offsets_t, flatten_ids, ed_normalize)
+                                               tile_size, isect_offsets_t, flatten_ids, ed_normalize, n_dev=n_dev)
+        ctx.n_dev = n_dev
         ctx.save_for_backward(means2d, conics_c, colors_c, opac_c, bg_c, masks_c, isect_offsets_t, flatten_ids, out,
                               alphas, last_ids, ws)
         ctx.cfg = (width, height, tile_size, absgrad, ed_normalize)
@@ -343,11 +402,12 @@ class RasterizeToPixels(torch.autograd.Function):
         v_alphas = _f32c(v_alphas) if v_alphas is not None else torch.zeros_like(alphas)
         v_means2d, v_abs, v_conics, v_colors, v_opac = raster_bwd(
             _f32c(means2d), conics, colors, opac, bg, masks, width, height, tile_size, isect_offsets_t, flatten_ids,
-            ed_normalize, ws, out, alphas, last_ids, v_out, v_alphas, absgrad, need_xy=ctx.needs_input_grad[0])
+            ed_normalize, ws, out, alphas, last_ids, v_out, v_alphas, absgrad, need_xy=ctx.needs_input_grad[0],
+            n_dev=ctx.n_dev)
         if absgrad and v_abs is not None:
             # same contract as gsplat: the tensor handed out as meta["means2d"] gets an .absgrad attribute
             means2d.absgrad = v_abs
         v_bg = None
         if bg is not None and ctx.needs_input_grad[4]:
             v_bg = (v_out * (1.0 - alphas)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None, None

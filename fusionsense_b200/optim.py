@@ -88,3 +88,73 @@ def fused_step(optimizers: Iterable[FusedAdam]) -> None:
     for (betas, eps), entries in buckets.items():
         _launch(entries, betas[0], betas[1], eps)
     kernel_timer.stop(ev)
+
+
+class CapturedAdam:
+    """The same update for a CUDA-graph-captured step (fsb_adam_multi_dev).
+
+    A captured launch freezes its by-value arguments, so the per-step scalars (lr / (1 - beta1^t), sqrt(1 - beta2^t))
+    live in a small device buffer that `advance()` refreshes before every replay with fsb_upload_small (the bytes
+    ride in kernel arguments: no pinned staging, no synchronisation).  `advance()` also moves the optimizers'
+    `state[p]["step"]` forward, so the state stays what torch.optim.Adam would hold; `rollback(k)` undoes k steps
+    that the device skipped (skip_flag raised by an overflowed static-capacity step)."""
+
+    def __init__(self, optimizers: Iterable[FusedAdam]):
+        self.entries = []  # (optimizer, group, param)
+        for opt in optimizers:
+            for group in opt.param_groups:
+                for p in group["params"]:
+                    self.entries.append((opt, group, p))
+        maxt = lib.fsb_adam_max_tensors()
+        if not 0 < len(self.entries) <= maxt:
+            raise RuntimeError(f"CapturedAdam handles 1..{maxt} parameter tensors, got {len(self.entries)}")
+        g0 = self.entries[0][1]
+        self.betas, self.eps = g0["betas"], g0["eps"]
+        for opt, group, p in self.entries:
+            if group["betas"] != self.betas or group["eps"] != self.eps:
+                raise RuntimeError("CapturedAdam needs one (betas, eps) setting for all groups")
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("CapturedAdam needs contiguous fp32 CUDA parameters (no CPU fallback)")
+            st = opt.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        self.maxt = maxt
+        self.hyper = torch.zeros(2 * maxt, dtype=torch.float32, device=self.entries[0][2].device)
+        self._host = (ctypes.c_float * (2 * maxt))()
+
+    @torch.no_grad()
+    def launch(self, skip_flag=None) -> None:
+        """Inside the capture, after backward(): one launch for all tensors, scalars read from `self.hyper`."""
+        n = len(self.entries)
+        VP = ctypes.c_void_p * n
+        ps, gs, ms, vs, ns = [], [], [], [], []
+        for opt, group, p in self.entries:
+            if p.grad is None:
+                raise RuntimeError("CapturedAdam.launch: a parameter has no gradient in the captured step")
+            st = opt.state[p]
+            ps.append(p.data_ptr()); gs.append(p.grad.contiguous().data_ptr())
+            ms.append(st["exp_avg"].data_ptr()); vs.append(st["exp_avg_sq"].data_ptr()); ns.append(p.numel())
+        p_, g_, m_, v_ = VP(*ps), VP(*gs), VP(*ms), VP(*vs)
+        numel = (ctypes.c_int64 * n)(*ns)
+        check(lib.fsb_adam_multi_dev(n, ctypes.addressof(p_), ctypes.addressof(g_), ctypes.addressof(m_),
+                                     ctypes.addressof(v_), ctypes.addressof(numel), self.hyper.data_ptr(),
+                                     None if skip_flag is None else skip_flag.data_ptr(), self.betas[0],
+                                     self.betas[1], self.eps, _stream()), "fsb_adam_multi_dev")
+
+    def advance(self) -> None:
+        """Before every replay: step counts += 1, then upload this step's scalars (stream-ordered)."""
+        b1, b2 = self.betas
+        for i, (opt, group, p) in enumerate(self.entries):
+            st = opt.state[p]
+            st["step"] = st["step"] + 1
+            t = float(st["step"])
+            self._host[i] = group["lr"] / (1.0 - b1 ** t)
+            self._host[self.maxt + i] = (1.0 - b2 ** t) ** 0.5
+        check(lib.fsb_upload_small(self.hyper.data_ptr(), ctypes.addressof(self._host), 8 * self.maxt, _stream()),
+              "fsb_upload_small")
+
+    def rollback(self, k: int) -> None:
+        for opt, group, p in self.entries:
+            opt.state[p]["step"] = opt.state[p]["step"] - k

@@ -73,24 +73,36 @@ size_t fsb_isect_scan_workspace(int64_t M);
 int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, int64_t* total_dev, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* STATIC-CAPACITY MODE (every function below that takes an `n_dev` / `n_isects_dev` pointer).
+ * gsplat reads the intersection count back to the host between the count and the emit stage (one stream sync per
+ * render).  When the pointer is non-NULL the host passes the CAPACITY of the list buffers as the count and a
+ * device pointer to the true count (the total written by fsb_isect_scan); kernels work on min(true, capacity),
+ * grids are sized for the capacity, and the whole render -> backward -> Adam step becomes a fixed launch sequence
+ * that a CUDA graph can capture.  fsb_isect_emit raises *overflow_flag when the true count exceeds the capacity;
+ * fsb_adam_multi_dev / fsb_densify_stats then leave the state untouched, so an overflowed step is a no-op that
+ * the host re-runs with a larger capacity. */
+
 /* I1 (emit): isect_ids[n_isects] = (cam << (32+tile_bits)) | (tile << 32) | float_bits(depth),
- * flatten_ids[n_isects] = cam*N + n.  replaces gsplat isect_tiles pass 2 / map_gaussian_to_intersects. */
+ * flatten_ids[n_isects] = cam*N + n.  replaces gsplat isect_tiles pass 2 / map_gaussian_to_intersects.
+ * n_dev nullable; with it, `capacity` entries are the most that is written and overflow_flag (nullable, i32,
+ * never cleared here) is set when *n_dev > capacity. */
 int fsb_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
                    const int64_t* offsets, int tile_size, int tile_w, int tile_h, int tile_bits,
-                   int legacy_bbox, int64_t* isect_ids, int32_t* flatten_ids, void* stream);
+                   int legacy_bbox, const int64_t* n_dev, int64_t capacity, int32_t* overflow_flag,
+                   int64_t* isect_ids, int32_t* flatten_ids, void* stream);
 
 /* I2: stable LSD radix sort of (u64 key, i32 value) pairs on key bits [0, end_bit).
  * replaces cub::DeviceRadixSort::SortPairs in gsplat isect_tiles and torch.sort in the legacy path.
  * Buffers A (input, clobbered) and B ping-pong; *result_in_b (host int) = 1 if B holds the result. */
 size_t fsb_radix_sort_workspace(int64_t n, int end_bit);
-int fsb_radix_sort_pairs(int64_t n, int end_bit, uint64_t* keys_a, int32_t* vals_a, uint64_t* keys_b,
-                         int32_t* vals_b, void* workspace, size_t workspace_bytes, int* result_in_b,
-                         void* stream);
+int fsb_radix_sort_pairs(int64_t n, const int64_t* n_dev, int end_bit, uint64_t* keys_a, int32_t* vals_a,
+                         uint64_t* keys_b, int32_t* vals_b, void* workspace, size_t workspace_bytes,
+                         int* result_in_b, void* stream);
 
 /* I3: offsets[C, n_tiles] i32 = first sorted position of each (camera, tile).
  * replaces gsplat isect_offset_encode / legacy get_tile_bin_edges. */
-int fsb_isect_offsets(int64_t n_isects, const int64_t* sorted_ids, int C, int n_tiles, int tile_bits,
-                      int32_t* offsets, void* stream);
+int fsb_isect_offsets(int64_t n_isects, const int64_t* n_dev, const int64_t* sorted_ids, int C, int n_tiles,
+                      int tile_bits, int32_t* offsets, void* stream);
 
 /* R1: tile compositing forward.  replaces gsplat rasterize_to_pixels fwd / legacy rasterize_forward.
  *   means2d[C*N,2] conics[C*N,3] colors[C*N,D] opacities[C*N] ; backgrounds[C,D] nullable ;
@@ -101,7 +113,7 @@ int fsb_isect_offsets(int64_t n_isects, const int64_t* sorted_ids, int C, int n_
  * D must be one of fsb_raster_supported_channels(); tile_size 8 or 16. */
 int fsb_raster_supported_channels(int D);
 size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D);
-int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
+int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d, const float* conics,
                    const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
                    int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
                    const int32_t* flatten_ids, int ed_normalize, void* workspace, size_t workspace_bytes,
@@ -111,7 +123,7 @@ int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const float* means2d, 
  *   workspace: the buffer filled by the matching fsb_raster_fwd call.
  *   v_means2d_abs nullable (absgrad=True in dn_splatter/dn_model.py:587); v_means2d nullable (2-D means detached,
  *   dn_model.py:638). */
-int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const float* means2d, const float* conics,
+int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d, const float* conics,
                    const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
                    int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
                    const int32_t* flatten_ids, int ed_normalize, void* workspace, size_t workspace_bytes,
@@ -212,6 +224,19 @@ int fsb_adam_max_tensors(void);
 int fsb_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                    const int64_t* n, const double* lr, const int64_t* step, double beta1, double beta2, double eps,
                    void* stream);
+/* Same update with the per-tensor scalars read from DEVICE memory, for a CUDA-graph-captured step whose launch
+ * arguments are frozen: hyper_dev[2 * fsb_adam_max_tensors()] fp32 = step_size[i] = lr_i / (1 - beta1^t_i) at
+ * [i] and sqrt(1 - beta2^t_i) at [fsb_adam_max_tensors() + i], refreshed by the host before every replay
+ * (fsb_upload_small).  skip_flag (nullable, device i32): non-zero -> nothing is updated (overflowed step). */
+int fsb_adam_multi_dev(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                       const int64_t* n, const float* hyper_dev, const int32_t* skip_flag, double beta1,
+                       double beta2, double eps, void* stream);
+
+/* Stream-ordered upload of up to fsb_upload_small_max() bytes from HOST memory to device memory: the bytes
+ * travel as kernel arguments, so the host buffer may be reused as soon as the call returns and nothing
+ * synchronises (per-replay scalars of a captured step: camera index, Adam step sizes). */
+int fsb_upload_small_max(void);
+int fsb_upload_small(void* dst_dev, const void* src_host, int bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DN-Splatter regulariser, fused.  replaces dn_splatter/dn_model.py:722-736 (EdgeAwareLogL1 on sensor depth,
@@ -247,9 +272,10 @@ int fsb_gaussian_normals_bwd(int N, const float* quats, const float* scales, con
 
 /* Per-step densification statistics.  replaces nerfstudio splatfacto after_train, whose outputs
  * dn_splatter/dn_model.py:326-451 (refinement_after) consumes.  For radii[n] > 0:
- *   vis_counts[n] += 1 ; xys_grad_norm[n] += |grads2d[n]|_2 ; max_2Dsize[n] = max(., radii[n] / max_dim) */
+ *   vis_counts[n] += 1 ; xys_grad_norm[n] += |grads2d[n]|_2 ; max_2Dsize[n] = max(., radii[n] / max_dim)
+ * skip_flag (nullable, device i32): non-zero -> no-op (static-capacity mode, overflowed step). */
 int fsb_densify_stats(int N, const int32_t* radii, const float* grads2d, float max_dim, float* xys_grad_norm,
-                      float* vis_counts, float* max_2Dsize, void* stream);
+                      float* vis_counts, float* max_2Dsize, const int32_t* skip_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a13: pseudo ground-truth normals from a depth image.  replaces normal_from_depth_image

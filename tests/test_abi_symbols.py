@@ -28,21 +28,21 @@ def test_header_symbols_are_exported():
 def test_pure_host_entry_points_answer_without_a_gpu():
     from fusionsense_b200._abi import lib
 
-    assert lib.fsb_abi_version() == 1
+    assert lib.fsb_abi_version() == 2
     assert lib.fsb_raster_supported_channels(3) == 3 and lib.fsb_raster_supported_channels(6) == 8
     assert lib.fsb_raster_supported_channels(33) == -1
     assert lib.fsb_isect_scan_workspace(5000) == 3 * 8
     assert lib.fsb_radix_sort_workspace(10000, 44) > 6 * 256 * 4
     assert lib.fsb_adam_max_tensors() == 8 and lib.fsb_vh_max_views() >= 9
     # argument validation happens before any CUDA call
-    assert lib.fsb_radix_sort_pairs(-1, 44, None, None, None, None, None, 0, None, None) == 10001
+    assert lib.fsb_radix_sort_pairs(-1, None, 44, None, None, None, None, None, 0, None, None) == 10001
     ws = lib.fsb_raster_workspace(0, 1, 8)
     assert ws > 0
-    assert lib.fsb_raster_fwd(1, 1, 7, 0, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None, 0, 1, ws,
+    assert lib.fsb_raster_fwd(1, 1, 7, 0, None, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None, 0, 1, ws,
                               None, None, None, None) == 10001  # D = 7 is not an instantiated channel count
-    assert lib.fsb_raster_fwd(1, 1, 3, 0, None, None, None, None, None, None, 16, 16, 5, 1, 1, None, None, 0, 1, ws,
+    assert lib.fsb_raster_fwd(1, 1, 3, 0, None, None, None, None, None, None, None, 16, 16, 5, 1, 1, None, None, 0, 1, ws,
                               None, None, None, None) == 10001  # tile_size 5: not whole warps
-    assert lib.fsb_raster_fwd(1, 1, 3, 0, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None, 0, None,
+    assert lib.fsb_raster_fwd(1, 1, 3, 0, None, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None, 0, None,
                               0, None, None, None, None) == 10001  # missing workspace
 
 

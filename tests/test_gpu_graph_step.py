@@ -1,0 +1,166 @@
+"""GPU: static-capacity mode of the intersection pipeline (no host read of n_isects) and the CUDA-graph-captured
+training iteration built on it, against the eager path."""
+import pytest
+import torch
+
+from fusionsense_b200.synthetic import make_scene
+from tests.parity import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _scene(n=20000, W=320, H=240, views=3):
+    return make_scene(n, W, H, n_views=views, cfg_id=61, kind="bunny", fx=300.0)
+
+
+def _render_inputs(sc, cam=0):
+    return dict(means=sc.means, quats=sc.quats / sc.quats.norm(dim=-1, keepdim=True), scales=torch.exp(sc.scales),
+                opacities=torch.sigmoid(sc.opacities).squeeze(-1),
+                colors=torch.cat((sc.features_dc[:, None, :], sc.features_rest), dim=1),
+                viewmats=sc.viewmats[cam:cam + 1], Ks=sc.Ks[cam:cam + 1], width=sc.width, height=sc.height,
+                packed=False, render_mode="RGB+ED", sh_degree=3, absgrad=True)
+
+
+@pytest.mark.parametrize("slack", [1, 4097, 300000])
+def test_static_capacity_lists_are_bit_exact(slack):
+    """Same keys, same sort order, same offsets, same image as the exact-size path; the tail of the buffers beyond
+    the true count is never read."""
+    from fusionsense_b200 import ops
+    from fusionsense_b200.gsplat import rasterization
+
+    sc = _scene().to(DEV)
+    img0, a0, meta0 = rasterization(**_render_inputs(sc))
+    n = meta0["flatten_ids"].numel()
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    with ops.static_capacity(n + slack, flag) as st:
+        img1, a1, meta1 = rasterization(**_render_inputs(sc))
+        assert len(st.counts) == 1 and int(st.counts[0]) == n
+    assert int(flag) == 0
+    assert meta1["flatten_ids"].numel() == n + slack
+    assert torch.equal(meta1["isect_ids"][:n], meta0["isect_ids"])
+    assert torch.equal(meta1["flatten_ids"][:n], meta0["flatten_ids"])
+    assert torch.equal(meta1["isect_offsets"], meta0["isect_offsets"])
+    assert torch.equal(img1, img0) and torch.equal(a1, a0)
+
+
+def test_static_capacity_backward_matches_and_overflow_is_flagged():
+    from fusionsense_b200 import ops
+    from fusionsense_b200.gsplat import rasterization
+
+    sc = _scene().to(DEV)
+    grads = []
+    n = None
+    for static in (False, True):
+        inp = _render_inputs(sc)
+        leaves = {k: inp[k].detach().clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "colors")}
+        inp.update(leaves)
+        flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+        if static:
+            with ops.static_capacity(n + 12345, flag):
+                img, alpha, meta = rasterization(**inp)
+                ((img * img).sum() + alpha.sum()).backward()
+            assert int(flag) == 0
+        else:
+            img, alpha, meta = rasterization(**inp)
+            n = meta["flatten_ids"].numel()
+            ((img * img).sum() + alpha.sum()).backward()
+        grads.append({k: v.grad.clone() for k, v in leaves.items()})
+    for k in grads[0]:
+        assert_close(grads[1][k], grads[0][k], f"static.grad.{k}", tol=1e-5, outlier_frac=1e-4)
+    # capacity too small: flagged, nothing out of bounds (compute-sanitizer clean by construction: writes clamp)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    with ops.static_capacity(max(1, n // 3), flag):
+        img, alpha, meta = rasterization(**_render_inputs(sc))
+    torch.cuda.synchronize()
+    assert int(flag) == 1 and torch.isfinite(img).all()
+
+
+def _pair(**kw):
+    from fusionsense_b200.dn_step import DNSplatterStep, DNSplatterStepConfig
+
+    sc = _scene(n=15000, W=256, H=192, views=3)
+    eager = DNSplatterStep(sc, DNSplatterStepConfig(**kw), device=DEV, step=3000)
+    graphed = DNSplatterStep(sc, DNSplatterStepConfig(**kw), device=DEV, step=3000)
+    targets = {v: eager.render_targets(v) for v in range(3)}
+    return eager, graphed, targets
+
+
+def test_graphed_iterations_track_eager_iterations():
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    eager, graphed, targets = _pair()
+    runner = GraphedDNSplatterStep(graphed, targets)
+    order = [0, 1, 2, 1, 0, 2, 2, 0]
+    losses_e, losses_g = [], []
+    for v in order:
+        losses_e.append(float(eager.train_iteration(v, targets[v])))
+        runner.train_iteration(v)
+        losses_g.append(runner.poll()["loss"])
+    info = runner.poll()
+    assert runner.captures == 1 and runner.replays == len(order) and info["overflowed_steps"] == 0
+    assert info["n_isects"] > 0 and info["n_isects_normals"] >= info["n_isects"]
+    assert graphed.step == eager.step
+    for a, b in zip(losses_g, losses_e):
+        assert a == pytest.approx(b, rel=2e-4)
+    # float atomics make the two runs differ in the last bits of every gradient; after 8 Adam steps with
+    # eps = 1e-15 a sign flip of a ~0 gradient moves a parameter by up to lr per step, hence the outlier budget
+    for k in eager.gauss_params:
+        assert_close(graphed.gauss_params[k].data, eager.gauss_params[k].data, f"graph.param.{k}", tol=2e-3,
+                     outlier_frac=2e-2)
+    for k in ("vis_counts", "max_2Dsize"):
+        assert_close(getattr(graphed, k), getattr(eager, k), f"graph.stats.{k}", tol=1e-6, outlier_frac=1e-3)
+    for name, opt in graphed.optimizers.items():
+        p = opt.param_groups[0]["params"][0]
+        assert float(opt.state[p]["step"]) == float(eager.optimizers[name].state[eager.gauss_params[name]]["step"])
+
+
+def test_graphed_single_step_matches_eager_step_closely():
+    """One step from identical state: same loss to fp32 rounding, same parameters after Adam."""
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    eager, graphed, targets = _pair()
+    runner = GraphedDNSplatterStep(graphed, targets)
+    le = float(eager.train_iteration(1, targets[1]))
+    runner.train_iteration(1)
+    assert runner.poll()["loss"] == pytest.approx(le, rel=1e-5)
+    for k in eager.gauss_params:
+        assert_close(graphed.gauss_params[k].data, eager.gauss_params[k].data, f"graph1.param.{k}", tol=1e-5,
+                     outlier_frac=2e-3)
+    assert_close(graphed.xys_grad_norm, eager.xys_grad_norm, "graph1.xys_grad_norm", tol=1e-5, outlier_frac=1e-3)
+
+
+def test_overflowed_step_is_a_noop_and_recovers():
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    eager, graphed, targets = _pair()
+    runner = GraphedDNSplatterStep(graphed, targets, capacity=1000)  # far too small
+    before = {k: v.data.clone() for k, v in graphed.gauss_params.items()}
+    runner.train_iteration(0)
+    info = runner.poll()
+    assert info["new_overflows"] == 1 and graphed.step == 3000
+    for k, v in graphed.gauss_params.items():
+        assert torch.equal(v.data, before[k]), k
+    p = graphed.optimizers["means"].param_groups[0]["params"][0]
+    assert float(graphed.optimizers["means"].state[p]["step"]) == 0.0
+    assert float(graphed.optimizers["means"].state[p]["exp_avg"].abs().max()) == 0.0
+    assert runner.capacity > info["n_isects_normals"]
+    # the re-captured step now applies and matches the eager one
+    le = float(eager.train_iteration(0, targets[0]))
+    runner.train_iteration(0)
+    info = runner.poll()
+    assert info["new_overflows"] == 0 and runner.captures == 2 and graphed.step == 3001
+    assert info["loss"] == pytest.approx(le, rel=1e-5)
+
+
+def test_staged_targets_feed_the_replay():
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    eager, graphed, targets = _pair()
+    runner = GraphedDNSplatterStep(graphed, targets)
+    other = {k: (t * 0.5).cpu().pin_memory() for k, t in targets[2].items()}
+    nbytes = runner.stage(2, other)
+    assert nbytes == sum(t.numel() * 4 for t in other.values())
+    le = float(eager.train_iteration(2, {k: t.cuda() for k, t in other.items()}))
+    runner.train_iteration(2)
+    assert runner.poll()["loss"] == pytest.approx(le, rel=1e-5)
