@@ -69,6 +69,7 @@ class DNSplatterStepConfig:
     fused_optimizer: bool = True
     fused_losses: bool = True  # dn_regularizer_loss instead of the torch loss classes
     fused_glue: bool = True  # gaussian_normals / densify_stats kernels instead of the inline torch ops
+    overlap_normals_pass: bool = True  # captured step only: the normals pass runs on a second stream beside the RGB+ED pass
 
 
 def _torch_normal_from_depth_image(depths, fx, fy, cx, cy, img_size, c2w, device, smooth=False):
@@ -207,7 +208,37 @@ class DNSplatterStep:
         depth_im = render[:, ..., 3:4]
         depth_im = torch.where(alpha > 0, depth_im, depth_im.detach().max()).squeeze(0)
 
-        # per-Gaussian normals (dn_model.py:617-636)
+        # The normals pass needs only the projection outputs.  In a captured step (static-capacity mode: it bins on
+        # its own, no host read) it is forked onto a second stream right after the projection, so its binning, sort
+        # and compositing fill the SMs that the RGB+ED pass leaves idle in its kernel tails; autograd runs each
+        # backward on its forward's stream, so the two raster backwards overlap the same way.
+        proj_done = info.get("projection_done") if cfg.overlap_normals_pass else None
+        main_stream = side_stream = None
+        if proj_done is not None:
+            main_stream = torch.cuda.current_stream()
+            if getattr(self, "_normals_stream", None) is None:
+                self._normals_stream = torch.cuda.Stream()
+            side_stream = self._normals_stream
+            side_stream.wait_event(proj_done)
+            for t in (self.xys, self.depths, self.radii, self.conics, self.num_tiles_hit, c2w):
+                t.record_stream(side_stream)
+            torch.cuda.set_stream(side_stream)
+        try:
+            normals_im = self._normals_pass(quats_crop, scales_crop, means_crop, opacities_crop, c2w, H, W, BLOCK_WIDTH)
+        finally:
+            if side_stream is not None:
+                torch.cuda.set_stream(main_stream)
+        if side_stream is not None:
+            main_stream.wait_stream(side_stream)
+            normals_im.record_stream(main_stream)
+        normals_im = normals_im / normals_im.norm(dim=-1, keepdim=True)
+        normals_im = (normals_im + 1) / 2
+        return {"rgb": rgb.squeeze(0), "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
+                "background": background}
+
+    def _normals_pass(self, quats_crop, scales_crop, means_crop, opacities_crop, c2w, H, W, BLOCK_WIDTH):
+        """dn_model.py:617-653: per-Gaussian normals, then the legacy `rasterize_gaussians` pass over them."""
+        cfg = self.config
         if cfg.fused_glue and self.device.type == "cuda":
             from .gaussians import gaussian_normals
 
@@ -226,13 +257,9 @@ class DNSplatterStep:
             self.normals_world = normals.detach()
             normals = normals @ c2w.squeeze(0)[:3, :3]
         xys = self.xys[0, ...].detach()
-        normals_im = self._rasterize_gaussians(xys, self.depths[0, ...], self.radii, self.conics[0, ...],
+        return self._rasterize_gaussians(xys, self.depths[0, ...], self.radii, self.conics[0, ...],
                                          self.num_tiles_hit[0, ...], normals, torch.sigmoid(opacities_crop), H, W,
                                          BLOCK_WIDTH)
-        normals_im = normals_im / normals_im.norm(dim=-1, keepdim=True)
-        normals_im = (normals_im + 1) / 2
-        return {"rgb": rgb.squeeze(0), "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
-                "background": background}
 
     # ---- splatfacto base loss + dn_model.py:673-925 -----------------------------------------
     def get_loss_dict(self, outputs, batch) -> Dict[str, Tensor]:

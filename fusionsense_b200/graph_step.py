@@ -140,6 +140,10 @@ class GraphedDNSplatterStep:
             self._body(warmup=True)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # parameters that already took part in an eager backward own AccumulateGrad nodes tagged with that stream;
+        # with zero_grad(set_to_none=True) those nodes only store the incoming gradient (no launch), so the
+        # stream-mismatch notice torch prints for them does not apply to this capture
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         g = torch.cuda.CUDAGraph()
         n0 = lib.fsb_launch_count()
         with torch.cuda.graph(g, stream=side):

@@ -102,6 +102,13 @@ def rasterization(
         radius_clip, tile_size, sh_degree if use_sh else None, color_stride, depth_channel, calc_comp,
         totals[1:] if C == 1 else None)
 
+    # static-capacity mode (captured step): a caller may start work that needs only the projection outputs (the
+    # DN-Splatter normals pass) on another stream while this one bins and composites
+    proj_done = None
+    if ops.static_mode() is not None:
+        proj_done = torch.cuda.Event()
+        proj_done.record()
+
     opac = opacities[None].expand(C, N)
     if comps is not None:
         opac = opac * comps
@@ -182,4 +189,6 @@ def rasterization(
         "tile_size": tile_size,
         "n_cameras": C,
     }
+    if proj_done is not None:
+        meta["projection_done"] = proj_done  # extension, static-capacity mode only
     return render_colors, render_alphas, meta
