@@ -170,21 +170,11 @@ def run_ours(args):
     params = [model.gauss_params[k] for k in model.config.lrs]
     graph_mode = args.mode == "graph"
 
-    def allreduce_grads(ps, overflow=None):
-        # one flat NCCL all-reduce (SUM) over all Gaussian parameter gradients (59 floats per Gaussian) plus the
-        # overflow flag of the static-capacity step; the loss is pre-scaled by 1/world, so the sum is the mean
-        parts = [p.grad.reshape(-1) for p in ps]
-        if overflow is not None:
-            parts.append(overflow.float())
-        flat = torch.cat(parts)
-        dist.all_reduce(flat)
-        o = 0
-        for p in ps:
-            n = p.numel()
-            p.grad = flat[o:o + n].view_as(p)
-            o += n
-        if overflow is not None:
-            overflow.copy_(flat[o:o + 1] > 0)
+    from fusionsense_b200.dist import GradSync
+
+    # one flat NCCL all-reduce (SUM) over all Gaussian parameter gradients (59 floats per Gaussian) plus the
+    # overflow flag of the static-capacity step; the loss is pre-scaled by 1/world, so the sum is the mean
+    allreduce_grads = GradSync()
 
     runner = None
     if graph_mode:

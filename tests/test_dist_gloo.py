@@ -105,3 +105,68 @@ def test_flat_gradient_allreduce_keeps_replicas_identical(tmp_path):
     a, b = torch.load(f"{ret}.0"), torch.load(f"{ret}.1")
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+class _StatsModel:
+    """the attributes sync_densify_stats reads from DNSplatterModel / DNSplatterStep"""
+
+    def __init__(self, n, rank):
+        g = torch.Generator().manual_seed(7 + rank)
+        self.gauss_params = {"means": torch.zeros(n, 3)}
+        self.num_points = n
+        self.xys_grad_norm = torch.rand(n, generator=g)
+        self.vis_counts = torch.ones(n) + torch.randint(0, 5, (n,), generator=g).float()
+        self.max_2Dsize = torch.rand(n, generator=g) if rank == 0 else None  # rank 1 accumulated nothing yet
+
+
+def _sync_worker(rank, world, port, ret):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fusionsense_b200.dist import GradSync, split_generator, sync_densify_stats
+
+        m = _StatsModel(64, rank)
+        sync_densify_stats(m)
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(64, 3)), torch.nn.Parameter(torch.randn(64, 1))]
+        g = torch.Generator().manual_seed(100 + rank)
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g)
+        overflow = torch.tensor([1 if rank == 1 else 0], dtype=torch.int32)
+        sync = GradSync()
+        sync(params, overflow)
+        draws = torch.randn(5, 3, generator=split_generator(3, 1200, "cpu"))
+        torch.save({"grad": [p.grad.clone() for p in params], "overflow": overflow, "draws": draws,
+                    "stats": (m.xys_grad_norm, m.vis_counts, m.max_2Dsize)}, f"{ret}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_sync_and_densify_stats_world2(tmp_path):
+    ret = str(tmp_path / "sync")
+    mp.spawn(_sync_worker, args=(2, 29535, ret), nprocs=2, join=True)
+    a, b = torch.load(f"{ret}.0"), torch.load(f"{ret}.1")
+    for x, y in zip(a["grad"], b["grad"]):
+        assert torch.equal(x, y)
+    g0, g1 = torch.Generator().manual_seed(100), torch.Generator().manual_seed(101)
+    want = torch.randn(64, 3, generator=g0) + torch.randn(64, 3, generator=g1)
+    assert torch.allclose(a["grad"][0], want)
+    assert int(a["overflow"]) == 1 and int(b["overflow"]) == 1  # any rank's overflow skips the step everywhere
+    assert torch.equal(a["draws"], b["draws"])
+    m0, m1 = _StatsModel(64, 0), _StatsModel(64, 1)
+    for x, y in zip(a["stats"], b["stats"]):
+        assert torch.equal(x, y)
+    assert torch.allclose(a["stats"][0], m0.xys_grad_norm + m1.xys_grad_norm)
+    assert torch.equal(a["stats"][1], m0.vis_counts + m1.vis_counts - 1.0)
+    assert torch.equal(a["stats"][2], m0.max_2Dsize)
+
+
+def test_shard_views_covers_global_batch():
+    from fusionsense_b200.dist import shard_views
+
+    for world in (1, 2, 4, 8):
+        for step in range(5):
+            got = sorted(v for r in range(world) for v in shard_views(step, r, world, n_views=1000))
+            assert got == list(range(step * world, (step + 1) * world))
+    assert shard_views(3, 1, 2, n_views=9) == [(3 * 2 + 1) % 9]
