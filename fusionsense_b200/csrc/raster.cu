@@ -27,7 +27,7 @@
 //   backward    needs no chain at all: the forward leaves, per (segment, pixel), the transmittance after the
 //               segment and the colour accumulated through it, so every segment replays independently.
 //
-// Inside a CTA (tile_size x tile_size threads, one pixel each, a warp owns a strip of 32/tile_size rows) warps
+// Inside a CTA (tile_size x tile_size threads, one pixel each, a warp owns an 8 x 4 pixel footprint) warps
 // walk only the entries whose reach mask has their bit (ballot + find-first-set); forward evaluates four
 // entries together for ILP; backward reduces the 8 + D per-Gaussian partials with a transposing butterfly
 // (16 shuffles) that leaves each total in its own lane, so one warp-wide red.global.add updates all of them.
@@ -64,7 +64,9 @@ struct Workspace {
     float* chain_T;      // [max_segs, 256]  transmittance after the segment; negative = pixel finished
     int32_t* chain_last; // [max_segs, 256]  last contributing list position so far (-1: none in a local state)
     float* prefix_C;     // [max_segs, 256, D] colour accumulated through the segment
-    int32_t* done_k;     // [n_tiles, 8]  per warp strip: the first segment after which all its pixels are finished
+    int32_t* done_k;     // [n_tiles, 8]  per warp footprint: the first segment after which all its pixels are finished
+    int32_t* seg_order;  // [max_segs]  launch order of the segments: longest first (see seg_table_kernel)
+    int32_t* tile_order; // [n_tiles]   launch order of the tiles' first segments: longest first
 };
 
 inline int64_t max_segments(int64_t n_isects, int64_t n_tiles, int D) { return n_isects / seg_len(D) + n_tiles; }
@@ -77,6 +79,8 @@ inline size_t ws_bytes(int64_t n_isects, int64_t n_tiles, int D) {
     b += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256) * 2;  // chain_T, chain_last
     b += fsb_align_up((size_t)ms * MAX_BLOCK * D * 4, 256);  // prefix_C
     b += fsb_align_up((size_t)n_tiles * 8 * 4, 256);         // done_k
+    b += fsb_align_up((size_t)ms * 4, 256);                  // seg_order
+    b += fsb_align_up((size_t)n_tiles * 4, 256);             // tile_order
     return b;
 }
 
@@ -90,18 +94,24 @@ inline Workspace carve_ws(void* base, int64_t n_isects, int64_t n_tiles, int D) 
     w.chain_T = (float*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
     w.chain_last = (int32_t*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * 4, 256);
     w.prefix_C = (float*)p; p += fsb_align_up((size_t)ms * MAX_BLOCK * D * 4, 256);
-    w.done_k = (int32_t*)p;
+    w.done_k = (int32_t*)p; p += fsb_align_up((size_t)n_tiles * 8 * 4, 256);
+    w.seg_order = (int32_t*)p; p += fsb_align_up((size_t)ms * 4, 256);
+    w.tile_order = (int32_t*)p;
     return w;
 }
+
+constexpr int LPT_BINS = 16;
 
 // ---- segment table: one block scans ceil(len / SEG) over the tiles -------------------------------------------
 __global__ void __launch_bounds__(1024)
 seg_table_kernel(int n_tiles, int64_t n_isects, const int64_t* __restrict__ n_dev, int SEG,
                  const int32_t* __restrict__ tile_offsets, int32_t* __restrict__ seg_start,
-                 int32_t* __restrict__ seg_tile, SegHeader* __restrict__ hdr) {
+                 int32_t* __restrict__ seg_tile, SegHeader* __restrict__ hdr, int32_t* __restrict__ seg_order,
+                 int32_t* __restrict__ tile_order) {
     n_isects = fsb_eff_n(n_isects, n_dev);
     __shared__ int s_warp[32];
     __shared__ int s_carry;
+    __shared__ int s_bins[2][LPT_BINS + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -137,15 +147,71 @@ seg_table_kernel(int n_tiles, int64_t n_isects, const int64_t* __restrict__ n_de
         seg_start[n_tiles] = s_carry;
         hdr->total_segs = s_carry;
     }
+    // Launch order, longest work unit first (LPT): CTA durations follow the segment length (1 .. SEG entries), and
+    // with grid order = tile order a few long segments picked up late leave most SMs idle in the kernel's tail
+    // (ncu: sm__cycles_active avg / max = 0.65 on the 640x480 bench scene).  Counting sort into LPT_BINS length
+    // classes; the order inside a class is arbitrary (results do not depend on which CTA runs which unit).
+    if (tid < 2 * (LPT_BINS + 1)) (&s_bins[0][0])[tid] = 0;
+    __syncthreads();
+    const int total = s_carry;
+    auto unit_len = [&](int t, int k) {
+        const int32_t b = tile_offsets[t];
+        const int32_t e = (t == n_tiles - 1) ? (int32_t)n_isects : tile_offsets[t + 1];
+        return min(SEG, max(0, e - b - k * SEG));
+    };
+    auto bin_of = [&](int n) { return (int)(((int64_t)(SEG - n) * LPT_BINS) / (SEG + 1)); };
+    for (int pass = 0; pass < 2; ++pass) {  // 0: count, 1: scatter
+        for (int base = 0; base < n_tiles; base += 1024) {
+            const int t = base + tid;
+            const int bin = (t < n_tiles) ? bin_of(unit_len(t, 0)) : LPT_BINS;
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            const int leader = __ffs(peers) - 1;
+            int at = 0;
+            if (lane == leader) at = atomicAdd(&s_bins[0][bin], __popc(peers));
+            at = __shfl_sync(0xffffffffu, at, leader) + __popc(peers & ((1u << lane) - 1u));
+            if (pass == 1 && t < n_tiles) tile_order[at] = t;
+        }
+        for (int base = 0; base < total; base += 1024) {
+            const int sg = base + tid;
+            int bin = LPT_BINS;
+            if (sg < total) {
+                const int t = seg_tile[sg];
+                bin = bin_of(unit_len(t, sg - seg_start[t]));
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            const int leader = __ffs(peers) - 1;
+            int at = 0;
+            if (lane == leader) at = atomicAdd(&s_bins[1][bin], __popc(peers));
+            at = __shfl_sync(0xffffffffu, at, leader) + __popc(peers & ((1u << lane) - 1u));
+            if (pass == 1 && sg < total) seg_order[at] = sg;
+        }
+        __syncthreads();
+        if (pass == 0 && tid < 2) {  // counts -> exclusive start positions
+            int run = 0;
+            for (int b = 0; b < LPT_BINS; ++b) {
+                const int c = s_bins[tid][b];
+                s_bins[tid][b] = run;
+                run += c;
+            }
+            s_bins[tid][LPT_BINS] = 0;
+        }
+        __syncthreads();
+    }
 }
 
 struct TileGeom {
     int cam, tile_x, tile_y;
-    int block_size, tr, lane, warp, n_warps, rows_per_warp;
+    int block_size, tr, lane, warp, n_warps, warps_x;
     int i, j;
     float px, py;
     bool inside;
 };
+
+// Pixel footprint of a warp: 8 x 4 pixels (lane = 8 * row + column), the warps of a 16 x 16 tile laid out 2 across
+// and 4 down.  A near-square footprint is hit by fewer splats than a 16 x 2 strip of rows (a splat of diameter d
+// touches ~(1 + d/8)(1 + d/4) footprints instead of (1 + d/16)(1 + d/2): 20 % fewer for d = 4..8 px), and every
+// footprint a splat misses is a list entry that warp never evaluates.
+constexpr int FOOT_W = 8, FOOT_H = 4;
 
 __device__ __forceinline__ TileGeom tile_geom(int64_t tile_lin, int tile_w, int tile_h, int tile_size, int width,
                                               int height) {
@@ -160,34 +226,47 @@ __device__ __forceinline__ TileGeom tile_geom(int64_t tile_lin, int tile_w, int 
     g.lane = g.tr & 31;
     g.warp = g.tr >> 5;
     g.n_warps = g.block_size >> 5;
-    g.rows_per_warp = 32 / tile_size;
-    g.i = g.tile_y * tile_size + threadIdx.y;
-    g.j = g.tile_x * tile_size + threadIdx.x;
+    g.warps_x = tile_size / FOOT_W;
+    const int wy = g.warp / g.warps_x, wx = g.warp - wy * g.warps_x;
+    g.i = g.tile_y * tile_size + wy * FOOT_H + (g.lane >> 3);
+    g.j = g.tile_x * tile_size + wx * FOOT_W + (g.lane & 7);
     g.px = (float)g.j + 0.5f;
     g.py = (float)g.i + 0.5f;
     g.inside = (g.i < height && g.j < width);
     return g;
 }
 
-// Which warp strips of this tile can the Gaussian reach with alpha >= 1/255 ?  Conservative by construction:
-// the ellipse {sigma <= ln(255 * opacity)} is inflated, and anything doubtful (non-PD conic, NaN) keeps all bits.
+// Which warp footprints of this tile can the Gaussian reach with alpha >= 1/255 ?  alpha >= 1/255 means
+// q(d) = a dx^2 + 2 b dx dy + c dy^2 <= 2 ln(255 opacity); the test is the exact minimum of q over the footprint's
+// rectangle of pixel centres (0 if the mean lies inside, else the smallest of the four edge minima, each a clamped
+// 1-D parabola), compared against an inflated threshold.  Projected surfels are thin rotated ellipses whose
+// bounding box is mostly empty, so this removes far more (footprint, entry) visits than a box test.  Anything
+// doubtful (non-PD conic, NaN) keeps all bits.
 __device__ __forceinline__ uint32_t strip_mask(float gx, float gy, float opac, float a, float b, float c,
-                                               float tile_px0, float tile_py0, int tile_size, int rows_per_warp,
+                                               float tile_px0, float tile_py0, int tile_size, int warps_x,
                                                int n_warps) {
     const uint32_t all = (1u << n_warps) - 1u;
-    const float tau = __logf(255.f * opac) + 2e-3f;
-    if (tau < 0.f) return 0u;  // opacity below 1/255: can never pass the alpha test
+    const float tau = __logf(255.f * opac);
+    if (tau + 2e-3f < 0.f) return 0u;  // opacity below 1/255: can never pass the alpha test
     const float det = a * c - b * b;
-    if (!(det > 0.f) || !(tau < 1e30f)) return all;
-    const float k = 2.f * tau / det;
-    const float ex = sqrtf(k * c) * 1.0001f + 1e-3f;
-    const float ey = sqrtf(k * a) * 1.0001f + 1e-3f;
-    if (gx + ex < tile_px0 + 0.5f || gx - ex > tile_px0 + (float)tile_size - 0.5f) return 0u;
+    if (!(det > 0.f) || !(a > 0.f) || !(tau < 1e30f)) return all;
+    const float thr = 2.f * tau * 1.0002f + 1e-2f;
+    const float nb_c = -b / c, nb_a = -b / a;
     uint32_t m = 0u;
     for (int w = 0; w < n_warps; ++w) {
-        const float y_lo = tile_py0 + (float)(w * rows_per_warp) + 0.5f;
-        const float y_hi = y_lo + (float)(rows_per_warp - 1);
-        if (!(gy + ey < y_lo) && !(gy - ey > y_hi)) m |= 1u << w;
+        const int wy = w / warps_x, wx = w - wy * warps_x;
+        // rectangle of this footprint's pixel centres, relative to the mean
+        const float x0 = tile_px0 + (float)(wx * FOOT_W) + 0.5f - gx, x1 = x0 + (float)(FOOT_W - 1);
+        const float y0 = tile_py0 + (float)(wy * FOOT_H) + 0.5f - gy, y1 = y0 + (float)(FOOT_H - 1);
+        float q = 0.f;
+        if (!(x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f)) {
+            float t, v;
+            t = fminf(fmaxf(nb_c * x0, y0), y1); q = a * x0 * x0 + 2.f * b * x0 * t + c * t * t;
+            t = fminf(fmaxf(nb_c * x1, y0), y1); v = a * x1 * x1 + 2.f * b * x1 * t + c * t * t; q = fminf(q, v);
+            t = fminf(fmaxf(nb_a * y0, x0), x1); v = a * t * t + 2.f * b * t * y0 + c * y0 * y0; q = fminf(q, v);
+            t = fminf(fmaxf(nb_a * y1, x0), x1); v = a * t * t + 2.f * b * t * y1 + c * y1 * y1; q = fminf(q, v);
+        }
+        if (!(q > thr)) m |= 1u << w;
     }
     return m;
 }
@@ -225,7 +304,7 @@ __device__ __forceinline__ void stage_entry(Stage<D>& s, int slot, int32_t g, co
     const float o = opacities[g];
     const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
     const uint32_t m = strip_mask(xy.x, xy.y, o, a, b, c, (float)(tg.tile_x * tile_size),
-                                  (float)(tg.tile_y * tile_size), tile_size, tg.rows_per_warp, tg.n_warps);
+                                  (float)(tg.tile_y * tile_size), tile_size, tg.warps_x, tg.n_warps);
     s.geo[slot] = make_float4(xy.x, xy.y, __log2f(o), __int_as_float((int)m));
     s.con[slot] = make_float4(-0.5f * LOG2E * a, -LOG2E * b, -0.5f * LOG2E * c, fast_rcp(o));
     const float* cp = colors + (size_t)g * D;
@@ -386,11 +465,11 @@ raster_seg_kernel(int C, int N, int64_t n_isects, const int64_t* __restrict__ n_
     int seg;
     int64_t tile_lin;
     if (PHASE == 0) {
-        tile_lin = blockIdx.x;
+        tile_lin = ws.tile_order[blockIdx.x];
         seg = ws.seg_start[tile_lin];
     } else {
-        seg = blockIdx.x;
-        if (seg >= ws.hdr->total_segs) return;
+        if ((int)blockIdx.x >= ws.hdr->total_segs) return;
+        seg = ws.seg_order[blockIdx.x];
         tile_lin = ws.seg_tile[seg];
         if (seg == ws.seg_start[tile_lin]) return;
     }
@@ -498,8 +577,8 @@ raster_stop_kernel(int C, int N, int64_t n_isects, const int64_t* __restrict__ n
                    const int32_t* __restrict__ flatten_ids, Workspace ws, FwdOut o) {
     __shared__ Stage<D> s;
     n_isects = fsb_eff_n(n_isects, n_dev);
-    const int seg = blockIdx.x;
-    if (seg >= ws.hdr->total_segs) return;
+    if ((int)blockIdx.x >= ws.hdr->total_segs) return;
+    const int seg = ws.seg_order[blockIdx.x];
     const int64_t tile_lin = ws.seg_tile[seg];
     if (seg == ws.seg_start[tile_lin]) return;  // first segments are exact already
     const int tr = threadIdx.y * blockDim.x + threadIdx.x;
@@ -603,8 +682,8 @@ raster_bwd_kernel(int C, int N, int64_t n_isects, const int64_t* __restrict__ n_
     __shared__ Stage<D> s;
     __shared__ int32_t s_wmax[MAX_BLOCK / 32];
     n_isects = fsb_eff_n(n_isects, n_dev);
-    const int seg = blockIdx.x;
-    if (seg >= ws.hdr->total_segs) return;
+    if ((int)blockIdx.x >= ws.hdr->total_segs) return;
+    const int seg = ws.seg_order[blockIdx.x];
     const int64_t tile_lin = ws.seg_tile[seg];
     if (masks != nullptr && !masks[tile_lin]) return;
     const int k = seg - ws.seg_start[tile_lin];
@@ -763,7 +842,8 @@ int launch_fwd(int C, int N, int64_t n_isects, const int64_t* n_dev, const float
                cudaStream_t st) {
     const int64_t n_tiles = (int64_t)C * tile_w * tile_h;
     Workspace ws = carve_ws(workspace, n_isects, n_tiles, D);
-    seg_table_kernel<<<1, 1024, 0, st>>>((int)n_tiles, n_isects, n_dev, seg_len(D), tile_offsets, ws.seg_start, ws.seg_tile, ws.hdr);
+    seg_table_kernel<<<1, 1024, 0, st>>>((int)n_tiles, n_isects, n_dev, seg_len(D), tile_offsets, ws.seg_start, ws.seg_tile, ws.hdr,
+                                         ws.seg_order, ws.tile_order);
     FSB_LAUNCH_CHECK();
     dim3 block(tile_size, tile_size);
     FwdOut o{backgrounds, ed_normalize, out_colors, out_alphas, last_ids};
@@ -816,8 +896,8 @@ int launch_bwd(int C, int N, int64_t n_isects, const int64_t* n_dev, const float
 }
 
 bool bad_geometry(int C, int tile_size, int64_t n_isects) {
-    // whole warps made of whole rows: tile_size 8 or 16 (the reference uses 16, dn_model.py:547)
-    return C <= 0 || tile_size < 2 || tile_size > 16 || (tile_size * tile_size) % 32 != 0 || 32 % tile_size != 0 ||
+    // whole 8 x 4 warp footprints: tile_size 8 or 16 (the reference uses 16, dn_model.py:547)
+    return C <= 0 || tile_size < 8 || tile_size > 16 || tile_size % 8 != 0 ||
            n_isects < 0 || n_isects > 0x7fffffffLL;
 }
 

@@ -49,7 +49,7 @@ class GradSync:
         self._flat: Optional[Tensor] = None
         self._layout = None
 
-    def _buffer(self, params, extra: int) -> Tensor:
+    def _buffer(self, params: List[Tensor], extra: int) -> Tensor:
         layout = (tuple(p.numel() for p in params), extra, params[0].device, params[0].dtype)
         if self._flat is None or self._layout != layout:
             total = sum(layout[0]) + extra
@@ -57,23 +57,31 @@ class GradSync:
             self._layout = layout
         return self._flat
 
-    def __call__(self, params: Iterable[torch.nn.Parameter], overflow: Optional[Tensor] = None) -> None:
-        params = list(params)
-        if world_size(self.group) == 1:
-            return
-        flat = self._buffer(params, 1 if overflow is not None else 0)
-        parts = [p.grad.reshape(-1) for p in params]
+    def reduce(self, grads: List[Tensor], overflow: Optional[Tensor] = None) -> List[Tensor]:
+        """Pack `grads` (+ the overflow flag) into the flat buffer, all-reduce it (SUM) and return views of the
+        reduced buffer shaped like `grads`; `overflow` is overwritten with "any rank overflowed"."""
+        flat = self._buffer(grads, 1 if overflow is not None else 0)
+        parts = [g.reshape(-1) for g in grads]
         if overflow is not None:
             parts.append(overflow.reshape(-1)[:1].to(flat.dtype))
         torch.cat(parts, out=flat)
-        dist.all_reduce(flat, group=self.group)
-        o = 0
-        for p in params:
-            n = p.numel()
-            p.grad = flat[o:o + n].view_as(p)
+        if world_size(self.group) > 1:
+            dist.all_reduce(flat, group=self.group)
+        views, o = [], 0
+        for g in grads:
+            n = g.numel()
+            views.append(flat[o:o + n].view_as(g))
             o += n
         if overflow is not None:
             overflow.copy_(flat[o:o + 1] > 0)
+        return views
+
+    def __call__(self, params: Iterable[torch.nn.Parameter], overflow: Optional[Tensor] = None) -> None:
+        params = [p for p in params if p.grad is not None]
+        if world_size(self.group) == 1 or not params:
+            return
+        for p, v in zip(params, self.reduce([p.grad for p in params], overflow)):
+            p.grad = v
 
 
 @torch.no_grad()

@@ -58,6 +58,7 @@ class GraphedDNSplatterStep:
         self._overflow_seen = 0
         self.max_isects_seen = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_tail: Optional[torch.cuda.CUDAGraph] = None  # N > 1: Adam + statistics, after the eager all-reduce
         self.signature = None
         self.adam: Optional[CapturedAdam] = None
         self.captures = 0
@@ -92,10 +93,10 @@ class GraphedDNSplatterStep:
             m.training = training
         return worst
 
-    def _body(self, warmup: bool = False):
-        """One iteration in static-capacity mode on the current stream.  `warmup`: run eagerly before the capture
-        with the skip flag raised, so every lazy initialisation happens outside the graph while parameters, Adam
-        state and statistics stay untouched."""
+    def _body_main(self, warmup: bool = False):
+        """zero_grad -> get_outputs -> get_loss_dict -> backward in static-capacity mode on the current stream.
+        `warmup`: run eagerly before the capture with the skip flag raised, so every lazy initialisation happens
+        outside the graph while parameters, Adam state and statistics stay untouched."""
         m = self.model
         for opt in m.optimizers.values():
             opt.zero_grad(set_to_none=True)
@@ -110,19 +111,32 @@ class GraphedDNSplatterStep:
             loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
             (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
             counts = list(st.counts)
-        if self.grad_sync is not None:
-            self.grad_sync([p for p in m.gauss_params.values() if p.grad is not None], self.overflow)
+        return loss.detach(), counts
+
+    def _body_tail(self, loss, counts, warmup: bool = False):
+        """Adam (all groups, one launch) -> after_train statistics -> result vector."""
+        m = self.model
         self.adam.launch(skip_flag=self.overflow)
         m.after_train(skip_flag=self.overflow)
         if warmup:
             return
         with torch.no_grad():
-            self.result[0:1].copy_(loss.detach().reshape(1))
+            self.result[0:1].copy_(loss.reshape(1))
             self.result[1:2].add_(self.overflow)
             for i, c in enumerate(counts[:2]):
                 self.result[2 + i:3 + i].copy_(c)
 
+    def _sync_grads(self):
+        """Multi-GPU exchange step between backward and Adam, launched eagerly on the current stream: the
+        gradients the captured backward left in its (address-stable) buffers are packed with the overflow flag,
+        all-reduced, and handed to Adam as views of the reduced buffer."""
+        views = self.grad_sync.reduce(self._grad_src, self.overflow)
+        return views
+
     def capture(self) -> None:
+        """Single GPU: the whole iteration is one graph.  With a `grad_sync` (N > 1) it is two graphs with the
+        NCCL all-reduce launched eagerly between them: a collective captured inside the replayed graph hung the
+        2-GPU bench on the B200 box (r01), and one extra graph launch per step is far below the step time."""
         m = self.model
         if self.capacity is None or self.capacity <= 0:
             seen = self.max_isects_seen or self._probe_capacity()
@@ -133,11 +147,17 @@ class GraphedDNSplatterStep:
         if m.max_2Dsize is None:
             m.max_2Dsize = torch.zeros(m.num_points, device=self.device, dtype=torch.float32)
         self.adam = CapturedAdam(m.optimizers.values())
-        self.graph = None
+        self.graph = self.graph_tail = None
+        params = [p for p in m.gauss_params.values()]
         side = self._side = getattr(self, "_side", None) or torch.cuda.Stream()  # warm-up and capture share it
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self._body(warmup=True)
+            loss, counts = self._body_main(warmup=True)
+            if self.grad_sync is not None:
+                self._grad_src = [p.grad for p in params if p.grad is not None]
+                for p, v in zip([p for p in params if p.grad is not None], self._sync_grads()):
+                    p.grad = v
+            self._body_tail(loss, counts, warmup=True)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         # parameters that already took part in an eager backward own AccumulateGrad nodes tagged with that stream;
@@ -146,10 +166,28 @@ class GraphedDNSplatterStep:
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         g = torch.cuda.CUDAGraph()
         n0 = lib.fsb_launch_count()
-        with torch.cuda.graph(g, stream=side):
-            self._body()
+        if self.grad_sync is None:
+            with torch.cuda.graph(g, stream=side):
+                loss, counts = self._body_main()
+                self._body_tail(loss, counts)
+            tail = None
+        else:
+            with torch.cuda.graph(g, stream=side):
+                loss, counts = self._body_main()
+            live = [p for p in params if p.grad is not None]
+            self._grad_src = [p.grad for p in live]  # address-stable: rewritten by every replay of `g`
+            with torch.cuda.stream(side):
+                views = self._sync_grads()  # on capture-time garbage; fixes the reduced buffer Adam will read
+            for p, v in zip(live, views):
+                p.grad = v
+            torch.cuda.synchronize()
+            tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(tail, stream=side, pool=g.pool()):
+                self._body_tail(loss, counts)
+            self._keep = (loss, counts)  # read by the tail graph: keep the main graph's buffers alive
         self.launches_per_replay = int(lib.fsb_launch_count() - n0)
         self.graph = g
+        self.graph_tail = tail
         self.signature = self._signature()
         self.captures += 1
 
@@ -166,6 +204,9 @@ class GraphedDNSplatterStep:
         check(lib.fsb_upload_small(self.cam.data_ptr(), ctypes.addressof(self._cam_host), 8, ops._stream()),
               "fsb_upload_small")
         self.graph.replay()
+        if self.graph_tail is not None:
+            self._sync_grads()
+            self.graph_tail.replay()
         m.step += 1
         self.replays += 1
         return self.result

@@ -164,3 +164,31 @@ def test_staged_targets_feed_the_replay():
     le = float(eager.train_iteration(2, {k: t.cuda() for k, t in other.items()}))
     runner.train_iteration(2)
     assert runner.poll()["loss"] == pytest.approx(le, rel=1e-5)
+
+
+def test_two_graph_step_with_grad_sync_matches_single_graph():
+    """The N > 1 structure (main graph -> eager gradient exchange -> tail graph) on one GPU, where the exchange is
+    just the pack into the flat buffer: same losses and parameters as the single-graph step, overflow still a no-op."""
+    from fusionsense_b200.dist import GradSync
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    single, split, targets = _pair()
+    r1 = GraphedDNSplatterStep(single, targets)
+    r2 = GraphedDNSplatterStep(split, targets, grad_sync=GradSync())
+    for v in [0, 2, 1, 1, 0]:
+        r1.train_iteration(v)
+        r2.train_iteration(v)
+        assert r2.poll()["loss"] == pytest.approx(r1.poll()["loss"], rel=2e-4)
+    assert r2.graph_tail is not None and r1.graph_tail is None and r2.captures == 1
+    assert r2.poll()["overflowed_steps"] == 0 and split.step == single.step
+    for k in single.gauss_params:
+        assert_close(split.gauss_params[k].data, single.gauss_params[k].data, f"split.param.{k}", tol=2e-3,
+                     outlier_frac=2e-2)
+    # overflow in the split structure: the tail graph sees the flag the exchange step produced and skips Adam
+    _, small, targets = _pair()
+    r3 = GraphedDNSplatterStep(small, targets, capacity=1000, grad_sync=GradSync())
+    before = {k: v.data.clone() for k, v in small.gauss_params.items()}
+    r3.train_iteration(0)
+    assert r3.poll()["new_overflows"] == 1
+    for k, v in small.gauss_params.items():
+        assert torch.equal(v.data, before[k]), k
