@@ -42,6 +42,26 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _fp32_roofline(pairs, ktimes, D, clocks):
+    """Compositing is bound by the FP32 pipe, so next to the HBM fraction BASELINE.json asks for: algorithmic
+    pair-flops (forward Q (14 + 2 D), backward Q (40 + 6 D), Q = blended (pixel, entry) pairs counted
+    on the device by fsb_raster_pair_count) over the kernels' CUDA-event times, against 148 SMs x 128 FP32 lanes x
+    2 flop x the SM clock sampled under load."""
+    q = pairs.get(f"D{D}")
+    if not q:
+        return None
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 148 * 128 * 2 * mhz * 1e6 / 1e12
+    out = {"pairs_blended": q["blended"], "pairs_visited": q["visited"], "peak_tflops": peak,
+           "peak_source": f"148 SM x 128 lanes x 2 x {mhz:.0f} MHz (nominal FP32 FMA rate, not measured)"}
+    for name, flop_per_pair in (("raster_fwd", 14 + 2 * D), ("raster_bwd", 40 + 6 * D)):
+        ms = ktimes.get(f"{name}_D{D}", (float("nan"), 0))[0]
+        if ms == ms and ms > 0:
+            tf = q["blended"] * flop_per_pair / (ms * 1e-3) / 1e12
+            out[name] = {"flop_per_pair": flop_per_pair, "achieved_tflops": tf, "frac": tf / peak, "kernel_ms": ms}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -277,6 +297,12 @@ def run_ours(args):
         for i in range(6):
             eager_step(i, resident)
         ktimes = ops.kernel_timer.summary()
+    # pair counts (Q of SURVEY.md §8d) of one more eager step, counted by fsb_raster_pair_count after each forward
+    ops.pair_probe.enabled = True
+    eager_step(5, resident)
+    torch.cuda.synchronize()
+    ops.pair_probe.enabled = False
+    pairs = ops.pair_probe.summary()
 
     ms_per_step = ms_total / args.steps
     value = world * 1e3 / ms_per_step
@@ -300,6 +326,7 @@ def run_ours(args):
         "n_isects": I, "n_visible": Nv,
         "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md §8d); the HBM fraction is reported as "
                 "BASELINE.json asks, the pipe utilisation is in profiles/",
+        "fp32": _fp32_roofline(pairs, ktimes, D, clocks if rank == 0 else None),
         "kernel_ms_all": {k: round(v[0], 4) for k, v in sorted(ktimes.items())},
         "raster_fwd_bwd_mpix_per_s": (P / ((ktimes.get("raster_fwd_D4", (0, 0))[0] + bwd_ms) * 1e-3) / 1e6)
         if bwd_ms == bwd_ms and bwd_ms > 0 else None,

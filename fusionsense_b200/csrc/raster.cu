@@ -895,6 +895,55 @@ int launch_bwd(int C, int N, int64_t n_isects, const int64_t* n_dev, const float
     return 0;
 }
 
+// Measurement aid (bench.py roofline, not on the training path): per tile, the number of (pixel, entry) pairs the
+// forward BLENDED (entry at or before the pixel's last id that passes the sigma / alpha tests: exactly the pairs the
+// backward differentiates) and the number a list walk has to visit (every entry up to each pixel's last id).
+// counts[0] += blended, counts[1] += visited.  One CTA per tile, entries read straight from global memory.
+__global__ void __launch_bounds__(MAX_BLOCK)
+raster_pair_count_kernel(int C, int64_t n_isects, const int64_t* __restrict__ n_dev, const float2* __restrict__ means2d,
+                         const float* __restrict__ conics, const float* __restrict__ opacities, int width, int height,
+                         int tile_size, int tile_w, int tile_h, const int32_t* __restrict__ tile_offsets,
+                         const int32_t* __restrict__ flatten_ids, const int32_t* __restrict__ last_ids,
+                         unsigned long long* __restrict__ counts) {
+    __shared__ int32_t s_wmax[MAX_BLOCK / 32];
+    __shared__ unsigned long long s_sum[2];
+    n_isects = fsb_eff_n(n_isects, n_dev);
+    const int64_t tile_lin = blockIdx.x;
+    const TileGeom tg = tile_geom(tile_lin, tile_w, tile_h, tile_size, width, height);
+    const int32_t range_start = tile_offsets[tile_lin];
+    const int32_t range_end =
+        (tile_lin == (int64_t)C * tile_w * tile_h - 1) ? (int32_t)n_isects : tile_offsets[tile_lin + 1];
+    int32_t last = -1;
+    if (tg.inside && range_end > range_start) last = last_ids[((int64_t)tg.cam * height + tg.i) * width + tg.j];
+    int32_t wmax = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (tg.lane == 0) s_wmax[tg.warp] = wmax;
+    if (tg.tr < 2) s_sum[tg.tr] = 0ull;
+    __syncthreads();
+    int32_t cmax = -1;
+    for (int w = 0; w < tg.n_warps; ++w) cmax = max(cmax, s_wmax[w]);
+    unsigned blended = 0u, visited = 0u;
+    for (int32_t e = range_start; e <= min(cmax, range_end - 1); ++e) {
+        const int32_t g = flatten_ids[e];
+        const float2 xy = means2d[g];
+        const float o = opacities[g];
+        const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
+        const float4 geo = make_float4(xy.x, xy.y, __log2f(o), 0.f);
+        const float4 con = make_float4(-0.5f * LOG2E * a, -LOG2E * b, -0.5f * LOG2E * c, 0.f);
+        float dx, dy, p, au;
+        const float alpha = eval_alpha(geo, con, tg.px, tg.py, dx, dy, p, au);
+        if (e <= last) {
+            ++visited;
+            if (p <= 0.f && alpha >= ALPHA_MIN) ++blended;
+        }
+    }
+    atomicAdd(&s_sum[0], (unsigned long long)blended);
+    atomicAdd(&s_sum[1], (unsigned long long)visited);
+    __syncthreads();
+    if (tg.tr < 2 && s_sum[tg.tr]) atomicAdd(counts + tg.tr, s_sum[tg.tr]);
+}
+
 bool bad_geometry(int C, int tile_size, int64_t n_isects) {
     // whole 8 x 4 warp footprints: tile_size 8 or 16 (the reference uses 16, dn_model.py:547)
     return C <= 0 || tile_size < 8 || tile_size > 16 || tile_size % 8 != 0 ||
@@ -972,4 +1021,21 @@ FSB_API int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const int64_t*
                                       workspace, render_colors, render_alphas, last_ids, v_render_colors,
                                       v_render_alphas, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities,
                                       st)));
+}
+
+// Measurement aid: counts[2] u64 (device, zero-filled by the caller) += {blended, visited} (pixel, entry) pairs of
+// a finished forward pass (see raster_pair_count_kernel).  bench.py turns them into the FP32 roofline of R1 / R2.
+FSB_API int fsb_raster_pair_count(int C, int N, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d,
+                                  const float* conics, const float* opacities, int width, int height, int tile_size,
+                                  int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                  const int32_t* last_ids, uint64_t* counts, void* stream) {
+    (void)N;
+    if (bad_geometry(C, tile_size, n_isects) || !counts) return FSB_E_ARG;
+    if (tile_w <= 0 || tile_h <= 0 || n_isects == 0) return 0;
+    dim3 block(tile_size, tile_size);
+    raster_pair_count_kernel<<<(unsigned)((int64_t)C * tile_w * tile_h), block, 0, (cudaStream_t)stream>>>(
+        C, n_isects, n_isects_dev, (const float2*)means2d, conics, opacities, width, height, tile_size, tile_w, tile_h,
+        tile_offsets, flatten_ids, last_ids, (unsigned long long*)counts);
+    FSB_LAUNCH_CHECK();
+    return 0;
 }

@@ -287,7 +287,34 @@ def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
                              ptr(isect_offsets_t), ptr(flatten_ids), int(ed_normalize), ptr(ws), ws_bytes, ptr(out),
                              ptr(alphas), ptr(last_ids), _stream()), "fsb_raster_fwd")
     kernel_timer.stop(ev)
+    if pair_probe.enabled:
+        pair_probe.count(f"D{D}", C, N, flatten_ids, n_dev, means2d, conics, opacities, width, height, tile_size,
+                         tile_w, tile_h, isect_offsets_t, last_ids)
     return out, alphas, last_ids, ws
+
+
+class _PairProbe:
+    """Measurement aid for bench.py (off by default): after a forward pass, count the (pixel, entry) pairs it blended
+    and the pairs a per-pixel list walk visits (fsb_raster_pair_count) — the Q of SURVEY.md §8d's flop figures."""
+
+    def __init__(self):
+        self.enabled = False
+        self.results = {}
+
+    def count(self, key, C, N, flatten_ids, n_dev, means2d, conics, opacities, width, height, tile_size, tile_w,
+              tile_h, isect_offsets_t, last_ids):
+        counts = torch.zeros(2, dtype=torch.int64, device=means2d.device)
+        check(lib.fsb_raster_pair_count(C, N, flatten_ids.numel(), ptr(n_dev), ptr(means2d), ptr(conics), ptr(opacities),
+                                        width, height, tile_size, tile_w, tile_h, ptr(isect_offsets_t),
+                                        ptr(flatten_ids), ptr(last_ids), ptr(counts), _stream()),
+              "fsb_raster_pair_count")
+        self.results[key] = counts
+
+    def summary(self):
+        return {k: {"blended": int(v[0]), "visited": int(v[1])} for k, v in self.results.items()}
+
+
+pair_probe = _PairProbe()
 
 
 def raster_bwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,

@@ -131,6 +131,14 @@ int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isect
                    const float* v_render_colors, const float* v_render_alphas, float* v_means2d_abs,
                    float* v_means2d, float* v_conics, float* v_colors, float* v_opacities, void* stream);
 
+/* Measurement aid for bench.py's FP32 roofline (SURVEY.md §8d "Q = pair count"): counts[2] u64 (device, zeroed by
+ * the caller) += { (pixel, entry) pairs the finished forward blended, pairs a per-pixel list walk visits }.
+ * Nothing comparable exists in the reference; not on the training path. */
+int fsb_raster_pair_count(int C, int N, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d,
+                          const float* conics, const float* opacities, int width, int height, int tile_size,
+                          int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                          const int32_t* last_ids, uint64_t* counts, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Visual hull (voxel carving).  replaces utils/VisualHull.py:149-191 (projection/vote loop, threshold
  * mask, occupied-voxel extraction) with InitializeVoxels (:15-57) folded into axis-table lookups.

@@ -221,8 +221,11 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_w: int, tile_h: int) -> 
 # A.5 compositing  (gsplat rasterize_to_pixels_{fwd,bwd}_kernel semantics; backward via autograd)
 # --------------------------------------------------------------------------------------------
 def rasterize_to_pixels(means2d, conics, colors, opacities, width, height, tile_size, isect_offsets, flatten_ids,
-                        backgrounds=None, return_last_ids=False):
+                        backgrounds=None, return_last_ids=False, stats=None):
     """means2d [C,N,2] conics [C,N,3] colors [C,N,D] opacities [C,N] -> colors [C,H,W,D], alphas [C,H,W,1].
+
+    `stats` (optional dict) receives the pair counts of SURVEY.md §8d: "blended" = (pixel, entry) pairs composited,
+    "visited" = entries a per-pixel walk passes up to each pixel's last blended entry.
 
     Vectorised per tile: alpha [P, G] for the tile's P pixels and G list entries, exclusive cumprod for the
     transmittance, the T <= 1e-4 stop rule as a cumulative mask.  Differentiable (masks are constants, the
@@ -280,6 +283,9 @@ def rasterize_to_pixels(means2d, conics, colors, opacities, width, height, tile_
                     idx = torch.arange(s, e, dtype=torch.int32)[None].expand_as(contrib)
                     li = torch.where(contrib, idx, torch.zeros_like(idx)).max(dim=1).values
                     last_ids[c, y0:y1, x0:x1] = li.reshape(ph, pw)
+                    if stats is not None:
+                        stats["blended"] = stats.get("blended", 0) + int(contrib.sum())
+                        stats["visited"] = stats.get("visited", 0) + int(torch.clamp(li.long() - s + 1, min=0).sum())
                 if backgrounds is not None:
                     col = col + T_fin * backgrounds[c][None, None, :]
                 out_tiles[(c, ty, tx)] = (col, a)

@@ -161,6 +161,28 @@ def test_raster_forward(n, W, H, C, D, bg, mult, oshift):
     assert (last.cpu() != l_ref).float().mean() < 1e-3
 
 
+@pytest.mark.parametrize("n,W,H,C,mult,oshift", [(20000, 640, 480, 1, 3.0, 0.0), (40000, 128, 96, 2, 8.0, 1.0)])
+def test_raster_pair_count_matches_oracle(n, W, H, C, mult, oshift):
+    """fsb_raster_pair_count (the Q behind bench.py's FP32 roofline) against the oracle's own count of composited
+    pairs; threshold flips (alpha >= 1/255, T <= 1e-4) may move a handful of pairs."""
+    ops = _ops()
+    m2, con, colors, opac, bgs, offs, flat, _ = _raster_inputs(n, W, H, C, 3, seed=12, scale_mult=mult,
+                                                               opac_shift=oshift)
+    ops.pair_probe.enabled = True
+    try:
+        ops.raster_fwd(m2, con, colors, opac, None, None, W, H, 16, offs, flat)
+        got = ops.pair_probe.summary()["D3"]
+    finally:
+        ops.pair_probe.enabled = False
+    stats = {}
+    ref.rasterize_to_pixels(m2.cpu(), con.cpu(), colors.cpu(), opac.cpu(), W, H, 16, offs.cpu(), flat.cpu(),
+                            stats=stats)
+    assert stats["blended"] > 10 * W * H // 16
+    assert abs(got["blended"] - stats["blended"]) <= 1e-3 * stats["blended"], (got, stats)
+    assert abs(got["visited"] - stats["visited"]) <= 2e-3 * stats["visited"], (got, stats)
+    assert got["visited"] >= got["blended"]
+
+
 @pytest.mark.parametrize("pattern", [0x80000000, 0xFFFFFFFF, 0x7FC00000])
 def test_raster_forward_backward_on_dirty_workspace(pattern):
     """The per-call workspace comes from torch's caching allocator, i.e. it usually holds the previous call's
