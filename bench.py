@@ -224,7 +224,7 @@ def run_ours(args):
     def from_host(v):
         return {k: t.to(device, non_blocking=True) for k, t in host_targets[v].items()}
 
-    def one_step(i, staged, read_loss):
+    def one_step(i, staged, read_loss, n_total=1 << 30):
         """One training iteration; `staged`: this step's targets come from pinned host memory; `read_loss`: the
         step's result is read back to the host."""
         if runner is None:
@@ -233,11 +233,17 @@ def run_ours(args):
                 float(loss)
             return
         v = (i * world + rank) % N_VIEWS
-        if staged:
-            runner.stage(v, host_targets[v])
-        runner.train_iteration(v)
+        if staged and i == 0:
+            runner.stage_async(v, host_targets[v])
+        runner.train_iteration(v)  # waits for this view's copy
+        if staged and i + 1 < n_total:
+            # the next step's inputs travel while this step's kernels run (copy stream, pinned source)
+            vn = ((i + 1) * world + rank) % N_VIEWS
+            runner.stage_async(vn, host_targets[vn])
         if read_loss:
-            runner.poll()  # 32-byte D2H read of [loss, overflow count, n_isects x2]
+            # 32-byte D2H read of [loss, overflow count, n_isects x2] per step; the host consumes step i - 1's
+            # values here and the last step's after the loop (timed() drains the ring before the closing event)
+            runner.read_result_async()
 
     def timed(n_steps, staged, read_loss):
         if world > 1:
@@ -246,7 +252,9 @@ def run_ours(args):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(n_steps):
-            one_step(i, staged, read_loss)
+            one_step(i, staged, read_loss, n_steps)
+        if read_loss and runner is not None:
+            runner.poll()  # the last step's result (synchronises)
         e.record()
         if world > 1:
             dist.barrier()

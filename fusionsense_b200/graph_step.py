@@ -66,6 +66,11 @@ class GraphedDNSplatterStep:
         self.grad_sync = grad_sync
         self.loss_scale = float(loss_scale)
         self.launches_per_replay = 0  # libfsb200 kernels inside one replay (counted while capturing)
+        self._copy_stream = None
+        self._slot_staged: Dict[int, torch.cuda.Event] = {}  # view -> "prefetch finished"
+        self._slot_read: Dict[int, torch.cuda.Event] = {}    # view -> "last replay that read the slot finished"
+        self._host_ring = None
+        self._ev_prev = self._ev_last = None  # end of the replay before the most recent one / of the most recent one
 
     # ---- what the capture freezes ------------------------------------------------------------
     def _signature(self):
@@ -203,13 +208,67 @@ class GraphedDNSplatterStep:
         self._cam_host[0] = int(cam_idx)
         check(lib.fsb_upload_small(self.cam.data_ptr(), ctypes.addressof(self._cam_host), 8, ops._stream()),
               "fsb_upload_small")
+        staged = self._slot_staged.pop(int(cam_idx), None)
+        if staged is not None:
+            torch.cuda.current_stream().wait_event(staged)
         self.graph.replay()
+        self._ev_prev, self._ev_last = self._ev_last, torch.cuda.Event()
+        self._ev_last.record()
+        self._slot_read[int(cam_idx)] = self._ev_last
         if self.graph_tail is not None:
             self._sync_grads()
             self.graph_tail.replay()
         m.step += 1
         self.replays += 1
         return self.result
+
+    # ---- pipelined host <-> device traffic (the e2e leg of bench.py) ---------------------------------------
+    def stage_async(self, cam_idx: int, host_batch: Dict[str, Tensor]) -> int:
+        """Prefetch a view's targets from pinned host memory into its resident slot on a copy stream, so the copy
+        of the NEXT step's inputs overlaps this step's kernels.  `train_iteration(cam_idx)` waits for it.  The slot
+        must not be the one a replay in flight reads (callers prefetch the following step's view); the copy is
+        ordered after the last replay that read the slot."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        # the slot was last read by `_slot_read[cam_idx]`; a slot no tracked replay has read can only have been
+        # touched before the replay launched most recently (that one reads another view's slot)
+        ev = self._slot_read.get(cam_idx) or self._ev_prev
+        if ev is not None:
+            cs.wait_event(ev)
+        else:
+            cs.wait_stream(torch.cuda.current_stream())
+        n = 0
+        with torch.cuda.stream(cs):
+            for k, t in host_batch.items():
+                self.targets[k][cam_idx].copy_(t, non_blocking=True)
+                n += t.numel() * t.element_size()
+            done = torch.cuda.Event()
+            done.record(cs)
+        self._slot_staged[cam_idx] = done
+        return n
+
+    def read_result_async(self):
+        """Queue a 32-byte device -> host copy of this step's result vector into a pinned ring slot and return the
+        PREVIOUS step's values (or None on the first call): the host reads every step's loss while staying one
+        step ahead of the device instead of draining the stream each iteration."""
+        if self._host_ring is None:
+            self._host_ring = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._host_events = [None, None]
+            self._ring_i = 0
+        i = self._ring_i
+        self._host_ring[i].copy_(self.result, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._host_events[i] = ev
+        prev = None
+        j = 1 - i
+        if self._host_events[j] is not None:
+            self._host_events[j].synchronize()
+            prev = self._host_ring[j].tolist()
+            self.max_isects_seen = max(self.max_isects_seen, int(prev[2]), int(prev[3]))
+        self._ring_i = j
+        return prev
 
     def stage(self, cam_idx: int, host_batch: Dict[str, Tensor]) -> int:
         """Copy a view's targets from (pinned) host memory into its resident slot; returns the bytes moved."""

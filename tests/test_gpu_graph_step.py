@@ -166,6 +166,36 @@ def test_staged_targets_feed_the_replay():
     assert runner.poll()["loss"] == pytest.approx(le, rel=1e-5)
 
 
+def test_prefetched_targets_and_async_result_ring_match_the_blocking_path():
+    """bench.py's e2e leg: step i + 1's targets are copied on the copy stream while step i runs, and step i's result
+    is read one step late from a pinned ring.  Same losses as staging + polling synchronously."""
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    a, b, targets = _pair()
+    ra, rb = GraphedDNSplatterStep(a, targets), GraphedDNSplatterStep(b, targets)
+    # every step trains on a DIFFERENT host-side version of its view, so a late or early copy changes the loss
+    order = [0, 1, 2, 0, 1, 2, 1]
+    host = [{k: (t * (1.0 - 0.05 * i)).cpu().pin_memory() for k, t in targets[v].items()} for i, v in enumerate(order)]
+    blocking = []
+    for i, v in enumerate(order):
+        ra.stage(v, host[i])
+        ra.train_iteration(v)
+        blocking.append(ra.poll()["loss"])
+    piped = []
+    rb.stage_async(order[0], host[0])
+    for i, v in enumerate(order):
+        rb.train_iteration(v)
+        if i + 1 < len(order):
+            rb.stage_async(order[i + 1], host[i + 1])
+        prev = rb.read_result_async()
+        if prev is not None:
+            piped.append(prev[0])
+    piped.append(rb.poll()["loss"])
+    assert len(piped) == len(order)
+    for x, y in zip(piped, blocking):
+        assert x == pytest.approx(y, rel=2e-4)
+
+
 def test_two_graph_step_with_grad_sync_matches_single_graph():
     """The N > 1 structure (main graph -> eager gradient exchange -> tail graph) on one GPU, where the exchange is
     just the pack into the flat buffer: same losses and parameters as the single-graph step, overflow still a no-op."""
