@@ -106,6 +106,7 @@ isect_emit_kernel(int C, int N, const float* __restrict__ means2d, const int32_t
     // static-capacity mode: entries past the end of the buffers are dropped and the step is flagged as invalid
     const int64_t limit = n_dev ? capacity : INT64_MAX;
     if (idx == 0 && n_dev && overflow_flag && *n_dev > capacity) *overflow_flag = 1;
+    if (n_dev && *n_dev == 0) return;  // nothing to emit (also the "lists are shared" gate of fsb_isect_share_gate)
     int r = radii[idx];
     if (r <= 0) return;
     float2 m = reinterpret_cast<const float2*>(means2d)[idx];
@@ -167,7 +168,56 @@ isect_offsets_kernel(int64_t n_isects, const int64_t* __restrict__ n_dev, const 
     }
 }
 
+// ---- static-capacity mode: device-side decision to share the first pass's sorted lists with the legacy pass ----
+// The 0.1.x bbox of a Gaussian is a superset of its 1.0 bbox (truncation vs floor agree after the clamp at 0;
+// (int)(x + 1) >= ceil(x)), so equal intersection totals <=> identical tile sets <=> identical keys and sort order.
+__global__ void isect_share_gate_kernel(const int64_t* __restrict__ n_first, const int64_t* __restrict__ n_legacy,
+                                        int64_t* __restrict__ gate) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) gate[0] = (*n_first == *n_legacy) ? 0 : *n_legacy;
+}
+
+__global__ void __launch_bounds__(256)
+isect_share_copy_kernel(const int64_t* __restrict__ gate, const int64_t* __restrict__ n_list, int64_t capacity,
+                        const int32_t* __restrict__ src_flat, const int32_t* __restrict__ src_offsets,
+                        int64_t n_offsets, int32_t* __restrict__ dst_flat, int32_t* __restrict__ dst_offsets) {
+    if (*gate != 0) return;  // the legacy pass built its own lists
+    int64_t n = *n_list;
+    if (n > capacity) n = capacity;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst_flat[i] = src_flat[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_offsets; i += stride)
+        dst_offsets[i] = src_offsets[i];
+}
+
 }  // namespace
+
+// Static-capacity mode (no host read), legacy normals pass right after a rasterization() on the same Gaussians:
+// gate[0] = 0 when the legacy bbox rule yields the same number of intersections as the 1.0 rule (*n_first ==
+// *n_legacy: the sorted lists are then identical and can be shared), else *n_legacy.  Passed as `n_dev` to
+// fsb_isect_emit / fsb_radix_sort_pairs / fsb_isect_offsets it turns them into no-ops in the shared case.
+// Replaces the host-side decision the eager path takes in gsplat/cuda_legacy/_wrapper.py (one D2H read there).
+FSB_API int fsb_isect_share_gate(const int64_t* n_first, const int64_t* n_legacy, int64_t* gate, void* stream) {
+    if (!n_first || !n_legacy || !gate) return FSB_E_ARG;
+    isect_share_gate_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n_first, n_legacy, gate);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Shared case (gate[0] == 0): dst_flat[0 .. min(*n_list, capacity)) = src_flat, dst_offsets[0 .. n_offsets) =
+// src_offsets; otherwise nothing is touched.
+FSB_API int fsb_isect_share_copy(const int64_t* gate, const int64_t* n_list, int64_t capacity, const int32_t* src_flat,
+                                 const int32_t* src_offsets, int64_t n_offsets, int32_t* dst_flat,
+                                 int32_t* dst_offsets, void* stream) {
+    if (!gate || !n_list || capacity < 0 || n_offsets < 0) return FSB_E_ARG;
+    int64_t work = capacity > n_offsets ? capacity : n_offsets;
+    if (work == 0) return 0;
+    int blocks = fsb_div_up(work, 256 * 4);
+    if (blocks > FSB_NUM_SMS * 8) blocks = FSB_NUM_SMS * 8;
+    isect_share_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gate, n_list, capacity, src_flat, src_offsets,
+                                                                      n_offsets, dst_flat, dst_offsets);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
 
 FSB_API size_t fsb_isect_scan_workspace(int64_t M) {
     int64_t n_blocks = (M + SCAN_TILE - 1) / SCAN_TILE;

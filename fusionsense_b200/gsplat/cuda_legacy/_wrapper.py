@@ -20,7 +20,7 @@ _LAST_BINNING: dict = {}
 
 def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int, height: int, tile_size: int,
                      n_isects: int, flatten_ids: Tensor, isect_offsets: Tensor,
-                     legacy_extra: Optional[int] = None) -> None:
+                     legacy_extra: Optional[int] = None, lists_done=None) -> None:
     """Called by `rasterization()` (single-camera case only).
 
     `legacy_extra`: number of tiles by which the 0.1.x bbox rule differs from the 1.0 rule on these Gaussians,
@@ -32,6 +32,7 @@ def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int,
         key=(means2d.data_ptr(), depths.data_ptr(), radii.data_ptr(), means2d._version, depths._version,
              radii._version, radii.shape[1], width, height, tile_size),
         n_isects=n_isects, flatten_ids=flatten_ids, isect_offsets=isect_offsets, legacy_extra=legacy_extra,
+        lists_done=lists_done,  # static-capacity mode: event recorded after the binning (another stream may wait)
     )
 
 
@@ -93,14 +94,27 @@ def rasterize_gaussians(
         rad_c = radii1.contiguous()
         static = ops.static_mode()
         n_dev = None
-        cached = _LAST_BINNING if static is None and _LAST_BINNING.get("key") == (
+        same_inputs = _LAST_BINNING.get("key") == (
             xys_c.data_ptr(), dep_c.data_ptr(), rad_c.data_ptr(), xys._version, depths._version, radii._version,
-            N, W, H, ts) else None
+            N, W, H, ts)
+        cached = _LAST_BINNING if static is None and same_inputs else None
         if static is not None:
             # static-capacity mode (CUDA-graph capture): no host read, so whether the 0.1.x bbox rule adds tiles
-            # is not known here; bin with the legacy rule on the device-side count
-            _, _, flatten_ids, isect_offsets = ops.isect_tiles(xys_c[None], rad_c[None], dep_c[None], ts, tile_w,
-                                                               tile_h, legacy_bbox=True)
+            # is not known here.  Same xys / depths / radii as the rasterization() call just before: the device
+            # compares the two intersection totals and either reuses that call's sorted lists or bins and sorts
+            # with the legacy rule; otherwise bin with the legacy rule on the device-side count.
+            first_flat = _LAST_BINNING.get("flatten_ids") if same_inputs else None
+            if first_flat is not None and getattr(first_flat, "n_dev", None) is not None:
+                first_offsets = _LAST_BINNING["isect_offsets"]
+                cur = torch.cuda.current_stream()
+                first_flat.record_stream(cur)
+                first_offsets.record_stream(cur)
+                flatten_ids, isect_offsets = ops.isect_tiles_legacy_shared(
+                    xys_c[None], rad_c[None], dep_c[None], ts, tile_w, tile_h, first_flat, first_offsets,
+                    lists_done=_LAST_BINNING.get("lists_done"))
+            else:
+                _, _, flatten_ids, isect_offsets = ops.isect_tiles(xys_c[None], rad_c[None], dep_c[None], ts, tile_w,
+                                                                   tile_h, legacy_bbox=True)
             n_dev, n_isects, offsets = flatten_ids.n_dev, static.capacity, None
         elif cached is not None and cached.get("legacy_extra") == 0:
             # same xys / depths / radii as the rasterization() call just before, and its projection kernel found

@@ -121,8 +121,13 @@ def rasterization(
             means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
             totals=totals)
         n_dev = getattr(flatten_ids, "n_dev", None)  # static-capacity mode (ops.static_capacity): count on device
+        lists_done = None
+        if n_dev is not None:
+            lists_done = torch.cuda.Event()
+            lists_done.record()
         remember_binning(means2d, depths, radii, width, height, tile_size, flatten_ids.numel(), flatten_ids,
-                         isect_offsets, legacy_extra=totals.host[1] if (C == 1 and n_dev is None) else None)
+                         isect_offsets, legacy_extra=totals.host[1] if (C == 1 and n_dev is None) else None,
+                         lists_done=lists_done)
 
     if use_sh:
         ras_colors = sh_colors  # [C, N, 3 or 4], depth already in channel 3

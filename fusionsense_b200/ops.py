@@ -264,6 +264,41 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
     return tiles_per_gauss, ids, flat, tile_offsets
 
 
+def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h, first_flat, first_offsets,
+                              lists_done=None):
+    """Static-capacity mode only: binning of the legacy (gsplat 0.1.x bbox rule) normals pass that follows a
+    rasterization() on the same projected Gaussians.  The device compares the legacy intersection total with the
+    first pass's; when they agree (identical lists) emit / sort / offsets degenerate to no-ops and the first pass's
+    sorted lists are copied over (fsb_isect_share_gate / fsb_isect_share_copy), otherwise the legacy lists are
+    built as usual.  `lists_done`: event recorded after the first pass's binning (the copy waits for it, so the
+    count and scan of this pass may run beside it on another stream).  Returns (flatten_ids, isect_offsets)."""
+    st = static_mode()
+    assert st is not None and getattr(first_flat, "n_dev", None) is not None
+    _req_cuda(means2d, radii, depths)
+    C, N = radii.shape
+    dev = radii.device
+    counts = isect_count(means2d, radii, tile_size, tile_w, tile_h, True)
+    totals = torch.zeros(1, dtype=torch.int64, device=dev)
+    offsets, _ = isect_scan(counts, totals, read_back=False)
+    n_list = totals[:1]
+    st.counts.append(n_list)
+    gate = torch.empty(1, dtype=torch.int64, device=dev)
+    check(lib.fsb_isect_share_gate(ptr(first_flat.n_dev), ptr(n_list), ptr(gate), _stream()), "fsb_isect_share_gate")
+    ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h, True,
+                           n_dev=gate, overflow=st.overflow)
+    end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
+    ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=gate)
+    tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=gate)
+    if lists_done is not None:
+        torch.cuda.current_stream().wait_event(lists_done)
+    cap = min(flat.numel(), first_flat.numel())
+    check(lib.fsb_isect_share_copy(ptr(gate), ptr(n_list), cap, ptr(first_flat), ptr(first_offsets),
+                                   first_offsets.numel(), ptr(flat), ptr(tile_offsets), _stream()),
+          "fsb_isect_share_copy")
+    flat.n_dev = n_list
+    return flat, tile_offsets
+
+
 def supported_channels(D: int) -> int:
     return lib.fsb_raster_supported_channels(D)
 

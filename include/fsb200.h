@@ -104,6 +104,17 @@ int fsb_radix_sort_pairs(int64_t n, const int64_t* n_dev, int end_bit, uint64_t*
 int fsb_isect_offsets(int64_t n_isects, const int64_t* n_dev, const int64_t* sorted_ids, int C, int n_tiles,
                       int tile_bits, int32_t* offsets, void* stream);
 
+/* Static-capacity mode, legacy normals pass (dn_model.py:644-653) right after rasterization() (:570-591) on the same
+ * Gaussians: decide ON THE DEVICE whether the 0.1.x binning equals the 1.0 binning (equal intersection totals; the
+ * legacy bbox is a superset per Gaussian) and, if so, reuse the first pass's sorted lists instead of emitting and
+ * sorting again.  gate[0] = 0 (shared) or *n_legacy; pass `gate` as n_dev to emit / sort / offsets (no-ops when 0),
+ * then fsb_isect_share_copy fills the legacy buffers from the first pass's.  The eager path takes the same decision
+ * on the host (one D2H read). */
+int fsb_isect_share_gate(const int64_t* n_first, const int64_t* n_legacy, int64_t* gate, void* stream);
+int fsb_isect_share_copy(const int64_t* gate, const int64_t* n_list, int64_t capacity, const int32_t* src_flat,
+                         const int32_t* src_offsets, int64_t n_offsets, int32_t* dst_flat, int32_t* dst_offsets,
+                         void* stream);
+
 /* R1: tile compositing forward.  replaces gsplat rasterize_to_pixels fwd / legacy rasterize_forward.
  *   means2d[C*N,2] conics[C*N,3] colors[C*N,D] opacities[C*N] ; backgrounds[C,D] nullable ;
  *   masks[C*tiles] u8 nullable ; ed_normalize: divide channel D-1 by max(alpha,1e-10) ("ED" modes).

@@ -76,6 +76,40 @@ def test_static_capacity_backward_matches_and_overflow_is_flagged():
     assert int(flag) == 1 and torch.isfinite(img).all()
 
 
+@pytest.mark.parametrize("force_mismatch", [False, True])
+def test_device_side_list_sharing_for_the_legacy_pass(force_mismatch):
+    """Static-capacity mode: the legacy (0.1.x bbox) binning that follows a 1.0 binning of the same Gaussians either
+    reuses its sorted lists (equal totals) or builds its own (a Gaussian whose bbox edge sits exactly on a tile
+    boundary gains a tile under the legacy rule) -- decided on the device, bit exact against the legacy binning
+    done from scratch in both cases."""
+    from fusionsense_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    N, W, H, ts = 5000, 320, 240, 16
+    tw, th = W // ts, H // ts
+    m2 = (torch.rand(1, N, 2, generator=g) * torch.tensor([W, H])).to(DEV)
+    radii = torch.randint(0, 40, (1, N), generator=g, dtype=torch.int32).to(DEV)
+    depths = (torch.rand(1, N, generator=g) * 5 + 0.1).to(DEV)
+    if force_mismatch:
+        m2[0, :50, 0] = 64.0  # (x + r) / 16 is an integer: ceil() keeps it, the legacy (int)(.. + 1) adds a tile
+        radii[0, :50] = 32
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _, _, flat_ref, offs_ref = ops.isect_tiles(m2, radii, depths, ts, tw, th, legacy_bbox=True)
+    _, _, flat_10, _ = ops.isect_tiles(m2, radii, depths, ts, tw, th, legacy_bbox=False)
+    n_ref = flat_ref.numel()
+    assert (flat_10.numel() != n_ref) == force_mismatch
+    with ops.static_capacity(n_ref + 1000, flag) as st:
+        _, _, first_flat, first_offs = ops.isect_tiles(m2, radii, depths, ts, tw, th, legacy_bbox=False)
+        done = torch.cuda.Event()
+        done.record()
+        flat, offs = ops.isect_tiles_legacy_shared(m2, radii, depths, ts, tw, th, first_flat, first_offs,
+                                                   lists_done=done)
+        assert int(flat.n_dev) == n_ref and int(st.counts[-1]) == n_ref
+    assert int(flag) == 0
+    assert torch.equal(flat[:n_ref], flat_ref)
+    assert torch.equal(offs, offs_ref)
+
+
 def _pair(**kw):
     from fusionsense_b200.dn_step import DNSplatterStep, DNSplatterStepConfig
 
