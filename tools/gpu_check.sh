@@ -11,7 +11,7 @@ timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; tail -
 timeout 600 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench_graph.json 2> $OUT/${TAG}_bench_graph.err; tail -c 600 $OUT/${TAG}_bench_graph.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
    --log-file $OUT/${TAG}_launches_graph.csv env FSB_PROFILE=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'raster_(bwd|seg)_kernel' -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'raster_bwd_kernel' -c 2 \
    -o $OUT/${TAG}_raster_full -f env FSB_PROFILE=1 python bench.py --steps 1 --warmup 3 --mode eager --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 timeout 300 python tools/stage_bench.py cfg4 10 > $OUT/${TAG}_stage_cfg4.json 2> $OUT/${TAG}_stage_cfg4.err; tail -c 400 $OUT/${TAG}_stage_cfg4.json
 echo "elapsed ${SECONDS}s"; ls -la $OUT | tail -12
