@@ -42,6 +42,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _ncu_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE raster_bwd_kernel<4> launch on this workload,
+    from the committed `ncu --set full` capture (profiles/raster_bwd_traffic.json, written by
+    tools/ncu_traffic.py from the raw page); None when no capture is committed."""
+    p = ROOT / "profiles" / "raster_bwd_traffic.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    return d.get("dram_bytes_per_launch"), d.get("source")
+
+
 def _fp32_roofline(pairs, ktimes, D, clocks):
     """Compositing is bound by the FP32 pipe, so next to the HBM fraction BASELINE.json asks for: algorithmic
     pair-flops (forward Q (14 + 2 D), backward Q (40 + 6 D), Q = blended (pixel, entry) pairs counted
@@ -301,7 +312,7 @@ def run_ours(args):
 
     # per-kernel CUDA-event times of the same workload: eager launches (a replayed graph offers no place to record
     # events between its kernels), same kernels, same sizes, same stream, after the timed legs
-    with ops.kernel_timer.collect():
+    with ops.kernel_timer.collect(pad_cycles=400_000):
         for i in range(6):
             eager_step(i, resident)
         ktimes = ops.kernel_timer.summary()
@@ -327,15 +338,39 @@ def run_ours(args):
     bwd_bytes = I * (28 + 4 * D) + P * (4 * D + 12) + Nv * (32 + 4 * D)
     peak, peak_src = _peaks()
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms == bwd_ms and bwd_ms > 0 else None
+    traffic, traffic_src = _ncu_traffic()
+    # every timed stage against the bound DESIGN.md §4 names for it: algorithmic bytes (SURVEY.md §8d formulas with
+    # this step's N, Nv, I, P, K) over the stage's mean CUDA-event time
+    N, K, C = N_GAUSS, 16, 1
+    tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+    key_bytes = -(-(32 + max(1, (tiles - 1).bit_length())) // 8)
+    stage_bytes = {
+        "project_sh_fwd": C * N * 68 + Nv * (12 * K + 12),
+        "project_sh_bwd": C * N * 4 + Nv * (76 + 12 * K) + N * (40 + 12 * K),
+        "radix_sort": I * 8 + I * 24 * key_bytes,
+        "adam_multi": sum(p.numel() for p in params) * 28,
+        "raster_fwd_D4": I * (28 + 16) + P * (16 + 8), "raster_fwd_D3": I * (28 + 12) + P * (12 + 8),
+        "raster_bwd_D4": bwd_bytes, "raster_bwd_D3": I * (28 + 12) + P * (12 + 12) + Nv * (32 + 12),
+    }
+    stages = {}
+    for name, nbytes in stage_bytes.items():
+        ms = ktimes.get(name, (float("nan"), 0))[0]
+        if ms == ms and ms > 0:
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            stages[name] = {"algorithmic_bytes": int(nbytes), "ms": round(ms, 4), "gbs": round(gbs, 1),
+                            "hbm_frac": round(gbs / peak, 4),
+                            "bound": "fp32" if name.startswith("raster") else "hbm"}
     roofline = {
         "kernel": "raster_bwd_kernel<4> (RGB+ED pass)", "bound": "hbm", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "kernel_ms": bwd_ms,
         "n_isects": I, "n_visible": Nv,
         "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md §8d); the HBM fraction is reported as "
                 "BASELINE.json asks, the pipe utilisation is in profiles/",
         "fp32": _fp32_roofline(pairs, ktimes, D, clocks if rank == 0 else None),
         "kernel_ms_all": {k: round(v[0], 4) for k, v in sorted(ktimes.items())},
+        "stages": stages,
         "raster_fwd_bwd_mpix_per_s": (P / ((ktimes.get("raster_fwd_D4", (0, 0))[0] + bwd_ms) * 1e-3) / 1e6)
         if bwd_ms == bwd_ms and bwd_ms > 0 else None,
     }

@@ -35,13 +35,17 @@ class KernelTimer:
     def __init__(self):
         self.enabled = False
         self.events = {}
+        self.pad_cycles = 0
 
-    def collect(self):
+    def collect(self, pad_cycles: int = 0):
+        """`pad_cycles` > 0: a spin kernel of that many SM cycles is queued before every start event, so the host
+        has recorded the event and launched the timed kernels before the device gets to them — otherwise, in an
+        eager (host-bound) step, the interval also counts the time the idle device waits for the launch."""
         timer = self
 
         class _Ctx:
             def __enter__(self_inner):
-                timer.enabled, timer.events = True, {}
+                timer.enabled, timer.events, timer.pad_cycles = True, {}, int(pad_cycles)
                 return timer
 
             def __exit__(self_inner, *exc):
@@ -54,6 +58,8 @@ class KernelTimer:
         if not self.enabled:
             return None
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if self.pad_cycles:
+            torch.cuda._sleep(self.pad_cycles)
         s.record(torch.cuda.current_stream())
         self.events.setdefault(name, []).append((s, e))
         return e

@@ -67,21 +67,22 @@ def _check_lists(s):
 def _window_vs_oracle(ops, s, ox, oy, win=64, seed=0, tag=""):
     """Forward inside, and backward of a cotangent supported on, the tile-aligned window [oy, oy+win) x [ox, ox+win)."""
     W, H = s["W"], s["H"]
+    hh, ww = min(win, H - oy), min(win, W - ox)  # a window over the ragged last tile row / column is clipped
     g = torch.Generator().manual_seed(seed)
     out, alpha, last, ws = ops.raster_fwd(s["m2"], s["con"], s["cols"], s["opac"], None, None, W, H, TS, s["offs"],
                                           s["flat"])
     v_out = torch.zeros_like(out)
     v_alpha = torch.zeros_like(alpha)
-    v_out[0, oy:oy + win, ox:ox + win] = torch.randn(win, win, 4, generator=g).to(DEV)
-    v_alpha[0, oy:oy + win, ox:ox + win] = torch.randn(win, win, 1, generator=g).to(DEV)
+    v_out[0, oy:oy + hh, ox:ox + ww] = torch.randn(win, win, 4, generator=g)[:hh, :ww].to(DEV)
+    v_alpha[0, oy:oy + hh, ox:ox + ww] = torch.randn(win, win, 1, generator=g)[:hh, :ww].to(DEV)
     v_m2, v_abs, v_con, v_col, v_op = ops.raster_bwd(s["m2"], s["con"], s["cols"], s["opac"], None, None, W, H, TS,
                                                      s["offs"], s["flat"], False, ws, out, alpha, last, v_out, v_alpha,
                                                      True)
     # the Gaussians in the window's tile lists
     offs = torch.cat([s["offs"].reshape(-1).long(), torch.tensor([s["flat"].numel()], device=DEV)])
     sel = []
-    for ty in range(oy // TS, (oy + win) // TS):
-        for tx in range(ox // TS, (ox + win) // TS):
+    for ty in range(oy // TS, min((oy + win) // TS, s["th"])):
+        for tx in range(ox // TS, min((ox + win) // TS, s["tw"])):
             t = ty * s["tw"] + tx
             sel.append(s["flat"][offs[t]:offs[t + 1]])
     gids = torch.unique(torch.cat(sel).long())  # ascending: ties in the sub-scene break the same way
@@ -102,9 +103,10 @@ def _window_vs_oracle(ops, s, ox, oy, win=64, seed=0, tag=""):
     _, ids_s, flat_s = ref.isect_tiles(m2s.detach(), radii, deps, TS, tw, tw)
     offs_s = ref.isect_offset_encode(ids_s, 1, tw, tw)
     o_ref, a_ref = ref.rasterize_to_pixels(m2s, cons, cols, opas, win, win, TS, offs_s, flat_s)
-    assert_close(out[0, oy:oy + win, ox:ox + win].cpu(), o_ref[0].detach(), f"full.fwd.colors{tag}", tol=1e-4)
-    assert_close(alpha[0, oy:oy + win, ox:ox + win].cpu(), a_ref[0].detach(), f"full.fwd.alpha{tag}", tol=1e-4)
-    loss = (o_ref * v_out[:, oy:oy + win, ox:ox + win].cpu()).sum() + (a_ref * v_alpha[:, oy:oy + win, ox:ox + win].cpu()).sum()
+    o_ref, a_ref = o_ref[:, :hh, :ww], a_ref[:, :hh, :ww]
+    assert_close(out[0, oy:oy + hh, ox:ox + ww].cpu(), o_ref[0].detach(), f"full.fwd.colors{tag}", tol=1e-4)
+    assert_close(alpha[0, oy:oy + hh, ox:ox + ww].cpu(), a_ref[0].detach(), f"full.fwd.alpha{tag}", tol=1e-4)
+    loss = (o_ref * v_out[:, oy:oy + hh, ox:ox + ww].cpu()).sum() + (a_ref * v_alpha[:, oy:oy + hh, ox:ox + ww].cpu()).sum()
     loss.backward()
     assert_close(v_col[0, gids].cpu(), cols.grad[0], f"full.bwd.v_colors{tag}", tol=1e-4, outlier_frac=2e-3)
     assert_close(v_op[0, gids].cpu(), opas.grad[0], f"full.bwd.v_opacities{tag}", tol=1e-4, outlier_frac=2e-3)
@@ -142,7 +144,8 @@ def test_cfg4_one_million_gaussians_1080p():
     _check_lists(s)
     _linearity_and_adjoint(ops, s)
     _window_vs_oracle(ops, s, ox=960, oy=512, tag="[cfg4,centre]")
-    _window_vs_oracle(ops, s, ox=1856, oy=1008, seed=3, tag="[cfg4,corner]")  # ragged bottom rows: 1080 = 67.5 tiles
+    # ragged bottom rows: 1080 = 67.5 tiles, the window covers tile rows 64..67 of which the last has 8 pixel rows
+    _window_vs_oracle(ops, s, ox=928, oy=1024, seed=3, tag="[cfg4,bottom]")
 
 
 def test_cfg5_three_million_gaussians_4k():
