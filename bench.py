@@ -169,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -387,6 +387,8 @@ def run_ours(args):
                                      "no host sync); every kernel of the eager step runs in every replay"
                                      if graph_mode else "eager launches"),
                        "graph": graph_info,
+                       "fused_outputs": bool(model.config.fused_outputs),  # dn_step.py: activations / SH concat /
+                       # image glue inside our kernels (True) or as the reference's torch ops (False)
                        "l2": "per-step working set (parameters, Adam state, gradients, intersection lists, images: "
                              ">400 MB touched per step) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -402,6 +404,28 @@ def run_ours(args):
     return line
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout must carry exactly one JSON line: NCCL prints its version banner to fd 1 at communicator creation
+    (seen in the N=2 run), so everything written to fd 1 during the run is sent to stderr and the line itself goes
+    to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -412,6 +436,7 @@ def main():
                     help="graph: the iteration is one CUDA graph replay (default); eager: per-kernel launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -424,7 +449,7 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 if __name__ == "__main__":

@@ -69,12 +69,32 @@ __device__ __forceinline__ int tile_count(float mx, float my, int radius, int ti
     return (by - ay) * (bx - ax);
 }
 
+// SH coefficient j (0 .. 3K-1) of Gaussian n.  One tensor coeffs[N,K,3], or — when `rest` is given — the layout the
+// model stores (dn_model.py:294-304): coeffs = features_dc[N,3] (band 0), rest = features_rest[N,K-1,3]; reading the
+// two tensors in place saves the torch.cat that builds [N,K,3] every step (and the split of its gradient).
+__device__ __forceinline__ size_t sh_index(bool split, int n, int L, int j, bool* in_rest) {
+    if (!split) { *in_rest = false; return (size_t)n * L + j; }
+    if (j < 3) { *in_rest = false; return (size_t)n * 3 + j; }
+    *in_rest = true;
+    return (size_t)n * (L - 3) + (j - 3);
+}
+__device__ __forceinline__ float sh_load(const float* __restrict__ coeffs, const float* __restrict__ rest, int n,
+                                         int L, int j) {
+    bool r;
+    const size_t i = sh_index(rest != nullptr, n, L, j, &r);
+    return r ? rest[i] : coeffs[i];
+}
+
+// act_flags: the parameters arrive as the model stores them and the activation is applied here
+constexpr int ACT_EXP_SCALES = 1;  // scales are log-scales: s = exp(raw)  (dn_model.py:573)
+
 __global__ void __launch_bounds__(256)
 project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float* __restrict__ quats,
                       const float* __restrict__ scales, const float* __restrict__ viewmats,
                       const float* __restrict__ Ks, int width, int height, float eps2d, float near_plane,
                       float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h, int sh_degree,
-                      int K, const float* __restrict__ coeffs, const float* __restrict__ campos, int color_stride,
+                      int K, const float* __restrict__ coeffs, const float* __restrict__ coeffs_rest, int act_flags,
+                      const float* __restrict__ campos, int color_stride,
                       int depth_channel, int32_t* __restrict__ radii, float* __restrict__ means2d,
                       float* __restrict__ depths, float* __restrict__ conics, float* __restrict__ comps,
                       float* __restrict__ colors, int32_t* __restrict__ tiles_per_gauss,
@@ -87,6 +107,7 @@ project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float
     float px = means[3 * (size_t)n + 0], py = means[3 * (size_t)n + 1], pz = means[3 * (size_t)n + 2];
     float4 q = reinterpret_cast<const float4*>(quats)[n];
     float sx = scales[3 * (size_t)n + 0], sy = scales[3 * (size_t)n + 1], sz = scales[3 * (size_t)n + 2];
+    if (act_flags & ACT_EXP_SCALES) { sx = expf(sx); sy = expf(sy); sz = expf(sz); }
     fs::ProjFwd o = fs::project_fwd(cam, px, py, pz, q.x, q.y, q.z, q.w, sx, sy, sz, width, height, eps2d,
                                     near_plane, far_plane, radius_clip);
     radii[idx] = o.radius;
@@ -119,12 +140,24 @@ project_sh_fwd_kernel(int C, int N, const float* __restrict__ means, const float
             float basis[16];
             fs::sh_basis(sh_degree, dx * inorm, dy * inorm, dz * inorm, basis);
             int nb = (sh_degree + 1) * (sh_degree + 1);
-            const float* cf = coeffs + (size_t)n * K * 3;
+            if (coeffs_rest) {
+                const float* dc = coeffs + (size_t)n * 3;
+                const float* cf = coeffs_rest + (size_t)n * (K - 1) * 3 - 3;  // band k >= 1 at cf[3 k + c]
+                r = basis[0] * dc[0]; g = basis[0] * dc[1]; b = basis[0] * dc[2];
 #pragma unroll 4
-            for (int k = 0; k < nb; ++k) {
-                r += basis[k] * cf[3 * k + 0];
-                g += basis[k] * cf[3 * k + 1];
-                b += basis[k] * cf[3 * k + 2];
+                for (int k = 1; k < nb; ++k) {
+                    r += basis[k] * cf[3 * k + 0];
+                    g += basis[k] * cf[3 * k + 1];
+                    b += basis[k] * cf[3 * k + 2];
+                }
+            } else {
+                const float* cf = coeffs + (size_t)n * K * 3;
+#pragma unroll 4
+                for (int k = 0; k < nb; ++k) {
+                    r += basis[k] * cf[3 * k + 0];
+                    g += basis[k] * cf[3 * k + 1];
+                    b += basis[k] * cf[3 * k + 2];
+                }
             }
             // host-side clamp_min(colors + 0.5, 0) of rendering.rasterization, fused here
             r = fmaxf(r + 0.5f, 0.f);
@@ -168,12 +201,14 @@ __global__ void __launch_bounds__(PB_THREADS)
 project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float* __restrict__ quats,
                       const float* __restrict__ scales, const float* __restrict__ viewmats,
                       const float* __restrict__ Ks, int width, int height, float eps2d, int sh_degree, int K,
-                      const float* __restrict__ coeffs, const float* __restrict__ campos, int color_stride,
+                      const float* __restrict__ coeffs, const float* __restrict__ coeffs_rest, int act_flags,
+                      const float* __restrict__ campos, int color_stride,
                       int depth_channel, const int32_t* __restrict__ radii, const float* __restrict__ v_means2d,
                       const float* __restrict__ v_depths, const float* __restrict__ v_conics,
                       const float* __restrict__ v_comps, const float* __restrict__ v_colors,
                       float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
-                      float* __restrict__ v_coeffs, float* __restrict__ v_viewmats, float* __restrict__ v_campos) {
+                      float* __restrict__ v_coeffs, float* __restrict__ v_coeffs_rest, float* __restrict__ v_viewmats,
+                      float* __restrict__ v_campos) {
     __shared__ float red[PB_WARPS];
     __shared__ float tiles[PB_WARPS][32][SH_ROW_MAX + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -190,7 +225,9 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
         px = means[3 * (size_t)n + 0]; py = means[3 * (size_t)n + 1]; pz = means[3 * (size_t)n + 2];
         q = reinterpret_cast<const float4*>(quats)[n];
         sx = scales[3 * (size_t)n + 0]; sy = scales[3 * (size_t)n + 1]; sz = scales[3 * (size_t)n + 2];
+        if (act_flags & ACT_EXP_SCALES) { sx = expf(sx); sy = expf(sy); sz = expf(sz); }
     }
+    const bool split = (coeffs_rest != nullptr);  // the host entry point guarantees `staged` in this case
     float am[3] = {0, 0, 0}, aq[4] = {0, 0, 0, 0}, as[3] = {0, 0, 0};
     int nb = sh_degree >= 0 ? (sh_degree + 1) * (sh_degree + 1) : 0;
     bool any_sh = false;
@@ -207,9 +244,8 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
             const unsigned vmask = __ballot_sync(0xffffffffu, vis);
             for (int r = 0; r < 32; ++r) {
                 if (!((vmask >> r) & 1u)) continue;
-                const float* row = coeffs + (size_t)(n0 + r) * L;
-                if (lane < L) tile[r][lane] = row[lane];
-                if (lane + 32 < L) tile[r][lane + 32] = row[lane + 32];
+                if (lane < L) tile[r][lane] = sh_load(coeffs, coeffs_rest, n0 + r, L, lane);
+                if (lane + 32 < L) tile[r][lane + 32] = sh_load(coeffs, coeffs_rest, n0 + r, L, lane + 32);
             }
             __syncwarp();
         }
@@ -236,12 +272,14 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 float ux = dx * inorm, uy = dy * inorm, uz = dz * inorm;
                 float basis[16];
                 fs::sh_basis(sh_degree, ux, uy, uz, basis);
-                const float* cf = coeffs_in_tile ? &tile[lane][0] : coeffs + (size_t)n * L;
+                auto cf = [&](int j) -> float {
+                    return coeffs_in_tile ? tile[lane][j] : sh_load(coeffs, coeffs_rest, n, L, j);
+                };
                 float r = 0.f, g = 0.f, b = 0.f;
                 for (int k = 0; k < nb; ++k) {
-                    r += basis[k] * cf[3 * k + 0];
-                    g += basis[k] * cf[3 * k + 1];
-                    b += basis[k] * cf[3 * k + 2];
+                    r += basis[k] * cf(3 * k + 0);
+                    g += basis[k] * cf(3 * k + 1);
+                    b += basis[k] * cf(3 * k + 2);
                 }
                 // clamp_min(x + 0.5, 0): gradient passes where x + 0.5 >= 0
                 float vr = (r + 0.5f >= 0.f) ? vc[0] : 0.f;
@@ -252,7 +290,7 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                     float bx[16], by[16], bz[16];
                     fs::sh_basis_grad(sh_degree, ux, uy, uz, bx, by, bz);
                     for (int k = 1; k < nb; ++k) {
-                        float w = cf[3 * k + 0] * vr + cf[3 * k + 1] * vg + cf[3 * k + 2] * vb;
+                        float w = cf(3 * k + 0) * vr + cf(3 * k + 1) * vg + cf(3 * k + 2) * vb;
                         gx += bx[k] * w; gy += by[k] * w; gz += bz[k] * w;
                     }
                 }
@@ -327,9 +365,14 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
             __syncwarp();
             const int rows = min(32, N - n0);
             for (int r = 0; r < rows; ++r) {
-                float* row = v_coeffs + (size_t)(n0 + r) * L;
-                if (lane < L) row[lane] = tile[r][lane];
-                if (lane + 32 < L) row[lane + 32] = tile[r][lane + 32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    if (j >= L) continue;
+                    bool in_rest;
+                    const size_t at = sh_index(split, n0 + r, L, j, &in_rest);
+                    (in_rest ? v_coeffs_rest : v_coeffs)[at] = tile[r][j];
+                }
             }
         } else if (live) {
             float* vcf = v_coeffs + (size_t)n * L;
@@ -340,6 +383,7 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
     if (!live) return;
     v_means[3 * (size_t)n + 0] = am[0]; v_means[3 * (size_t)n + 1] = am[1]; v_means[3 * (size_t)n + 2] = am[2];
     reinterpret_cast<float4*>(v_quats)[n] = make_float4(aq[0], aq[1], aq[2], aq[3]);
+    if (act_flags & ACT_EXP_SCALES) { as[0] *= sx; as[1] *= sy; as[2] *= sz; }  // d exp(raw) / d raw = exp(raw)
     v_scales[3 * (size_t)n + 0] = as[0]; v_scales[3 * (size_t)n + 1] = as[1]; v_scales[3 * (size_t)n + 2] = as[2];
 }
 
@@ -375,8 +419,33 @@ FSB_API int fsb_project_sh_fwd(int C, int N, const float* means, const float* qu
     int64_t total = (int64_t)C * N;
     project_sh_fwd_kernel<<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
-        tile_w, tile_h, sh_degree, K, coeffs, campos, color_stride, depth_channel, radii, means2d, depths, conics,
-        comps, colors, tiles_per_gauss, (unsigned long long*)legacy_extra);
+        tile_w, tile_h, sh_degree, K, coeffs, nullptr, 0, campos, color_stride, depth_channel, radii, means2d, depths,
+        conics, comps, colors, tiles_per_gauss, (unsigned long long*)legacy_extra);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// The same stage fed with the model's parameters as stored: log-scales (exp applied here when exp_scales != 0; the
+// quaternion is normalised inside either way) and the SH coefficients as two tensors, features_dc[N,3] and
+// features_rest[N,K-1,3].  Saves the activation launches and the [N,K,3] concatenation of dn_model.py:566-574.
+FSB_API int fsb_project_params_fwd(int C, int N, const float* means, const float* quats, const float* scales,
+                                   int exp_scales, const float* viewmats, const float* Ks, int width, int height,
+                                   float eps2d, float near_plane, float far_plane, float radius_clip, int tile_size,
+                                   int tile_w, int tile_h, int sh_degree, int K, const float* features_dc,
+                                   const float* features_rest, int color_stride, int depth_channel, int32_t* radii,
+                                   float* means2d, float* depths, float* conics, float* colors,
+                                   int32_t* tiles_per_gauss, int64_t* legacy_extra, void* stream) {
+    if (C <= 0 || N < 0 || sh_degree < 0 || sh_degree > 3 || tile_size <= 0) return FSB_E_ARG;
+    if (!features_dc || !colors || K < 1 || K > 16 || (sh_degree + 1) * (sh_degree + 1) > K) return FSB_E_ARG;
+    if (K > 1 && !features_rest) return FSB_E_ARG;
+    if (color_stride < 3 || depth_channel >= color_stride) return FSB_E_ARG;
+    if (N == 0) return 0;
+    int64_t total = (int64_t)C * N;
+    project_sh_fwd_kernel<<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+        tile_w, tile_h, sh_degree, K, features_dc, K > 1 ? features_rest : nullptr, exp_scales ? ACT_EXP_SCALES : 0,
+        nullptr, color_stride, depth_channel, radii, means2d, depths, conics, nullptr, colors, tiles_per_gauss,
+        (unsigned long long*)legacy_extra);
     FSB_LAUNCH_CHECK();
     return 0;
 }
@@ -393,9 +462,32 @@ FSB_API int fsb_project_sh_bwd(int C, int N, const float* means, const float* qu
     if (v_campos && !campos) return FSB_E_ARG;
     if (N == 0) return 0;
     project_sh_bwd_kernel<<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(
-        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, coeffs, campos, color_stride,
-        depth_channel, radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_means, v_quats, v_scales, v_coeffs,
-        v_viewmats, v_campos);
+        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, coeffs, nullptr, 0, campos,
+        color_stride, depth_channel, radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_means, v_quats, v_scales,
+        v_coeffs, nullptr, v_viewmats, v_campos);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Backward of fsb_project_params_fwd: gradients w.r.t. the stored parameters (v_scales is d/d log-scale when
+// exp_scales != 0; v_quats is w.r.t. the un-normalised quaternion), v_features_dc[N,3] and v_features_rest[N,K-1,3]
+// written in place of a [N,K,3] gradient that torch would have to split.  All outputs are overwritten.
+FSB_API int fsb_project_params_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                                   int exp_scales, const float* viewmats, const float* Ks, int width, int height,
+                                   float eps2d, int sh_degree, int K, const float* features_dc,
+                                   const float* features_rest, int color_stride, int depth_channel,
+                                   const int32_t* radii, const float* v_means2d, const float* v_depths,
+                                   const float* v_conics, const float* v_colors, float* v_means, float* v_quats,
+                                   float* v_scales, float* v_features_dc, float* v_features_rest, void* stream) {
+    if (C <= 0 || N < 0 || sh_degree < 0 || sh_degree > 3) return FSB_E_ARG;
+    if (!features_dc || !v_features_dc || !v_colors || K < 1 || K > 16) return FSB_E_ARG;
+    if (K > 1 && (!features_rest || !v_features_rest)) return FSB_E_ARG;
+    if (N == 0) return 0;
+    project_sh_bwd_kernel<<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(
+        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, features_dc,
+        K > 1 ? features_rest : nullptr, exp_scales ? ACT_EXP_SCALES : 0, nullptr, color_stride, depth_channel, radii,
+        v_means2d, v_depths, v_conics, nullptr, v_colors, v_means, v_quats, v_scales, v_features_dc,
+        K > 1 ? v_features_rest : nullptr, nullptr, nullptr);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -15,6 +15,7 @@ calls the reference makes; bench.py and smoke() drive this class.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -69,6 +70,11 @@ class DNSplatterStepConfig:
     fused_optimizer: bool = True
     fused_losses: bool = True  # dn_regularizer_loss instead of the torch loss classes
     fused_glue: bool = True  # gaussian_normals / densify_stats kernels instead of the inline torch ops
+    # get_outputs through rasterization_from_params / compose_rgbd / normal_map and the flatness term through
+    # flatness_loss (compose.py): the activations, the SH concatenation and the image-space glue of
+    # dn_model.py:566-574, :602-613, :655-656, :817-819 run inside our kernels instead of ~55 torch launches
+    # (FSB_FUSED_OUTPUTS=0 switches it off for A/B runs)
+    fused_outputs: bool = field(default_factory=lambda: os.environ.get("FSB_FUSED_OUTPUTS", "1") != "0")
     overlap_normals_pass: bool = True  # captured step only: the normals pass runs on a second stream beside the RGB+ED pass
 
 
@@ -97,6 +103,7 @@ class DNSplatterStep:
         if gsplat_module is None:
             from . import gsplat as gsplat_module
         self._rasterization = gsplat_module.rasterization
+        self._rasterization_from_params = getattr(gsplat_module, "rasterization_from_params", None)
         self._rasterize_gaussians = gsplat_module.rasterize_gaussians
         self._quat_to_rotmat = gsplat_module.quat_to_rotmat
         sc = scene.to(self.device)
@@ -163,7 +170,6 @@ class DNSplatterStep:
                 self.opacities.data.ge_(cfg.binary_opacities_threshold)
         opacities_crop, means_crop = self.opacities, self.means
         scales_crop, quats_crop = self.scales, self.quats
-        colors_crop = torch.cat((self.features_dc[:, None, :], self.features_rest), dim=1)
         BLOCK_WIDTH = 16
         if isinstance(cam_idx, Tensor):  # device index (captured step: the view is chosen at replay time)
             viewmat, K, c2w = (t.index_select(0, cam_idx) for t in (sc.viewmats, sc.Ks, sc.c2w))
@@ -175,6 +181,9 @@ class DNSplatterStep:
         self.last_size = (H, W)
         self._last_cam = cam_idx
         sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)
+        if cfg.fused_outputs and self.device.type == "cuda" and self._rasterization_from_params is not None:
+            return self._get_outputs_fused(viewmat, K, c2w, W, H, BLOCK_WIDTH, sh_degree_to_use)
+        colors_crop = torch.cat((self.features_dc[:, None, :], self.features_rest), dim=1)
         render, alpha, info = self._rasterization(
             means=means_crop,
             quats=quats_crop / quats_crop.norm(dim=-1, keepdim=True),
@@ -236,7 +245,53 @@ class DNSplatterStep:
         return {"rgb": rgb.squeeze(0), "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
                 "background": background}
 
-    def _normals_pass(self, quats_crop, scales_crop, means_crop, opacities_crop, c2w, H, W, BLOCK_WIDTH):
+    def _get_outputs_fused(self, viewmat, K, c2w, W, H, BLOCK_WIDTH, sh_degree_to_use) -> Dict[str, Tensor]:
+        """get_outputs with the torch glue folded into the kernels: same values as the path above (the literal
+        restatement of dn_model.py:566-671) to fp32 rounding, ~55 fewer launches per iteration.
+        tests/test_gpu_step.py compares the two paths output by output and gradient by gradient."""
+        from .compose import compose_rgbd, normal_map
+
+        cfg = self.config
+        opac = torch.sigmoid(self.opacities)  # [N,1]; the reference evaluates it twice (dn_model.py:574, :650)
+        render, alpha, info = self._rasterization_from_params(
+            self.means, self.quats, self.scales, opac.squeeze(-1), self.features_dc, self.features_rest,
+            viewmats=viewmat, Ks=K, width=W, height=H, sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10,
+            tile_size=BLOCK_WIDTH, render_mode="RGB+ED", absgrad=True)
+        if self.training and info["means2d"].requires_grad:
+            info["means2d"].retain_grad()
+        self.xys = info["means2d"]
+        self.radii = info["radii"][0]
+        self.depths = info["depths"]
+        self.conics = info["conics"]
+        self.num_tiles_hit = info["tiles_per_gauss"]
+        background = self.background
+        proj_done = info.get("projection_done") if cfg.overlap_normals_pass else None
+        main_stream = side_stream = None
+        if proj_done is not None:
+            main_stream = torch.cuda.current_stream()
+            if getattr(self, "_normals_stream", None) is None:
+                self._normals_stream = torch.cuda.Stream()
+            side_stream = self._normals_stream
+            side_stream.wait_event(proj_done)
+            for t in (self.xys, self.depths, self.radii, self.conics, self.num_tiles_hit, c2w, opac):
+                t.record_stream(side_stream)
+            torch.cuda.set_stream(side_stream)
+        try:
+            normals_im = self._normals_pass(self.quats, self.scales, self.means, self.opacities, c2w, H, W,
+                                            BLOCK_WIDTH, opac=opac)
+        finally:
+            if side_stream is not None:
+                torch.cuda.set_stream(main_stream)
+        # the RGB / depth composition runs on the main stream beside the normals pass
+        rgb, depth_im = compose_rgbd(render, alpha, background)
+        if side_stream is not None:
+            main_stream.wait_stream(side_stream)
+            normals_im.record_stream(main_stream)
+        normals_im = normal_map(normals_im)
+        return {"rgb": rgb, "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
+                "background": background}
+
+    def _normals_pass(self, quats_crop, scales_crop, means_crop, opacities_crop, c2w, H, W, BLOCK_WIDTH, opac=None):
         """dn_model.py:617-653: per-Gaussian normals, then the legacy `rasterize_gaussians` pass over them."""
         cfg = self.config
         if cfg.fused_glue and self.device.type == "cuda":
@@ -258,8 +313,8 @@ class DNSplatterStep:
             normals = normals @ c2w.squeeze(0)[:3, :3]
         xys = self.xys[0, ...].detach()
         return self._rasterize_gaussians(xys, self.depths[0, ...], self.radii, self.conics[0, ...],
-                                         self.num_tiles_hit[0, ...], normals, torch.sigmoid(opacities_crop), H, W,
-                                         BLOCK_WIDTH)
+                                         self.num_tiles_hit[0, ...], normals,
+                                         torch.sigmoid(opacities_crop) if opac is None else opac, H, W, BLOCK_WIDTH)
 
     # ---- splatfacto base loss + dn_model.py:673-925 -----------------------------------------
     def get_loss_dict(self, outputs, batch) -> Dict[str, Tensor]:
@@ -305,7 +360,12 @@ class DNSplatterStep:
                 if cfg.use_normal_tv_loss:
                     normal_loss = normal_loss + self.tv_loss(pred_normal)
         if cfg.two_d_gaussians:
-            normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
+            if fused and cfg.fused_outputs:
+                from .compose import flatness_loss
+
+                normal_loss = normal_loss + flatness_loss(self.scales)
+            else:
+                normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
         main_loss = rgb_loss + depth_loss + cfg.normal_lambda * normal_loss
         return {"main_loss": main_loss, "scale_reg": torch.zeros((), device=self.device)}
 

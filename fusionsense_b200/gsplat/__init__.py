@@ -6,10 +6,10 @@
 Use `fusionsense_b200.install_gsplat_shim()` (or put `<repo>/shim` on PYTHONPATH) to make
 `import gsplat` resolve here.
 """
-from .rendering import rasterization  # noqa: F401
+from .rendering import rasterization, rasterization_from_params  # noqa: F401
 from .cuda_legacy._wrapper import num_sh_bases, rasterize_gaussians  # noqa: F401
 from .cuda_legacy._torch_impl import quat_to_rotmat  # noqa: F401
 
 __version__ = "1.0.0"
 
-__all__ = ["rasterization", "rasterize_gaussians", "quat_to_rotmat", "num_sh_bases"]
+__all__ = ["rasterization", "rasterize_gaussians", "quat_to_rotmat", "num_sh_bases", "rasterization_from_params"]

@@ -49,6 +49,45 @@ def rasterization(
     flattened nnz form that neither DN-Splatter nor splatfacto use — they are refused loudly instead of being
     emulated; (3) there is no CPU path.
     """
+    return _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane,
+                               far_plane, radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode,
+                               sparse_grad, absgrad, rasterize_mode, channel_chunk)
+
+
+def rasterization_from_params(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]  as stored (any norm)
+    log_scales: Tensor,  # [N, 3]  as stored (exp applied inside the projection kernel)
+    opacities: Tensor,  # [N]  activated (sigmoid applied by the caller, shared with the normals pass)
+    features_dc: Tensor,  # [N, 3]
+    features_rest: Tensor,  # [N, K-1, 3]
+    viewmats: Tensor,
+    Ks: Tensor,
+    width: int,
+    height: int,
+    sh_degree: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: Literal["RGB", "RGB+D", "RGB+ED"] = "RGB",
+    absgrad: bool = False,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Extension (not part of gsplat): `rasterization(packed=False, rasterize_mode="classic")` of
+    `quats / |quats|, exp(log_scales), cat(features_dc[:, None], features_rest)` with those three torch
+    expressions (dn_model.py:566-574) evaluated inside the projection kernel and differentiated in place.
+    Same return tuple and meta keys as `rasterization()`."""
+    assert render_mode in ["RGB", "RGB+D", "RGB+ED"], render_mode
+    return _rasterization_impl(means, quats, log_scales, opacities, None, viewmats, Ks, width, height, near_plane,
+                               far_plane, radius_clip, eps2d, sh_degree, False, tile_size, backgrounds, render_mode,
+                               False, absgrad, "classic", 32, stored=(features_dc, features_rest))
+
+
+def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane, far_plane,
+                        radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode, sparse_grad,
+                        absgrad, rasterize_mode, channel_chunk, stored=None):
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -67,7 +106,9 @@ def rasterization(
             "DN-Splatter (dn_model.py:580,586) and splatfacto use"
         )
 
-    if sh_degree is None:
+    if stored is not None:
+        assert sh_degree is not None and stored[0].shape == (N, 3), stored[0].shape
+    elif sh_degree is None:
         assert (colors.dim() == 2 and colors.shape[0] == N) or (
             colors.dim() == 3 and colors.shape[:2] == (C, N)
         ), colors.shape
@@ -97,10 +138,16 @@ def rasterization(
 
     # totals[0] <- n_isects (scan), totals[1] <- tiles by which the legacy 0.1.x bbox rule would differ; one D2H read
     totals = torch.zeros(2, dtype=torch.int64, device=means.device)
-    radii, means2d, depths, conics, comps, sh_colors, tiles_per_gauss = ops.ProjectSH.apply(
-        means, quats, scales, coeffs, viewmats, Ks, campos, width, height, eps2d, near_plane, far_plane,
-        radius_clip, tile_size, sh_degree if use_sh else None, color_stride, depth_channel, calc_comp,
-        totals[1:] if C == 1 else None)
+    if stored is not None:
+        comps = None
+        radii, means2d, depths, conics, sh_colors, tiles_per_gauss = ops.ProjectParams.apply(
+            means, quats, scales, stored[0], stored[1], viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+            radius_clip, tile_size, sh_degree, color_stride, depth_channel, totals[1:] if C == 1 else None)
+    else:
+        radii, means2d, depths, conics, comps, sh_colors, tiles_per_gauss = ops.ProjectSH.apply(
+            means, quats, scales, coeffs, viewmats, Ks, campos, width, height, eps2d, near_plane, far_plane,
+            radius_clip, tile_size, sh_degree if use_sh else None, color_stride, depth_channel, calc_comp,
+            totals[1:] if C == 1 else None)
 
     # static-capacity mode (captured step): a caller may start work that needs only the projection outputs (the
     # DN-Splatter normals pass) on another stream while this one bins and composites

@@ -443,6 +443,73 @@ class ProjectSH(torch.autograd.Function):
                 None, None, None, None, None, None, None, None, None, None, None, None)
 
 
+class ProjectParams(torch.autograd.Function):
+    """ProjectSH fed with the model's parameters as stored (fsb_project_params_fwd / _bwd): un-normalised
+    quaternions, log-scales (exp inside) and the SH coefficients as features_dc[N,3] + features_rest[N,K-1,3].
+    Saves the activation launches, the [N,K,3] torch.cat of dn_model.py:566-574 and the autograd mirrors of both."""
+
+    @staticmethod
+    def forward(ctx, means, quats, log_scales, features_dc, features_rest, viewmats, Ks, width, height, eps2d,
+                near_plane, far_plane, radius_clip, tile_size, sh_degree, color_stride, depth_channel,
+                legacy_extra=None):
+        means, quats, log_scales = _f32c(means), _f32c(quats), _f32c(log_scales)
+        features_dc, features_rest = _f32c(features_dc), _f32c(features_rest)
+        viewmats, Ks = _f32c(viewmats), _f32c(Ks)
+        _req_cuda(means, quats, log_scales, features_dc, features_rest, viewmats, Ks)
+        if viewmats.requires_grad:
+            raise NotImplementedError("ProjectParams has no view-matrix gradient (camera optimiser off in the "
+                                      "reference, dn_model.py:128-130); use rasterization() for that")
+        C, N = viewmats.shape[0], means.shape[0]
+        assert features_dc.shape == (N, 3), features_dc.shape
+        K = 1 + (features_rest.shape[1] if features_rest is not None else 0)
+        assert features_rest is None or features_rest.shape == (N, K - 1, 3), features_rest.shape
+        dev = means.device
+        tile_w, tile_h = math.ceil(width / tile_size), math.ceil(height / tile_size)
+        radii = torch.empty((C, N), dtype=torch.int32, device=dev)
+        means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+        conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+        colors = torch.empty((C, N, color_stride), dtype=torch.float32, device=dev)
+        tiles = torch.empty((C, N), dtype=torch.int32, device=dev)
+        ev = kernel_timer.start("project_sh_fwd")
+        check(lib.fsb_project_params_fwd(C, N, ptr(means), ptr(quats), ptr(log_scales), 1, ptr(viewmats), ptr(Ks),
+                                         width, height, eps2d, near_plane, far_plane, radius_clip, tile_size, tile_w,
+                                         tile_h, sh_degree, K, ptr(features_dc), ptr(features_rest), color_stride,
+                                         depth_channel, ptr(radii), ptr(means2d), ptr(depths), ptr(conics),
+                                         ptr(colors), ptr(tiles), ptr(legacy_extra), _stream()),
+              "fsb_project_params_fwd")
+        kernel_timer.stop(ev)
+        ctx.save_for_backward(means, quats, log_scales, features_dc, features_rest, viewmats, Ks, radii)
+        ctx.cfg = (width, height, eps2d, sh_degree, K, color_stride, depth_channel)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii, tiles)
+        return radii, means2d, depths, conics, colors, tiles
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_colors, _v_tiles):
+        means, quats, log_scales, features_dc, features_rest, viewmats, Ks, radii = ctx.saved_tensors
+        width, height, eps2d, sh_degree, K, color_stride, depth_channel = ctx.cfg
+        C, N = radii.shape
+        dev = means.device
+        v_means2d = _f32c(v_means2d) if v_means2d is not None else torch.zeros((C, N, 2), device=dev)
+        v_conics = _f32c(v_conics) if v_conics is not None else torch.zeros((C, N, 3), device=dev)
+        v_colors = _f32c(v_colors) if v_colors is not None else torch.zeros((C, N, color_stride), device=dev)
+        v_depths = _f32c(v_depths)
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(log_scales)
+        v_dc = torch.empty_like(features_dc)
+        v_rest = torch.empty_like(features_rest) if features_rest is not None else None
+        ev = kernel_timer.start("project_sh_bwd")
+        check(lib.fsb_project_params_bwd(C, N, ptr(means), ptr(quats), ptr(log_scales), 1, ptr(viewmats), ptr(Ks),
+                                         width, height, eps2d, sh_degree, K, ptr(features_dc), ptr(features_rest),
+                                         color_stride, depth_channel, ptr(radii), ptr(v_means2d), ptr(v_depths),
+                                         ptr(v_conics), ptr(v_colors), ptr(v_means), ptr(v_quats), ptr(v_scales),
+                                         ptr(v_dc), ptr(v_rest), _stream()), "fsb_project_params_bwd")
+        kernel_timer.stop(ev)
+        return (v_means, v_quats, v_scales, v_dc, v_rest) + (None,) * 13
+
+
 class RasterizeToPixels(torch.autograd.Function):
     """rasterize_to_pixels of gsplat 1.0.0 (optionally with the ED normalisation fused in)."""
 

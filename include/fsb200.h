@@ -61,6 +61,29 @@ int fsb_project_sh_bwd(int C, int N, const float* means, const float* quats, con
                        float* v_quats, float* v_scales, float* v_coeffs, float* v_viewmats, float* v_campos,
                        void* stream);
 
+/* P1+P2+I1(count) and P3 fed with the model's parameters AS STORED (dn_splatter/dn_model.py:294-304), fusing the
+ * activations and the concatenation that dn_model.py:566-574 issues as separate torch launches before the call:
+ *   scales: log-scales when exp_scales != 0 (exp applied inside; v_scales is then d/d log-scale);
+ *   quats: any norm (normalised inside either way; v_quats is w.r.t. the stored quaternion);
+ *   SH coefficients as two tensors, features_dc[N,3] (band 0) and features_rest[N,K-1,3] (NULL iff K == 1), read
+ *   and differentiated in place instead of through torch.cat -> [N,K,3] and the split of its gradient.
+ * K <= 16, 0 <= sh_degree <= 3, camera centres are evaluated inside, no compensation output, no view-matrix
+ * gradient (camera optimiser off: dn_model.py:128-130).  Outputs as fsb_project_sh_fwd / _bwd, all overwritten. */
+int fsb_project_params_fwd(int C, int N, const float* means, const float* quats, const float* scales,
+                           int exp_scales, const float* viewmats, const float* Ks, int width, int height,
+                           float eps2d, float near_plane, float far_plane, float radius_clip, int tile_size,
+                           int tile_w, int tile_h, int sh_degree, int K, const float* features_dc,
+                           const float* features_rest, int color_stride, int depth_channel, int32_t* radii,
+                           float* means2d, float* depths, float* conics, float* colors,
+                           int32_t* tiles_per_gauss, int64_t* legacy_extra, void* stream);
+int fsb_project_params_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                           int exp_scales, const float* viewmats, const float* Ks, int width, int height,
+                           float eps2d, int sh_degree, int K, const float* features_dc,
+                           const float* features_rest, int color_stride, int depth_channel,
+                           const int32_t* radii, const float* v_means2d, const float* v_depths,
+                           const float* v_conics, const float* v_colors, float* v_means, float* v_quats,
+                           float* v_scales, float* v_features_dc, float* v_features_rest, void* stream);
+
 /* I1 (count only) for callers that bring their own 2-D means / radii.
  * legacy_bbox = 1 selects the gsplat 0.1.x rule ((int) truncation, +1 on the max side) used by
  * gsplat.rasterize_gaussians (dn_splatter/dn_model.py:644-653); 0 = floor/ceil rule of gsplat 1.0. */
@@ -277,6 +300,27 @@ int fsb_dn_loss_bwd(int H, int W, const float* depth, const float* sensor, const
                     float depth_tol, float rgb_clamp_min, float l_sensor, float l_smooth, float l_nl1, float l_ntv,
                     float l_rgb, const void* workspace, const float* v_loss, float* v_depth, float* v_normal,
                     float* v_rgb, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image-space glue of DNSplatterModel.get_outputs, fused (P = H*W pixels of ONE camera).
+ * fsb_compose_rgbd_*: replaces dn_splatter/dn_model.py:602-604 and :609-613
+ *   rgb[P,3] = clamp(render[P,0:3] + (1 - alpha[P]) * background[3], 0, 1)
+ *   depth[P] = alpha > 0 ? render[P,3] : max_p render[p,3]     (the maximum is detached, as in the reference)
+ *   render[P,4] must be 16-byte aligned; background is a DEVICE pointer; scratch: 4 bytes.
+ *   bwd: v_rgb[P,3] / v_depth[P] (nullable = zero) -> v_render[P,4], v_alpha[P] (overwritten).
+ * fsb_normal_map_*: replaces dn_model.py:655-656, out[P,3] = (n / ||n|| + 1) / 2 (no epsilon, as there). */
+int fsb_compose_rgbd_fwd(int64_t P, const float* render, const float* alpha, const float* background, float* rgb,
+                         float* depth, float* scratch, void* stream);
+int fsb_compose_rgbd_bwd(int64_t P, const float* render, const float* alpha, const float* background,
+                         const float* v_rgb, const float* v_depth, float* v_render, float* v_alpha, void* stream);
+int fsb_normal_map_fwd(int64_t P, const float* normals_raw, float* out, void* stream);
+int fsb_normal_map_bwd(int64_t P, const float* normals_raw, const float* v_out, float* v_normals_raw, void* stream);
+
+/* Flatness regulariser ("two_d_gaussians").  replaces dn_splatter/dn_model.py:817-819:
+ *   out = mean_i min_k exp(log_scales[i,k])     (device scalar; workspace: 16 bytes)
+ * bwd: v_loss is a DEVICE scalar; v_log_scales[N,3] overwritten (non-zero on the arg-min axis only). */
+int fsb_flatness_fwd(int N, const float* log_scales, void* workspace, float* out, void* stream);
+int fsb_flatness_bwd(int N, const float* log_scales, const float* v_loss, float* v_log_scales, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-Gaussian normals.  replaces dn_splatter/dn_model.py:617-636: one_hot(argmin(scales)) -> R(q) column ->

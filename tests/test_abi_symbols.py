@@ -28,7 +28,7 @@ def test_header_symbols_are_exported():
 def test_pure_host_entry_points_answer_without_a_gpu():
     from fusionsense_b200._abi import lib
 
-    assert lib.fsb_abi_version() == 2
+    assert lib.fsb_abi_version() == 3
     assert lib.fsb_raster_supported_channels(3) == 3 and lib.fsb_raster_supported_channels(6) == 8
     assert lib.fsb_raster_supported_channels(33) == -1
     assert lib.fsb_isect_scan_workspace(5000) == 3 * 8

@@ -14,7 +14,8 @@ def _models(n=20000, W=320, H=240, **kw):
 
     sc = make_scene(n, W, H, n_views=3, cfg_id=51, kind="bunny", fx=300.0)
     fused = DNSplatterStep(sc, DNSplatterStepConfig(**kw), device="cuda", step=3000)
-    plain = DNSplatterStep(sc, DNSplatterStepConfig(fused_optimizer=False, fused_losses=False, fused_glue=False, **kw),
+    plain = DNSplatterStep(sc, DNSplatterStepConfig(fused_optimizer=False, fused_losses=False, fused_glue=False,
+                                                     fused_outputs=False, **kw),
                            device="cuda", step=3000)
     return sc, fused, plain
 
