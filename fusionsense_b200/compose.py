@@ -8,6 +8,7 @@ reference's own file keeps issuing the torch ops, which stay correct on the shim
 * `compose_rgbd`      — dn_model.py:602-604 + :609-613  (background blend, clamp, depth fill with the detached max)
 * `normal_map`        — dn_model.py:655-656            ((n / |n| + 1) / 2)
 * `flatness_loss`     — dn_model.py:817-819            (mean_i min_k exp(scales[i, k]))
+* `combine_losses`    — dn_model.py:683-690, :925      (ssim_lambda (1 - ssim) + regulariser + normal_lambda flatness)
 """
 from __future__ import annotations
 
@@ -108,3 +109,33 @@ class _Flatness(torch.autograd.Function):
 def flatness_loss(log_scales: Tensor) -> Tensor:
     """torch.min(torch.exp(log_scales), dim=1, keepdim=True)[0].mean() -> scalar tensor."""
     return _Flatness.apply(log_scales)
+
+
+class _LossCombine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ssim, reg, flat, w_ssim, w_flat):
+        ts = [None if t is None else _f32c(t) for t in (ssim, reg, flat)]
+        ref = next(t for t in ts if t is not None)
+        _req_cuda(ref)
+        out = torch.empty((), dtype=torch.float32, device=ref.device)
+        check(lib.fsb_loss_combine_fwd(ptr(ts[0]), ptr(ts[1]), ptr(ts[2]), float(w_ssim), float(w_flat), ptr(out),
+                                       _stream()), "fsb_loss_combine_fwd")
+        ctx.present = [t is not None for t in ts]
+        ctx.w = (float(w_ssim), float(w_flat))
+        return out
+
+    @staticmethod
+    def backward(ctx, v_out):
+        v_out = v_out.contiguous().float()
+        need = ctx.needs_input_grad
+        vs = [torch.empty((), dtype=torch.float32, device=v_out.device) if (p and n) else None
+              for p, n in zip(ctx.present, need[:3])]
+        check(lib.fsb_loss_combine_bwd(ptr(v_out), ctx.w[0], ctx.w[1], ptr(vs[0]), ptr(vs[1]), ptr(vs[2]), _stream()),
+              "fsb_loss_combine_bwd")
+        return vs[0], vs[1], vs[2], None, None
+
+
+def combine_losses(ssim, reg, flat, ssim_lambda: float, flat_lambda: float) -> Tensor:
+    """ssim_lambda * (1 - ssim) + reg + flat_lambda * flat -> scalar tensor, in one launch each way (the reference
+    assembles main_loss from ~7 scalar torch ops, dn_model.py:683-690 / :925).  Any term may be None."""
+    return _LossCombine.apply(ssim, reg, flat, ssim_lambda, flat_lambda)

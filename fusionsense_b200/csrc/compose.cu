@@ -161,6 +161,27 @@ flatness_bwd_kernel(int N, const float* __restrict__ log_scales, const float* __
     v_log_scales[3 * (size_t)n + 2] = (k == 2) ? g : 0.f;
 }
 
+// main_loss = w_ssim * (1 - ssim) + reg + w_flat * flat, evaluated in the order torch evaluates
+// dn_model.py:683-690 / :925 (each product and sum rounded on its own), and its three scalar cotangents.
+__global__ void loss_combine_fwd_kernel(const float* __restrict__ ssim, const float* __restrict__ reg,
+                                        const float* __restrict__ flat, float w_ssim, float w_flat,
+                                        float* __restrict__ out) {
+    float v = 0.f;
+    if (ssim) v = __fmul_rn(w_ssim, __fsub_rn(1.f, *ssim));
+    if (reg) v = __fadd_rn(v, *reg);
+    if (flat) v = __fadd_rn(v, __fmul_rn(w_flat, *flat));
+    *out = v;
+}
+
+__global__ void loss_combine_bwd_kernel(const float* __restrict__ v_out, float w_ssim, float w_flat,
+                                        float* __restrict__ v_ssim, float* __restrict__ v_reg,
+                                        float* __restrict__ v_flat) {
+    const float v = *v_out;
+    if (v_ssim) *v_ssim = -(w_ssim * v);
+    if (v_reg) *v_reg = v;
+    if (v_flat) *v_flat = w_flat * v;
+}
+
 }  // namespace
 
 // render[P,4] (RGB premultiplied + expected depth), alpha[P], background[3] (device) ->
@@ -228,6 +249,25 @@ FSB_API int fsb_flatness_bwd(int N, const float* log_scales, const float* v_loss
     if (N <= 0 || !log_scales || !v_loss || !v_log_scales) return FSB_E_ARG;
     flatness_bwd_kernel<<<fsb_div_up(N, C_THREADS), C_THREADS, 0, (cudaStream_t)stream>>>(N, log_scales, v_loss,
                                                                                          v_log_scales);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// out = w_ssim * (1 - *ssim) + *reg + w_flat * *flat  (device scalars; a NULL term is left out).
+// Replaces the scalar torch launches that assemble main_loss (dn_splatter/dn_model.py:683-690, :925).
+FSB_API int fsb_loss_combine_fwd(const float* ssim, const float* reg, const float* flat, float w_ssim, float w_flat,
+                                 float* out, void* stream) {
+    if (!out) return FSB_E_ARG;
+    loss_combine_fwd_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ssim, reg, flat, w_ssim, w_flat, out);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// v_out: DEVICE scalar; v_ssim / v_reg / v_flat: device scalars, nullable, overwritten.
+FSB_API int fsb_loss_combine_bwd(const float* v_out, float w_ssim, float w_flat, float* v_ssim, float* v_reg,
+                                 float* v_flat, void* stream) {
+    if (!v_out) return FSB_E_ARG;
+    loss_combine_bwd_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(v_out, w_ssim, w_flat, v_ssim, v_reg, v_flat);
     FSB_LAUNCH_CHECK();
     return 0;
 }

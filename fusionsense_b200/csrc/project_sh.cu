@@ -242,10 +242,46 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
         bool vis = live && radii[idx] > 0;
         if (coeffs_in_tile) {
             const unsigned vmask = __ballot_sync(0xffffffffu, vis);
-            for (int r = 0; r < 32; ++r) {
-                if (!((vmask >> r) & 1u)) continue;
-                if (lane < L) tile[r][lane] = sh_load(coeffs, coeffs_rest, n0 + r, L, lane);
-                if (lane + 32 < L) tile[r][lane + 32] = sh_load(coeffs, coeffs_rest, n0 + r, L, lane + 32);
+            if (split) {
+                // The warp's 32 rows of features_rest are one contiguous run of 32 (L - 3) floats: copy it flat,
+                // lane-contiguous (every request is a full 128-B line), and in batches of independent loads — a
+                // row-at-a-time loop waits for each row's data before it asks for the next (first split version:
+                // 108 us against 60 us for the same bytes).  Rows of culled Gaussians are skipped.
+                if (vis) {
+                    tile[lane][0] = coeffs[3 * (size_t)n + 0];
+                    tile[lane][1] = coeffs[3 * (size_t)n + 1];
+                    tile[lane][2] = coeffs[3 * (size_t)n + 2];
+                }
+                const int LR = L - 3;
+                const int total = min(32, N - n0) * LR;
+                const float* base = coeffs_rest + (size_t)n0 * LR;
+                constexpr int UB = 8;
+                int r = 0, col = lane;          // element e = lane + 32 it  ->  (row r, column col) of the run
+                while (col >= LR) { col -= LR; ++r; }
+                for (int e0 = lane; e0 < total; e0 += 32 * UB) {
+                    float v[UB];
+                    int rr[UB], cc[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const int e = e0 + 32 * u;
+                        rr[u] = r; cc[u] = col;
+                        const bool ok = e < total && ((vmask >> r) & 1u);
+                        v[u] = ok ? base[e] : 0.f;
+                        if (!ok) rr[u] = -1;
+                        col += 32;
+                        while (col >= LR) { col -= LR; ++r; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u)
+                        if (rr[u] >= 0) tile[rr[u]][3 + cc[u]] = v[u];
+                }
+            } else {
+                for (int r = 0; r < 32; ++r) {
+                    if (!((vmask >> r) & 1u)) continue;
+                    const float* row = coeffs + (size_t)(n0 + r) * L;
+                    if (lane < L) tile[r][lane] = row[lane];
+                    if (lane + 32 < L) tile[r][lane + 32] = row[lane + 32];
+                }
             }
             __syncwarp();
         }
@@ -364,14 +400,28 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
             }
             __syncwarp();
             const int rows = min(32, N - n0);
-            for (int r = 0; r < rows; ++r) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = lane + 32 * h;
-                    if (j >= L) continue;
-                    bool in_rest;
-                    const size_t at = sh_index(split, n0 + r, L, j, &in_rest);
-                    (in_rest ? v_coeffs_rest : v_coeffs)[at] = tile[r][j];
+            if (split) {
+                if (live) {
+                    v_coeffs[3 * (size_t)n + 0] = tile[lane][0];
+                    v_coeffs[3 * (size_t)n + 1] = tile[lane][1];
+                    v_coeffs[3 * (size_t)n + 2] = tile[lane][2];
+                }
+                const int LR = L - 3;
+                const int total = rows * LR;
+                float* base = v_coeffs_rest + (size_t)n0 * LR;
+                int r = 0, col = lane;
+                while (col >= LR) { col -= LR; ++r; }
+#pragma unroll 4
+                for (int e = lane; e < total; e += 32) {
+                    base[e] = tile[r][3 + col];
+                    col += 32;
+                    while (col >= LR) { col -= LR; ++r; }
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    float* row = v_coeffs + (size_t)(n0 + r) * L;
+                    if (lane < L) row[lane] = tile[r][lane];
+                    if (lane + 32 < L) row[lane + 32] = tile[r][lane + 32];
                 }
             }
         } else if (live) {

@@ -1,5 +1,7 @@
-// radix_sort.cu — stable LSD radix sort of (uint64 key, int32 value) pairs, 8-bit digits,
+// radix_sort.cu — stable LSD radix sort of (uint64 key, int32 value) pairs, 8- or 9-bit digits,
 // one read + one write of the pairs per pass ("onesweep": chained-scan with decoupled look-back).
+// The digit width is the one that needs fewer passes for the caller's end_bit: the intersection keys of a
+// single-camera 640x480 .. 1080p frame have 43 .. 45 significant bits, which is 6 passes of 8 bits but 5 of 9.
 //
 // Replaces the cub::DeviceRadixSort::SortPairs call inside gsplat 1.0.0's isect_tiles and the
 // torch.sort of the legacy bin_and_sort_gaussians, reached from
@@ -12,7 +14,7 @@
 
 namespace {
 
-constexpr int RADIX = 256;
+constexpr int MAX_RADIX = 512;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int KPT = 16;                         // keys per thread
@@ -24,9 +26,18 @@ constexpr uint32_t FLAG_INC = 2u << 30;
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VAL_MASK = ~FLAG_MASK;
 
+// digit of pass p: key bits [BITS p, min(BITS (p + 1), end_bit))
+template <int BITS>
+__device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, int end_bit) {
+    const int w = min(BITS, end_bit - shift);
+    return (uint32_t)((key >> shift) & ((1u << w) - 1u));
+}
+
+template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ keys, int passes,
-                  uint32_t* __restrict__ hist) {
+                  int end_bit, uint32_t* __restrict__ hist) {
+    constexpr int RADIX = 1 << BITS;
     n = fsb_eff_n(n, n_dev);
     __shared__ uint32_t sh[MAX_PASSES][RADIX];
     for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += SORT_THREADS) (&sh[0][0])[i] = 0;
@@ -40,9 +51,16 @@ radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* 
         bool valid = i < n;
         uint64_t key = valid ? keys[i] : 0;
         for (int p = 0; p < passes; ++p) {
-            uint32_t d = valid ? (uint32_t)((key >> (8 * p)) & 0xff) : 0xffffffffu;
-            uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&sh[p][d], __popc(peers));
+            uint32_t d = valid ? digit_of<BITS>(key, BITS * p, end_bit) : 0xffffffffu;
+            if (BITS * (p + 1) <= 23) {
+                // digit inside the mantissa of the depth: values are spread, same-address conflicts are rare, and a
+                // plain shared-memory atomic is cheaper than MATCH.ANY (the unit the ranking loop also leans on)
+                if (valid) atomicAdd(&sh[p][d], 1u);
+            } else {
+                // exponent / tile / camera bits: neighbouring keys share them, so combine equal digits first
+                uint32_t peers = __match_any_sync(0xffffffffu, d);
+                if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&sh[p][d], __popc(peers));
+            }
         }
     }
     __syncthreads();
@@ -52,12 +70,16 @@ radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* 
     }
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ keys_in,
                      const int32_t* __restrict__ vals_in,
                      uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ pass_hist, volatile uint32_t* status, uint32_t* tile_counter,
-                     int shift) {
+                     int shift, int end_bit) {
+    constexpr int RADIX = 1 << BITS;
+    constexpr int DPT = RADIX / SORT_THREADS;  // digits owned by a thread: DPT t .. DPT t + DPT - 1
+    static_assert(DPT >= 1 && RADIX <= MAX_RADIX, "digit width");
     __shared__ uint32_t warp_hist[SORT_WARPS][RADIX];
     __shared__ uint32_t digit_base[RADIX];
     __shared__ uint32_t scan_tmp[SORT_WARPS];
@@ -88,7 +110,7 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
     for (int k = 0; k < KPT; ++k) {
         int64_t i = tile_base + k * 32 + lane;
         bool valid = i < n;
-        uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+        uint32_t d = digit_of<BITS>(key[k], shift, end_bit);
         uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
         int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
@@ -102,34 +124,72 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
     }
     __syncthreads();
 
-    // thread d owns digit d: exclusive prefix over the CTA's warps, chained scan over earlier tiles
+    // a thread owns DPT adjacent digits: exclusive prefix over the CTA's warps, chained scan over earlier tiles
     {
-        const int d = tid;
-        uint32_t total = 0;
+        uint32_t total[DPT], excl[DPT];
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            uint32_t c = warp_hist[w][d];
-            warp_hist[w][d] = total;
-            total += c;
-        }
-        volatile uint32_t* my = status + (size_t)tile * RADIX + d;
-        *my = (tile == 0 ? FLAG_INC : FLAG_AGG) | total;
-        uint32_t excl = 0;
-        if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint32_t v = status[(size_t)t * RADIX + d];
-                uint32_t f = v & FLAG_MASK;
-                if (f == 0) continue;  // predecessor has not published yet
-                excl += v & VAL_MASK;
-                if (f == FLAG_INC) break;
-                --t;
+        for (int j = 0; j < DPT; ++j) {
+            const int d = tid * DPT + j;
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                uint32_t c = warp_hist[w][d];
+                warp_hist[w][d] = tot;
+                tot += c;
             }
-            *my = FLAG_INC | (excl + total);
+            total[j] = tot;
+            status[(size_t)tile * RADIX + d] = (tile == 0 ? FLAG_INC : FLAG_AGG) | tot;
         }
-        // exclusive scan of the pass histogram over digits -> global base of digit d
-        uint32_t h = pass_hist[d];
-        uint32_t inc = h;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const int d = tid * DPT + j;
+            uint32_t ex = 0;
+            if (tile > 0) {
+                // Look-back in windows of LB predecessors: the LB status words are requested together and then
+                // consumed nearest-first up to the first one that is not published yet (re-read from there) or
+                // the first inclusive prefix.  At these sizes every tile is resident at once, so a one-word-at-a-
+                // time walk is a serial chain of ~tiles / 2 dependent L2 round trips per pass (r01h: 14 us per
+                // pass for 104 tiles); the window divides that chain by LB.
+                constexpr int LB = 8;
+                int64_t t = (int64_t)tile - 1;
+                bool found = false;
+                while (!found) {
+                    uint32_t v[LB];
+#pragma unroll
+                    for (int u = 0; u < LB; ++u) {
+                        const int64_t tt = t - u;
+                        v[u] = FLAG_INC + 0u;  // before tile 0: an inclusive prefix of 0
+                        if (tt >= 0) v[u] = status[(size_t)tt * RADIX + d];
+                    }
+                    int adv = 0;
+                    bool stop = false;
+#pragma unroll
+                    for (int u = 0; u < LB; ++u) {
+                        if (stop) continue;
+                        const uint32_t f = v[u] & FLAG_MASK;
+                        if (f == 0) {
+                            stop = true;  // not published yet: everything behind it is read again
+                        } else {
+                            ex += v[u] & VAL_MASK;
+                            adv = u + 1;
+                            if (f == FLAG_INC) { found = true; stop = true; }
+                        }
+                    }
+                    t -= adv;
+                }
+                status[(size_t)tile * RADIX + d] = FLAG_INC | (ex + total[j]);
+            }
+            excl[j] = ex;
+        }
+        // exclusive scan of the pass histogram over digits -> global base of each digit
+        uint32_t h[DPT];
+        uint32_t hsum = 0;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            h[j] = pass_hist[tid * DPT + j];
+            hsum += h[j];
+        }
+        uint32_t inc = hsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, o);
@@ -137,11 +197,15 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
         }
         if (lane == 31) scan_tmp[warp] = inc;
         __syncthreads();
-        uint32_t wbase = 0;
+        uint32_t run = inc - hsum;  // digits of earlier threads of this warp
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w)
-            if (w < warp) wbase += scan_tmp[w];
-        digit_base[d] = wbase + inc - h + excl;
+            if (w < warp) run += scan_tmp[w];
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            digit_base[tid * DPT + j] = run + excl[j];
+            run += h[j];
+        }
     }
     __syncthreads();
 
@@ -149,7 +213,7 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
     for (int k = 0; k < KPT; ++k) {
         int64_t i = tile_base + k * 32 + lane;
         if (i < n) {
-            uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+            uint32_t d = digit_of<BITS>(key[k], shift, end_bit);
             uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[k];
             keys_out[pos] = key[k];
             vals_out[pos] = val[k];
@@ -160,14 +224,44 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
 }  // namespace
 
 static inline int64_t sort_num_tiles(int64_t n) { return n > 0 ? (n + SORT_TILE - 1) / SORT_TILE : 1; }
-static inline int sort_num_passes(int end_bit) { return (end_bit + 7) / 8; }
+// 9-bit digits when they save a pass (end_bit 41..45, 49..54, 57..63), else 8-bit
+static inline int sort_digit_bits(int end_bit) { return (end_bit + 8) / 9 < (end_bit + 7) / 8 ? 9 : 8; }
+static inline int sort_num_passes(int end_bit) {
+    const int b = sort_digit_bits(end_bit);
+    return (end_bit + b - 1) / b;
+}
 
 FSB_API size_t fsb_radix_sort_workspace(int64_t n, int end_bit) {
-    int passes = sort_num_passes(end_bit);
-    size_t bytes = (size_t)passes * RADIX * sizeof(uint32_t);                  // histograms
+    const int passes = sort_num_passes(end_bit);
+    const size_t radix = (size_t)1 << sort_digit_bits(end_bit);
+    size_t bytes = (size_t)passes * radix * sizeof(uint32_t);                  // histograms
     bytes += fsb_align_up((size_t)passes * sizeof(uint32_t), 256);             // tile counters
-    bytes += (size_t)passes * (size_t)sort_num_tiles(n) * RADIX * sizeof(uint32_t);  // look-back status
+    bytes += (size_t)passes * (size_t)sort_num_tiles(n) * radix * sizeof(uint32_t);  // look-back status
     return fsb_align_up(bytes, 256);
+}
+
+template <int BITS>
+static int sort_launch(int64_t n, const int64_t* n_dev, int end_bit, int passes, uint64_t* keys_a, int32_t* vals_a,
+                       uint64_t* keys_b, int32_t* vals_b, void* workspace, cudaStream_t st) {
+    constexpr int RADIX = 1 << BITS;
+    int64_t tiles = sort_num_tiles(n);
+    uint32_t* hist = (uint32_t*)workspace;
+    uint32_t* counters = hist + (size_t)passes * RADIX;
+    uint32_t* status = (uint32_t*)((char*)counters + fsb_align_up((size_t)passes * sizeof(uint32_t), 256));
+    int hist_blocks = (int)(tiles < FSB_NUM_SMS * 8 ? tiles : FSB_NUM_SMS * 8);
+    radix_hist_kernel<BITS><<<hist_blocks, SORT_THREADS, 0, st>>>(n, n_dev, keys_a, passes, end_bit, hist);
+    FSB_LAUNCH_CHECK();
+    uint64_t* kin = keys_a; int32_t* vin = vals_a;
+    uint64_t* kout = keys_b; int32_t* vout = vals_b;
+    for (int p = 0; p < passes; ++p) {
+        onesweep_pass_kernel<BITS><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
+            n, n_dev, kin, vin, kout, vout, hist + (size_t)p * RADIX, status + (size_t)p * tiles * RADIX, counters + p,
+            BITS * p, end_bit);
+        FSB_LAUNCH_CHECK();
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        int32_t* tv = vin; vin = vout; vout = tv;
+    }
+    return 0;
 }
 
 // Sorts pairs by key bits [0, end_bit).  Buffers A (input, clobbered) and B ping-pong;
@@ -183,23 +277,8 @@ FSB_API int fsb_radix_sort_pairs(int64_t n, const int64_t* n_dev, int end_bit, u
     if (result_in_b) *result_in_b = passes & 1;
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t tiles = sort_num_tiles(n);
-    uint32_t* hist = (uint32_t*)workspace;
-    uint32_t* counters = hist + (size_t)passes * RADIX;
-    uint32_t* status = (uint32_t*)((char*)counters + fsb_align_up((size_t)passes * sizeof(uint32_t), 256));
     FSB_CUDA(cudaMemsetAsync(workspace, 0, fsb_radix_sort_workspace(n, end_bit), st));
-    int hist_blocks = (int)(tiles < FSB_NUM_SMS * 8 ? tiles : FSB_NUM_SMS * 8);
-    radix_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(n, n_dev, keys_a, passes, hist);
-    FSB_LAUNCH_CHECK();
-    uint64_t* kin = keys_a; int32_t* vin = vals_a;
-    uint64_t* kout = keys_b; int32_t* vout = vals_b;
-    for (int p = 0; p < passes; ++p) {
-        onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
-            n, n_dev, kin, vin, kout, vout, hist + (size_t)p * RADIX, status + (size_t)p * tiles * RADIX, counters + p,
-            8 * p);
-        FSB_LAUNCH_CHECK();
-        uint64_t* tk = kin; kin = kout; kout = tk;
-        int32_t* tv = vin; vin = vout; vout = tv;
-    }
-    return 0;
+    if (sort_digit_bits(end_bit) == 9)
+        return sort_launch<9>(n, n_dev, end_bit, passes, keys_a, vals_a, keys_b, vals_b, workspace, st);
+    return sort_launch<8>(n, n_dev, end_bit, passes, keys_a, vals_a, keys_b, vals_b, workspace, st);
 }

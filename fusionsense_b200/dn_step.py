@@ -322,8 +322,12 @@ class DNSplatterStep:
         gt_rgb = batch["image"]  # already composited / on device
         pred_img = outputs["rgb"]
         fused = cfg.fused_losses and self.device.type == "cuda"
-        simloss = 1 - self.ssim(gt_rgb.permute(2, 0, 1)[None, ...], pred_img.permute(2, 0, 1)[None, ...])
-        if fused:
+        combine = fused and cfg.fused_outputs  # main_loss assembled by one launch (compose.combine_losses)
+        ssim_val = self.ssim(gt_rgb.permute(2, 0, 1)[None, ...], pred_img.permute(2, 0, 1)[None, ...])
+        simloss = None if combine else 1 - ssim_val
+        if combine:
+            rgb_loss = None
+        elif fused:
             rgb_loss = cfg.ssim_lambda * simloss  # the L1 half rides in the fused kernel below
         else:
             Ll1 = torch.abs(gt_rgb - pred_img).mean()
@@ -359,13 +363,14 @@ class DNSplatterStep:
                 normal_loss = normal_loss + torch.abs(gt_normal - pred_normal).mean()
                 if cfg.use_normal_tv_loss:
                     normal_loss = normal_loss + self.tv_loss(pred_normal)
-        if cfg.two_d_gaussians:
-            if fused and cfg.fused_outputs:
-                from .compose import flatness_loss
+        if combine:
+            from .compose import combine_losses, flatness_loss
 
-                normal_loss = normal_loss + flatness_loss(self.scales)
-            else:
-                normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
+            flat = flatness_loss(self.scales) if cfg.two_d_gaussians else None
+            main_loss = combine_losses(ssim_val, reg, flat, cfg.ssim_lambda, cfg.normal_lambda)
+            return {"main_loss": main_loss, "scale_reg": torch.zeros((), device=self.device)}
+        if cfg.two_d_gaussians:
+            normal_loss = normal_loss + torch.min(torch.exp(self.scales), dim=1, keepdim=True)[0].mean()
         main_loss = rgb_loss + depth_loss + cfg.normal_lambda * normal_loss
         return {"main_loss": main_loss, "scale_reg": torch.zeros((), device=self.device)}
 

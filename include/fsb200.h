@@ -322,6 +322,14 @@ int fsb_normal_map_bwd(int64_t P, const float* normals_raw, const float* v_out, 
 int fsb_flatness_fwd(int N, const float* log_scales, void* workspace, float* out, void* stream);
 int fsb_flatness_bwd(int N, const float* log_scales, const float* v_loss, float* v_log_scales, void* stream);
 
+/* main_loss assembly.  replaces the scalar torch launches of dn_splatter/dn_model.py:683-690 and :925:
+ *   out = w_ssim * (1 - *ssim) + *reg + w_flat * *flat     (device scalars; a NULL term is left out)
+ * bwd: v_out is a DEVICE scalar; v_ssim = -w_ssim v, v_reg = v, v_flat = w_flat v (nullable, overwritten). */
+int fsb_loss_combine_fwd(const float* ssim, const float* reg, const float* flat, float w_ssim, float w_flat,
+                         float* out, void* stream);
+int fsb_loss_combine_bwd(const float* v_out, float w_ssim, float w_flat, float* v_ssim, float* v_reg, float* v_flat,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Per-Gaussian normals.  replaces dn_splatter/dn_model.py:617-636: one_hot(argmin(scales)) -> R(q) column ->
  * normalize -> flip towards the camera -> rotate into the camera frame (normals @ c2w[:3,:3]).

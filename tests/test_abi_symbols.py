@@ -101,3 +101,33 @@ def test_gsplat_shim_resolves_reference_imports():
         for k in [k for k in sys.modules if k == "gsplat" or k.startswith("gsplat.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_every_call_site_passes_the_declared_number_of_arguments():
+    """ctypes checks types, not meaning: a call with a missing or extra argument would only fail on the GPU box.
+    Walk the Python sources and compare every `lib.fsb_*(...)` call with the prototype parsed from the header."""
+    import ast
+    from pathlib import Path
+
+    from fusionsense_b200._abi import parse_header
+
+    protos = parse_header()
+    root = Path(__file__).resolve().parent.parent
+    files = list((root / "fusionsense_b200").rglob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]
+    files += list((root / "tools").glob("*.py"))
+    seen = 0
+    for f in files:
+        for node in ast.walk(ast.parse(f.read_text())):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)
+                    and node.func.attr.startswith("fsb_") and isinstance(node.func.value, ast.Name)
+                    and node.func.value.id == "lib"):
+                continue
+            name = node.func.attr
+            assert name in protos, f"{f.name}:{node.lineno}: {name} is not declared in include/fsb200.h"
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            seen += 1
+            assert len(node.args) == len(protos[name][1]), (
+                f"{f.name}:{node.lineno}: {name} called with {len(node.args)} arguments, header declares "
+                f"{len(protos[name][1])}")
+    assert seen > 40

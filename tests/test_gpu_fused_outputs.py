@@ -91,6 +91,23 @@ def test_flatness_loss_matches_torch(N):
     assert_close(a.grad, b.grad, "flatness.grad", tol=1e-6, outlier_frac=0)
 
 
+def test_combine_losses_matches_torch_bitwise():
+    from fusionsense_b200.compose import combine_losses
+
+    vals = [torch.tensor(v, device="cuda", requires_grad=True) for v in (0.7312345, 0.0412345, 0.0034567)]
+    ref = [v.detach().clone().requires_grad_(True) for v in vals]
+    out = combine_losses(vals[0], vals[1], vals[2], 0.2, 0.4)
+    (out * 0.5).backward()
+    exp = 0.2 * (1 - ref[0]) + ref[1] + 0.4 * (0 + ref[2])
+    (exp * 0.5).backward()
+    assert float(out) == float(exp)
+    for a, b in zip(vals, ref):
+        assert float(a.grad) == pytest.approx(float(b.grad), rel=1e-7)
+    # absent terms
+    o2 = combine_losses(vals[0].detach(), None, None, 0.2, 0.4)
+    assert float(o2) == float(0.2 * (1 - ref[0].detach()))
+
+
 @pytest.mark.parametrize("sh_degree,C", [(3, 1), (1, 1), (0, 1), (2, 2)])
 def test_rasterization_from_params_matches_rasterization(sh_degree, C):
     from fusionsense_b200.gsplat import rasterization, rasterization_from_params

@@ -95,7 +95,7 @@ def test_isect_keys_sort_offsets_bit_exact(n, W, H, C):
 
 
 @pytest.mark.parametrize("n", [0, 1, 33, 4096, 4097, 100003, 3_000_000])
-@pytest.mark.parametrize("end_bit", [8, 13, 44, 64])
+@pytest.mark.parametrize("end_bit", [8, 13, 43, 44, 45, 50, 64])  # 43..45 and 50 take the 9-bit digit path
 def test_radix_sort_pairs_stable(n, end_bit):
     ops = _ops()
     g = torch.Generator().manual_seed(n * 131 + end_bit)
