@@ -172,7 +172,13 @@ class DNSplatterStep:
         scales_crop, quats_crop = self.scales, self.quats
         BLOCK_WIDTH = 16
         if isinstance(cam_idx, Tensor):  # device index (captured step: the view is chosen at replay time)
-            viewmat, K, c2w = (t.index_select(0, cam_idx) for t in (sc.viewmats, sc.Ks, sc.c2w))
+            # one gather for the three camera matrices: rows of [viewmat | K | c2w] (41 floats per view)
+            if getattr(self, "_cam_pack", None) is None:
+                V = sc.viewmats.shape[0]
+                self._cam_pack = torch.cat([sc.viewmats.reshape(V, 16), sc.Ks.reshape(V, 9), sc.c2w.reshape(V, 16)],
+                                           dim=1).contiguous()
+            row = self._cam_pack.index_select(0, cam_idx)[0]
+            viewmat, K, c2w = row[0:16].view(1, 4, 4), row[16:25].view(1, 3, 3), row[25:41].view(1, 4, 4)
         else:
             viewmat = sc.viewmats[cam_idx:cam_idx + 1]
             K = sc.Ks[cam_idx:cam_idx + 1]
