@@ -10,7 +10,7 @@ SECONDS=0; timeout 900 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/
 tail -3 $OUT/${TAG}_pytest_gpu.log; echo "t=${SECONDS}s"
 timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; tail -1 $OUT/${TAG}_smoke.log
 timeout 600 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench_graph.json 2> $OUT/${TAG}_bench_graph.err; tail -c 300 $OUT/${TAG}_bench_graph.json; echo "t=${SECONDS}s"
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; tail -c 300 $OUT/${TAG}_bench_reference.json; echo "t=${SECONDS}s"
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; tail -c 300 $OUT/${TAG}_bench_reference.json; echo "t=${SECONDS}s"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
    --log-file $OUT/${TAG}_launches_graph.csv env FSB_PROFILE=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'raster_(bwd|seg)_kernel' -c 6 \

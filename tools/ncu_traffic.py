@@ -74,7 +74,7 @@ def main(path, needle="raster_bwd_kernel<4", out=None):
             "dram_bytes_per_launch": d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0),
             "dram_bytes_read": d.get("dram__bytes_read.sum"),
             "dram_bytes_write": d.get("dram__bytes_write.sum"),
-            "ncu_duration_ns": d.get("gpu__time_duration.sum"),
+            "ncu_duration_us": d.get("gpu__time_duration.sum"),
             "source": f"ncu --set full --clock-control none, launch id {d['id']} of `bench.py --mode eager` on cfg2 ({path.split('/')[-1]})",
         }
         with open(out, "w") as f:
