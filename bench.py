@@ -74,7 +74,9 @@ def _fp32_roofline(pairs, ktimes, D, clocks):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up on; every sample is stamped on
+    arrival and `stop(t0, t1)` reports the ones that fall inside the timed region (all of them, flagged, if the region
+    was too short to catch one)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -86,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -94,15 +96,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
+        rows = list(self.rows)
+        have = t0 is not None and t1 is not None
+        inside = [r for t, r in rows if have and t0 <= t <= t1 + 0.05]
+        # a region shorter than the sampling period: the samples next to it (warm-up steps before, e2e leg after —
+        # the same workload) stand in
+        near = [r for t, r in rows if have and t0 - 0.3 <= t <= t1 + 0.3]
+        window = "timed region" if inside else ("timed region +- 0.3 s (warm-up / e2e leg)" if near else "whole run")
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in (inside or near or [r for _, r in rows]):
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -112,7 +121,8 @@ class ClockSampler:
                 if len(r) > idx and r[idx].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def build_model(device, gsplat_module=None, fused=True):
@@ -275,6 +285,9 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # warm-up (also primes the caching allocator and, in graph mode, captures the step)
     for i in range(args.warmup):
         one_step(i, False, False)
@@ -284,15 +297,14 @@ def run_ours(args):
             one_step(i, False, False)
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.fsb_launch_count()
     replays0 = runner.replays if runner else 0
     profiling = os.environ.get("FSB_PROFILE") == "1"  # ncu --profile-from-start off: capture the timed steps only
     if profiling:
         torch.cuda.profiler.start()
+    t_region0 = time.perf_counter()
     ms_total = timed(args.steps, False, False)
+    t_region1 = time.perf_counter()
     if profiling:
         torch.cuda.profiler.stop()
     launches = lib.fsb_launch_count() - launches0
@@ -305,7 +317,7 @@ def run_ours(args):
         launches += (runner.replays - replays0) * runner.launches_per_replay
         graph_info = {"captures": runner.captures, "capacity": runner.capacity, "n_isects": info["n_isects"],
                       "n_isects_normals": info["n_isects_normals"], "libfsb200_launches_per_replay": runner.launches_per_replay}
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     ms_e2e = timed(args.steps, True, True)
     if runner is not None and runner.poll()["overflowed_steps"]:
         raise SystemExit("bench: a step of the e2e leg overflowed the intersection capacity; rerun")
@@ -429,7 +441,7 @@ def _emit(line: dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
