@@ -74,9 +74,11 @@ def _fp32_roofline(pairs, ktimes, D, clocks):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up on; every sample is stamped on
+    """nvidia-smi clocks / throttle reasons sampled every 500 ms from before the warm-up on; every sample is stamped on
     arrival and `stop(t0, t1)` reports the ones that fall inside the timed region (all of them, flagged, if the region
-    was too short to catch one)."""
+    was too short to catch one).  The period is deliberately long: every nvidia-smi query stalls the GPU for ~3.6 ms
+    (r01l: five samples inside a 219 ms region cost 8 % of the measured rate), so the default run times 1000 steps
+    (~1 s) and takes two samples inside it."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -88,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "500", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -441,7 +443,7 @@ def _emit(line: dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
