@@ -25,6 +25,29 @@ SEG = 512
 FOOT = [(8, 4), (16, 2), (4, 8)]  # (width, height) of a warp's pixel footprint inside the 16x16 tile
 
 
+def rect_reach(gx, gy, opac, a, b, c, x0, x1, y0, y1):
+    """The test of csrc/raster.cu::strip_mask on one rectangle of pixel centres [x0, x1] x [y0, y1] (float32, the
+    kernel's arithmetic): can alpha reach 1/255 anywhere in it?  min over the rectangle of
+    q(d) = a dx^2 + 2 b dx dy + c dy^2 against 2 ln(255 opacity), inflated; doubtful inputs answer yes."""
+    f = np.float32
+    gx, gy, opac, a, b, c = (np.asarray(v, dtype=f) for v in (gx, gy, opac, a, b, c))
+    tau = np.log(f(255.0) * opac).astype(f)
+    never = tau + f(2e-3) < 0
+    det = a * c - b * b
+    doubtful = ~(det > 0) | ~(a > 0) | ~(tau < f(1e30))
+    thr = f(2.0) * tau * f(1.0002) + f(1e-2)
+    X0, X1, Y0, Y1 = f(x0) - gx, f(x1) - gx, f(y0) - gy, f(y1) - gy
+    inside = (X0 <= 0) & (X1 >= 0) & (Y0 <= 0) & (Y1 >= 0)
+    with np.errstate(all="ignore"):
+        nb_c, nb_a = -b / c, -b / a
+        t = np.minimum(np.maximum(nb_c * X0, Y0), Y1); q = a * X0 * X0 + f(2) * b * X0 * t + c * t * t
+        t = np.minimum(np.maximum(nb_c * X1, Y0), Y1); q = np.minimum(q, a * X1 * X1 + f(2) * b * X1 * t + c * t * t)
+        t = np.minimum(np.maximum(nb_a * Y0, X0), X1); q = np.minimum(q, a * t * t + f(2) * b * t * Y0 + c * Y0 * Y0)
+        t = np.minimum(np.maximum(nb_a * Y1, X0), X1); q = np.minimum(q, a * t * t + f(2) * b * t * Y1 + c * Y1 * Y1)
+    q = np.where(inside, f(0), q)
+    return ~never & (doubtful | ~(q > thr))
+
+
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
     view = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -55,6 +78,7 @@ def main():
     segs_needed = 0                                               # segments up to the tile's deepest last id
     geo_miss = 0                                                  # (tile, entry): alpha test fails on every pixel
     pruned_lens = np.zeros(tw * th, dtype=np.int64)               # list lengths without the geometric misses
+    rect_kept = rect_false_prunes = 0                             # the kernel's rectangle test at tile granularity
     for lin in range(tw * th):
         s, e = offs[lin], offs[lin + 1]
         if e <= s:
@@ -87,6 +111,10 @@ def main():
         hit = valid.any(axis=0)
         geo_miss += int((~hit).sum())
         pruned_lens[lin] = int(hit.sum())
+        keep = rect_reach(m2[g, 0], m2[g, 1], op[g], conics[g, 0], conics[g, 1], conics[g, 2],
+                          tx * ts + 0.5, min(tx * ts + ts, W) - 0.5, ty * ts + 0.5, min(ty * ts + ts, H) - 0.5)
+        rect_kept += int(keep.sum())
+        rect_false_prunes += int((hit & ~keep).sum())
         grid_c = contrib.reshape(ts, ts, -1)
         grid_v = valid.reshape(ts, ts, -1)
         for (fw, fh) in FOOT:
@@ -121,6 +149,8 @@ def main():
             "p99": float(np.percentile(pruned_lens, 99)), "max": int(pruned_lens.max()),
             "tiles_over_one_segment": int((pruned_lens > SEG).sum()),
             "segments_total": int(np.maximum(1, -(-pruned_lens // SEG)).sum())},
+        "tile_rectangle_test": {"kept": rect_kept, "pruned": int(lens.sum()) - rect_kept,
+                                "entries_pruned_that_touch_a_pixel": rect_false_prunes},
         "stop": {"pixels_that_stop": stop_pixels, "of_pixels": W * H,
                  "stop_segment_hist": {str(i): int(v) for i, v in enumerate(stop_segment_hist) if v}},
         "per_warp_entry": {f"{fw}x{fh}": {**summarize(hist_warp[(fw, fh)]), "reached_pairs": reach_warp[(fw, fh)]}
