@@ -75,6 +75,10 @@ class DNSplatterStepConfig:
     # dn_model.py:566-574, :602-613, :655-656, :817-819 run inside our kernels instead of ~55 torch launches
     # (FSB_FUSED_OUTPUTS=0 switches it off for A/B runs)
     fused_outputs: bool = field(default_factory=lambda: os.environ.get("FSB_FUSED_OUTPUTS", "1") != "0")
+    # EXPERIMENTAL, off (built in round 1, not yet run on a GPU): bin only the (Gaussian, tile) pairs that can pass
+    # the alpha test somewhere in the tile (csrc/isect_reach.cu; 35 % fewer list entries on the bench scene, same
+    # images and gradients).  Needs fused_outputs; FSB_PRUNE_LISTS=1 switches it on.
+    prune_lists: bool = field(default_factory=lambda: os.environ.get("FSB_PRUNE_LISTS", "0") == "1")
     overlap_normals_pass: bool = True  # captured step only: the normals pass runs on a second stream beside the RGB+ED pass
 
 
@@ -262,7 +266,7 @@ class DNSplatterStep:
         render, alpha, info = self._rasterization_from_params(
             self.means, self.quats, self.scales, opac.squeeze(-1), self.features_dc, self.features_rest,
             viewmats=viewmat, Ks=K, width=W, height=H, sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10,
-            tile_size=BLOCK_WIDTH, render_mode="RGB+ED", absgrad=True)
+            tile_size=BLOCK_WIDTH, render_mode="RGB+ED", absgrad=True, **({"prune_lists": True} if cfg.prune_lists else {}))
         if self.training and info["means2d"].requires_grad:
             info["means2d"].retain_grad()
         self.xys = info["means2d"]

@@ -20,7 +20,7 @@ _LAST_BINNING: dict = {}
 
 def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int, height: int, tile_size: int,
                      n_isects: int, flatten_ids: Tensor, isect_offsets: Tensor,
-                     legacy_extra: Optional[int] = None, lists_done=None) -> None:
+                     legacy_extra: Optional[int] = None, lists_done=None, pruned: bool = False) -> None:
     """Called by `rasterization()` (single-camera case only).
 
     `legacy_extra`: number of tiles by which the 0.1.x bbox rule differs from the 1.0 rule on these Gaussians,
@@ -33,6 +33,7 @@ def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int,
              radii._version, radii.shape[1], width, height, tile_size),
         n_isects=n_isects, flatten_ids=flatten_ids, isect_offsets=isect_offsets, legacy_extra=legacy_extra,
         lists_done=lists_done,  # static-capacity mode: event recorded after the binning (another stream may wait)
+        pruned=pruned,  # EXPERIMENTAL: the lists hold only the reached (Gaussian, tile) pairs (ops.isect_tiles reach=)
     )
 
 
@@ -109,9 +110,12 @@ def rasterize_gaussians(
                 cur = torch.cuda.current_stream()
                 first_flat.record_stream(cur)
                 first_offsets.record_stream(cur)
+                reach = None
+                if _LAST_BINNING.get("pruned"):
+                    reach = (conics.detach()[None], opacity.detach().reshape(1, N))
                 flatten_ids, isect_offsets = ops.isect_tiles_legacy_shared(
                     xys_c[None], rad_c[None], dep_c[None], ts, tile_w, tile_h, first_flat, first_offsets,
-                    lists_done=_LAST_BINNING.get("lists_done"))
+                    lists_done=_LAST_BINNING.get("lists_done"), reach=reach)
             else:
                 _, _, flatten_ids, isect_offsets = ops.isect_tiles(xys_c[None], rad_c[None], dep_c[None], ts, tile_w,
                                                                    tile_h, legacy_bbox=True)

@@ -74,20 +74,26 @@ def rasterization_from_params(
     backgrounds: Optional[Tensor] = None,
     render_mode: Literal["RGB", "RGB+D", "RGB+ED"] = "RGB",
     absgrad: bool = False,
+    prune_lists: bool = False,
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Extension (not part of gsplat): `rasterization(packed=False, rasterize_mode="classic")` of
     `quats / |quats|, exp(log_scales), cat(features_dc[:, None], features_rest)` with those three torch
     expressions (dn_model.py:566-574) evaluated inside the projection kernel and differentiated in place.
-    Same return tuple and meta keys as `rasterization()`."""
+    Same return tuple and meta keys as `rasterization()`.
+
+    `prune_lists` (EXPERIMENTAL, off): bin only the (Gaussian, tile) pairs that can pass the alpha test somewhere in
+    the tile (csrc/isect_reach.cu).  Images and gradients are unchanged; `meta["isect_ids"] / ["flatten_ids"] /
+    ["isect_offsets"]` then hold the pruned lists instead of gsplat's bounding-box lists, `tiles_per_gauss` stays
+    the bounding-box count."""
     assert render_mode in ["RGB", "RGB+D", "RGB+ED"], render_mode
     return _rasterization_impl(means, quats, log_scales, opacities, None, viewmats, Ks, width, height, near_plane,
                                far_plane, radius_clip, eps2d, sh_degree, False, tile_size, backgrounds, render_mode,
-                               False, absgrad, "classic", 32, stored=(features_dc, features_rest))
+                               False, absgrad, "classic", 32, stored=(features_dc, features_rest), prune=prune_lists)
 
 
 def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane, far_plane,
                         radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode, sparse_grad,
-                        absgrad, rasterize_mode, channel_chunk, stored=None):
+                        absgrad, rasterize_mode, channel_chunk, stored=None, prune=False):
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -166,7 +172,7 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
     with torch.no_grad():
         _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(
             means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
-            totals=totals)
+            totals=totals, reach=(conics, opac) if prune else None)
         n_dev = getattr(flatten_ids, "n_dev", None)  # static-capacity mode (ops.static_capacity): count on device
         lists_done = None
         if n_dev is not None:
@@ -174,7 +180,7 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
             lists_done.record()
         remember_binning(means2d, depths, radii, width, height, tile_size, flatten_ids.numel(), flatten_ids,
                          isect_offsets, legacy_extra=totals.host[1] if (C == 1 and n_dev is None) else None,
-                         lists_done=lists_done)
+                         lists_done=lists_done, pruned=prune)
 
     if use_sh:
         ras_colors = sh_colors  # [C, N, 3 or 4], depth already in channel 3

@@ -163,6 +163,18 @@ def isect_count(means2d: Tensor, radii: Tensor, tile_size: int, tile_w: int, til
     return tiles
 
 
+def isect_count_reach(means2d: Tensor, radii: Tensor, conics: Tensor, opacities: Tensor, tile_size: int, tile_w: int,
+                      tile_h: int, legacy_bbox: bool):
+    """EXPERIMENTAL (csrc/isect_reach.cu): tiles of each Gaussian's bounding box on which it can pass the alpha test.
+    means2d [C,N,2], radii [C,N], conics [C,N,3], opacities [C,N] -> counts [C,N] int32."""
+    _req_cuda(means2d, radii, conics, opacities)
+    C, N = radii.shape
+    counts = torch.empty(radii.shape, dtype=torch.int32, device=radii.device)
+    check(lib.fsb_isect_count_reach(C, N, ptr(means2d), ptr(radii), ptr(conics), ptr(opacities), tile_size, tile_w,
+                                    tile_h, int(legacy_bbox), ptr(counts), _stream()), "fsb_isect_count_reach")
+    return counts
+
+
 def isect_scan(counts: Tensor, totals: Optional[Tensor] = None, read_back: bool = True):
     """Exclusive int64 offsets of `counts` and the total (one small D2H read, like gsplat's).
 
@@ -189,16 +201,24 @@ def tile_bits_for(n_tiles: int) -> int:
 
 
 def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox, n_dev=None,
-               overflow=None):
-    """`n_dev` (device int64[1]) selects static-capacity mode: `n_isects` is then the capacity of the buffers."""
+               overflow=None, reach=None):
+    """`n_dev` (device int64[1]) selects static-capacity mode: `n_isects` is then the capacity of the buffers.
+    `reach` = (conics [C,N,3], opacities [C,N]): EXPERIMENTAL, emit only the reached tiles (`offsets` must then be
+    the scan of `isect_count_reach`)."""
     dev = means2d.device
     ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
     flat = torch.empty((n_isects,), dtype=torch.int32, device=dev)
     tb = tile_bits_for(tile_w * tile_h)
     ev = kernel_timer.start("isect_emit")
-    check(lib.fsb_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h, tb,
-                             int(legacy_bbox), ptr(n_dev), n_isects, ptr(overflow), ptr(ids), ptr(flat), _stream()),
-          "fsb_isect_emit")
+    if reach is None:
+        check(lib.fsb_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h,
+                                 tb, int(legacy_bbox), ptr(n_dev), n_isects, ptr(overflow), ptr(ids), ptr(flat),
+                                 _stream()), "fsb_isect_emit")
+    else:
+        check(lib.fsb_isect_emit_reach(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(reach[0]), ptr(reach[1]),
+                                       ptr(offsets), tile_size, tile_w, tile_h, tb, int(legacy_bbox), ptr(n_dev),
+                                       n_isects, ptr(overflow), ptr(ids), ptr(flat), _stream()),
+              "fsb_isect_emit_reach")
     kernel_timer.stop(ev)
     return ids, flat
 
@@ -232,7 +252,7 @@ def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int, n_dev: O
 
 
 def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gauss=None, legacy_bbox=False,
-                sort=True, totals=None):
+                sort=True, totals=None, reach=None):
     """gsplat.isect_tiles + isect_offset_encode in one go (unpacked layout).
 
     means2d [C,N,2], radii [C,N] int32, depths [C,N] -> tiles_per_gauss [C,N], isect_ids [n_isects] int64 (sorted),
@@ -242,27 +262,35 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
     C, N = radii.shape
     if tiles_per_gauss is None:
         tiles_per_gauss = isect_count(means2d, radii, tile_size, tile_w, tile_h, legacy_bbox)
+    # `reach` = (conics [C,N,3], opacities [C,N]), EXPERIMENTAL: the lists hold only the (Gaussian, tile) pairs that can
+    # pass the alpha test somewhere in the tile (csrc/isect_reach.cu); `tiles_per_gauss` stays the bounding-box count
+    # the API reports, the lists are built from the reach counts
+    list_counts = tiles_per_gauss
+    if reach is not None:
+        reach = (_f32c(reach[0]), _f32c(reach[1]))
+        list_counts = isect_count_reach(means2d, radii, reach[0], reach[1], tile_size, tile_w, tile_h, legacy_bbox)
     st = static_mode()
     if st is not None:
         # no host read: buffers for the capacity, the true count stays in totals[0] on the device
         if totals is None:
             totals = torch.zeros(1, dtype=torch.int64, device=radii.device)
-        offsets, _ = isect_scan(tiles_per_gauss, totals, read_back=False)
+        offsets, _ = isect_scan(list_counts, totals, read_back=False)
         n_dev = totals[:1]
         st.counts.append(n_dev)
         ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h,
-                               legacy_bbox, n_dev=n_dev, overflow=st.overflow)
+                               legacy_bbox, n_dev=n_dev, overflow=st.overflow, reach=reach)
         if sort:
             end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
             ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=n_dev)
         tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=n_dev)
         flat.n_dev = n_dev
         return tiles_per_gauss, ids, flat, tile_offsets
-    offsets, n_isects = isect_scan(tiles_per_gauss, totals)
+    offsets, n_isects = isect_scan(list_counts, totals)
     if totals is not None:
         totals.host = n_isects  # the values that came back with the one D2H read
         n_isects = n_isects[0]
-    ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox)
+    ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox,
+                           reach=reach)
     if sort:
         end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
         ids, flat = radix_sort_pairs(ids, flat, end_bit)
@@ -271,7 +299,7 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
 
 
 def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h, first_flat, first_offsets,
-                              lists_done=None):
+                              lists_done=None, reach=None):
     """Static-capacity mode only: binning of the legacy (gsplat 0.1.x bbox rule) normals pass that follows a
     rasterization() on the same projected Gaussians.  The device compares the legacy intersection total with the
     first pass's; when they agree (identical lists) emit / sort / offsets degenerate to no-ops and the first pass's
@@ -283,7 +311,13 @@ def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h,
     _req_cuda(means2d, radii, depths)
     C, N = radii.shape
     dev = radii.device
-    counts = isect_count(means2d, radii, tile_size, tile_w, tile_h, True)
+    # `reach`: the first pass's lists were pruned (isect_tiles(reach=...)), so this pass counts the same way: the
+    # reached tiles of the legacy box are a superset of the reached tiles of the 1.0 box, equal totals <=> same lists
+    if reach is not None:
+        reach = (_f32c(reach[0]), _f32c(reach[1]))
+        counts = isect_count_reach(means2d, radii, reach[0], reach[1], tile_size, tile_w, tile_h, True)
+    else:
+        counts = isect_count(means2d, radii, tile_size, tile_w, tile_h, True)
     totals = torch.zeros(1, dtype=torch.int64, device=dev)
     offsets, _ = isect_scan(counts, totals, read_back=False)
     n_list = totals[:1]
@@ -291,7 +325,7 @@ def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h,
     gate = torch.empty(1, dtype=torch.int64, device=dev)
     check(lib.fsb_isect_share_gate(ptr(first_flat.n_dev), ptr(n_list), ptr(gate), _stream()), "fsb_isect_share_gate")
     ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h, True,
-                           n_dev=gate, overflow=st.overflow)
+                           n_dev=gate, overflow=st.overflow, reach=reach)
     end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
     ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=gate)
     tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=gate)

@@ -90,6 +90,22 @@ int fsb_project_params_bwd(int C, int N, const float* means, const float* quats,
 int fsb_isect_count(int64_t M, const float* means2d, const int32_t* radii, int tile_size, int tile_w,
                     int tile_h, int legacy_bbox, int32_t* tiles_per_gauss, void* stream);
 
+/* EXPERIMENTAL (declared and built in round 1, not yet exercised on a GPU; nothing calls them by default).
+ * I1 with an exact reach test: count / emit only the tiles of the bounding box on which the Gaussian can pass the
+ * alpha test (alpha >= 1/255) at some pixel centre — the pairs the compositing kernels would stage and then skip.
+ * The reference's lists (fsb_isect_count / fsb_isect_emit: gsplat isect_tiles, dn_splatter/dn_model.py:570-591) stay
+ * the bit-exact contract; these serve callers that do not expose the lists (DNSplatterStepConfig.prune_lists).
+ *   conics[C*N,3], opacities[C*N]: what the compositing kernels receive; legacy_bbox as in fsb_isect_count.
+ *   emit: offsets = exclusive scan of the reach counts; static-capacity arguments as in fsb_isect_emit. */
+int fsb_isect_count_reach(int C, int N, const float* means2d, const int32_t* radii, const float* conics,
+                          const float* opacities, int tile_size, int tile_w, int tile_h, int legacy_bbox,
+                          int32_t* counts, void* stream);
+int fsb_isect_emit_reach(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
+                         const float* conics, const float* opacities, const int64_t* offsets, int tile_size,
+                         int tile_w, int tile_h, int tile_bits, int legacy_bbox, const int64_t* n_dev,
+                         int64_t capacity, int32_t* overflow_flag, int64_t* isect_ids, int32_t* flatten_ids,
+                         void* stream);
+
 /* exclusive int64 prefix sum of counts[M] (replaces torch.cumsum inside gsplat isect_tiles);
  * total_dev receives the grand total (= n_isects), a device scalar the caller copies back. */
 size_t fsb_isect_scan_workspace(int64_t M);
