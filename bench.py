@@ -1,15 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — DN-Splatter train step throughput on B200 (BASELINE.json metric, configs[1]).
+"""bench.py — DN-Splatter train step throughput on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg4|cfg2]
 
-Workload (config.workload = "cfg2"): FusionSense sparse-view DN-Splatter training, 9 views 640x480
-RealSense-shaped synthetic bunny scene, 300k Gaussians, one camera view per GPU per iteration:
-get_outputs (RGB+ED rasterization + legacy normals pass) -> losses -> backward -> Adam -> after_train.
-One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for the definition of every key.
+Default workload (config.workload starts with "cfg4" = BASELINE.json configs[3], the configuration the north-star
+target is quoted on): 1M Gaussians, 1920x1080, 8 training views, one camera view per GPU per iteration (at --gpus 8
+the step's camera batch of 8 is sharded over the 8 GPUs): get_outputs (RGB+ED rasterization + legacy normals pass)
+-> losses -> backward -> [gradient all-reduce] -> Adam -> after_train, one CUDA-graph replay per iteration.  The
+FusionSense-sized scene (cfg2 = configs[1]: 300k Gaussians, 640x480, 9 views) rides along in the same line as
+`secondary` (value, e2e and, at N = 1, the shim-only eager value).  One JSON line on stdout (rank 0); DESIGN.md
+§Measurement defines every key.
 
---impl reference: the same step through the CPU oracle (oracle/gsplat_ref.py standing in for gsplat, which is
-not vendored in the reference tree) on the box's host cores, each step a bounded sample of the workload.
+--impl reference: a real gsplat CUDA build if one is importable from baseline/_ref (reported as
+`gsplat_cuda_baseline`; never the case so far: gsplat==1.0.0 is not vendored and there is no wheel), else the same
+step through the CPU oracle (oracle/gsplat_ref.py standing in for gsplat) on the box's host cores, each step a
+bounded sample of the workload.
 """
 from __future__ import annotations
 
@@ -26,10 +31,16 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-N_GAUSS = 300_000
-WIDTH, HEIGHT = 640, 480
-N_VIEWS = 9
-WORKLOAD = "cfg2: DN-Splatter train step, 9 views 640x480 synthetic bunny, 300k Gaussians, 1 view/GPU/iter"
+CONFIGS = {
+    # BASELINE.json configs[1]
+    "cfg2": dict(n=300_000, w=640, h=480, views=9, kind="bunny", cfg_id=2,
+                 workload="cfg2: DN-Splatter train step, 9 views 640x480 synthetic bunny, 300k Gaussians, "
+                          "1 view/GPU/iter"),
+    # BASELINE.json configs[3]: camera batch 8 sharded across 8 GPUs = one view per GPU per iteration
+    "cfg4": dict(n=1_000_000, w=1920, h=1080, views=8, kind="random", cfg_id=4,
+                 workload="cfg4: DN-Splatter train step (render + backprop + Adam), 1M Gaussians 1920x1080, 8 views, "
+                          "1 view/GPU/iter (the camera batch of 8 is sharded over the GPUs at N = 8)"),
+}
 METRIC = "dn_splatter_train_iter_per_s"
 UNIT = "iter/s"
 
@@ -42,23 +53,25 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _ncu_traffic():
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE raster_bwd_kernel<4> launch on this workload,
-    from the committed `ncu --set full` capture (profiles/raster_bwd_traffic.json, written by
-    tools/ncu_traffic.py from the raw page); None when no capture is committed."""
-    p = ROOT / "profiles" / "raster_bwd_traffic.json"
-    if not p.exists():
-        return None, None
-    d = json.loads(p.read_text())
-    return d.get("dram_bytes_per_launch"), d.get("source")
+def _ncu_traffic(cfg_name: str):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the roofline kernel on this
+    workload, from the committed `ncu --set full` capture (profiles/raster_bwd_traffic_<cfg>.json, written by
+    tools/ncu_traffic.py from the raw page); None when no capture is committed for this configuration."""
+    for name in (f"raster_bwd_traffic_{cfg_name}.json",) + (("raster_bwd_traffic.json",) if cfg_name == "cfg2" else ()):
+        p = ROOT / "profiles" / name
+        if p.exists():
+            d = json.loads(p.read_text())
+            return d.get("dram_bytes_per_launch"), d.get("source")
+    return None, None
 
 
-def _fp32_roofline(pairs, ktimes, D, clocks):
+def _fp32_roofline(pairs, ktimes, D, clocks, key=None):
     """Compositing is bound by the FP32 pipe, so next to the HBM fraction BASELINE.json asks for: algorithmic
     pair-flops (forward Q (14 + 2 D), backward Q (40 + 6 D), Q = blended (pixel, entry) pairs counted
     on the device by fsb_raster_pair_count) over the kernels' CUDA-event times, against 148 SMs x 128 FP32 lanes x
     2 flop x the SM clock sampled under load."""
-    q = pairs.get(f"D{D}")
+    key = key or f"D{D}"
+    q = pairs.get("D4") if key == "D4+3" else pairs.get(f"D{D}")
     if not q:
         return None
     mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
@@ -66,7 +79,7 @@ def _fp32_roofline(pairs, ktimes, D, clocks):
     out = {"pairs_blended": q["blended"], "pairs_visited": q["visited"], "peak_tflops": peak,
            "peak_source": f"148 SM x 128 lanes x 2 x {mhz:.0f} MHz (nominal FP32 FMA rate, not measured)"}
     for name, flop_per_pair in (("raster_fwd", 14 + 2 * D), ("raster_bwd", 40 + 6 * D)):
-        ms = ktimes.get(f"{name}_D{D}", (float("nan"), 0))[0]
+        ms = ktimes.get(f"{name}_{key}", (float("nan"), 0))[0]
         if ms == ms and ms > 0:
             tf = q["blended"] * flop_per_pair / (ms * 1e-3) / 1e12
             out[name] = {"flop_per_pair": flop_per_pair, "achieved_tflops": tf, "frac": tf / peak, "kernel_ms": ms}
@@ -75,10 +88,9 @@ def _fp32_roofline(pairs, ktimes, D, clocks):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 500 ms from before the warm-up on; every sample is stamped on
-    arrival and `stop(t0, t1)` reports the ones that fall inside the timed region (all of them, flagged, if the region
-    was too short to catch one).  The period is deliberately long: every nvidia-smi query stalls the GPU for ~3.6 ms
-    (r01l: five samples inside a 219 ms region cost 8 % of the measured rate), so the default run times 1000 steps
-    (~1 s) and takes two samples inside it."""
+    arrival and `window(t0, t1)` reports the ones that fall inside a timed region (the neighbouring ones, flagged, if
+    the region was too short to catch one).  The period is deliberately long: every nvidia-smi query stalls the GPU
+    for ~3.6 ms (r01l: five samples inside a 219 ms region cost 8 % of the measured rate)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -100,18 +112,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0=None, t1=None):
+    def window(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.1)
-        self.proc.terminate()
         rows = list(self.rows)
         have = t0 is not None and t1 is not None
         inside = [r for t, r in rows if have and t0 <= t <= t1 + 0.05]
         # a region shorter than the sampling period: the samples next to it (warm-up steps before, e2e leg after —
         # the same workload) stand in
-        near = [r for t, r in rows if have and t0 - 0.3 <= t <= t1 + 0.3]
-        window = "timed region" if inside else ("timed region +- 0.3 s (warm-up / e2e leg)" if near else "whole run")
+        near = [r for t, r in rows if have and t0 - 0.6 <= t <= t1 + 0.6]
+        window = "timed region" if inside else ("timed region +- 0.6 s (warm-up / e2e leg)" if near else "whole run")
         sm, mx, reasons = [], [], set()
         for r in (inside or near or [r for _, r in rows]):
             try:
@@ -123,62 +133,185 @@ class ClockSampler:
                 if len(r) > idx and r[idx].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm),
-                "window": window}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
 
 
-def build_model(device, gsplat_module=None, fused=True):
-    import torch
+def build_model(cfg_name, device, gsplat_module=None, fused=True, literal=False, crop=None):
+    """`literal`: the structure an unmodified dn_model.py executes on the gsplat shim — the reference's torch ops
+    around the two gsplat calls, torch loss classes, torch.optim.Adam per group (no fused_* switch of dn_step.py).
+    `crop` = (x0, y0, w, h): the same scene seen through a sub-window of the image (principal point shifted), the
+    bounded sample of the CPU legs."""
     from fusionsense_b200.dn_step import DNSplatterStep, DNSplatterStepConfig
     from fusionsense_b200.synthetic import make_scene
 
-    scene = make_scene(N_GAUSS, WIDTH, HEIGHT, n_views=N_VIEWS, cfg_id=2, kind="bunny")
+    c = CONFIGS[cfg_name]
+    scene = make_scene(c["n"], c["w"], c["h"], n_views=c["views"], cfg_id=c["cfg_id"], kind=c["kind"])
+    if crop is not None:
+        x0, y0, w, h = crop
+        scene.Ks = scene.Ks.clone()
+        scene.Ks[:, 0, 2] -= x0
+        scene.Ks[:, 1, 2] -= y0
+        scene.width, scene.height = w, h
     cfg = DNSplatterStepConfig(fused_optimizer=fused)
+    if literal:
+        cfg.fused_optimizer = cfg.fused_losses = cfg.fused_glue = cfg.fused_outputs = False
     if not fused:
         cfg.stop_split_at = 0  # the CPU oracle has no absgrad side channel; after_train is skipped there
     return DNSplatterStep(scene, cfg, device=device, step=3000, gsplat_module=gsplat_module)
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm: CPU oracle
+# reference arm: gsplat CUDA build when importable, else the CPU oracle
 # ---------------------------------------------------------------------------------------------
-def cpu_step_seconds(steps: int, warmup: int, sample_tiles_frac: float = 1.0):
-    """Time the oracle-driven train step on the host cores. Returns (seconds per full step, cores, sample text)."""
+def _cpu_step_once(cfg_name, crop, steps, warmup):
     import torch
     from oracle import gsplat_ref as ref
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    model = build_model("cpu", gsplat_module=ref, fused=False)
-    targets = {0: model.render_targets(0)}
+    model = build_model(cfg_name, "cpu", gsplat_module=ref, fused=False, crop=crop)
+    targets = model.render_targets(0)
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        model.train_iteration(0, targets[0])
+        model.train_iteration(0, targets)
         dt = time.perf_counter() - t0
         if i >= warmup:
             ts.append(dt)
-    sample = (f"{steps} full train step(s) (RGB+ED pass, normals pass, losses, backward, torch Adam) of the same "
-              f"300k-Gaussian 640x480 scene through oracle/gsplat_ref.py, torch CPU fp32, {cores} threads")
-    return statistics.median(ts), cores, sample
+    del model
+    return statistics.median(ts)
+
+
+def cpu_step_seconds(cfg_name: str, steps: int, warmup: int):
+    """Time the oracle-driven train step on the host cores -> (seconds per FULL step, cores, sample text).
+
+    cfg2 runs whole steps (~6 s each).  cfg4 (1M Gaussians, 1080p) would take minutes per step, so its sample is
+    bounded: the same 1M-Gaussian scene rendered and differentiated through two centred sub-windows of the image
+    (1/16 and 1/32 of the pixels: every Gaussian is still projected, binned and culled), and the full-step time is
+    the linear extrapolation t(P) = a + b P of the two to the full pixel count — a is the per-Gaussian work
+    (projection, SH, Adam), b the per-pixel work (compositing, losses)."""
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = CONFIGS[cfg_name]
+    if cfg_name == "cfg2":
+        sec = _cpu_step_once(cfg_name, None, steps, warmup)
+        sample = (f"{steps} full train step(s) (RGB+ED pass, normals pass, losses, backward, torch Adam) of the same "
+                  f"300k-Gaussian 640x480 scene through oracle/gsplat_ref.py, torch CPU fp32, {cores} threads")
+        return sec, cores, sample
+    W, H = c["w"], c["h"]
+    wa, ha = W // 4, (H // 4) // 16 * 16 + 16 if (H // 4) % 16 else H // 4
+    wb, hb = W // 4, max(16, (ha // 2) // 16 * 16)
+    crop_a = ((W - wa) // 2, (H - ha) // 2, wa, ha)
+    crop_b = ((W - wb) // 2, (H - hb) // 2, wb, hb)
+    ta = _cpu_step_once(cfg_name, crop_a, 1, 0)
+    tb = _cpu_step_once(cfg_name, crop_b, 1, 0)
+    pa, pb, pf = wa * ha, wb * hb, W * H
+    slope = max(0.0, (ta - tb) / (pa - pb))
+    base = max(0.0, tb - slope * pb)
+    sec = base + slope * pf
+    sample = (f"two train steps of the same {c['n']}-Gaussian scene through centred sub-windows {wa}x{ha} "
+              f"({ta:.1f} s) and {wb}x{hb} ({tb:.1f} s) of the {W}x{H} image, all Gaussians projected; full step = "
+              f"linear extrapolation in the pixel count ({base:.1f} s + {slope * pf:.1f} s); oracle/gsplat_ref.py, "
+              f"torch CPU fp32, {cores} threads")
+    return sec, cores, sample
+
+
+def _real_gsplat():
+    """A gsplat that is NOT this repository's shim (the driver's baseline/_ref install), or None."""
+    ref_dir = ROOT / "baseline" / "_ref"
+    if not ref_dir.is_dir():
+        return None
+    sys.path.insert(0, str(ref_dir))
+    try:
+        import importlib
+
+        g = importlib.import_module("gsplat")
+        f = Path(getattr(g, "__file__", "") or "").resolve()
+        if str(f).startswith(str(ROOT / "fusionsense_b200")) or str(f).startswith(str(ROOT / "shim")):
+            return None
+        from gsplat.rendering import rasterization  # noqa: F401
+        return g
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        sys.path.remove(str(ref_dir))
+
+
+def gsplat_cuda_step_ms(g, cfg_name, steps, warmup):
+    """The two gsplat calls of dn_model.py:570-591 / :644-653 (rasterization RGB+ED with absgrad, then the legacy
+    rasterize_gaussians normals pass) forward + backward on the real gsplat CUDA build, same scene, CUDA events."""
+    import torch
+    from fusionsense_b200.synthetic import make_scene
+
+    c = CONFIGS[cfg_name]
+    sc = make_scene(c["n"], c["w"], c["h"], n_views=c["views"], cfg_id=c["cfg_id"], kind=c["kind"]).to("cuda")
+    P = lambda t: t.clone().requires_grad_(True)  # noqa: E731
+    means, quats, scales, opac = P(sc.means), P(sc.quats), P(sc.scales), P(sc.opacities)
+    dc, rest = P(sc.features_dc), P(sc.features_rest)
+    normals = torch.nn.functional.normalize(torch.randn_like(sc.means), dim=-1).requires_grad_(True)
+
+    def step(v):
+        colors = torch.cat((dc[:, None, :], rest), dim=1)
+        render, alpha, info = g.rendering.rasterization(
+            means=means, quats=quats / quats.norm(dim=-1, keepdim=True), scales=torch.exp(scales),
+            opacities=torch.sigmoid(opac).squeeze(-1), colors=colors, viewmats=sc.viewmats[v:v + 1],
+            Ks=sc.Ks[v:v + 1], width=c["w"], height=c["h"], tile_size=16, packed=False, near_plane=0.01,
+            far_plane=1e10, render_mode="RGB+ED", sh_degree=3, sparse_grad=False, absgrad=True,
+            rasterize_mode="classic")
+        nim = g.rasterize_gaussians(info["means2d"][0].detach(), info["depths"][0], info["radii"][0],
+                                    info["conics"][0], info["tiles_per_gauss"][0], normals, torch.sigmoid(opac),
+                                    c["h"], c["w"], 16)
+        (render.sum() + nim.sum()).backward()
+
+    for i in range(warmup):
+        step(i % c["views"])
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        step(i % c["views"])
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    c = CONFIGS[args.config]
     steps = max(1, min(args.steps, 3))
-    sec, cores, sample = cpu_step_seconds(steps, warmup=min(args.warmup, 1))
+    gsplat_cuda = None
+    g = _real_gsplat()
+    if g is not None:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                ms = gsplat_cuda_step_ms(g, args.config, max(3, min(args.steps, 20)), max(1, min(args.warmup, 5)))
+                gsplat_cuda = {"ms_render_fwd_bwd": ms, "unit": "ms", "version": getattr(g, "__version__", "?"),
+                               "what": "gsplat.rendering.rasterization (RGB+ED, absgrad) + gsplat.rasterize_gaussians "
+                                       "forward + backward on the same scene, CUDA events"}
+        except Exception as exc:  # noqa: BLE001
+            gsplat_cuda = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    sec, cores, sample = cpu_step_seconds(args.config, steps, warmup=min(args.warmup, 1))
     v = 1.0 / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT,
+        "config": {"workload": c["workload"], "gaussians": c["n"], "width": c["w"], "height": c["h"],
                    "note": "gsplat==1.0.0 is not vendored in the reference tree and not installed; the reference's "
                            "CPU path is its algorithm restated in oracle/ (kind=port)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gsplat_cuda_baseline": gsplat_cuda if gsplat_cuda is not None else
+        "unavailable: no gsplat other than this repository's shim is importable (baseline/_ref absent)",
         "gpu_launches": 0,
     }
     _emit(line)
@@ -187,38 +320,51 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
+class Ctx:
+    """Process-wide state of one bench run (one rank)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl=ours) needs a CUDA device: fusionsense_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        self.sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            self.sampler.start()
+
+
+def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, detail: bool, literal_leg: bool):
+    """Time one configuration: resident-targets leg, end-to-end leg and (detail) the per-kernel roofline legs.
+    Returns a dict on every rank (timings are max-over-ranks)."""
     import torch
     import torch.distributed as dist
 
     from fusionsense_b200 import ops
     from fusionsense_b200._abi import lib
+    from fusionsense_b200.dist import GradSync
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl=ours) needs a CUDA device: fusionsense_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
-    model = build_model(device)
-    views = list(range(N_VIEWS))
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    c = CONFIGS[cfg_name]
+    n_views = c["views"]
+    model = build_model(cfg_name, device)
+    views = list(range(n_views))
     dev_targets = {v: model.render_targets(v) for v in views}
     host_targets = {v: {k: t.cpu().pin_memory() for k, t in d.items()} for v, d in dev_targets.items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values())
-
     params = [model.gauss_params[k] for k in model.config.lrs]
-    graph_mode = args.mode == "graph"
-
-    from fusionsense_b200.dist import GradSync
+    graph_mode = mode == "graph"
 
     # one flat NCCL all-reduce (SUM) over all Gaussian parameter gradients (59 floats per Gaussian) plus the
     # overflow flag of the static-capacity step; the loss is pre-scaled by 1/world, so the sum is the mean
     allreduce_grads = GradSync()
-
     runner = None
     if graph_mode:
         from fusionsense_b200.graph_step import GraphedDNSplatterStep
@@ -226,19 +372,19 @@ def run_ours(args):
         runner = GraphedDNSplatterStep(model, dev_targets, grad_sync=allreduce_grads if world > 1 else None,
                                        loss_scale=1.0 / world)
 
-    def eager_step(i, batch):
-        v = (i * world + rank) % N_VIEWS
-        for opt in model.optimizers.values():
+    def eager_step(m, i, batch):
+        v = (i * world + rank) % n_views
+        for opt in m.optimizers.values():
             opt.zero_grad(set_to_none=True)
-        outputs = model.get_outputs(v)
-        loss = model.get_loss_dict(outputs, batch(v))["main_loss"]
+        outputs = m.get_outputs(v)
+        loss = m.get_loss_dict(outputs, batch(v))["main_loss"]
         (loss / world if world > 1 else loss).backward()
         if world > 1:
-            allreduce_grads(params)
-        model.optimizers["means"].param_groups[0]["lr"] = model._means_lr()
-        model.optimizer_step()
-        model.after_train()
-        model.step += 1
+            allreduce_grads([m.gauss_params[k] for k in m.config.lrs])
+        m.optimizers["means"].param_groups[0]["lr"] = m._means_lr()
+        m.optimizer_step()
+        m.after_train()
+        m.step += 1
         return loss
 
     def resident(v):
@@ -251,33 +397,33 @@ def run_ours(args):
         """One training iteration; `staged`: this step's targets come from pinned host memory; `read_loss`: the
         step's result is read back to the host."""
         if runner is None:
-            loss = eager_step(i, from_host if staged else resident)
+            loss = eager_step(model, i, from_host if staged else resident)
             if read_loss:
                 float(loss)
             return
-        v = (i * world + rank) % N_VIEWS
+        v = (i * world + rank) % n_views
         if staged and i == 0:
             runner.stage_async(v, host_targets[v])
         runner.train_iteration(v)  # waits for this view's copy
         if staged and i + 1 < n_total:
             # the next step's inputs travel while this step's kernels run (copy stream, pinned source)
-            vn = ((i + 1) * world + rank) % N_VIEWS
+            vn = ((i + 1) * world + rank) % n_views
             runner.stage_async(vn, host_targets[vn])
         if read_loss:
             # 32-byte D2H read of [loss, overflow count, n_isects x2] per step; the host consumes step i - 1's
             # values here and the last step's after the loop (timed() drains the ring before the closing event)
             runner.read_result_async()
 
-    def timed(n_steps, staged, read_loss):
+    def timed(n_steps, step_fn, drain=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(n_steps):
-            one_step(i, staged, read_loss, n_steps)
-        if read_loss and runner is not None:
-            runner.poll()  # the last step's result (synchronises)
+            step_fn(i)
+        if drain is not None:
+            drain()
         e.record()
         if world > 1:
             dist.barrier()
@@ -287,25 +433,22 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # warm-up (also primes the caching allocator and, in graph mode, captures the step)
-    for i in range(args.warmup):
+    for i in range(warmup):
         one_step(i, False, False)
     torch.cuda.synchronize()
     if runner is not None and runner.poll()["new_overflows"]:
-        for i in range(args.warmup):  # capacity grew: capture again before timing
+        for i in range(warmup):  # capacity grew: capture again before timing
             one_step(i, False, False)
         torch.cuda.synchronize()
 
     launches0 = lib.fsb_launch_count()
     replays0 = runner.replays if runner else 0
-    profiling = os.environ.get("FSB_PROFILE") == "1"  # ncu --profile-from-start off: capture the timed steps only
+    profiling = os.environ.get("FSB_PROFILE") == cfg_name  # ncu --profile-from-start off: capture the timed steps only
     if profiling:
         torch.cuda.profiler.start()
     t_region0 = time.perf_counter()
-    ms_total = timed(args.steps, False, False)
+    ms_total = timed(steps, lambda i: one_step(i, False, False, steps))
     t_region1 = time.perf_counter()
     if profiling:
         torch.cuda.profiler.stop()
@@ -318,45 +461,81 @@ def run_ours(args):
         # replays launch the captured kernels without passing through the library's entry points
         launches += (runner.replays - replays0) * runner.launches_per_replay
         graph_info = {"captures": runner.captures, "capacity": runner.capacity, "n_isects": info["n_isects"],
-                      "n_isects_normals": info["n_isects_normals"], "libfsb200_launches_per_replay": runner.launches_per_replay}
-    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
-    ms_e2e = timed(args.steps, True, True)
+                      "n_isects_normals": info["n_isects_normals"],
+                      "libfsb200_launches_per_replay": runner.launches_per_replay,
+                      "graph_launches_per_step": 1 if runner.graph_tail is None else 2}
+    clocks = ctx.sampler.window(t_region0, t_region1) if rank == 0 else None
+    ms_e2e = timed(steps, lambda i: one_step(i, True, True, steps),
+                   drain=(lambda: runner.poll()) if runner is not None else None)
     if runner is not None and runner.poll()["overflowed_steps"]:
         raise SystemExit("bench: a step of the e2e leg overflowed the intersection capacity; rerun")
 
-    # per-kernel CUDA-event times of the same workload: eager launches (a replayed graph offers no place to record
-    # events between its kernels), same kernels, same sizes, same stream, after the timed legs
-    with ops.kernel_timer.collect(pad_cycles=400_000):
-        for i in range(6):
-            eager_step(i, resident)
-        ktimes = ops.kernel_timer.summary()
-    # pair counts (Q of SURVEY.md §8d) of one more eager step, counted by fsb_raster_pair_count after each forward
-    ops.pair_probe.enabled = True
-    eager_step(5, resident)
-    torch.cuda.synchronize()
-    ops.pair_probe.enabled = False
-    pairs = ops.pair_probe.summary()
+    ms_per_step = ms_total / steps
+    out = {
+        "cfg": cfg_name, "value": world * 1e3 / ms_per_step, "ms_per_step": ms_per_step,
+        "optimizer_steps_per_s": 1e3 / ms_per_step, "views_per_s": world * 1e3 / ms_per_step,
+        "e2e": {"value": world * steps * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 32 if graph_mode else 4},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / steps, "clocks": clocks,
+        "graph": graph_info, "fused_outputs": bool(model.config.fused_outputs),
+        "prune_lists": bool(model.config.prune_lists),
+    }
 
-    ms_per_step = ms_total / args.steps
-    value = world * 1e3 / ms_per_step
-    e2e_value = world * args.steps * 1e3 / ms_e2e
+    if detail:
+        # per-kernel CUDA-event times of the same workload: eager launches (a replayed graph offers no place to
+        # record events between its kernels), same kernels, same sizes, same stream, after the timed legs
+        with ops.kernel_timer.collect(pad_cycles=400_000):
+            for i in range(6):
+                eager_step(model, i, resident)
+            ktimes = ops.kernel_timer.summary()
+        # pair counts (Q of SURVEY.md §8d) of one more eager step, counted by fsb_raster_pair_count after each forward
+        ops.pair_probe.enabled = True
+        eager_step(model, 5, resident)
+        torch.cuda.synchronize()
+        ops.pair_probe.enabled = False
+        pairs = ops.pair_probe.summary()
+        out["roofline"] = _roofline(cfg_name, model, params, ktimes, pairs, clocks)
 
-    # roofline of the dominant kernel: raster backward of the RGB+ED pass (D = 4)
+    if literal_leg:
+        # what an UNMODIFIED dn_model.py gets from the shim alone: the reference's torch ops around the two gsplat
+        # calls, torch loss classes, one torch.optim.Adam per group, eager launches, one host sync per step
+        del runner
+        lit = build_model(cfg_name, device, literal=True)
+        for i in range(max(3, warmup)):
+            eager_step(lit, i, resident)
+        n_lit = min(steps, 100)
+        ms_lit = timed(n_lit, lambda i: eager_step(lit, i, resident))
+        out["shim_only_eager"] = {"value": world * n_lit * 1e3 / ms_lit, "unit": UNIT, "steps": n_lit,
+                                  "what": "DNSplatterStep(fused_outputs=fused_losses=fused_glue=fused_optimizer=False)"
+                                          ", eager: the literal restatement of dn_model.py on rasterization() / "
+                                          "rasterize_gaussians() with torch losses and torch.optim.Adam"}
+        del lit
+    del model, dev_targets, host_targets
+    torch.cuda.empty_cache()
+    return out
+
+
+def _roofline(cfg_name, model, params, ktimes, pairs, clocks):
+    """Roofline of the dominant kernel (raster backward of the RGB+ED pass, D = 4) and the per-stage table: algorithmic
+    bytes (SURVEY.md §8d formulas with this step's N, Nv, I, P, K) over the stage's mean CUDA-event time."""
     from fusionsense_b200.gsplat.cuda_legacy import _wrapper as _legacy
 
-    I = int(_legacy._LAST_BINNING.get("n_isects", 0))  # intersections of the last timed step
+    c = CONFIGS[cfg_name]
+    I = int(_legacy._LAST_BINNING.get("n_isects", 0))  # intersections of the last eager step
     Nv = int((model.radii > 0).sum().item())
-    P = WIDTH * HEIGHT
-    D = 4
-    bwd_ms = ktimes.get("raster_bwd_D4", (float("nan"), 0))[0]
+    P = c["w"] * c["h"]
+    # fused_passes (default): ONE kernel composites RGB + depth (4 channels) and the normals (3): D = 7 in the
+    # SURVEY §8d formulas, one read of the list, one write of the per-Gaussian gradients
+    fused = "raster_bwd_D4+3" in ktimes
+    D = 7 if fused else 4
+    key = "D4+3" if fused else "D4"
+    bwd_ms = ktimes.get(f"raster_bwd_{key}", (float("nan"), 0))[0]
     bwd_bytes = I * (28 + 4 * D) + P * (4 * D + 12) + Nv * (32 + 4 * D)
     peak, peak_src = _peaks()
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms == bwd_ms and bwd_ms > 0 else None
-    traffic, traffic_src = _ncu_traffic()
-    # every timed stage against the bound DESIGN.md §4 names for it: algorithmic bytes (SURVEY.md §8d formulas with
-    # this step's N, Nv, I, P, K) over the stage's mean CUDA-event time
-    N, K, C = N_GAUSS, 16, 1
-    tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+    traffic, traffic_src = _ncu_traffic(cfg_name)
+    N, K, C = c["n"], 16, 1
+    tiles = ((c["w"] + 15) // 16) * ((c["h"] + 15) // 16)
     key_bytes = -(-(32 + max(1, (tiles - 1).bit_length())) // 8)
     stage_bytes = {
         "project_sh_fwd": C * N * 68 + Nv * (12 * K + 12),
@@ -364,7 +543,9 @@ def run_ours(args):
         "radix_sort": I * 8 + I * 24 * key_bytes,
         "adam_multi": sum(p.numel() for p in params) * 28,
         "raster_fwd_D4": I * (28 + 16) + P * (16 + 8), "raster_fwd_D3": I * (28 + 12) + P * (12 + 8),
-        "raster_bwd_D4": bwd_bytes, "raster_bwd_D3": I * (28 + 12) + P * (12 + 12) + Nv * (32 + 12),
+        "raster_bwd_D4": I * (28 + 16) + P * (16 + 12) + Nv * (32 + 16),
+        "raster_bwd_D3": I * (28 + 12) + P * (12 + 12) + Nv * (32 + 12),
+        "raster_fwd_D4+3": I * (28 + 28) + P * (28 + 8), "raster_bwd_D4+3": I * (28 + 28) + P * (28 + 12) + Nv * (32 + 28),
     }
     stages = {}
     for name, nbytes in stage_bytes.items():
@@ -374,44 +555,72 @@ def run_ours(args):
             stages[name] = {"algorithmic_bytes": int(nbytes), "ms": round(ms, 4), "gbs": round(gbs, 1),
                             "hbm_frac": round(gbs / peak, 4),
                             "bound": "fp32" if name.startswith("raster") else "hbm"}
-    roofline = {
-        "kernel": "raster_bwd_kernel<4> (RGB+ED pass)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    fwd_ms = ktimes.get(f"raster_fwd_{key}", (0, 0))[0]
+    return {
+        "kernel": ("raster_bwd_kernel<7,4,2> (RGB + expected depth + normals in one walk)" if fused
+                   else "raster_bwd_kernel<4,4,2> (RGB+ED pass)"), "bound": "hbm", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-        "traffic_source": traffic_src,
-        "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "kernel_ms": bwd_ms,
+        "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "kernel_ms": bwd_ms,
         "n_isects": I, "n_visible": Nv,
         "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md §8d); the HBM fraction is reported as "
                 "BASELINE.json asks, the pipe utilisation is in profiles/",
-        "fp32": _fp32_roofline(pairs, ktimes, D, clocks if rank == 0 else None),
+        "fp32": _fp32_roofline(pairs, ktimes, D, clocks, key),
         "kernel_ms_all": {k: round(v[0], 4) for k, v in sorted(ktimes.items())},
         "stages": stages,
-        "raster_fwd_bwd_mpix_per_s": (P / ((ktimes.get("raster_fwd_D4", (0, 0))[0] + bwd_ms) * 1e-3) / 1e6)
-        if bwd_ms == bwd_ms and bwd_ms > 0 else None,
+        "raster_fwd_mpix_per_s": (P / (fwd_ms * 1e-3) / 1e6) if fwd_ms > 0 else None,
+        "raster_fwd_bwd_mpix_per_s": (P / ((fwd_ms + bwd_ms) * 1e-3) / 1e6) if bwd_ms == bwd_ms and bwd_ms > 0 else None,
     }
 
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    ctx = Ctx()
+    world, rank = ctx.world, ctx.rank
+    graph_mode = args.mode == "graph"
+    main = run_workload(ctx, args.config, args.steps, args.warmup, args.mode, detail=True, literal_leg=False)
+    secondary = None
+    if args.config != "cfg2" and not args.no_secondary:
+        # the FusionSense-sized scene: long enough a region for stable numbers (1 ms steps)
+        secondary = run_workload(ctx, "cfg2", max(args.steps, 200), args.warmup, args.mode, detail=False,
+                                 literal_leg=(world == 1))
+    ctx.sampler.stop()
     line = None
     if rank == 0:
+        c = CONFIGS[args.config]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT,
-                       "views": N_VIEWS, "views_per_iter_per_gpu": 1, "global_views_per_iter": world,
+            "value_is": "camera views trained per second over all GPUs (= optimizer steps/s x n_gpus: every rank "
+                        "renders one view per iteration and all ranks apply the same all-reduced update)",
+            "optimizer_steps_per_s": main["optimizer_steps_per_s"], "views_per_s": main["views_per_s"],
+            "config": {"workload": c["workload"], "gaussians": c["n"], "width": c["w"], "height": c["h"],
+                       "views": c["views"], "views_per_iter_per_gpu": 1, "global_views_per_iter": world,
                        "execution": ("one CUDA graph replay per iteration (static-capacity intersection lists, "
                                      "no host sync); every kernel of the eager step runs in every replay"
                                      if graph_mode else "eager launches"),
-                       "graph": graph_info,
-                       "fused_outputs": bool(model.config.fused_outputs),  # dn_step.py: activations / SH concat /
-                       # image glue inside our kernels (True) or as the reference's torch ops (False)
+                       "graph": main["graph"],
+                       "fused_outputs": main["fused_outputs"],  # dn_step.py: activations / SH concat / image glue
+                       # inside our kernels (True) or as the reference's torch ops (False)
+                       "prune_lists": main["prune_lists"],
                        "l2": "per-step working set (parameters, Adam state, gradients, intersection lists, images: "
-                             ">400 MB touched per step) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 32 if graph_mode else 4},
-            "gpu_launches": int(launches),
-            "gpu_launches_per_step": launches / args.steps,
-            "clocks": clocks,
-            "roofline": roofline,
+                             ">1 GB touched per step at cfg4, >400 MB at cfg2) exceeds the 126 MB L2; no explicit "
+                             "flush"},
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
+            "gpu_launches_per_step": main["gpu_launches_per_step"],
+            "clocks": main["clocks"],
+            "roofline": main.get("roofline"),
         }
+        if secondary is not None:
+            line["secondary"] = {
+                "workload": CONFIGS["cfg2"]["workload"], "value": secondary["value"], "unit": UNIT,
+                "ms_per_step": secondary["ms_per_step"], "steps": max(args.steps, 200),
+                "optimizer_steps_per_s": secondary["optimizer_steps_per_s"], "e2e": secondary["e2e"],
+                "shim_only_eager": secondary.get("shim_only_eager"), "graph": secondary["graph"],
+                "clocks": secondary["clocks"], "gpu_launches_per_step": secondary["gpu_launches_per_step"],
+            }
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -443,12 +652,14 @@ def _emit(line: dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: the iteration is one CUDA graph replay (default); eager: per-kernel launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 leg")
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == "reference":
@@ -459,7 +670,7 @@ def main():
     if line is None:
         return
     if line["n_gpus"] == 1 and not args.no_cpu_baseline:
-        sec, cores, sample = cpu_step_seconds(1, warmup=0)
+        sec, cores, sample = cpu_step_seconds(args.config, 1, warmup=0)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     else:
         line["cpu_baseline"] = None

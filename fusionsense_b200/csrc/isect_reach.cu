@@ -59,8 +59,41 @@ __device__ __forceinline__ Box tile_box(float mx, float my, int r, int tile_size
     return b;
 }
 
-// COUNT_ONLY: counts[idx] = number of reached tiles; else emit keys / values for them in row-major tile order
-// (the order fsb_isect_emit uses, so ties in the sort resolve identically).
+// COUNT_ONLY: counts[idx] = number of reached tiles; else emit keys / values for them.
+// legacy_bbox: 0 = gsplat 1.0 box, 1 = 0.1.x box, 2 = UNION list for the two-colour-set compositing pass
+// (csrc/raster.cu): the 0.1.x box (a superset of the 1.0 box), with FSB_LEGACY_FLAG set in the value of the tiles
+// that only the 0.1.x rule yields.
+// A Gaussian whose box holds more than WIDE_TILES tiles is handled by its whole warp (a wall close to the camera
+// covers hundreds of tiles; one thread testing them serially was the long pole of the kernel on object scenes).
+// The order of one Gaussian's entries among themselves is free: their keys differ (different tiles), and entries with
+// equal keys (same tile, same depth, different Gaussians) keep the order of the offsets = Gaussian index, which is what
+// the stable sort preserves.
+constexpr int WIDE_TILES = 24;
+constexpr int32_t LEGACY_FLAG = (int32_t)0x80000000;
+
+struct GaussTile {
+    float mx, my, a, b, c, o;
+    Box box, inner;
+    int64_t cam_part, depth_part, cur;
+    int32_t idx;
+};
+
+template <bool COUNT_ONLY>
+__device__ __forceinline__ int reach_one_tile(const GaussTile& g, int i, int j, int tile_size, int tile_w, bool flag_outer,
+                                              int64_t limit, int64_t cur, int64_t* __restrict__ isect_ids,
+                                              int32_t* __restrict__ flatten_ids) {
+    // pixel centres of the tile; the part of an edge tile beyond the image only makes the test more generous
+    const float px0 = (float)(j * tile_size) + 0.5f, py0 = (float)(i * tile_size) + 0.5f;
+    if (!rect_reach(g.mx, g.my, g.o, g.a, g.b, g.c, px0, px0 + (float)(tile_size - 1), py0, py0 + (float)(tile_size - 1)))
+        return 0;
+    if (!COUNT_ONLY && cur < limit) {
+        const bool outer = flag_outer && !(i >= g.inner.ay && i < g.inner.by && j >= g.inner.ax && j < g.inner.bx);
+        isect_ids[cur] = g.cam_part | ((int64_t)(i * tile_w + j) << 32) | g.depth_part;
+        flatten_ids[cur] = outer ? (g.idx | LEGACY_FLAG) : g.idx;
+    }
+    return 1;
+}
+
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(256)
 isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_t* __restrict__ radii,
@@ -70,46 +103,94 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
                    int32_t* __restrict__ overflow_flag, int32_t* __restrict__ counts, int64_t* __restrict__ isect_ids,
                    int32_t* __restrict__ flatten_ids) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)C * N) return;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = idx < (int64_t)C * N;
     if (!COUNT_ONLY) {
         if (idx == 0 && n_dev && overflow_flag && *n_dev > capacity) *overflow_flag = 1;
         if (n_dev && *n_dev == 0) return;
     }
-    const int r = radii[idx];
-    if (r <= 0) {
-        if (COUNT_ONLY) counts[idx] = 0;
-        return;
-    }
-    const float2 m = reinterpret_cast<const float2*>(means2d)[idx];
-    const float a = conics[3 * idx + 0], b = conics[3 * idx + 1], c = conics[3 * idx + 2];
-    const float o = opacities[idx];
-    const Box bx = tile_box(m.x, m.y, r, tile_size, tile_w, tile_h, legacy_bbox);
-    const int64_t limit = n_dev ? capacity : INT64_MAX;
-    int64_t cam_part = 0, depth_part = 0, cur = 0;
-    if (!COUNT_ONLY) {
-        cam_part = (idx / N) << (32 + tile_bits);
-        depth_part = (int64_t)(uint32_t)__float_as_int(depths[idx]);
-        cur = offsets[idx];
-    }
-    int n = 0;
-    for (int i = bx.ay; i < bx.by; ++i)
-        for (int j = bx.ax; j < bx.bx; ++j) {
-            // pixel centres of the tile; the part of an edge tile beyond the image only makes the test more generous
-            const float px0 = (float)(j * tile_size) + 0.5f, py0 = (float)(i * tile_size) + 0.5f;
-            if (!rect_reach(m.x, m.y, o, a, b, c, px0, px0 + (float)(tile_size - 1), py0,
-                            py0 + (float)(tile_size - 1)))
-                continue;
-            if (COUNT_ONLY) {
-                ++n;
-            } else {
-                if (cur < limit) {
-                    isect_ids[cur] = cam_part | ((int64_t)(i * tile_w + j) << 32) | depth_part;
-                    flatten_ids[cur] = (int32_t)idx;
-                }
-                ++cur;
-            }
+    const int r = in_range ? radii[idx] : 0;
+    GaussTile g;
+    g.box = Box{0, 0, 0, 0};
+    if (r > 0) {
+        const float2 m = reinterpret_cast<const float2*>(means2d)[idx];
+        g.mx = m.x; g.my = m.y;
+        g.a = conics[3 * idx + 0]; g.b = conics[3 * idx + 1]; g.c = conics[3 * idx + 2];
+        g.o = opacities[idx];
+        g.box = tile_box(m.x, m.y, r, tile_size, tile_w, tile_h, legacy_bbox != 0);
+        g.inner = (legacy_bbox == 2) ? tile_box(m.x, m.y, r, tile_size, tile_w, tile_h, 0) : g.box;
+        g.idx = (int32_t)idx;
+        g.cam_part = g.depth_part = g.cur = 0;
+        if (!COUNT_ONLY) {
+            g.cam_part = (idx / N) << (32 + tile_bits);
+            g.depth_part = (int64_t)(uint32_t)__float_as_int(depths[idx]);
+            g.cur = offsets[idx];
         }
-    if (COUNT_ONLY) counts[idx] = n;
+    }
+    const int64_t limit = n_dev ? capacity : INT64_MAX;
+    const bool flag_outer = (legacy_bbox == 2);
+    const int bw = g.box.bx - g.box.ax, bh = g.box.by - g.box.ay;
+    const int n_box = (r > 0) ? bw * bh : 0;
+    const bool wide = n_box > WIDE_TILES;
+    int n = 0;
+    if (r > 0 && !wide) {
+        int64_t cur = g.cur;
+        for (int i = g.box.ay; i < g.box.by; ++i)
+            for (int j = g.box.ax; j < g.box.bx; ++j) {
+                const int hit = reach_one_tile<COUNT_ONLY>(g, i, j, tile_size, tile_w, flag_outer, limit, cur, isect_ids,
+                                                           flatten_ids);
+                cur += hit;
+                n += hit;
+            }
+    }
+    // wide boxes: the warp takes them one at a time, 32 tiles per round
+    unsigned todo = __ballot_sync(0xffffffffu, wide);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        GaussTile w;
+        w.mx = __shfl_sync(0xffffffffu, g.mx, src); w.my = __shfl_sync(0xffffffffu, g.my, src);
+        w.a = __shfl_sync(0xffffffffu, g.a, src); w.b = __shfl_sync(0xffffffffu, g.b, src);
+        w.c = __shfl_sync(0xffffffffu, g.c, src); w.o = __shfl_sync(0xffffffffu, g.o, src);
+        w.box.ax = __shfl_sync(0xffffffffu, g.box.ax, src); w.box.ay = __shfl_sync(0xffffffffu, g.box.ay, src);
+        w.box.bx = __shfl_sync(0xffffffffu, g.box.bx, src); w.box.by = __shfl_sync(0xffffffffu, g.box.by, src);
+        w.inner.ax = __shfl_sync(0xffffffffu, g.inner.ax, src); w.inner.ay = __shfl_sync(0xffffffffu, g.inner.ay, src);
+        w.inner.bx = __shfl_sync(0xffffffffu, g.inner.bx, src); w.inner.by = __shfl_sync(0xffffffffu, g.inner.by, src);
+        w.idx = __shfl_sync(0xffffffffu, g.idx, src);
+        w.cam_part = __shfl_sync(0xffffffffu, g.cam_part, src);
+        w.depth_part = __shfl_sync(0xffffffffu, g.depth_part, src);
+        int64_t cur = __shfl_sync(0xffffffffu, g.cur, src);
+        const int wbw = w.box.bx - w.box.ax;
+        const int total = wbw * (w.box.by - w.box.ay);
+        int found = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int k = base + lane;
+            int hit = 0;
+            int i = 0, j = 0;
+            bool reach = false;
+            if (k < total) {
+                i = w.box.ay + k / wbw;
+                j = w.box.ax + k % wbw;
+                const float px0 = (float)(j * tile_size) + 0.5f, py0 = (float)(i * tile_size) + 0.5f;
+                reach = rect_reach(w.mx, w.my, w.o, w.a, w.b, w.c, px0, px0 + (float)(tile_size - 1), py0,
+                                   py0 + (float)(tile_size - 1));
+            }
+            const unsigned hits = __ballot_sync(0xffffffffu, reach);
+            if (!COUNT_ONLY && reach) {
+                const int64_t at = cur + __popc(hits & ((1u << lane) - 1u));
+                if (at < limit) {
+                    const bool outer = flag_outer && !(i >= w.inner.ay && i < w.inner.by && j >= w.inner.ax && j < w.inner.bx);
+                    isect_ids[at] = w.cam_part | ((int64_t)(i * tile_w + j) << 32) | w.depth_part;
+                    flatten_ids[at] = outer ? (w.idx | LEGACY_FLAG) : w.idx;
+                }
+            }
+            (void)hit;
+            cur += __popc(hits);
+            found += __popc(hits);
+        }
+        if (lane == src) n = found;
+    }
+    if (COUNT_ONLY && in_range) counts[idx] = n;
 }
 
 }  // namespace

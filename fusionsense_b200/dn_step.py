@@ -75,10 +75,13 @@ class DNSplatterStepConfig:
     # dn_model.py:566-574, :602-613, :655-656, :817-819 run inside our kernels instead of ~55 torch launches
     # (FSB_FUSED_OUTPUTS=0 switches it off for A/B runs)
     fused_outputs: bool = field(default_factory=lambda: os.environ.get("FSB_FUSED_OUTPUTS", "1") != "0")
-    # EXPERIMENTAL, off (built in round 1, not yet run on a GPU): bin only the (Gaussian, tile) pairs that can pass
-    # the alpha test somewhere in the tile (csrc/isect_reach.cu; 35 % fewer list entries on the bench scene, same
-    # images and gradients).  Needs fused_outputs; FSB_PRUNE_LISTS=1 switches it on.
-    prune_lists: bool = field(default_factory=lambda: os.environ.get("FSB_PRUNE_LISTS", "0") == "1")
+    # bin only the (Gaussian, tile) pairs that can pass the alpha test somewhere in the tile (csrc/isect_reach.cu;
+    # 35-49 % fewer list entries, same images and gradients: tests/test_gpu_prune_lists.py).  Needs fused_outputs.
+    prune_lists: bool = field(default_factory=lambda: os.environ.get("FSB_PRUNE_LISTS", "1") == "1")
+    # the RGB + depth pass and the legacy normals pass composited by ONE walk of one (pruned, union) list
+    # (rasterization_from_params(colors_b=...), csrc/raster.cu): one binning, one sort, one forward and one backward
+    # compositing kernel per iteration instead of two of each.  Needs fused_outputs and fused_glue.
+    fused_passes: bool = field(default_factory=lambda: os.environ.get("FSB_FUSED_PASSES", "1") == "1")
     overlap_normals_pass: bool = True  # captured step only: the normals pass runs on a second stream beside the RGB+ED pass
 
 
@@ -263,6 +266,25 @@ class DNSplatterStep:
 
         cfg = self.config
         opac = torch.sigmoid(self.opacities)  # [N,1]; the reference evaluates it twice (dn_model.py:574, :650)
+        if cfg.fused_passes and cfg.fused_glue:
+            from .gaussians import gaussian_normals
+
+            normals, self.normals_world = gaussian_normals(self.quats, self.scales, self.means, c2w.squeeze(0))
+            render, alpha, info = self._rasterization_from_params(
+                self.means, self.quats, self.scales, opac.squeeze(-1), self.features_dc, self.features_rest,
+                viewmats=viewmat, Ks=K, width=W, height=H, sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10,
+                tile_size=BLOCK_WIDTH, render_mode="RGB+ED", absgrad=True, colors_b=normals)
+            if self.training and info["means2d"].requires_grad:
+                info["means2d"].retain_grad()
+            self.xys = info["means2d"]
+            self.radii = info["radii"][0]
+            self.depths = info["depths"]
+            self.conics = info["conics"]
+            self.num_tiles_hit = info["tiles_per_gauss"]
+            rgb, depth_im = compose_rgbd(render, alpha, self.background)
+            normals_im = normal_map(info["render_b"][0])
+            return {"rgb": rgb, "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
+                    "background": self.background}
         render, alpha, info = self._rasterization_from_params(
             self.means, self.quats, self.scales, opac.squeeze(-1), self.features_dc, self.features_rest,
             viewmats=viewmat, Ks=K, width=W, height=H, sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10,

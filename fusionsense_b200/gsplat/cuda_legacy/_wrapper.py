@@ -20,13 +20,18 @@ _LAST_BINNING: dict = {}
 
 def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int, height: int, tile_size: int,
                      n_isects: int, flatten_ids: Tensor, isect_offsets: Tensor,
-                     legacy_extra: Optional[int] = None, lists_done=None, pruned: bool = False) -> None:
+                     legacy_extra: Optional[int] = None, lists_done=None, pruned: bool = False,
+                     union: bool = False) -> None:
     """Called by `rasterization()` (single-camera case only).
 
     `legacy_extra`: number of tiles by which the 0.1.x bbox rule differs from the 1.0 rule on these Gaussians,
     counted by the projection kernel and read back together with n_isects; None = not counted."""
     _LAST_BINNING.clear()
     if radii.shape[0] != 1:
+        return
+    if union:
+        # union lists (FSB_LEGACY_FLAG entries) serve fsb_raster_dn_* only: nothing for rasterize_gaussians to share
+        _LAST_BINNING.update(n_isects=n_isects)
         return
     _LAST_BINNING.update(
         key=(means2d.data_ptr(), depths.data_ptr(), radii.data_ptr(), means2d._version, depths._version,

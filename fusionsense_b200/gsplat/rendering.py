@@ -75,25 +75,35 @@ def rasterization_from_params(
     render_mode: Literal["RGB", "RGB+D", "RGB+ED"] = "RGB",
     absgrad: bool = False,
     prune_lists: bool = False,
+    colors_b: Optional[Tensor] = None,  # [N, 3]
+    backgrounds_b: Optional[Tensor] = None,  # [C, 3]
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Extension (not part of gsplat): `rasterization(packed=False, rasterize_mode="classic")` of
     `quats / |quats|, exp(log_scales), cat(features_dc[:, None], features_rest)` with those three torch
     expressions (dn_model.py:566-574) evaluated inside the projection kernel and differentiated in place.
     Same return tuple and meta keys as `rasterization()`.
 
-    `prune_lists` (EXPERIMENTAL, off): bin only the (Gaussian, tile) pairs that can pass the alpha test somewhere in
-    the tile (csrc/isect_reach.cu).  Images and gradients are unchanged; `meta["isect_ids"] / ["flatten_ids"] /
+    `prune_lists`: bin only the (Gaussian, tile) pairs that can pass the alpha test somewhere in the tile
+    (csrc/isect_reach.cu).  Images and gradients are unchanged; `meta["isect_ids"] / ["flatten_ids"] /
     ["isect_offsets"]` then hold the pruned lists instead of gsplat's bounding-box lists, `tiles_per_gauss` stays
-    the bounding-box count."""
+    the bounding-box count.
+
+    `colors_b` (+ `backgrounds_b`): a second colour set composited by the SAME walk with the semantics of
+    `gsplat.rasterize_gaussians(means2d.detach(), depths, radii, conics, tiles_per_gauss, colors_b, opacities[:, None],
+    H, W, tile_size, background=backgrounds_b)` — the normals pass of dn_model.py:644-653 — including the 0.1.x
+    bounding-box rule of that call (union lists with FSB_LEGACY_FLAG, include/fsb200.h).  The result comes back as
+    `meta["render_b"]` [C, H, W, 3]; implies `prune_lists`."""
     assert render_mode in ["RGB", "RGB+D", "RGB+ED"], render_mode
     return _rasterization_impl(means, quats, log_scales, opacities, None, viewmats, Ks, width, height, near_plane,
                                far_plane, radius_clip, eps2d, sh_degree, False, tile_size, backgrounds, render_mode,
-                               False, absgrad, "classic", 32, stored=(features_dc, features_rest), prune=prune_lists)
+                               False, absgrad, "classic", 32, stored=(features_dc, features_rest),
+                               prune=prune_lists or colors_b is not None, colors_b=colors_b, backgrounds_b=backgrounds_b)
 
 
 def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane, far_plane,
                         radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode, sparse_grad,
-                        absgrad, rasterize_mode, channel_chunk, stored=None, prune=False):
+                        absgrad, rasterize_mode, channel_chunk, stored=None, prune=False, colors_b=None,
+                        backgrounds_b=None):
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -172,7 +182,7 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
     with torch.no_grad():
         _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(
             means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
-            totals=totals, reach=(conics, opac) if prune else None)
+            totals=totals, reach=(conics, opac) if prune else None, legacy_bbox=2 if colors_b is not None else False)
         n_dev = getattr(flatten_ids, "n_dev", None)  # static-capacity mode (ops.static_capacity): count on device
         lists_done = None
         if n_dev is not None:
@@ -180,7 +190,7 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
             lists_done.record()
         remember_binning(means2d, depths, radii, width, height, tile_size, flatten_ids.numel(), flatten_ids,
                          isect_offsets, legacy_extra=totals.host[1] if (C == 1 and n_dev is None) else None,
-                         lists_done=lists_done, pruned=prune)
+                         lists_done=lists_done, pruned=prune, union=colors_b is not None)
 
     if use_sh:
         ras_colors = sh_colors  # [C, N, 3 or 4], depth already in channel 3
@@ -215,7 +225,17 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
             out = torch.cat([out[..., :-1], out[..., -1:] / alpha.clamp(min=1e-10)], dim=-1)
         return out, alpha
 
-    if D > channel_chunk:
+    render_b = None
+    if colors_b is not None:
+        # both colour sets in one walk (csrc/raster.cu); set A must be the 4-channel RGB + depth colours
+        assert D == 4 and colors_b.shape[-1] == 3, (D, colors_b.shape)
+        cb = colors_b if colors_b.dim() == 3 else colors_b[None].expand(C, N, 3)
+        if backgrounds_b is None:
+            backgrounds_b = torch.ones((C, 3), dtype=torch.float32, device=means.device)
+        render_colors, render_b, render_alphas = ops.RasterizeDN.apply(
+            means2d, conics, ras_colors, cb.contiguous(), opac, backgrounds, backgrounds_b, width, height, tile_size,
+            isect_offsets, flatten_ids, absgrad, 3 if ed_normalize else -1, n_dev)
+    elif D > channel_chunk:
         n_chunks = (D + channel_chunk - 1) // channel_chunk
         outs, render_alphas = [], None
         for i in range(n_chunks):
@@ -247,6 +267,8 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
         "tile_size": tile_size,
         "n_cameras": C,
     }
+    if render_b is not None:
+        meta["render_b"] = render_b  # extension: the second colour set (rasterization_from_params(colors_b=...))
     if proj_done is not None:
         meta["projection_done"] = proj_done  # extension, static-capacity mode only
     return render_colors, render_alphas, meta

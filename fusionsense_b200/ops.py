@@ -343,6 +343,65 @@ def supported_channels(D: int) -> int:
     return lib.fsb_raster_supported_channels(D)
 
 
+LEGACY_FLAG = 0x80000000  # FSB_LEGACY_FLAG: bit 31 of a flatten id = entry of the 0.1.x list only (union lists)
+
+
+def raster_dn_fwd(means2d, conics, colors_a, colors_b, opacities, backgrounds_a, backgrounds_b, width, height,
+                  tile_size, isect_offsets_t, flatten_ids, ed_channel=-1, n_dev=None):
+    """fsb_raster_dn_fwd: colour sets A [C,N,DA] and B [C,N,DB] composited by one walk of the (union) lists.
+    -> out_a [C,H,W,DA], out_b [C,H,W,DB], alphas [C,H,W,1], last_ids [C,H,W], workspace."""
+    _req_cuda(means2d, conics, colors_a, colors_b, opacities)
+    C = isect_offsets_t.shape[0]
+    tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
+    N = means2d.shape[-2]
+    DA, DB = colors_a.shape[-1], colors_b.shape[-1]
+    dev = means2d.device
+    out_a = torch.empty((C, height, width, DA), dtype=torch.float32, device=dev)
+    out_b = torch.empty((C, height, width, DB), dtype=torch.float32, device=dev)
+    alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+    last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+    ws_bytes = lib.fsb_raster_dn_workspace(flatten_ids.numel(), C * tile_h * tile_w, DA, DB)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    ev = kernel_timer.start(f"raster_fwd_D{DA}+{DB}")
+    check(lib.fsb_raster_dn_fwd(C, N, DA, DB, flatten_ids.numel(), ptr(n_dev), ptr(means2d), ptr(conics), ptr(colors_a),
+                                ptr(colors_b), ptr(opacities), ptr(backgrounds_a), ptr(backgrounds_b), None, width,
+                                height, tile_size, tile_w, tile_h, ptr(isect_offsets_t), ptr(flatten_ids),
+                                int(ed_channel), ptr(ws), ws_bytes, ptr(out_a), ptr(out_b), ptr(alphas), ptr(last_ids),
+                                _stream()), "fsb_raster_dn_fwd")
+    kernel_timer.stop(ev)
+    if pair_probe.enabled:
+        pair_probe.count(f"D{DA}", C, N, flatten_ids, n_dev, means2d, conics, opacities, width, height, tile_size,
+                         tile_w, tile_h, isect_offsets_t, last_ids)
+    return out_a, out_b, alphas, last_ids, ws
+
+
+def raster_dn_bwd(shape_cn, DA, DB, backgrounds_a, backgrounds_b, width, height, tile_size, isect_offsets_t, n_list,
+                  ed_channel, ws, render_a, render_alphas, last_ids, v_a, v_b, v_alphas, absgrad, need_xy=True,
+                  n_dev=None):
+    C = isect_offsets_t.shape[0]
+    tile_h, tile_w = isect_offsets_t.shape[1], isect_offsets_t.shape[2]
+    Cn, N = shape_cn
+    CN = Cn * N
+    dev = render_alphas.device
+    sizes = [2 * CN if need_xy else 0, 2 * CN if (absgrad and need_xy) else 0, 3 * CN, DA * CN, DB * CN, CN]
+    flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
+    parts = torch.split(flat, sizes)
+    v_means2d = parts[0].view(Cn, N, 2) if need_xy else None
+    v_abs = parts[1].view(Cn, N, 2) if (absgrad and need_xy) else None
+    v_conics = parts[2].view(Cn, N, 3)
+    v_colors_a = parts[3].view(Cn, N, DA)
+    v_colors_b = parts[4].view(Cn, N, DB)
+    v_opac = parts[5].view(Cn, N)
+    ev = kernel_timer.start(f"raster_bwd_D{DA}+{DB}")
+    check(lib.fsb_raster_dn_bwd(C, N, DA, DB, n_list, ptr(n_dev), ptr(backgrounds_a), ptr(backgrounds_b), None, width,
+                                height, tile_size, tile_w, tile_h, ptr(isect_offsets_t), int(ed_channel), ptr(ws),
+                                ws.numel(), ptr(render_a), ptr(render_alphas), ptr(last_ids), ptr(v_a), ptr(v_b),
+                                ptr(v_alphas), ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors_a),
+                                ptr(v_colors_b), ptr(v_opac), _stream()), "fsb_raster_dn_bwd")
+    kernel_timer.stop(ev)
+    return v_means2d, v_abs, v_conics, v_colors_a, v_colors_b, v_opac
+
+
 def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets_t,
                flatten_ids, ed_normalize=False, n_dev=None):
     _req_cuda(means2d, conics, colors, opacities)
@@ -580,3 +639,39 @@ class RasterizeToPixels(torch.autograd.Function):
         if bg is not None and ctx.needs_input_grad[4]:
             v_bg = (v_out * (1.0 - alphas)).sum(dim=(1, 2))
         return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None, None
+
+
+class RasterizeDN(torch.autograd.Function):
+    """The two compositing passes of a DN-Splatter iteration in one walk (fsb_raster_dn_fwd / _bwd): colour set A =
+    rasterization()'s RGB + depth colours, colour set B = the per-Gaussian normals of the legacy rasterize_gaussians
+    pass (dn_model.py:644-653), same means2d / conics / opacities.  The 2-D mean gradient comes from set A only."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, colors_a, colors_b, opacities, backgrounds_a, backgrounds_b, width, height,
+                tile_size, isect_offsets_t, flatten_ids, absgrad, ed_channel, n_dev=None):
+        means2d_c, conics_c = _f32c(means2d), _f32c(conics)
+        ca, cb, opac_c = _f32c(colors_a), _f32c(colors_b), _f32c(opacities)
+        bga, bgb = _f32c(backgrounds_a), _f32c(backgrounds_b)
+        out_a, out_b, alphas, last_ids, ws = raster_dn_fwd(means2d_c, conics_c, ca, cb, opac_c, bga, bgb, width,
+                                                           height, tile_size, isect_offsets_t, flatten_ids, ed_channel,
+                                                           n_dev=n_dev)
+        ctx.n_dev = n_dev
+        ctx.save_for_backward(means2d, bga, bgb, isect_offsets_t, out_a, alphas, last_ids, ws)
+        ctx.cfg = (width, height, tile_size, absgrad, ed_channel, tuple(opac_c.shape), ca.shape[-1], cb.shape[-1],
+                   flatten_ids.numel())
+        ctx.set_materialize_grads(False)
+        return out_a, out_b, alphas
+
+    @staticmethod
+    def backward(ctx, v_a, v_b, v_alphas):
+        means2d, bga, bgb, isect_offsets_t, out_a, alphas, last_ids, ws = ctx.saved_tensors
+        width, height, tile_size, absgrad, ed_channel, shape_cn, DA, DB, n_list = ctx.cfg
+        v_a = _f32c(v_a) if v_a is not None else torch.zeros_like(out_a)
+        v_b = _f32c(v_b) if v_b is not None else out_a.new_zeros(out_a.shape[:-1] + (DB,))
+        v_alphas = _f32c(v_alphas) if v_alphas is not None else torch.zeros_like(alphas)
+        v_means2d, v_abs, v_conics, v_ca, v_cb, v_opac = raster_dn_bwd(
+            shape_cn, DA, DB, bga, bgb, width, height, tile_size, isect_offsets_t, n_list, ed_channel, ws, out_a,
+            alphas, last_ids, v_a, v_b, v_alphas, absgrad, need_xy=ctx.needs_input_grad[0], n_dev=ctx.n_dev)
+        if absgrad and v_abs is not None:
+            means2d.absgrad = v_abs  # same contract as gsplat: meta["means2d"] gets an .absgrad attribute
+        return (v_means2d, v_conics, v_ca, v_cb, v_opac) + (None,) * 10

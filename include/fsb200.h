@@ -90,13 +90,17 @@ int fsb_project_params_bwd(int C, int N, const float* means, const float* quats,
 int fsb_isect_count(int64_t M, const float* means2d, const int32_t* radii, int tile_size, int tile_w,
                     int tile_h, int legacy_bbox, int32_t* tiles_per_gauss, void* stream);
 
-/* EXPERIMENTAL (declared and built in round 1, not yet exercised on a GPU; nothing calls them by default).
- * I1 with an exact reach test: count / emit only the tiles of the bounding box on which the Gaussian can pass the
- * alpha test (alpha >= 1/255) at some pixel centre — the pairs the compositing kernels would stage and then skip.
+/* I1 with an exact reach test: count / emit only the tiles of the bounding box on which the Gaussian can pass the
+ * alpha test (alpha >= 1/255) at some pixel centre — the pairs the compositing kernels would stage and then skip
+ * (35-49 % of the bounding-box pairs; validated on B200 in round 2, tests/test_gpu_prune_lists.py).
  * The reference's lists (fsb_isect_count / fsb_isect_emit: gsplat isect_tiles, dn_splatter/dn_model.py:570-591) stay
- * the bit-exact contract; these serve callers that do not expose the lists (DNSplatterStepConfig.prune_lists).
- *   conics[C*N,3], opacities[C*N]: what the compositing kernels receive; legacy_bbox as in fsb_isect_count.
+ * the bit-exact contract; these serve callers that do not expose the lists (the fused DN-Splatter step).
+ *   conics[C*N,3], opacities[C*N]: what the compositing kernels receive.
+ *   legacy_bbox: 0 / 1 as in fsb_isect_count; 2 = UNION list for fsb_raster_dn_*: the 0.1.x box (a superset of the 1.0
+ *   box) with FSB_LEGACY_FLAG set in flatten_ids for the tiles that only the 0.1.x rule of rasterize_gaussians yields
+ *   (dn_model.py:644-653), so ONE sorted list serves rasterization() and the legacy normals pass.
  *   emit: offsets = exclusive scan of the reach counts; static-capacity arguments as in fsb_isect_emit. */
+#define FSB_LEGACY_FLAG 0x80000000u
 int fsb_isect_count_reach(int C, int N, const float* means2d, const int32_t* radii, const float* conics,
                           const float* opacities, int tile_size, int tile_w, int tile_h, int legacy_bbox,
                           int32_t* counts, void* stream);
@@ -158,8 +162,9 @@ int fsb_isect_share_copy(const int64_t* gate, const int64_t* n_list, int64_t cap
  *   means2d[C*N,2] conics[C*N,3] colors[C*N,D] opacities[C*N] ; backgrounds[C,D] nullable ;
  *   masks[C*tiles] u8 nullable ; ed_normalize: divide channel D-1 by max(alpha,1e-10) ("ED" modes).
  *   out_colors[C,H,W,D] out_alphas[C,H,W] last_ids[C,H,W] i32.
- * Work is split into (tile, list segment) units chained through `workspace` (fsb_raster_workspace() bytes,
- * n_tiles = C*tile_w*tile_h); the forward leaves per-segment state there that the backward consumes.
+ * The forward first packs the sorted list into contiguous per-entry records inside `workspace`
+ * (fsb_raster_workspace() bytes, n_tiles = C*tile_w*tile_h) that the compositing kernels stage with bulk async
+ * copies; it also leaves the per-unit state there that the backward consumes (csrc/raster.cu).
  * D must be one of fsb_raster_supported_channels(); tile_size 8 or 16. */
 int fsb_raster_supported_channels(int D);
 size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D);
@@ -180,6 +185,33 @@ int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isect
                    const float* render_colors, const float* render_alphas, const int32_t* last_ids,
                    const float* v_render_colors, const float* v_render_alphas, float* v_means2d_abs,
                    float* v_means2d, float* v_conics, float* v_colors, float* v_opacities, void* stream);
+
+/* R1 + R2 for the two compositing passes of one DN-Splatter iteration in ONE walk: colour set A (DA channels:
+ * rasterization() RGB + expected depth, dn_splatter/dn_model.py:570-591) and colour set B (DB channels: the
+ * per-Gaussian normals of the legacy gsplat.rasterize_gaussians pass, dn_model.py:644-653) share means2d / conics /
+ * opacities, hence every alpha.  (DA, DB) must be (D, 0) with D from fsb_raster_supported_channels() — then these are
+ * fsb_raster_fwd / fsb_raster_bwd — or (4, 3).
+ *   flatten_ids may carry FSB_LEGACY_FLAG (fsb_isect_emit_reach legacy_bbox=2): such an entry exists only in the
+ *   0.1.x list, i.e. it is composited into set B only; set A, out_alphas and last_ids follow the unflagged entries.
+ *   ed_channel: channel of set A divided by max(alpha, 1e-10) on output (-1: none).
+ *   backward: the 2-D mean gradients take set A's dL/dalpha only (dn_model.py:638 detaches the means of the legacy
+ *   pass); conics / opacities receive both.  Gradient outputs are ACCUMULATED; the caller zero-fills them. */
+size_t fsb_raster_dn_workspace(int64_t n_isects, int64_t n_tiles, int DA, int DB);
+int fsb_raster_dn_fwd(int C, int N, int DA, int DB, int64_t n_isects, const int64_t* n_isects_dev,
+                      const float* means2d, const float* conics, const float* colors_a, const float* colors_b,
+                      const float* opacities, const float* backgrounds_a, const float* backgrounds_b,
+                      const uint8_t* masks, int width, int height, int tile_size, int tile_w, int tile_h,
+                      const int32_t* tile_offsets, const int32_t* flatten_ids, int ed_channel, void* workspace,
+                      size_t workspace_bytes, float* out_a, float* out_b, float* out_alphas, int32_t* last_ids,
+                      void* stream);
+int fsb_raster_dn_bwd(int C, int N, int DA, int DB, int64_t n_isects, const int64_t* n_isects_dev,
+                      const float* backgrounds_a, const float* backgrounds_b, const uint8_t* masks, int width,
+                      int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
+                      int ed_channel, void* workspace, size_t workspace_bytes, const float* render_a,
+                      const float* render_alphas, const int32_t* last_ids, const float* v_render_a,
+                      const float* v_render_b, const float* v_render_alphas, float* v_means2d_abs,
+                      float* v_means2d, float* v_conics, float* v_colors_a, float* v_colors_b,
+                      float* v_opacities, void* stream);
 
 /* Measurement aid for bench.py's FP32 roofline (SURVEY.md §8d "Q = pair count"): counts[2] u64 (device, zeroed by
  * the caller) += { (pixel, entry) pairs the finished forward blended, pairs a per-pixel list walk visits }.

@@ -133,7 +133,8 @@ def test_graphed_iterations_track_eager_iterations():
         losses_g.append(runner.poll()["loss"])
     info = runner.poll()
     assert runner.captures == 1 and runner.replays == len(order) and info["overflowed_steps"] == 0
-    assert info["n_isects"] > 0 and info["n_isects_normals"] >= info["n_isects"]
+    # fused_passes (default): one union list serves both colour sets, there is no second binning to count
+    assert info["n_isects"] > 0 and info["n_isects_normals"] in (0, info["n_isects"], info["n_isects"] + 1)
     assert graphed.step == eager.step
     for a, b in zip(losses_g, losses_e):
         assert a == pytest.approx(b, rel=2e-4)

@@ -1,6 +1,5 @@
-"""GPU, EXPERIMENTAL (skipped unless FSB_EXPERIMENTAL=1): intersection lists pruned by the exact reach test
-(csrc/isect_reach.cu, DNSplatterStepConfig.prune_lists).  Built and wired in round 1 without GPU time left to run
-it; the first GPU visit of the next round runs `FSB_EXPERIMENTAL=1 python -m pytest tests/test_gpu_prune_lists.py`.
+"""GPU: intersection lists pruned by the exact reach test (csrc/isect_reach.cu, DNSplatterStepConfig.prune_lists;
+first run on a B200 in round 2: profiles/r02a_pytest_prune.log).
 
 What has to hold: the pruned sorted list is the full sorted list with entries removed (same order, same keys); no
 removed entry reaches a pixel; images and gradients of the render are unchanged; the captured step agrees with the
@@ -15,8 +14,7 @@ import torch
 from fusionsense_b200.synthetic import make_scene
 from tests.parity import assert_close
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FSB_EXPERIMENTAL") != "1", reason="experimental path, opt-in")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda"
 
 
@@ -106,8 +104,8 @@ def test_step_eager_and_captured_agree_with_unpruned():
     from fusionsense_b200.graph_step import GraphedDNSplatterStep
 
     sc = make_scene(20000, 320, 240, n_views=3, cfg_id=51, kind="bunny", fx=300.0)
-    on = DNSplatterStep(sc, DNSplatterStepConfig(prune_lists=True), device=DEV, step=3000)
-    off = DNSplatterStep(sc, DNSplatterStepConfig(prune_lists=False), device=DEV, step=3000)
+    on = DNSplatterStep(sc, DNSplatterStepConfig(prune_lists=True, fused_passes=False), device=DEV, step=3000)
+    off = DNSplatterStep(sc, DNSplatterStepConfig(prune_lists=False, fused_passes=False), device=DEV, step=3000)
     batch = off.render_targets(1)
     outs = {}
     for name, m in (("on", on), ("off", off)):
@@ -125,7 +123,7 @@ def test_step_eager_and_captured_agree_with_unpruned():
     targets = {v: off.render_targets(v) for v in range(3)}
     runs = {}
     for name, prune in (("on", True), ("off", False)):
-        m = DNSplatterStep(sc, DNSplatterStepConfig(prune_lists=prune), device=DEV, step=3000)
+        m = DNSplatterStep(sc, DNSplatterStepConfig(prune_lists=prune, fused_passes=False), device=DEV, step=3000)
         r = GraphedDNSplatterStep(m, targets)
         for i in range(4):
             r.train_iteration(i % 3)

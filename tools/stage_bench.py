@@ -21,6 +21,7 @@ CFGS = {
     "cfg1": dict(n=50_000, w=640, h=480, kind="random", views=3, cfg_id=1),
     "cfg2": dict(n=300_000, w=640, h=480, kind="bunny", views=9, cfg_id=2),
     "cfg4": dict(n=1_000_000, w=1920, h=1080, kind="random", views=8, cfg_id=4),
+    "cfg5": dict(n=3_000_000, w=3840, h=2160, kind="random", views=4, cfg_id=5),
 }
 
 
@@ -47,8 +48,9 @@ def main():
             model.train_iteration(i % c["views"], targets[i % c["views"]])
         kt = ops.kernel_timer.summary()
     P = c["w"] * c["h"]
-    fwd = kt.get("raster_fwd_D4", (float("nan"),))[0]
-    bwd = kt.get("raster_bwd_D4", (float("nan"),))[0]
+    # fused_passes (default): one kernel pair composites RGB + depth and the normals ("D4+3")
+    fwd = kt.get("raster_fwd_D4+3", kt.get("raster_fwd_D4", (float("nan"),)))[0]
+    bwd = kt.get("raster_bwd_D4+3", kt.get("raster_bwd_D4", (float("nan"),)))[0]
     out = {
         "config": name, **c, "steps": steps, "ms_per_step": ms_step, "iter_per_s": 1e3 / ms_step,
         "n_isects": int(legacy._LAST_BINNING.get("n_isects", 0)), "n_visible": int((model.radii > 0).sum()),
