@@ -213,37 +213,41 @@ __device__ __forceinline__ uint32_t reach_mask(float gx, float gy, float opac, f
     const float det = a * c - b * b;
     if (!(det > 0.f) || !(a > 0.f) || !(tau < 1e30f)) return all;
     const float thr = 2.f * tau * 1.0002f + 1e-2f;
-    const float inv_a = 1.f / a;
+    const float inv_a = __frcp_rn(a);
     const float ta = thr * a;
     const float nb = -b * inv_a;
     const int warps_x = tile_size >> 3;
     const int n_bands = tile_size >> 1, n_cols = tile_size >> 2;
+    // rows the ellipse can touch at all: |dy| <= sqrt(thr a / det)  (inflated; rsqrt.approx is good to 2 ulp)
+    const float dy_max = ta * rsqrtf(ta * det) * 1.001f + 1e-3f;
+    const float y_rel = ty0 + 0.5f - gy;  // dy of pixel row 0
+    const int band_lo = max(0, (int)floorf((-dy_max - y_rel - 1.f) * 0.5f));
+    const int band_hi = min(n_bands - 1, (int)ceilf((dy_max - y_rel) * 0.5f));
+    const float x_rel = tx0 + 0.5f - gx;  // dx of pixel column 0
     uint32_t m = 0u;
-    for (int band = 0; band < n_bands; ++band) {
+    for (int band = band_lo; band <= band_hi; ++band) {
         float lo = 1e30f, hi = -1e30f;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const float dy = ty0 + (float)(2 * band + r) + 0.5f - gy;
-            const float disc = ta - det * dy * dy;
+            const float dy = y_rel + (float)(2 * band + r);
+            const float disc = fmaf(-det * dy, dy, ta);
             if (disc >= 0.f) {
-                const float h = sqrtf(disc) * inv_a;
+                const float h = disc * rsqrtf(fmaxf(disc, 1e-30f)) * inv_a;  // sqrt(disc) / a
                 const float ctr = nb * dy;
                 lo = fminf(lo, ctr - h);
                 hi = fmaxf(hi, ctr + h);
             }
         }
         if (!(hi >= lo)) continue;
-        // pixel centres of column block k: gx-relative x in [tx0 + 4k + 0.5 - gx, + 3]
-        const float pad = 2e-3f + 1e-6f * fmaxf(fabsf(lo), fabsf(hi));
-        const float x_rel = tx0 + 0.5f - gx;
+        // pixel centres of column block k: dx in [x_rel + 4k, x_rel + 4k + 3]
+        const float pad = 2e-3f + 2e-6f * fmaxf(fabsf(lo), fabsf(hi));
         const float fl = (lo - pad - x_rel - 3.f) * 0.25f, fh = (hi + pad - x_rel) * 0.25f;
         const int k_lo = max(0, (int)ceilf(fmaxf(fl, -1.f)));
         const int k_hi = min(n_cols - 1, (int)floorf(fminf(fh, 64.f)));
-        const int wy = band >> 1, qy = band & 1;
-        for (int k = k_lo; k <= k_hi; ++k) {
-            const int wx = k >> 1, qx = k & 1;
-            m |= 1u << (4 * (wy * warps_x + wx) + 2 * qx + qy);
-        }
+        if (k_hi < k_lo) continue;
+        // column block k = 2 wx + qx sits at bit 4 (wy warps_x + wx) + 2 qx + qy = base + 2 k: every second bit
+        const uint32_t cols = ((1u << (2 * (k_hi + 1))) - 1u) & ~((1u << (2 * k_lo)) - 1u) & 0x55555555u;
+        m |= cols << (4 * (band >> 1) * warps_x + (band & 1));
     }
     return m;
 }

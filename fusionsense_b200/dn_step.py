@@ -23,7 +23,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-from .losses import SSIM, DepthLoss, DepthLossType, FusedSSIM, TVLoss
+from .losses import DepthLoss, DepthLossType, FusedSSIM, TVLoss
 from .synthetic import Scene
 
 
@@ -101,10 +101,13 @@ def _torch_normal_from_depth_image(depths, fx, fy, cx, cy, img_size, c2w, device
 
 class DNSplatterStep:
     def __init__(self, scene: Scene, config: Optional[DNSplatterStepConfig] = None, device="cuda", step: int = 3000,
-                 gsplat_module=None):
+                 gsplat_module=None, torch_losses=None):
         """`gsplat_module`: whatever `import gsplat` resolves to for dn_model.py (default: this package's sm_100a
         implementation).  bench.py's reference arm passes the CPU oracle here, the way the reference would run on
-        an installed gsplat."""
+        an installed gsplat.
+        `torch_losses`: a module with plain-torch `SSIM`, `DepthLoss`, `TVLoss` classes (the reference's
+        dn_splatter/losses.py semantics).  Needed only with `fused_losses=False` or on the CPU: this package holds
+        no torch loss arithmetic of its own (tests and the CPU arm pass oracle/dn_losses_ref.py)."""
         self.config = config or DNSplatterStepConfig()
         self.device = torch.device(device)
         if gsplat_module is None:
@@ -125,11 +128,17 @@ class DNSplatterStep:
         self.training = True
         if self.config.fused_losses and self.device.type == "cuda":
             self.ssim = FusedSSIM(data_range=1.0, kernel_size=11)
+            self.depth_loss = DepthLoss(self.config.depth_loss_type)
+            self.smooth_loss = DepthLoss(DepthLossType.TV)
+            self.tv_loss = TVLoss()
         else:
-            self.ssim = SSIM(data_range=1.0, kernel_size=11).to(self.device)
-        self.depth_loss = DepthLoss(self.config.depth_loss_type)
-        self.smooth_loss = DepthLoss(DepthLossType.TV)
-        self.tv_loss = TVLoss()
+            if torch_losses is None:
+                raise RuntimeError("DNSplatterStep(fused_losses=False) / a CPU device needs `torch_losses` (a module "
+                                   "with the reference's torch loss classes): fusionsense_b200 has no torch fallback")
+            self.ssim = torch_losses.SSIM(data_range=1.0, kernel_size=11).to(self.device)
+            self.depth_loss = torch_losses.DepthLoss(self.config.depth_loss_type)
+            self.smooth_loss = torch_losses.DepthLoss(DepthLossType.TV)
+            self.tv_loss = torch_losses.TVLoss()
         self.background = torch.ones(3, device=self.device)  # background_color = "white" (dn_model.py:141)
         self.xys_grad_norm = None
         self.vis_counts = None

@@ -64,6 +64,12 @@ class GraphedDNSplatterStep:
         self.captures = 0
         self.replays = 0
         self.grad_sync = grad_sync
+        # N > 1: capture the gradient exchange inside the one graph (True) or launch it eagerly between two graphs
+        import os as _os
+
+        # (captured by default: r02e ran it at N = 2 without the round-1 hang, 1.15 ms per cfg2 step against 1.36 ms with
+        # two graphs; FSB_CAPTURE_NCCL=0 brings the two-graph form back)
+        self.capture_collective = _os.environ.get("FSB_CAPTURE_NCCL", "1") != "0"
         self.loss_scale = float(loss_scale)
         self.launches_per_replay = 0  # libfsb200 kernels inside one replay (counted while capturing)
         self._copy_stream = None
@@ -150,9 +156,9 @@ class GraphedDNSplatterStep:
         return views
 
     def capture(self) -> None:
-        """Single GPU: the whole iteration is one graph.  With a `grad_sync` (N > 1) it is two graphs with the
-        NCCL all-reduce launched eagerly between them: a collective captured inside the replayed graph hung the
-        2-GPU bench on the B200 box (r01), and one extra graph launch per step is far below the step time."""
+        """The whole iteration is one graph; with a `grad_sync` (N > 1) the gradient exchange is captured between
+        backward and Adam.  (`capture_collective=False`: two graphs with the exchange launched eagerly between
+        them, the round-1 form.)"""
         m = self.model
         if self.capacity is None or self.capacity <= 0:
             seen = self.max_isects_seen or self._probe_capacity()
@@ -182,7 +188,17 @@ class GraphedDNSplatterStep:
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         g = torch.cuda.CUDAGraph()
         n0 = lib.fsb_launch_count()
-        if self.grad_sync is None:
+        if self.grad_sync is not None and self.capture_collective:
+            # ONE graph: the gradient exchange is captured between backward and Adam
+            with torch.cuda.graph(g, stream=side):
+                loss, counts = self._body_main()
+                live = [p for p in params if p.grad is not None]
+                self._grad_src = [p.grad for p in live]
+                for p, v in zip(live, self._sync_grads()):
+                    p.grad = v
+                self._body_tail(loss, counts)
+            tail = None
+        elif self.grad_sync is None:
             with torch.cuda.graph(g, stream=side):
                 loss, counts = self._body_main()
                 self._body_tail(loss, counts)

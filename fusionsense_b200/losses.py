@@ -1,10 +1,12 @@
-"""DN-Splatter loss terms behind the reference's class names.
+"""DN-Splatter loss terms on fused CUDA kernels, behind the reference's class names.
 
-Mirrors /root/reference/dn_splatter/losses.py (`DepthLossType`, `DepthLoss`, `LogL1` :161-174,
-`EdgeAwareLogL1` :177-214, `EdgeAwareTV` :241-266, `TVLoss` :269-285) and the SSIM the base splatfacto loss
-uses (torchmetrics `StructuralSimilarityIndexMeasure(data_range=1.0, kernel_size=11)`, dn_model.py:244).
-`dn_regularizer_loss` evaluates the whole FusionSense depth/normal regulariser of
-dn_model.py:722-819 in ONE fused CUDA kernel pair (forward + analytic backward), see csrc/losses.cu.
+`dn_regularizer_loss` evaluates the whole FusionSense depth / normal regulariser of dn_model.py:722-819
+(/root/reference/dn_splatter/losses.py `EdgeAwareLogL1` :177-214, `TVLoss` :269-285, normal L1) in ONE fused
+kernel pair (forward + analytic backward, csrc/losses.cu); `FusedSSIM` is the SSIM of the base splatfacto loss
+(torchmetrics `StructuralSimilarityIndexMeasure(data_range=1.0, kernel_size=11)`, dn_model.py:244) in one launch each
+way (csrc/ssim.cu).  `DepthLossType`, `DepthLoss`, `EdgeAwareLogL1`, `TVLoss` keep the reference's names and call
+those kernels.  No torch arithmetic lives here: the plain-torch restatement that checks the kernels is
+oracle/dn_losses_ref.py (test infrastructure).
 """
 from __future__ import annotations
 
@@ -26,127 +28,64 @@ class DepthLossType(Enum):
     EdgeAwareTV = "EdgeAwareTV"
 
 
-class LogL1(nn.Module):
-    def __init__(self, implementation: Literal["scalar", "per-pixel"] = "scalar", **kwargs):
+class _FusedOnly(nn.Module):
+    """Base of the class shells below: the reference's loss class names (dn_splatter/losses.py) on the fused CUDA
+    kernel of csrc/losses.cu.  There is no torch arithmetic in this package; the plain-torch restatement that
+    checks these kernels lives in oracle/dn_losses_ref.py (test infrastructure)."""
+
+    @staticmethod
+    def _refuse(what: str):
+        raise NotImplementedError(
+            f"{what} has no fused kernel in fusionsense_b200 (the FusionSense configuration does not use it, "
+            "configs/config.py:3-39); use dn_splatter.losses from the reference for it")
+
+
+class TVLoss(_FusedOnly):
+    """losses.py:269-285: mean |d/dx| + mean |d/dy| of an [H,W,1] or [H,W,3] image, one fused launch."""
+
+    def forward(self, pred: Tensor) -> Tensor:
+        if pred.shape[-1] == 1:
+            return dn_regularizer_loss(pred, None, None, None, None, sensor_depth_lambda=0.0, smooth_loss_lambda=1.0,
+                                       normal_l1_lambda=0.0, normal_tv_lambda=0.0)
+        if pred.shape[-1] == 3:
+            return dn_regularizer_loss(None, None, None, pred, None, sensor_depth_lambda=0.0, smooth_loss_lambda=0.0,
+                                       normal_l1_lambda=0.0, normal_tv_lambda=1.0)
+        self._refuse(f"TVLoss on {pred.shape[-1]} channels")
+
+
+class EdgeAwareLogL1(_FusedOnly):
+    """losses.py:177-214 in its "scalar" form.  The valid mask is the one dn_model.py:724 builds,
+    `gt > depth_tolerance`; it is evaluated inside the kernel, so `mask` may be omitted (a mask passed in must be
+    that one)."""
+
+    def __init__(self, implementation: Literal["scalar", "per-pixel"] = "scalar", depth_tolerance: float = 0.1,
+                 rgb_clamp_min: float = 0.0, **kwargs):
         super().__init__()
-        self.implementation = implementation
+        if implementation != "scalar":
+            self._refuse("EdgeAwareLogL1(implementation='per-pixel')")
+        self.depth_tolerance, self.rgb_clamp_min = float(depth_tolerance), float(rgb_clamp_min)
 
-    def forward(self, pred, gt):
-        v = torch.log(1 + torch.abs(pred - gt))
-        return v.mean() if self.implementation == "scalar" else v
-
-
-class L1(nn.Module):
-    def __init__(self, implementation: Literal["scalar", "per-pixel"] = "scalar", **kwargs):
-        super().__init__()
-        self.implementation = implementation
-
-    def forward(self, pred, gt):
-        v = torch.abs(pred - gt)
-        return v.mean() if self.implementation == "scalar" else v
+    def forward(self, pred: Tensor, gt: Tensor, rgb: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+        return dn_regularizer_loss(pred, gt, rgb, None, None, depth_tolerance=self.depth_tolerance,
+                                   sensor_depth_lambda=1.0, smooth_loss_lambda=0.0, normal_l1_lambda=0.0,
+                                   normal_tv_lambda=0.0, rgb_clamp_min=self.rgb_clamp_min)
 
 
-class EdgeAwareLogL1(nn.Module):
-    """log(1+|d - d_gt|) weighted by exp(-mean_c |grad rgb|) in x and y, masked means (losses.py:177-214)."""
-
-    def __init__(self, implementation: Literal["scalar", "per-pixel"] = "scalar", **kwargs):
-        super().__init__()
-        self.implementation = implementation
-        self.logl1 = LogL1(implementation="per-pixel")
-
-    def forward(self, pred: Tensor, gt: Tensor, rgb: Tensor, mask: Optional[Tensor]):
-        logl1 = self.logl1(pred, gt)
-        grad_img_x = torch.mean(torch.abs(rgb[..., :, :-1, :] - rgb[..., :, 1:, :]), -1, keepdim=True)
-        grad_img_y = torch.mean(torch.abs(rgb[..., :-1, :, :] - rgb[..., 1:, :, :]), -1, keepdim=True)
-        lambda_x = torch.exp(-grad_img_x)
-        lambda_y = torch.exp(-grad_img_y)
-        loss_x = lambda_x * logl1[..., :, :-1, :]
-        loss_y = lambda_y * logl1[..., :-1, :, :]
-        if self.implementation == "per-pixel":
-            if mask is not None:
-                loss_x[~mask[..., :, :-1, :]] = 0
-                loss_y[~mask[..., :-1, :, :]] = 0
-            return loss_x[..., :-1, :, :] + loss_y[..., :, :-1, :]
-        if mask is not None:
-            assert mask.shape[:2] == pred.shape[:2]
-            loss_x = loss_x[mask[..., :, :-1, :]]
-            loss_y = loss_y[mask[..., :-1, :, :]]
-        return loss_x.mean() + loss_y.mean()
-
-
-class EdgeAwareTV(nn.Module):
-    def forward(self, depth: Tensor, rgb: Tensor):
-        grad_depth_x = torch.abs(depth[..., :, :-1, :] - depth[..., :, 1:, :])
-        grad_depth_y = torch.abs(depth[..., :-1, :, :] - depth[..., 1:, :, :])
-        grad_img_x = torch.mean(torch.abs(rgb[..., :, :-1, :] - rgb[..., :, 1:, :]), -1, keepdim=True)
-        grad_img_y = torch.mean(torch.abs(rgb[..., :-1, :, :] - rgb[..., 1:, :, :]), -1, keepdim=True)
-        grad_depth_x = grad_depth_x * torch.exp(-grad_img_x)
-        grad_depth_y = grad_depth_y * torch.exp(-grad_img_y)
-        return grad_depth_x.mean() + grad_depth_y.mean()
-
-
-class TVLoss(nn.Module):
-    def forward(self, pred):
-        h_diff = pred[..., :, :-1, :] - pred[..., :, 1:, :]
-        w_diff = pred[..., :-1, :, :] - pred[..., 1:, :, :]
-        return torch.mean(torch.abs(h_diff)) + torch.mean(torch.abs(w_diff))
-
-
-class DepthLoss(nn.Module):
-    """Factory with the reference's dispatch (losses.py:31-60)."""
+class DepthLoss(_FusedOnly):
+    """Factory with the reference's dispatch (losses.py:31-60) over the loss types that have a fused kernel."""
 
     def __init__(self, depth_loss_type: DepthLossType, **kwargs):
         super().__init__()
         self.depth_loss_type = depth_loss_type
-        self.kwargs = kwargs
-        t = depth_loss_type
-        if t == DepthLossType.MSE:
-            self.loss = torch.nn.MSELoss()
-        elif t == DepthLossType.L1:
-            self.loss = L1(**kwargs)
-        elif t == DepthLossType.LogL1:
-            self.loss = LogL1(**kwargs)
-        elif t == DepthLossType.EdgeAwareLogL1:
+        if depth_loss_type == DepthLossType.EdgeAwareLogL1:
             self.loss = EdgeAwareLogL1(**kwargs)
-        elif t == DepthLossType.EdgeAwareTV:
-            self.loss = EdgeAwareTV()
-        elif t == DepthLossType.TV:
+        elif depth_loss_type == DepthLossType.TV:
             self.loss = TVLoss()
         else:
-            raise ValueError(f"Unsupported loss type: {depth_loss_type}")
+            self._refuse(f"DepthLoss({depth_loss_type})")
 
     def forward(self, *args) -> Tensor:
         return self.loss(*args)
-
-
-# ---------------------------------------------------------------------------------------------
-# SSIM as torchmetrics' StructuralSimilarityIndexMeasure computes it (gaussian 11x11, sigma 1.5,
-# reflect padding, border crop, mean).  Plain-torch restatement: the checker of FusedSSIM below and what the CPU
-# reference arm runs; the CUDA product path uses FusedSSIM.
-# ---------------------------------------------------------------------------------------------
-class SSIM(nn.Module):
-    def __init__(self, data_range: float = 1.0, kernel_size: int = 11, sigma: float = 1.5, k1=0.01, k2=0.03):
-        super().__init__()
-        self.data_range, self.kernel_size, self.k1, self.k2 = data_range, kernel_size, k1, k2
-        dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1.0)
-        g = torch.exp(-((dist / sigma) ** 2) / 2)
-        g = (g / g.sum())[None]
-        self.register_buffer("kernel2d", (g.t() @ g)[None, None], persistent=False)
-
-    def forward(self, preds: Tensor, target: Tensor) -> Tensor:  # [B,C,H,W]
-        c1, c2 = (self.k1 * self.data_range) ** 2, (self.k2 * self.data_range) ** 2
-        ch = preds.shape[1]
-        pad = (self.kernel_size - 1) // 2
-        kernel = self.kernel2d.to(preds.dtype).expand(ch, 1, -1, -1)
-        p = F.pad(preds, (pad, pad, pad, pad), mode="reflect")
-        t = F.pad(target, (pad, pad, pad, pad), mode="reflect")
-        x = torch.cat((p, t, p * p, t * t, p * t))
-        out = F.conv2d(x, kernel, groups=ch)
-        mu_p, mu_t, e_pp, e_tt, e_pt = out.split(preds.shape[0])
-        mu_pp, mu_tt, mu_pt = mu_p * mu_p, mu_t * mu_t, mu_p * mu_t
-        s_p, s_t, s_pt = e_pp - mu_pp, e_tt - mu_tt, e_pt - mu_pt
-        ssim = ((2 * mu_pt + c1) * (2 * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_p + s_t + c2))
-        return ssim[..., pad:-pad, pad:-pad].reshape(ssim.shape[0], -1).mean(-1).mean()
 
 
 class _FusedSSIMFn(torch.autograd.Function):

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from fusionsense_b200.synthetic import make_scene
+from oracle import dn_losses_ref as torch_losses
 from tests.parity import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -16,7 +17,7 @@ def _models(n=20000, W=320, H=240, **kw):
     fused = DNSplatterStep(sc, DNSplatterStepConfig(**kw), device="cuda", step=3000)
     plain = DNSplatterStep(sc, DNSplatterStepConfig(fused_optimizer=False, fused_losses=False, fused_glue=False,
                                                      fused_outputs=False, **kw),
-                           device="cuda", step=3000)
+                           device="cuda", step=3000, torch_losses=torch_losses)
     return sc, fused, plain
 
 
@@ -89,7 +90,7 @@ def test_whole_step_against_cpu_oracle():
     sc = make_scene(6000, 256, 192, n_views=3, cfg_id=7, kind="bunny", fx=240.0)
     gpu = DNSplatterStep(sc, DNSplatterStepConfig(), device="cuda", step=3000)
     cpu = DNSplatterStep(sc, DNSplatterStepConfig(fused_optimizer=False, stop_split_at=0), device="cpu", step=3000,
-                         gsplat_module=ref)
+                         gsplat_module=ref, torch_losses=torch_losses)
     batch = gpu.render_targets(2)
     og, oc = gpu.get_outputs(0), cpu.get_outputs(0)
     for k in ("rgb", "depth", "normal", "accumulation"):
@@ -108,7 +109,8 @@ def test_whole_step_against_cpu_oracle():
 def test_fused_ssim_matches_torch_restatement(H, W, C):
     """csrc/ssim.cu vs the plain-torch restatement of torchmetrics' SSIM (evaluated in fp64): value within 1e-5
     relative, gradient within 1e-4 of its max magnitude; called the way dn_model.py does, ssim(gt, pred)."""
-    from fusionsense_b200.losses import SSIM, FusedSSIM
+    from fusionsense_b200.losses import FusedSSIM
+    from oracle.dn_losses_ref import SSIM
 
     g = torch.Generator().manual_seed(H * 1000 + W)
     gt = torch.rand(H, W, C, generator=g).cuda()

@@ -1,4 +1,4 @@
-"""The loss classes mirrored in fusionsense_b200/losses.py (CPU) and the fused CUDA regulariser (GPU) against
+"""The plain-torch loss restatement (oracle/dn_losses_ref.py, CPU) and the fused CUDA regulariser (GPU) against
 outputs of the unmodified reference dn_splatter/losses.py (tests/golden/dn_losses.npz,
 generator: oracle/make_golden_losses.py)."""
 import numpy as np
@@ -15,7 +15,8 @@ def _load(device="cpu"):
 
 
 def test_mirrored_torch_classes_match_reference_outputs():
-    from fusionsense_b200.losses import DepthLoss, DepthLossType, TVLoss
+    from fusionsense_b200.losses import DepthLossType
+    from oracle.dn_losses_ref import DepthLoss, TVLoss
 
     z, t = _load()
     gt_img = t["rgb"].clamp(min=10 / 255.0)
@@ -29,7 +30,7 @@ def test_mirrored_torch_classes_match_reference_outputs():
 
 
 def test_ssim_restatement_properties():
-    from fusionsense_b200.losses import SSIM
+    from oracle.dn_losses_ref import SSIM
 
     g = torch.Generator().manual_seed(1)
     a = torch.rand(1, 3, 48, 64, generator=g)
@@ -61,7 +62,8 @@ def test_fused_regulariser_matches_reference_golden():
 @pytest.mark.gpu
 def test_fused_regulariser_single_terms_and_full_frame():
     """Each term alone against the mirrored torch classes on a 640x480 frame (the bench size)."""
-    from fusionsense_b200.losses import DepthLoss, DepthLossType, TVLoss, dn_regularizer_loss
+    from fusionsense_b200.losses import DepthLossType, dn_regularizer_loss
+    from oracle.dn_losses_ref import DepthLoss, TVLoss
 
     g = torch.Generator().manual_seed(3)
     H, W = 480, 640
