@@ -334,6 +334,9 @@ class Ctx:
         self.device = torch.device("cuda", self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.device)
+        # N > 1 gradient exchange: "peer" = this library's kernels over NVLink peer memory (default), "nccl" = one flat
+        # NCCL all-reduce; both captured in the step's graph
+        self.exchange = os.environ.get("FSB_EXCHANGE", "peer")
         self.sampler = ClockSampler(self.local_rank)
         if self.rank == 0:
             self.sampler.start()
@@ -367,8 +370,22 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
     if graph_mode:
         from fusionsense_b200.graph_step import GraphedDNSplatterStep
 
-        runner = GraphedDNSplatterStep(model, dev_targets, grad_sync=allreduce_grads if world > 1 else None,
-                                       loss_scale=1.0 / world)
+        sync = None
+        if world > 1:
+            sync = allreduce_grads
+            if ctx.exchange == "peer":
+                # our own kernels over NVLink peer memory (csrc/grad_exchange.cu) instead of the NCCL all-reduce
+                from fusionsense_b200.dist import PeerGradExchange
+
+                try:
+                    sync = PeerGradExchange()
+                    sync.probe(device)
+                except Exception as exc:  # noqa: BLE001  (no symmetric-memory support on this box: say so, use NCCL)
+                    print(f"bench: PeerGradExchange unavailable ({type(exc).__name__}: {exc}); using NCCL",
+                          file=sys.stderr)
+                    ctx.exchange = "nccl (peer exchange unavailable)"
+                    sync = allreduce_grads
+        runner = GraphedDNSplatterStep(model, dev_targets, grad_sync=sync, loss_scale=1.0 / world)
 
     def eager_step(m, i, batch):
         v = (i * world + rank) % n_views
@@ -638,6 +655,11 @@ def run_ours(args):
                        "fused_outputs": main["fused_outputs"],  # dn_step.py: activations / SH concat / image glue
                        # inside our kernels (True) or as the reference's torch ops (False)
                        "prune_lists": main["prune_lists"],
+                       "grad_exchange": (None if world == 1 else
+                                         ("own kernels over NVLink peer memory (pack, barrier, reduce-scatter, barrier, "
+                                          "Adam gathering the reduced slices), captured in the step's graph"
+                                          if ctx.exchange == "peer" else
+                                          "one flat NCCL all-reduce captured in the step's graph")),
                        "l2": "per-step working set (parameters, Adam state, gradients, intersection lists, images: "
                              ">1 GB touched per step at cfg4, >400 MB at cfg2) exceeds the 126 MB L2; no explicit "
                              "flush"},

@@ -63,11 +63,13 @@ class _Lib:
         if self._cdll is not None:
             return self._cdll
         path = _build.LIB_PATH
-        if not path.exists():
+        if not path.exists() or _build.is_stale():
+            # a library built from other sources than the ones on disk would be bound to prototypes parsed from the
+            # current header: silent ABI drift.  Rebuild (no-op when the stamp matches) or refuse.
             if _build.find_nvcc() is None:
                 raise FsbError(
-                    f"{path} is missing and nvcc is not available to build it; "
-                    "fusionsense_b200 has no CPU fallback. Run `python -m fusionsense_b200._build`."
+                    f"{path} is missing or was built from different sources (stamp mismatch) and nvcc is not "
+                    "available to build it; fusionsense_b200 has no CPU fallback. Run `python -m fusionsense_b200._build`."
                 )
             _build.build()
         try:

@@ -30,7 +30,8 @@ def _sources():
 
 def _source_hash() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh"))):
+    header = PKG_DIR.parent / "include" / "fsb200.h"
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh"))) + ([header] if header.exists() else []):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -13,8 +13,13 @@ densification (parameters are replaced every `refine_every` steps).  What keeps 
   * `split_generator`     the split children's normal draws come from a generator seeded by (seed, step) on every
                           rank, so the new Gaussians are bit-identical without a parameter broadcast.
 
-All collectives go through `torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests); nothing
-here launches a kernel of its own.
+  * `PeerGradExchange`    the same exchange as kernels of this library over NVLink peer memory (csrc/grad_exchange.cu):
+                          pack -> barrier -> reduce-scatter -> barrier, and an Adam whose gradient load gathers the
+                          reduced slices from their owners; no NCCL call on the step's path, capturable in the step's
+                          CUDA graph.  torch symmetric memory provides the peer mappings (plumbing).
+
+`GradSync`, the densification statistics and the hull slabs go through `torch.distributed` (NCCL over NVLink on the
+GPU box, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -82,6 +87,122 @@ class GradSync:
             return
         for p, v in zip(params, self.reduce([p.grad for p in params], overflow)):
             p.grad = v
+
+
+class PeerGradExchange:
+    """Gradient exchange over NVLink peer memory with this library's own kernels (include/fsb200.h, fsb_xchg_*).
+
+    Rank r owns slice r of the flat gradient (59 floats per Gaussian, tensor offsets rounded to 4 floats).
+    `exchange(grads, overflow)` — inside or outside a CUDA-graph capture — packs this rank's gradients into its
+    symmetric buffer, meets the other ranks (the overflow flag is OR-ed on the way), reduces its own slice from every
+    rank's buffer (peer loads, or NVSwitch multimem.ld_reduce with `multicast=True`) and meets them again.  After that
+    `adam_args()` tells CapturedAdam where the reduced slices live; its kernel (fsb_adam_multi_xchg) reads them from
+    the owners' memory: the all-gather half of the all-reduce is the optimizer's gradient load.
+
+    Every element is reduced once, by its owner, in rank order, so all replicas apply bit-identical updates."""
+
+    capturable = True
+    N_SLOTS = 4
+
+    def __init__(self, group=None, multicast: Optional[bool] = None):
+        import os
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        from ._abi import lib
+
+        if self.world > lib.fsb_xchg_max_world():
+            raise RuntimeError(f"PeerGradExchange handles up to {lib.fsb_xchg_max_world()} ranks (one NVSwitch box)")
+        if multicast is None:
+            multicast = os.environ.get("FSB_XCHG_MULTICAST", "0") == "1"
+        self.want_multicast = bool(multicast)
+        self._layout = None
+
+    def _setup(self, grads: List[Tensor]) -> None:
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dev = grads[0].device
+        ns = [g.numel() for g in grads]
+        off = [0]
+        for n in ns:
+            off.append(off[-1] + (n + 3) // 4 * 4)
+        per = -(-off[-1] // self.world)
+        self.S = (per + 3) // 4 * 4
+        self.total = self.S * self.world
+        self.ns, self.off = ns, off
+        self.G = symm_mem.empty(self.total, dtype=torch.float32, device=dev)
+        self.R = symm_mem.empty(self.S, dtype=torch.float32, device=dev)
+        self.pad = symm_mem.empty(self.N_SLOTS * 8, dtype=torch.int32, device=dev)
+        self.G.zero_(); self.R.zero_(); self.pad.zero_()
+        torch.cuda.synchronize(dev)
+        hG = symm_mem.rendezvous(self.G, self.group)
+        hR = symm_mem.rendezvous(self.R, self.group)
+        hP = symm_mem.rendezvous(self.pad, self.group)
+        self._handles = (hG, hR, hP)  # keep the mappings alive
+        W = self.world
+        self._g_ptrs = (ctypes.c_void_p * W)(*[int(p) for p in hG.buffer_ptrs])
+        self._r_ptrs = (ctypes.c_void_p * W)(*[int(p) for p in hR.buffer_ptrs])
+        self._pad_ptrs = (ctypes.c_void_p * W)(*[int(p) for p in hP.buffer_ptrs])
+        self.g_mc = None
+        if self.want_multicast and getattr(hG, "has_multicast_support", False) and int(hG.multicast_ptr or 0) != 0:
+            self.g_mc = int(hG.multicast_ptr)
+        self.epoch = torch.zeros(self.N_SLOTS, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)  # every pad is zeroed before anybody signals
+        self._layout = (tuple(ns), dev)
+
+    def exchange(self, grads: List[Tensor], overflow: Optional[Tensor] = None) -> None:
+        import ctypes
+
+        from ._abi import check, lib
+        from .ops import _stream
+
+        grads = [g.contiguous() for g in grads]
+        if self._layout != (tuple(g.numel() for g in grads), grads[0].device):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PeerGradExchange: the gradient layout changed inside a capture; run one eager "
+                                   "step first (symmetric buffers cannot be created while capturing)")
+            self._setup(grads)
+        n = len(grads)
+        st = _stream()
+        src = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads])
+        ns = (ctypes.c_int64 * n)(*self.ns)
+        off = (ctypes.c_int64 * (n + 1))(*self.off)
+        check(lib.fsb_xchg_pack(n, ctypes.addressof(src), ctypes.addressof(ns), ctypes.addressof(off), self.G.data_ptr(),
+                                self.total, st), "fsb_xchg_pack")
+        self._keep = grads
+        flag = None if overflow is None else overflow.data_ptr()
+        check(lib.fsb_xchg_barrier(self.world, self.rank, ctypes.addressof(self._pad_ptrs), 0, self.epoch.data_ptr(),
+                                   flag, st), "fsb_xchg_barrier")
+        check(lib.fsb_xchg_reduce_scatter(self.world, self.rank, ctypes.addressof(self._g_ptrs), self.g_mc, self.S,
+                                          self.R.data_ptr(), st), "fsb_xchg_reduce_scatter")
+        # "my slice is reduced" — and every rank has finished reading G, so the next step may overwrite it.  The slices
+        # themselves are safe until barrier 0 of the next step, which a rank enters only after its Adam has read them.
+        check(lib.fsb_xchg_barrier(self.world, self.rank, ctypes.addressof(self._pad_ptrs), 1, self.epoch.data_ptr(),
+                                   None, st), "fsb_xchg_barrier")
+
+    def probe(self, device) -> None:
+        """Collective: establish a tiny symmetric buffer, so that a box without peer-memory support fails here (before
+        any capture) rather than in the first step."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = symm_mem.empty(64, dtype=torch.float32, device=device)
+        t.zero_()
+        h = symm_mem.rendezvous(t, self.group)
+        if len(h.buffer_ptrs) != self.world:
+            raise RuntimeError("symmetric memory rendezvous returned the wrong number of peers")
+
+    def adam_args(self):
+        """(flat offsets, world, host array of the reduced slices' peer pointers, S) for fsb_adam_multi_xchg."""
+        return self.off, self.world, self._r_ptrs, self.S
+
+    def reduced_flat(self) -> Tensor:
+        """Test helper: the whole reduced gradient gathered from the owners (a copy)."""
+        hR = self._handles[1]
+        parts = [hR.get_buffer(w, (self.S,), torch.float32).clone() for w in range(self.world)]
+        return torch.cat(parts)
 
 
 @torch.no_grad()

@@ -70,8 +70,16 @@ class GraphedDNSplatterStep:
         # (captured by default: r02e ran it at N = 2 without the round-1 hang, 1.15 ms per cfg2 step against 1.36 ms with
         # two graphs; FSB_CAPTURE_NCCL=0 brings the two-graph form back)
         self.capture_collective = _os.environ.get("FSB_CAPTURE_NCCL", "1") != "0"
+        # a dist.PeerGradExchange: the exchange is this library's kernels over NVLink peer memory, folded into Adam
+        self._peer = grad_sync is not None and hasattr(grad_sync, "exchange")
         self.loss_scale = float(loss_scale)
         self.launches_per_replay = 0  # libfsb200 kernels inside one replay (counted while capturing)
+        # overflowed steps are no-ops on the device but advance the host's step counters; callers that never poll()
+        # would keep replaying with a capacity that is too small, so every `check_every` replays the result vector
+        # is copied to pinned memory and looked at once the copy has landed (no stream synchronisation)
+        self.check_every = 16
+        self._last_check = 0
+        self._check_slot = None
         self._copy_stream = None
         self._slot_staged: Dict[int, torch.cuda.Event] = {}  # view -> "prefetch finished"
         self._slot_read: Dict[int, torch.cuda.Event] = {}    # view -> "last replay that read the slot finished"
@@ -84,8 +92,12 @@ class GraphedDNSplatterStep:
         skip_steps = cfg.reset_alpha_every * cfg.refine_every
         binary = (cfg.use_binary_opacities and m.step > cfg.warmup_length and not m.step % skip_steps == 0
                   and m.step % skip_steps not in range(1, 200 + 1))
+        # the densification statistics are written by the captured fsb_densify_stats: refinement_after drops them
+        # (None) on EVERY refine step, also on the ones that neither densify nor cull, so their identity is part of
+        # what the capture froze (round-1 advisor finding: the graph kept writing into the freed tensors)
+        stats = tuple(id(t) if t is not None else None for t in (m.xys_grad_norm, m.vis_counts, m.max_2Dsize))
         return (m.num_points, min(m.step // cfg.sh_degree_interval, cfg.sh_degree), binary,
-                m.step >= cfg.stop_split_at, self.capacity, tuple(id(p) for p in m.gauss_params.values()))
+                m.step >= cfg.stop_split_at, self.capacity, tuple(id(p) for p in m.gauss_params.values()), stats)
 
     @torch.no_grad()
     def _probe_capacity(self) -> int:
@@ -138,7 +150,13 @@ class GraphedDNSplatterStep:
     def _body_tail(self, loss, counts, warmup: bool = False):
         """Adam (all groups, one launch) -> after_train statistics -> result vector."""
         m = self.model
-        self.adam.launch(skip_flag=self.overflow)
+        if self._peer:
+            # gradients of the Adam entries, in its order, through our own NVLink exchange; Adam gathers the result
+            grads = [p.grad for _, _, p in self.adam.entries]
+            self.grad_sync.exchange(grads, self.overflow)
+            self.adam.launch_xchg(self.grad_sync, skip_flag=self.overflow)
+        else:
+            self.adam.launch(skip_flag=self.overflow)
         m.after_train(skip_flag=self.overflow)
         if warmup:
             return
@@ -175,7 +193,7 @@ class GraphedDNSplatterStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             loss, counts = self._body_main(warmup=True)
-            if self.grad_sync is not None:
+            if self.grad_sync is not None and not self._peer:
                 self._grad_src = [p.grad for p in params if p.grad is not None]
                 for p, v in zip([p for p in params if p.grad is not None], self._sync_grads()):
                     p.grad = v
@@ -188,7 +206,12 @@ class GraphedDNSplatterStep:
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         g = torch.cuda.CUDAGraph()
         n0 = lib.fsb_launch_count()
-        if self.grad_sync is not None and self.capture_collective:
+        if self._peer:
+            with torch.cuda.graph(g, stream=side):
+                loss, counts = self._body_main()
+                self._body_tail(loss, counts)
+            tail = None
+        elif self.grad_sync is not None and self.capture_collective:
             # ONE graph: the gradient exchange is captured between backward and Adam
             with torch.cuda.graph(g, stream=side):
                 loss, counts = self._body_main()
@@ -247,6 +270,8 @@ class GraphedDNSplatterStep:
             self.graph_tail.replay()
         m.step += 1
         self.replays += 1
+        if self.replays - self._last_check >= self.check_every:
+            self._check_async()
         return self.result
 
     # ---- pipelined host <-> device traffic (the e2e leg of bench.py) ---------------------------------------
@@ -305,11 +330,25 @@ class GraphedDNSplatterStep:
             n += t.numel() * t.element_size()
         return n
 
-    def poll(self) -> Dict[str, float]:
-        """Read the result vector (one 32-byte D2H copy; synchronises with the last replay) and handle overflowed
-        steps: they changed nothing on the device, so the host counters are rolled back, the capacity grows and the
-        next call re-captures."""
-        loss, overflowed, n0, n1 = self.result.tolist()
+    def _check_async(self) -> None:
+        self._last_check = self.replays
+        if self._check_slot is not None:
+            host, ev = self._check_slot
+            if not ev.query():
+                return  # the previous probe has not landed yet: look again next time
+            vals = host.tolist()
+            self._check_slot = None
+            self._handle(vals)
+        host = torch.zeros(4, dtype=torch.float64).pin_memory() if getattr(self, "_check_host", None) is None \
+            else self._check_host
+        self._check_host = host
+        host.copy_(self.result, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._check_slot = (host, ev)
+
+    def _handle(self, vals):
+        loss, overflowed, n0, n1 = vals
         self.max_isects_seen = max(self.max_isects_seen, int(n0), int(n1))
         new = int(overflowed) - self._overflow_seen
         if new > 0:
@@ -318,5 +357,14 @@ class GraphedDNSplatterStep:
             self.adam.rollback(new)
             self.capacity = int(max(self.capacity * 1.5, self.max_isects_seen * self.margin)) + 65536
             self.graph = None
+        return new
+
+    def poll(self) -> Dict[str, float]:
+        """Read the result vector (one 32-byte D2H copy; synchronises with the last replay) and handle overflowed
+        steps: they changed nothing on the device, so the host counters are rolled back, the capacity grows and the
+        next call re-captures."""
+        loss, overflowed, n0, n1 = vals = self.result.tolist()
+        self._check_slot = None
+        new = self._handle(vals)
         return {"loss": loss, "overflowed_steps": int(overflowed), "n_isects": int(n0), "n_isects_normals": int(n1),
                 "capacity": self.capacity, "new_overflows": new}

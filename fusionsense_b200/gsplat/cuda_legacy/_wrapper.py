@@ -36,6 +36,9 @@ def remember_binning(means2d: Tensor, depths: Tensor, radii: Tensor, width: int,
     _LAST_BINNING.update(
         key=(means2d.data_ptr(), depths.data_ptr(), radii.data_ptr(), means2d._version, depths._version,
              radii._version, radii.shape[1], width, height, tile_size),
+        # strong references: while the cache lives, the allocator cannot hand these addresses to other tensors, so a
+        # matching key really means "the same projected Gaussians" (round-1 advisor finding)
+        owners=(means2d, depths, radii),
         n_isects=n_isects, flatten_ids=flatten_ids, isect_offsets=isect_offsets, legacy_extra=legacy_extra,
         lists_done=lists_done,  # static-capacity mode: event recorded after the binning (another stream may wait)
         pruned=pruned,  # EXPERIMENTAL: the lists hold only the reached (Gaussian, tile) pairs (ops.isect_tiles reach=)
@@ -144,7 +147,7 @@ def rasterize_gaussians(
         elif n_isects > 0:
             ids, flat = ops.isect_emit(xys_c[None], rad_c[None], dep_c[None], offsets, n_isects, 1, N, ts, tile_w,
                                        tile_h, legacy_bbox=True)
-            ids, flatten_ids = ops.radix_sort_pairs(ids, flat, 32 + ops.tile_bits_for(tile_w * tile_h) + 1)
+            ids, flatten_ids = ops.radix_sort_pairs(ids, flat, ops.sort_end_bit(tile_w * tile_h, 1))
             isect_offsets = ops.isect_offsets(ids, 1, tile_w, tile_h)
         else:
             flatten_ids = isect_offsets = None

@@ -25,6 +25,12 @@ def _stream() -> int:
         return torch.cuda.current_stream().cuda_stream
 
 
+# FSB_NVTX=1: every stage call wrapped by kernel_timer.start / stop (projection, emit, sort, compositing forward /
+# backward, SSIM, Adam) is also an NVTX range "fsb.<stage>", so nsys / ncu --nvtx timelines name the stages
+# (SURVEY.md §5 asked for ranges; off by default: a push / pop pair costs ~1 us of host time per call)
+NVTX = __import__("os").environ.get("FSB_NVTX", "0") == "1"
+
+
 class KernelTimer:
     """Optional CUDA-event timing of individual ABI calls on the launching stream (bench.py's roofline leg).
 
@@ -55,6 +61,8 @@ class KernelTimer:
         return _Ctx()
 
     def start(self, name):
+        if NVTX:
+            torch.cuda.nvtx.range_push(f"fsb.{name}")
         if not self.enabled:
             return None
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -66,6 +74,8 @@ class KernelTimer:
 
     @staticmethod
     def stop(e):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
         if e is not None:
             e.record(torch.cuda.current_stream())
 
@@ -200,6 +210,13 @@ def tile_bits_for(n_tiles: int) -> int:
     return int(n_tiles).bit_length()
 
 
+def sort_end_bit(n_tiles: int, C: int) -> int:
+    """Key bits that can differ: 32 depth bits + tile bits (+ camera bits when there is more than one camera; gsplat
+    reserves floor(log2 C) + 1 bits even for C = 1, whose value is always 0).  One bit less is one radix pass less at
+    1080p: 45 bits sort in five 9-bit passes, 46 in six 8-bit ones (csrc/radix_sort.cu)."""
+    return 32 + tile_bits_for(n_tiles) + (tile_bits_for(C) if C > 1 else 0)
+
+
 def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox, n_dev=None,
                overflow=None, reach=None):
     """`n_dev` (device int64[1]) selects static-capacity mode: `n_isects` is then the capacity of the buffers.
@@ -280,7 +297,7 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
         ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h,
                                legacy_bbox, n_dev=n_dev, overflow=st.overflow, reach=reach)
         if sort:
-            end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
+            end_bit = sort_end_bit(tile_w * tile_h, C)
             ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=n_dev)
         tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=n_dev)
         flat.n_dev = n_dev
@@ -292,7 +309,7 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
     ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox,
                            reach=reach)
     if sort:
-        end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
+        end_bit = sort_end_bit(tile_w * tile_h, C)
         ids, flat = radix_sort_pairs(ids, flat, end_bit)
     tile_offsets = isect_offsets(ids, C, tile_w, tile_h)
     return tiles_per_gauss, ids, flat, tile_offsets
@@ -326,7 +343,7 @@ def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h,
     check(lib.fsb_isect_share_gate(ptr(first_flat.n_dev), ptr(n_list), ptr(gate), _stream()), "fsb_isect_share_gate")
     ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h, True,
                            n_dev=gate, overflow=st.overflow, reach=reach)
-    end_bit = 32 + tile_bits_for(tile_w * tile_h) + tile_bits_for(C)
+    end_bit = sort_end_bit(tile_w * tile_h, C)
     ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=gate)
     tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=gate)
     if lists_done is not None:

@@ -125,6 +125,30 @@ class CapturedAdam:
         self._host = (ctypes.c_float * (2 * maxt))()
 
     @torch.no_grad()
+    def launch_xchg(self, exchange, skip_flag=None) -> None:
+        """Multi-GPU: the same update with the gradient gathered from the ranks' reduced slices in peer memory
+        (fsb_adam_multi_xchg, csrc/grad_exchange.cu); `exchange` = a dist.PeerGradExchange whose exchange() has run
+        on this step's gradients, in the order of `self.entries`."""
+        n = len(self.entries)
+        off, world, r_ptrs, S = exchange.adam_args()
+        VP = ctypes.c_void_p * n
+        ps, ms, vs, ns = [], [], [], []
+        for opt, group, p in self.entries:
+            st = opt.state[p]
+            ps.append(p.data_ptr()); ms.append(st["exp_avg"].data_ptr()); vs.append(st["exp_avg_sq"].data_ptr())
+            ns.append(p.numel())
+        if ns != list(exchange.ns):
+            raise RuntimeError("CapturedAdam.launch_xchg: the exchange was run on a different tensor list")
+        p_, m_, v_ = VP(*ps), VP(*ms), VP(*vs)
+        numel = (ctypes.c_int64 * n)(*ns)
+        offs = (ctypes.c_int64 * n)(*off[:n])
+        check(lib.fsb_adam_multi_xchg(n, ctypes.addressof(p_), ctypes.addressof(m_), ctypes.addressof(v_),
+                                      ctypes.addressof(numel), ctypes.addressof(offs), world,
+                                      ctypes.addressof(r_ptrs), S, self.hyper.data_ptr(), self.maxt,
+                                      None if skip_flag is None else skip_flag.data_ptr(), self.betas[0],
+                                      self.betas[1], self.eps, _stream()), "fsb_adam_multi_xchg")
+
+    @torch.no_grad()
     def launch(self, skip_flag=None) -> None:
         """Inside the capture, after backward(): one launch for all tensors, scalars read from `self.hyper`."""
         n = len(self.entries)

@@ -222,6 +222,28 @@ int fsb_raster_pair_count(int C, int N, int64_t n_isects, const int64_t* n_isect
                           const int32_t* last_ids, uint64_t* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU gradient exchange over NVLink peer memory (csrc/grad_exchange.cu): what DDP's all-reduce would do for
+ * dn_splatter/dn_pipeline.py:161-167, as kernels of this library that a CUDA graph can capture — no NCCL call on the
+ * step's path.  One process per GPU; rank r owns slice r = [r S, (r + 1) S) of the flat gradient.  "peer mapping" =
+ * a device pointer into another rank's buffer, valid in this process (torch symmetric memory / CUDA IPC).
+ *   pack            the step's gradient tensors -> this rank's flat buffer (offsets multiples of 4, gaps zeroed)
+ *   barrier         all ranks arrived; ORs an int32 flag over the ranks (the static-capacity overflow flag)
+ *   reduce_scatter  out[i] = sum_w grads[w][rank S + i]  (peer loads, or NVSwitch multimem.ld_reduce via grads_mc)
+ *   adam_multi_xchg fsb_adam_multi_dev whose gradient load gathers from the ranks' reduced slices (peer loads)
+ * Every pointer-array argument is a HOST array; signal pads and epoch counters are zero-initialised once. */
+int fsb_xchg_max_world(void);
+int fsb_xchg_barrier(int world, int rank, uint32_t* const* pads, int slot, uint32_t* epoch_dev, int32_t* flag,
+                     void* stream);
+int fsb_xchg_pack(int n_tensors, const float* const* src, const int64_t* n, const int64_t* off, float* dst,
+                  int64_t total, void* stream);
+int fsb_xchg_reduce_scatter(int world, int rank, const float* const* grads, const float* grads_mc, int64_t S,
+                            float* out, void* stream);
+int fsb_adam_multi_xchg(int n_tensors, float* const* p, float* const* m, float* const* v, const int64_t* n,
+                        const int64_t* off, int world, const float* const* reduced, int64_t S,
+                        const float* hyper_dev, int hyper_stride, const int32_t* skip_flag, double beta1,
+                        double beta2, double eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Visual hull (voxel carving).  replaces utils/VisualHull.py:149-191 (projection/vote loop, threshold
  * mask, occupied-voxel extraction) with InitializeVoxels (:15-57) folded into axis-table lookups.
  * Voxel l = (iz*nx + ix)*ny + iy, zs given in the reference's loop order (descending).

@@ -231,20 +231,23 @@ def test_prefetched_targets_and_async_result_ring_match_the_blocking_path():
         assert x == pytest.approx(y, rel=2e-4)
 
 
-def test_two_graph_step_with_grad_sync_matches_single_graph():
-    """The N > 1 structure (main graph -> eager gradient exchange -> tail graph) on one GPU, where the exchange is
-    just the pack into the flat buffer: same losses and parameters as the single-graph step, overflow still a no-op."""
+@pytest.mark.parametrize("captured", [True, False])
+def test_step_with_grad_sync_matches_single_gpu_step(captured):
+    """The N > 1 structures on one GPU, where the exchange is just the pack into the flat buffer: the exchange captured
+    inside the one graph (default), and main graph -> eager exchange -> tail graph.  Same losses and parameters as
+    the single-GPU step, overflow still a no-op."""
     from fusionsense_b200.dist import GradSync
     from fusionsense_b200.graph_step import GraphedDNSplatterStep
 
     single, split, targets = _pair()
     r1 = GraphedDNSplatterStep(single, targets)
     r2 = GraphedDNSplatterStep(split, targets, grad_sync=GradSync())
+    r2.capture_collective = captured
     for v in [0, 2, 1, 1, 0]:
         r1.train_iteration(v)
         r2.train_iteration(v)
         assert r2.poll()["loss"] == pytest.approx(r1.poll()["loss"], rel=2e-4)
-    assert r2.graph_tail is not None and r1.graph_tail is None and r2.captures == 1
+    assert (r2.graph_tail is None) == captured and r1.graph_tail is None and r2.captures == 1
     assert r2.poll()["overflowed_steps"] == 0 and split.step == single.step
     for k in single.gauss_params:
         assert_close(split.gauss_params[k].data, single.gauss_params[k].data, f"split.param.{k}", tol=2e-3,
@@ -252,8 +255,38 @@ def test_two_graph_step_with_grad_sync_matches_single_graph():
     # overflow in the split structure: the tail graph sees the flag the exchange step produced and skips Adam
     _, small, targets = _pair()
     r3 = GraphedDNSplatterStep(small, targets, capacity=1000, grad_sync=GradSync())
+    r3.capture_collective = captured
     before = {k: v.data.clone() for k, v in small.gauss_params.items()}
     r3.train_iteration(0)
     assert r3.poll()["new_overflows"] == 1
     for k, v in small.gauss_params.items():
         assert torch.equal(v.data, before[k]), k
+
+
+def test_graph_step_survives_refine_steps_that_drop_the_statistics():
+    """refinement_after ends every refine step with xys_grad_norm = vis_counts = max_2Dsize = None, also when it
+    neither densifies nor culls (step % 3000 in {0, 100} with the defaults): the parameters keep their identity
+    there, so only the statistics tell the captured step that it must be re-captured (round-1 advisor finding)."""
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    _, graphed, targets = _pair()
+    graphed.step = 2998
+    runner = GraphedDNSplatterStep(graphed, targets)
+    n0 = graphed.num_points
+    for i in range(2):
+        runner.train_iteration(i % 3)
+    assert graphed.step == 3000 and runner.captures == 1
+    runner.poll()
+    deleted = graphed.refinement_after()  # step 3000: 3000 % 3000 = 0 -> no densification, no cull, stats dropped
+    assert deleted is None and graphed.num_points == n0 and graphed.xys_grad_norm is None
+    for i in range(3):
+        runner.train_iteration(i % 3)
+    assert runner.captures == 2, "dropping the statistics must re-capture"
+    assert graphed.xys_grad_norm is not None and float(graphed.xys_grad_norm.abs().sum()) > 0
+    assert float(graphed.vis_counts.max()) == 4.0  # ones + three accumulated iterations, not stale memory
+    # and a densifying refine step right after works on live statistics
+    graphed.step = 3200
+    runner.poll()
+    graphed.refinement_after()
+    runner.train_iteration(0)
+    assert runner.captures == 3 and runner.poll()["overflowed_steps"] == 0

@@ -1,0 +1,149 @@
+"""Multi-GPU check of the NVLink gradient exchange (csrc/grad_exchange.cu, dist.PeerGradExchange):
+
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/peer_exchange_check.py [n_gauss]
+
+Every rank: random parameters (same on all ranks), gradients seeded by the rank.  Path A: our exchange + the Adam that
+gathers from peer memory, eagerly, with the overflow flag raised on one rank (step must be skipped everywhere), and
+captured in a CUDA graph replayed several times.  Path B: NCCL all-reduce of the same gradients + fsb_adam_multi_dev.
+Prints one JSON line (rank 0) with the worst differences and the timings of both paths."""
+import json
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+import torch.distributed as dist
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_003
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    from fusionsense_b200.dist import PeerGradExchange
+    from fusionsense_b200.optim import CapturedAdam, FusedAdam
+
+    shapes = {"means": (N, 3), "features_dc": (N, 3), "features_rest": (N, 15, 3), "opacities": (N, 1),
+              "scales": (N, 3), "quats": (N, 4)}
+    lrs = {"means": 1.6e-4, "features_dc": 0.0025, "features_rest": 0.0025 / 20, "opacities": 0.05, "scales": 0.005,
+           "quats": 0.001}
+
+    def make():
+        g = torch.Generator(device="cpu").manual_seed(1)
+        ps = {k: torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for k, s in shapes.items()}
+        opts = [FusedAdam([ps[k]], lr=lrs[k], eps=1e-15) for k in shapes]
+        return ps, opts, CapturedAdam(opts)
+
+    pa, oa, adam_a = make()
+    pb, ob, adam_b = make()
+    ex = PeerGradExchange(multicast=os.environ.get("FSB_XCHG_MULTICAST") == "1")
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def set_grads(step):
+        g = torch.Generator(device="cpu").manual_seed(1000 * step + rank)
+        for k in shapes:
+            gr = torch.randn(shapes[k], generator=g).to(dev) * 1e-3
+            pa[k].grad = gr.clone()
+            pb[k].grad = gr.clone()
+
+    def step_a():
+        ex.exchange([p.grad for _, _, p in adam_a.entries], overflow)
+        adam_a.launch_xchg(ex, skip_flag=overflow)
+
+    def step_b():
+        for k in shapes:
+            dist.all_reduce(pb[k].grad)
+        adam_b.launch(skip_flag=None)
+
+    out = {"world": world, "n_gauss": N, "multicast": ex.want_multicast}
+    # 1) overflow on one rank: everybody skips
+    set_grads(0)
+    before = {k: v.detach().clone() for k, v in pa.items()}
+    overflow.fill_(1 if rank == world - 1 else 0)
+    adam_a.advance()
+    step_a()
+    torch.cuda.synchronize()
+    out["overflow_seen_everywhere"] = bool(int(overflow.item()) == 1)
+    out["skipped_step_is_noop"] = all(torch.equal(before[k], pa[k].detach()) for k in shapes)
+    adam_a.rollback(1)
+    overflow.zero_()
+    # 2) eager steps against NCCL + plain Adam
+    worst = 0.0
+    for s in range(1, 4):
+        set_grads(s)
+        adam_a.advance(); adam_b.advance()
+        step_a(); step_b()
+        torch.cuda.synchronize()
+        flat_ref = torch.cat([pb[k].grad.reshape(-1) for k in shapes])
+        red = ex.reduced_flat()
+        got = torch.cat([red[ex.off[i]:ex.off[i] + ex.ns[i]] for i in range(len(ex.ns))])
+        worst = max(worst, float((got - flat_ref).abs().max() / flat_ref.abs().max()))
+        for k in shapes:
+            worst = max(worst, float((pa[k] - pb[k]).abs().max() / pb[k].abs().max()))
+    out["eager_worst_rel_diff"] = worst
+    out["g_mc_used"] = ex.g_mc is not None
+    # 3) captured in a graph, replayed
+    set_grads(10)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=side):
+        step_a()
+    worst_g = 0.0
+    for s in range(3):
+        adam_a.advance(); adam_b.advance()
+        gr.replay()
+        for k in shapes:  # same gradients every replay; path B all-reduces a fresh copy
+            pb[k].grad = pa[k].grad.clone()
+        step_b()
+        torch.cuda.synchronize()
+        for k in shapes:
+            worst_g = max(worst_g, float((pa[k] - pb[k]).abs().max() / pb[k].abs().max()))
+    out["graph_worst_rel_diff"] = worst_g
+    # replicas identical across ranks
+    ident = True
+    for k in shapes:
+        ref = pa[k].detach().clone()
+        dist.broadcast(ref, src=0)
+        ident = ident and bool(torch.equal(ref, pa[k].detach()))
+    flag = torch.tensor([1 if ident else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["replicas_bit_identical"] = bool(flag.item())
+    # 4) timings (CUDA events, max over ranks)
+    def timed(fn, n=20):
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flat_b = torch.cat([pb[k].grad.reshape(-1) for k in shapes])
+
+    def nccl_flat():
+        torch.cat([pb[k].grad.reshape(-1) for k in shapes], out=flat_b)
+        dist.all_reduce(flat_b)
+        adam_b.launch(skip_flag=None)
+
+    for _ in range(3):
+        gr.replay(); nccl_flat()
+    out["ms_ours_graph"] = timed(gr.replay)
+    out["ms_nccl_pack_allreduce_adam"] = timed(nccl_flat)
+    out["payload_mb"] = ex.total * 4 / 1e6
+    ok = (out["overflow_seen_everywhere"] and out["skipped_step_is_noop"] and out["eager_worst_rel_diff"] < 1e-6
+          and out["graph_worst_rel_diff"] < 1e-6 and out["replicas_bit_identical"])
+    out["ok"] = bool(ok)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
