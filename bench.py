@@ -506,7 +506,7 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
                 "d2h_bytes_per_step": 32 if graph_mode else 4},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / steps, "clocks": clocks,
         "graph": graph_info, "warmup_actual": warmup + warm_extra, "fused_outputs": bool(model.config.fused_outputs),
-        "prune_lists": bool(model.config.prune_lists),
+        "prune_lists": bool(model.config.prune_lists), "step_metrics": bool(model.config.step_metrics),
     }
 
     if detail:
@@ -624,6 +624,7 @@ def _roofline(cfg_name, model, params, ktimes, pairs, clocks):
 
 
 def run_ours(args):
+    import torch
     import torch.distributed as dist
 
     ctx = Ctx()
@@ -655,6 +656,9 @@ def run_ours(args):
                        "fused_outputs": main["fused_outputs"],  # dn_step.py: activations / SH concat / image glue
                        # inside our kernels (True) or as the reference's torch ops (False)
                        "prune_lists": main["prune_lists"],
+                       # FSB_STEP_METRICS=1: get_metrics_dict (PSNR / SSIM / depth metrics, fused, no host sync) runs
+                       # inside every iteration as under nerfstudio's Trainer
+                       "step_metrics": main["step_metrics"],
                        "grad_exchange": (None if world == 1 else
                                          ("own kernels over NVLink peer memory (pack, barrier, reduce-scatter, barrier, "
                                           "Adam gathering the reduced slices), captured in the step's graph"
@@ -678,8 +682,16 @@ def run_ours(args):
                 "clocks": secondary["clocks"], "gpu_launches_per_step": secondary["gpu_launches_per_step"],
             }
     if world > 1:
+        # the line first, teardown after: rank 0 prints, everybody meets, and the processes leave without
+        # destroy_process_group (tearing down a communicator whose collectives sit in captured graphs hung a 2-GPU
+        # tool run until its timeout, r02g)
+        if line is not None:
+            line["cpu_baseline"] = None
+            _emit(line)
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     return line
 
 

@@ -42,6 +42,7 @@
 //                    red.global.add updates all of them.
 // The per-pixel loops are FP32 / MUFU / issue bound, not HBM bound.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -198,12 +199,17 @@ __device__ __forceinline__ TileGeom tile_geom(int64_t tile_lin, int tile_w, int 
     return g;
 }
 
-// Reach mask of a Gaussian on a tile (origin tx0, ty0 in pixels): bit 4 w + q is set when alpha >= 1/255 can hold on a
-// pixel centre of that 4 x 2 block.  alpha >= 1/255 means q(d) = a dx^2 + 2 b dx dy + c dy^2 <= 2 ln(255 opacity); on a
-// pixel row (fixed dy) that is the interval dx in [-b dy / a -+ sqrt(thr a - det dy^2) / a].  Per band of two rows the
-// union of the two intervals (taken as [min, max]: a superset) selects the column blocks.  The threshold is inflated
-// (1e-2 absolute, 2e-4 relative: alpha may be 0.5 % below 1/255) and the interval ends by 2e-3 px, far above the
-// fp32 error of this arithmetic; anything doubtful (non-PD conic, NaN, opacity ~ inf) keeps all bits.
+// Reach mask of a Gaussian on a tile (origin tx0, ty0 in pixels): bits 4 w .. 4 w + 3 are set when alpha >= 1/255 can
+// hold on a pixel centre of warp w's 8 x 4 footprint.  alpha >= 1/255 means q(d) = a dx^2 + 2 b dx dy + c dy^2 <= thr =
+// 2 ln(255 opacity): an ellipse with |dy| <= Y = sqrt(thr a / det), whose right / left boundary at height dy is
+// dx = -b dy / a +- sqrt(thr a - det dy^2) / a — concave / convex in dy with the extreme points at dy = -+ s,
+// s = b sqrt(thr / (det c)).  For a band of four pixel rows [d0, d0 + 3] (clipped to [-Y, Y]) the x-extent of the
+// ellipse over the band is therefore [L(clamp(s)), R(clamp(-s))]: two square roots per band, no loop over rows; the
+// continuous band is a superset of its four discrete rows.  The column blocks (8 pixel centres each) that meet the
+// extent get their bits.  The threshold is inflated (1e-2 absolute, 2e-4 relative: alpha may be 0.5 % below 1/255),
+// Y by 1e-3 and the extent by 2e-3 px, far above the fp32 error of this arithmetic (rsqrt.approx is good to 2 ulp);
+// anything doubtful (non-PD conic, NaN, opacity ~ inf) keeps all bits.  Uniform control flow: every lane of the
+// packing warp runs the same four (two for 8 x 8 tiles) band iterations.
 __device__ __forceinline__ uint32_t reach_mask(float gx, float gy, float opac, float a, float b, float c, float tx0,
                                                float ty0, int tile_size) {
     const int n_warps = (tile_size * tile_size) >> 5;
@@ -211,45 +217,40 @@ __device__ __forceinline__ uint32_t reach_mask(float gx, float gy, float opac, f
     const float tau = __logf(255.f * opac);
     if (tau + 2e-3f < 0.f) return 0u;  // opacity below 1/255: can never pass the alpha test
     const float det = a * c - b * b;
-    if (!(det > 0.f) || !(a > 0.f) || !(tau < 1e30f)) return all;
+    if (!(det > 0.f) || !(a > 0.f) || !(c > 0.f) || !(tau < 1e30f)) return all;
     const float thr = 2.f * tau * 1.0002f + 1e-2f;
     const float inv_a = __frcp_rn(a);
     const float ta = thr * a;
     const float nb = -b * inv_a;
-    const int warps_x = tile_size >> 3;
-    const int n_bands = tile_size >> 1, n_cols = tile_size >> 2;
-    // rows the ellipse can touch at all: |dy| <= sqrt(thr a / det)  (inflated; rsqrt.approx is good to 2 ulp)
-    const float dy_max = ta * rsqrtf(ta * det) * 1.001f + 1e-3f;
-    const float y_rel = ty0 + 0.5f - gy;  // dy of pixel row 0
-    const int band_lo = max(0, (int)floorf((-dy_max - y_rel - 1.f) * 0.5f));
-    const int band_hi = min(n_bands - 1, (int)ceilf((dy_max - y_rel) * 0.5f));
-    const float x_rel = tx0 + 0.5f - gx;  // dx of pixel column 0
+    const float Y = ta * rsqrtf(ta * det) * 1.001f + 1e-3f;  // sqrt(thr a / det), inflated
+    const float sx = b * (thr * rsqrtf(thr * det * c));      // b sqrt(thr / (det c))
+    const float y_rel = ty0 + 0.5f - gy;                     // dy of pixel row 0
+    const float x_rel = tx0 + 0.5f - gx;                     // dx of pixel column 0
+    const int warps_x = tile_size >> 3, n_bands = tile_size >> 2;
     uint32_t m = 0u;
-    for (int band = band_lo; band <= band_hi; ++band) {
-        float lo = 1e30f, hi = -1e30f;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const float dy = y_rel + (float)(2 * band + r);
-            const float disc = fmaf(-det * dy, dy, ta);
-            if (disc >= 0.f) {
-                const float h = disc * rsqrtf(fmaxf(disc, 1e-30f)) * inv_a;  // sqrt(disc) / a
-                const float ctr = nb * dy;
-                lo = fminf(lo, ctr - h);
-                hi = fmaxf(hi, ctr + h);
-            }
+    for (int band = 0; band < 4; ++band) {
+        if (band < n_bands) {
+            const float d0 = y_rel + (float)(4 * band);
+            const float e0 = fmaxf(d0, -Y), e1 = fminf(d0 + 3.f, Y);
+            const float tR = fminf(fmaxf(-sx, e0), e1), tL = fminf(fmaxf(sx, e0), e1);
+            const float dR = fmaxf(fmaf(-det * tR, tR, ta), 0.f), dL = fmaxf(fmaf(-det * tL, tL, ta), 0.f);
+            const float hi = fmaf(nb, tR, dR * rsqrtf(fmaxf(dR, 1e-30f)) * inv_a);
+            const float lo = fmaf(nb, tL, -(dL * rsqrtf(fmaxf(dL, 1e-30f)) * inv_a));
+            const float pad = 2e-3f + 2e-6f * fmaxf(fabsf(lo), fabsf(hi));
+            // pixel centres of column block k: dx in [x_rel + 8 k, x_rel + 8 k + 7]
+            const float fl = (lo - pad - x_rel - 7.f) * 0.125f, fh = (hi + pad - x_rel) * 0.125f;
+            int k_lo = max(0, __float2int_ru(fmaxf(fl, -1.f)));
+            int k_hi = min(warps_x - 1, __float2int_rd(fminf(fh, 64.f)));
+            if (!(e1 >= e0)) k_hi = -1;  // the band misses the ellipse's rows
+            k_lo = min(k_lo, 4);
+            k_hi = max(k_hi, -1);
+            // footprint (wy = band, wx = k) owns bits 4 (band warps_x + k) .. + 3
+            const uint32_t cols = ((1u << (4 * (k_hi + 1))) - 1u) & ~((1u << (4 * k_lo)) - 1u);
+            m |= cols << (4 * band * warps_x);
         }
-        if (!(hi >= lo)) continue;
-        // pixel centres of column block k: dx in [x_rel + 4k, x_rel + 4k + 3]
-        const float pad = 2e-3f + 2e-6f * fmaxf(fabsf(lo), fabsf(hi));
-        const float fl = (lo - pad - x_rel - 3.f) * 0.25f, fh = (hi + pad - x_rel) * 0.25f;
-        const int k_lo = max(0, (int)ceilf(fmaxf(fl, -1.f)));
-        const int k_hi = min(n_cols - 1, (int)floorf(fminf(fh, 64.f)));
-        if (k_hi < k_lo) continue;
-        // column block k = 2 wx + qx sits at bit 4 (wy warps_x + wx) + 2 qx + qy = base + 2 k: every second bit
-        const uint32_t cols = ((1u << (2 * (k_hi + 1))) - 1u) & ~((1u << (2 * k_lo)) - 1u) & 0x55555555u;
-        m |= cols << (4 * (band >> 1) * warps_x + (band & 1));
     }
-    return m;
+    return m & all;
 }
 
 // ---- unit table: one block scans the per-tile unit counts and orders the work ------------------------------------
@@ -343,6 +344,15 @@ unit_table_kernel(int n_tiles, int64_t n_isects, const int64_t* __restrict__ n_d
     // Launch orders, longest work unit first (LPT): CTA durations follow the unit length, and with grid order = tile
     // order a few long units picked up late leave most SMs idle in the kernel's tail.  Counting sort into LPT_BINS
     // length classes; the order inside a class is arbitrary (results do not depend on which CTA runs which unit).
+    // A deep grid of sequential tiles only (a uniform 1080p scene: 8160 units for ~600 CTA slots, nothing segment-
+    // parallel) gains nothing from the ordering, and this single-CTA kernel sits on the forward's critical path
+    // (r02d: 43 us with the sort, at cfg4): identity orders there.
+    if (s_heavy == 0 && n_tiles >= 4 * FSB_NUM_SMS * 4) {
+        for (int t = tid; t < n_tiles; t += 1024) ws.tile_order[t] = t;
+        for (int u = tid; u < total; u += 1024) ws.unit_order[u] = u;
+        if (tid == 0) ws.hdr->n_later = 0;
+        return;
+    }
     if (tid < 3 * (LPT_BINS + 1)) (&s_bins[0][0])[tid] = 0;
     __syncthreads();
     const int max_len = MAX_LIGHT_CHUNKS * CH;
@@ -558,25 +568,29 @@ struct Loader {
 // Work list of this warp over entries [0, n) of buffer b: the entries whose reach mask touches the warp's footprint
 // (skip_flagged: and that are not LEGACY_FLAG entries).  Padded to a multiple of four with the dummy slot.
 template <int D>
-__device__ __forceinline__ int build_list(Stage<D>& s, int b, int n, const TileGeom& tg, bool skip_flagged) {
+__device__ __forceinline__ int build_list_bits(Stage<D>& s, int b, int n, int warp, int lane, uint32_t wbits,
+                                               bool skip_flagged) {
     constexpr int CH = Stage<D>::CH;
-    uint16_t* wl = s.wlist[tg.warp];
-    const uint32_t wbits = 0xfu << (4 * tg.warp);
+    uint16_t* wl = s.wlist[warp];
     int base = 0;
     for (int k0 = 0; k0 < n; k0 += 32) {
-        const int tt = k0 + tg.lane;
+        const int tt = k0 + lane;
         bool bit = false;
         if (tt < n) {
             bit = ((uint32_t)__float_as_int(s.geo[b][tt].w) & wbits) != 0u;
             if (skip_flagged && __float_as_int(s.con[b][tt].w) < 0) bit = false;
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, bit);
-        if (bit) wl[base + __popc(bits & ((1u << tg.lane) - 1u))] = (uint16_t)tt;
+        if (bit) wl[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)tt;
         base += __popc(bits);
     }
-    if (tg.lane < 4) wl[base + tg.lane] = (uint16_t)CH;
+    if (lane < 4) wl[base + lane] = (uint16_t)CH;
     __syncwarp();
     return base;
+}
+template <int D>
+__device__ __forceinline__ int build_list(Stage<D>& s, int b, int n, const TileGeom& tg, bool skip_flagged) {
+    return build_list_bits<D>(s, b, n, tg.warp, tg.lane, 0xfu << (4 * tg.warp), skip_flagged);
 }
 
 // alpha of a staged entry at this thread's pixel; `p` receives -log2e * sigma, `au` the unclamped opacity * vis
@@ -1174,6 +1188,252 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     }
 }
 
+// ---- backward, two pixels per lane ---------------------------------------------------------------------------------------
+// Same arithmetic as raster_bwd_kernel; a warp owns an 8 x 8 pixel block (lane = 8 row + column over the upper four rows,
+// its second pixel four rows below), four warps per 16 x 16 tile.  The per-(warp, entry) costs that do not depend on the
+// number of pixels — list walk, record loads, the transposing butterfly and its atomics: about half of the 1-pixel
+// kernel's instructions at 19 live lanes of 32 (profiles/r02d_ncu_raster_cfg4.txt) — are paid once for 64 pixels; each
+// lane adds its two pixels' partials before the butterfly.
+struct Px2 {
+    float T, K_a, K_b, py;
+    int32_t bin_final;
+    bool inside;
+};
+
+// thread index the FORWARD gave the pixel (ti, tj) of a tile: the per-unit state is stored in that order
+__device__ __forceinline__ int fwd_thread_of(int ti, int tj, int warps_x) {
+    const int wy = ti >> 2, wx = tj >> 3;
+    const int q = (((tj & 7) >> 2) << 1) | ((ti & 3) >> 1);
+    const int s_ = ((ti & 1) << 2) | (tj & 3);
+    return ((wy * warps_x + wx) << 5) | (q << 3) | s_;
+}
+
+template <int D, int DA, int XYMODE>
+__global__ void __launch_bounds__(MAX_BLOCK / 2)
+raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
+    constexpr int CH = chunk_len(D), DP = color_stride(D), DB = D - DA;
+    constexpr bool SPLIT = (DB > 0);
+    static_assert(D <= 8, "two-pixel backward: transposing butterfly only");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage<D>& s = *reinterpret_cast<Stage<D>*>(smem_raw);
+    __shared__ int32_t s_wmax[MAX_BLOCK / 64];
+    const int64_t n_isects = fsb_eff_n(a.n_isects, a.n_dev);
+    if ((int)blockIdx.x >= ws.hdr->total_units) return;
+    const int u = ws.unit_order[blockIdx.x];
+    const int64_t tile_lin = ws.unit_tile[u];
+    if (a.masks != nullptr && !a.masks[tile_lin]) return;
+    const UnitGeom ug = unit_geom(ws, u, tile_lin, (int64_t)a.C * a.tile_w * a.tile_h, n_isects, a.tile_offsets,
+                                  a.masks, SPLIT, CH, a.light_chunks);
+    if (ug.c0 >= ug.c1) return;
+    // geometry: warp w = 8 x 8 block (bx, by) of the tile
+    const int tr = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tr & 31, warp = tr >> 5;
+    const int n_warps = (blockDim.x * blockDim.y) >> 5;
+    const int blocks_x = a.tile_size >> 3, warps_x = blocks_x;  // forward warps across = 8-pixel columns across
+    const int by = warp / blocks_x, bx = warp - by * blocks_x;
+    const int n_tiles = a.tile_w * a.tile_h;
+    const int cam = (int)(tile_lin / n_tiles);
+    const int tile_id = (int)(tile_lin - (int64_t)cam * n_tiles);
+    const int tile_y = tile_id / a.tile_w, tile_x = tile_id - tile_y * a.tile_w;
+    const int tj = bx * 8 + (lane & 7);
+    const int ti0 = by * 8 + (lane >> 3);
+    const float px = (float)(tile_x * a.tile_size + tj) + 0.5f;
+    // forward warps covered by this block: (wy = 2 by, wx = bx) and (wy = 2 by + 1, wx = bx)
+    const uint32_t wbits = (0xfu << (4 * ((2 * by) * warps_x + bx))) | (0xfu << (4 * ((2 * by + 1) * warps_x + bx)));
+    const int which = ug.flagged ? ug.k + 1 : 0;
+    const int u_last = ws.unit_start[tile_lin + 1] - 1;
+    const int32_t unit_b = ug.rb + ug.c0 * CH;
+
+    Px2 P[2];
+    float v_rc[2][D], buffer[2][D];
+    size_t cidx[2];
+    int64_t pix[2];
+    int32_t warp_bin_final = -1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int ti = ti0 + 4 * h;
+        const int gi = tile_y * a.tile_size + ti, gj = tile_x * a.tile_size + tj;
+        P[h].inside = (gi < a.height && gj < a.width);
+        P[h].py = (float)gi + 0.5f;
+        pix[h] = P[h].inside ? ((int64_t)cam * a.height + gi) * a.width + gj : 0;
+        cidx[h] = (size_t)u * MAX_BLOCK + fwd_thread_of(ti, tj, warps_x);
+        P[h].bin_final = -1;
+        if (P[h].inside) P[h].bin_final = (which == 2) ? ws.chain_last[cidx[h]] : in.last_ids[pix[h]];
+        warp_bin_final = max(warp_bin_final, P[h].bin_final);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
+    if (lane == 0) s_wmax[warp] = warp_bin_final;
+    __syncthreads();
+    int32_t cta_bin_final = -1;
+    for (int w = 0; w < n_warps; ++w) cta_bin_final = max(cta_bin_final, s_wmax[w]);
+    if (cta_bin_final < unit_b) return;  // no pixel of the tile reaches into this unit
+
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float T_final = 1.f, v_ra = 0.f;
+        P[h].T = 1.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { v_rc[h][c] = 0.f; buffer[h][c] = 0.f; }
+        if (P[h].inside) {
+            const float alpha_out = in.render_alphas[pix[h]];
+            P[h].T = fabsf(ws.chain_T[cidx[h]]);  // state at the END of this unit, left behind by the forward pass
+            T_final = ug.light ? P[h].T : 1.f - alpha_out;
+            if (which != 2) {
+                v_ra = in.v_render_alphas[pix[h]];
+#pragma unroll
+                for (int c = 0; c < DA; ++c) v_rc[h][c] = in.v_render_a[pix[h] * DA + c];
+                if (a.ed_channel >= 0) {
+                    const float den = fmaxf(alpha_out, 1e-10f);
+#pragma unroll
+                    for (int c = 0; c < DA; ++c) {
+                        if (c == a.ed_channel) {
+                            const float v_ed = v_rc[h][c];
+                            v_rc[h][c] = v_ed / den;
+                            if (alpha_out >= 1e-10f) v_ra += -v_ed * in.render_a[pix[h] * DA + c] / den;
+                        }
+                    }
+                }
+            }
+            if constexpr (SPLIT) {
+                if (which != 1) {
+#pragma unroll
+                    for (int c = 0; c < DB; ++c) v_rc[h][DA + c] = in.v_render_b[pix[h] * DB + c];
+                }
+            }
+            if (!ug.light) {
+                const size_t lidx = (size_t)u_last * MAX_BLOCK + (cidx[h] - (size_t)u * MAX_BLOCK);
+#pragma unroll
+                for (int c = 0; c < D; ++c) buffer[h][c] = ws.prefix_C[lidx * D + c] - ws.prefix_C[cidx[h] * D + c];
+            }
+        }
+        float bg_dot_a = 0.f, bg_dot_b = 0.f;
+        if (a.backgrounds_a) {
+#pragma unroll
+            for (int c = 0; c < DA; ++c) bg_dot_a += a.backgrounds_a[cam * DA + c] * v_rc[h][c];
+        }
+        if constexpr (SPLIT) {
+            if (a.backgrounds_b) {
+#pragma unroll
+                for (int c = 0; c < DB; ++c) bg_dot_b += a.backgrounds_b[cam * DB + c] * v_rc[h][DA + c];
+            }
+        }
+        P[h].K_a = T_final * (v_ra - bg_dot_a);
+        P[h].K_b = -T_final * bg_dot_b;
+    }
+
+    constexpr bool want_xy = (XYMODE >= 1);
+    constexpr bool want_abs = (XYMODE >= 2);
+    constexpr int NG = 4 + 2 * XYMODE;
+    constexpr int NV = D + NG;
+    constexpr int B = D;
+    const int slot = slot_of_lane<NV>(lane);
+    float* slot_base = nullptr;
+    int slot_stride = 0;
+    if (slot >= 0) {
+        if (slot < B) {
+            if (slot < DA) { slot_base = out.v_colors_a + slot; slot_stride = DA; }
+            else { slot_base = out.v_colors_b + (slot - DA); slot_stride = DB; }
+        }
+        else if (slot < B + 3) { slot_base = out.v_conics + (slot - B); slot_stride = 3; }
+        else if (slot == B + 3) { slot_base = out.v_opacities; slot_stride = 1; }
+        else if (slot < B + 6) { slot_base = out.v_means2d + (slot - B - 4); slot_stride = 2; }
+        else { slot_base = out.v_means2d_abs + (slot - B - 6); slot_stride = 2; }
+    }
+    const bool opac_slot = (slot == B + 3);
+    const bool skip_flagged = (which == 1);
+
+    Loader<D> ld(s, ws);
+    ld.init(tr);
+    const int c_hi = min(ug.c1 - 1, (int)((cta_bin_final - ug.rb) / CH));
+    auto chunk_n = [&](int c) { return min(min(CH, (int)(ug.re - ug.rb) - c * CH), (int)(cta_bin_final - (ug.rb + c * CH) + 1)); };
+    if (tr == 0) ld.issue(0, ug.rb + c_hi * CH, chunk_n(c_hi));
+    for (int c = c_hi; c >= ug.c0; --c) {
+        const int b = (c_hi - c) & 1;
+        const bool more = c - 1 >= ug.c0;
+        if (more && tr == 0) ld.issue(b ^ 1, ug.rb + (c - 1) * CH, chunk_n(c - 1));
+        const int n = chunk_n(c);
+        ld.wait(b, n);
+        const int cnt = build_list_bits<D>(s, b, n, warp, lane, wbits, skip_flagged);
+        const int32_t chunk_b = ug.rb + c * CH;
+        const uint16_t* wl = s.wlist[warp];
+        const float4* sgeo = s.geo[b];
+        const float4* scon = s.con[b];
+        const float* scol = s.col[b];
+        const int t_hi = warp_bin_final - chunk_b;
+        for (int i = cnt - 1; i >= 0; --i) {
+            const int t = wl[i];
+            if (t > t_hi) continue;  // warp-uniform
+            const float4 con = scon[t];
+            const float4 geo = sgeo[t];
+            float dx, dy[2], p[2], au[2], alpha[2];
+            bool valid[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                alpha[h] = eval_alpha(geo, con, px, P[h].py, dx, dy[h], p[h], au[h]);
+                valid[h] = P[h].inside && (chunk_b + t <= P[h].bin_final) && (p[h] <= 0.f) && (alpha[h] >= ALPHA_MIN);
+            }
+            if (!__any_sync(0xffffffffu, valid[0] || valid[1])) continue;
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.f;
+            float col[DP];
+            {
+                const float4* cp = reinterpret_cast<const float4*>(scol + t * DP);
+#pragma unroll
+                for (int k4 = 0; k4 < DP / 4; ++k4) {
+                    const float4 c4 = cp[k4];
+                    col[4 * k4] = c4.x; col[4 * k4 + 1] = c4.y; col[4 * k4 + 2] = c4.z; col[4 * k4 + 3] = c4.w;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (valid[h]) {
+                    const float ra = fast_rcp(1.f - alpha[h]);
+                    P[h].T *= ra;
+                    const float T = P[h].T;
+                    const float fac = alpha[h] * T;
+                    float va_a = P[h].K_a * ra, va_b = P[h].K_b * ra;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const float ck = col[k];
+                        v[k] = fmaf(fac, v_rc[h][k], v[k]);
+                        const float term = (ck * T - buffer[h][k] * ra) * v_rc[h][k];
+                        if (k < DA) va_a += term; else va_b += term;
+                        buffer[h][k] += ck * fac;
+                    }
+                    if (au[h] <= ALPHA_MAX) {
+                        const float nvs_a = au[h] * va_a;
+                        const float nvs = SPLIT ? au[h] * (va_a + va_b) : nvs_a;
+                        const float hs = -0.5f * nvs;
+                        v[B + 0] = fmaf(hs * dx, dx, v[B + 0]);
+                        v[B + 1] = fmaf(-nvs * dx, dy[h], v[B + 1]);
+                        v[B + 2] = fmaf(hs * dy[h], dy[h], v[B + 2]);
+                        v[B + 3] += nvs;
+                        if constexpr (want_xy) {
+                            const float vk = nvs_a * (1.f / LOG2E);
+                            const float gx = vk * fmaf(2.f * con.x, dx, con.y * dy[h]);
+                            const float gy = vk * fmaf(2.f * con.z, dy[h], con.y * dx);
+                            v[B + 4] += gx;
+                            v[B + 5] += gy;
+                            if constexpr (want_abs) {
+                                v[B + 6] += fabsf(gx);
+                                v[B + 7] += fabsf(gy);
+                            }
+                        }
+                    }
+                }
+            }
+            const int32_t g = __float_as_int(con.w) & ~LEGACY_FLAG;
+            float total = warp_transpose_sum(v, lane);
+            if (opac_slot) total *= fast_ex2(-geo.z);  // 1 / opacity
+            if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
+        }
+        __syncthreads();
+    }
+}
+
 template <typename K>
 inline int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -1259,11 +1519,26 @@ int launch_bwd(const BwdCall& f, cudaStream_t st) {
     dim3 block(a.tile_size, a.tile_size);
     const unsigned grid = (unsigned)max_units(a.n_isects, n_tiles, D);
     const size_t smem = sizeof(Stage<D>);
-#define FSB_BWD_LAUNCH(MODE)                                   \
-    do {                                                       \
-        auto k = raster_bwd_kernel<D, DA, MODE>;               \
-        int e = set_smem(k, smem); if (e) return e;            \
-        k<<<grid, block, smem, st>>>(a, ws, f.in, f.out);      \
+    // Two pixels per lane (8 x 8 block per warp) for the narrow colour vectors on frames with many tiles: r02h, cfg4
+    // (1080p, blob-like splats, 19 of 32 lanes live): 1.06 ms against 1.30 ms.  On the 640 x 480 object scene (thin
+    // surfels, 1200 tiles for 592 CTA slots) the finer 8 x 4 footprints and twice the warps win: 0.19 ms against
+    // 0.23 ms.  FSB_RASTER_BWD_PX=1 / 2 forces a kernel (A/B runs).
+    static const int forced_px = [] { const char* e = getenv("FSB_RASTER_BWD_PX"); return e ? atoi(e) : 0; }();
+    const bool one_px = forced_px == 1 || (forced_px != 2 && n_tiles < 4 * FSB_NUM_SMS * 4);
+    dim3 block2(a.tile_size, a.tile_size / 2);
+#define FSB_BWD_LAUNCH(MODE)                                                   \
+    do {                                                                       \
+        if constexpr (D <= 8) {                                                \
+            if (!one_px) {                                                     \
+                auto k2 = raster_bwd2_kernel<D, DA, MODE>;                     \
+                int e2 = set_smem(k2, smem); if (e2) return e2;                \
+                k2<<<grid, block2, smem, st>>>(a, ws, f.in, f.out);            \
+                break;                                                         \
+            }                                                                  \
+        }                                                                      \
+        auto k = raster_bwd_kernel<D, DA, MODE>;                               \
+        int e = set_smem(k, smem); if (e) return e;                            \
+        k<<<grid, block, smem, st>>>(a, ws, f.in, f.out);                      \
     } while (0)
     if (f.out.v_means2d_abs) FSB_BWD_LAUNCH(2);
     else if (f.out.v_means2d) FSB_BWD_LAUNCH(1);

@@ -82,6 +82,10 @@ class DNSplatterStepConfig:
     # (rasterization_from_params(colors_b=...), csrc/raster.cu): one binning, one sort, one forward and one backward
     # compositing kernel per iteration instead of two of each.  Needs fused_outputs and fused_glue.
     fused_passes: bool = field(default_factory=lambda: os.environ.get("FSB_FUSED_PASSES", "1") == "1")
+    # get_metrics_dict (dn_model.py:927-1000) as part of every iteration, the way nerfstudio's Trainer calls it: PSNR /
+    # MSE / depth metrics by one fused launch + one SSIM launch, left on the device (metrics.py); LPIPS needs backbone
+    # weights that this image does not have and is left to a user-supplied callable (metrics.RGBMetrics)
+    step_metrics: bool = field(default_factory=lambda: os.environ.get("FSB_STEP_METRICS", "0") == "1")
     overlap_normals_pass: bool = True  # captured step only: the normals pass runs on a second stream beside the RGB+ED pass
 
 
@@ -438,6 +442,20 @@ class DNSplatterStep:
         raise RuntimeError("normal supervision with monocular normals enabled but the batch holds none "
                            "(dn_model.py:796-803 quits here)")
 
+    # ---- dn_model.py:927-1000 -------------------------------------------------------------------
+    @torch.no_grad()
+    def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
+        """rgb_mse / rgb_psnr / rgb_ssim / depth_* as device scalars (no float(): nothing synchronises) plus
+        gaussian_count; `rgb_lpips` is absent (no backbone weights offline)."""
+        from .metrics import step_metrics
+
+        if getattr(self, "_metrics_ssim", None) is None:
+            self._metrics_ssim = FusedSSIM(data_range=1.0, kernel_size=11)
+            self._metrics_out = torch.empty((10,), dtype=torch.float32, device=self.device)
+        d = step_metrics(outputs, batch, self.config.depth_tolerance, ssim=self._metrics_ssim, out=self._metrics_out)
+        d["gaussian_count"] = self.num_points
+        return d
+
     # ---- splatfacto after_train (SURVEY.md A.7) ---------------------------------------------
     @torch.no_grad()
     def after_train(self, skip_flag=None):
@@ -483,6 +501,8 @@ class DNSplatterStep:
         for opt in self.optimizers.values():
             opt.zero_grad(set_to_none=True)
         outputs = self.get_outputs(cam_idx)
+        if self.config.step_metrics:
+            self.last_metrics = self.get_metrics_dict(outputs, batch)
         loss_dict = self.get_loss_dict(outputs, batch)
         loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
         loss.backward()

@@ -141,6 +141,8 @@ class GraphedDNSplatterStep:
             cur.wait_stream(sel)
             for t in batch.values():
                 t.record_stream(cur)
+            if m.config.step_metrics:
+                m.last_metrics = m.get_metrics_dict(outputs, batch)  # device tensors, rewritten by every replay
             loss_dict = m.get_loss_dict(outputs, batch)
             loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
             (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()

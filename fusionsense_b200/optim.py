@@ -182,3 +182,45 @@ class CapturedAdam:
     def rollback(self, k: int) -> None:
         for opt, group, p in self.entries:
             opt.state[p]["step"] = opt.state[p]["step"] - k
+
+
+# ---------------------------------------------------------------------------------------------
+# nerfstudio plug point
+# ---------------------------------------------------------------------------------------------
+from dataclasses import dataclass as _dataclass  # noqa: E402
+from typing import Optional as _Optional  # noqa: E402
+from typing import Type as _Type  # noqa: E402
+
+
+@_dataclass
+class FusedAdamOptimizerConfig:
+    """Drop-in for `nerfstudio.engine.optimizers.AdamOptimizerConfig` in the method config
+    (/root/reference/dn_splatter/dn_config.py:36-75 names one `AdamOptimizerConfig(lr=..., eps=1e-15)` per Gaussian
+    parameter group): same fields, same `setup(params)` protocol, `_target` = FusedAdam.  nerfstudio's `Optimizers`
+    then builds one FusedAdam per group; `FusedAdam.step()` is one launch per group, `fused_step(optimizers)` /
+    `CapturedAdam` update all groups with one.  `use_fused_adam(method_config)` swaps it into an existing config."""
+
+    _target: _Type = FusedAdam
+    lr: float = 0.0005
+    eps: float = 1e-08
+    max_norm: _Optional[float] = None
+    weight_decay: float = 0
+
+    def setup(self, params) -> FusedAdam:
+        if self.max_norm is not None:
+            raise ValueError("FusedAdamOptimizerConfig: gradient clipping (max_norm) is not implemented "
+                             "(the reference does not use it)")
+        return self._target(params, lr=self.lr, eps=self.eps, weight_decay=self.weight_decay)
+
+
+def use_fused_adam(optimizers_config: dict, groups=("means", "features_dc", "features_rest", "opacities", "scales",
+                                                     "quats")) -> dict:
+    """`optimizers` dict of a nerfstudio method config (dn_config.py:36-75) with the Gaussian groups' Adam configs
+    replaced by FusedAdamOptimizerConfig (same lr / eps; schedulers untouched).  Returns the same dict."""
+    for name in groups:
+        if name in optimizers_config:
+            old = optimizers_config[name]["optimizer"]
+            optimizers_config[name]["optimizer"] = FusedAdamOptimizerConfig(
+                lr=old.lr, eps=old.eps, max_norm=getattr(old, "max_norm", None),
+                weight_decay=getattr(old, "weight_decay", 0))
+    return optimizers_config

@@ -222,6 +222,15 @@ int fsb_raster_pair_count(int C, int N, int64_t n_isects, const int64_t* n_isect
                           const int32_t* last_ids, uint64_t* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Per-step image metrics.  replaces, in dn_splatter/dn_model.py:962-1000 (get_metrics_dict, run
+ * every training iteration), torchmetrics PSNR + MSELoss and dn_splatter/metrics.py:111-150 DepthMetrics: one launch,
+ * results stay on the device (the reference does eleven float() host syncs per step here).
+ *   out[10] fp32 = { rgb_mse, rgb_psnr, depth_abs_rel, depth_sq_rel, depth_rmse, depth_rmse_log, a1, a2, a3, n_valid } */
+size_t fsb_image_metrics_workspace(void);
+int fsb_image_metrics(int H, int W, const float* pred_rgb, const float* gt_rgb, const float* pred_depth,
+                      const float* gt_depth, float depth_tol, void* workspace, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-GPU gradient exchange over NVLink peer memory (csrc/grad_exchange.cu): what DDP's all-reduce would do for
  * dn_splatter/dn_pipeline.py:161-167, as kernels of this library that a CUDA graph can capture — no NCCL call on the
  * step's path.  One process per GPU; rank r owns slice r = [r S, (r + 1) S) of the flat gradient.  "peer mapping" =

@@ -57,6 +57,12 @@ def assert_close(a, b, name, tol=1e-4, outlier_frac=1e-3):
     return m
 
 
+def record(name, values: dict):
+    """Store a free-form measurement next to the parity metrics (gpurun_out/parity_metrics.json)."""
+    _METRICS[name] = values
+    _dump()
+
+
 def _dump():
     out = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parent.parent)) / "gpurun_out"
     try:

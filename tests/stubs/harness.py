@@ -67,14 +67,19 @@ def camera_for(scene, cam_idx: int, device="cuda"):
                    K[1, 2].item(), scene.width, scene.height, metadata={"cam_idx": cam_idx})
 
 
-def build_optimizers(model, lrs):
+def build_optimizers(model, lrs, fused: bool = False):
     """One torch.optim.Adam(lr, eps=1e-15) per Gaussian parameter group (dn_config.py:36-75) behind nerfstudio's
-    `Optimizers` (the `normals` group exists and never receives a gradient, dn_config.py:69-74)."""
+    `Optimizers` (the `normals` group exists and never receives a gradient, dn_config.py:69-74).
+    `fused`: the same method config passed through fusionsense_b200.optim.use_fused_adam."""
     from nerfstudio.engine.optimizers import AdamOptimizerConfig, Optimizers
 
     groups = model.get_gaussian_param_groups()
     config = {name: {"optimizer": AdamOptimizerConfig(lr=lrs.get(name, 1e-3), eps=1e-15), "scheduler": None}
               for name in groups}
+    if fused:
+        from fusionsense_b200.optim import use_fused_adam
+
+        use_fused_adam(config)
     return Optimizers(config, groups)
 
 

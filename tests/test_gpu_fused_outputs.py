@@ -173,3 +173,25 @@ def test_step_with_fused_outputs_matches_step_without(step):
         assert_close(on.gauss_params[k].grad, off.gauss_params[k].grad, f"fused_outputs.grad.{k}", tol=1e-4,
                      outlier_frac=2e-3)
     assert_close(on.xys.absgrad, off.xys.absgrad, "fused_outputs.absgrad", tol=1e-4, outlier_frac=2e-3)
+
+
+def test_batched_render_views_match_single_camera_outputs():
+    """eval_render.render_views (C cameras per rasterization call, both colour sets in one walk) against
+    get_outputs in eval mode, view by view."""
+    from fusionsense_b200.dn_step import DNSplatterStep, DNSplatterStepConfig
+    from fusionsense_b200.eval_render import render_views
+    from fusionsense_b200.synthetic import make_scene
+    from tests.parity import assert_close
+
+    sc = make_scene(15000, 256, 192, n_views=5, cfg_id=67, kind="bunny", fx=240.0)
+    m = DNSplatterStep(sc, DNSplatterStepConfig(), device="cuda", step=3000)
+    m.training = False
+    singles = []
+    with torch.no_grad():
+        for v in range(5):
+            singles.append({k: t.clone() for k, t in m.get_outputs(v).items()})
+    batched = list(render_views(m, range(5), chunk=3))
+    assert [b["view"] for b in batched] == list(range(5))
+    for v in range(5):
+        for k in ("rgb", "depth", "normal", "accumulation"):
+            assert_close(batched[v][k], singles[v][k], f"render_views.{v}.{k}", tol=1e-6, outlier_frac=1e-5)

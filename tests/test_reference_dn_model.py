@@ -142,10 +142,12 @@ def _launches():
 
 @needs_ref
 @pytest.mark.gpu
-def test_reference_train_iterations_track_the_fused_step():
+@pytest.mark.parametrize("fused_adam", [False, True])
+def test_reference_train_iterations_track_the_fused_step(fused_adam):
     """Three Trainer.train_iteration()s of the reference model (stub `Optimizers`: one torch.optim.Adam(eps=1e-15) per
     group, dn_config.py:36-75) against three iterations of the fused step (one fused Adam launch): losses and
-    parameters stay together."""
+    parameters stay together.  `fused_adam`: the method config's optimizers swapped for FusedAdamOptimizerConfig
+    (optim.use_fused_adam), i.e. the reference model trained by our optimizer behind nerfstudio's `Optimizers`."""
     _import_reference()
     from fusionsense_b200.dn_step import DNSplatterStep, DNSplatterStepConfig
     from tests.stubs.harness import build_optimizers, build_reference_model, camera_for, train_iteration
@@ -157,7 +159,8 @@ def test_reference_train_iterations_track_the_fused_step():
     targets = {v: fused.render_targets(v) for v in range(3)}
     _, model = build_reference_model(scene, step0, dev)
     lrs = dict(fused.config.lrs)
-    opts = build_optimizers(model, lrs)
+    opts = build_optimizers(model, lrs, fused=fused_adam)
+    assert type(opts.optimizers["means"]).__name__ == ("FusedAdam" if fused_adam else "Adam")
     for i, v in enumerate([0, 2, 1]):
         opts.optimizers["means"].param_groups[0]["lr"] = fused._means_lr()  # ExponentialDecayScheduler on means
         loss_ref = train_iteration(model, opts, camera_for(scene, v, dev), targets[v], step0 + i)

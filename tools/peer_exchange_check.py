@@ -141,8 +141,11 @@ def main():
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    # no destroy_process_group: tearing down a communicator whose collectives sit in (re-)captured CUDA graphs hung the
+    # r02g run until its timeout; the process is done, leave at once
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -58,13 +58,16 @@ def main():
     out["captures"] = runner.captures
     out["graph_launches_per_step"] = 1 if runner.graph_tail is None else 2
     ok = (out["identical_before_refine"] and out["identical_after_refine"] and out["identical_after_more_steps"]
-          and out["n1"] != out["n0"] and out["captures"] == 2)
+          and out["n1"] != out["n0"] and out["captures"] >= 2)  # + 1 when the binary-opacity window opens (step 3201)
     out["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    # no destroy_process_group: tearing down a communicator whose collectives sit in (re-)captured CUDA graphs hung the
+    # r02g run until its timeout; the process is done, leave at once
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
