@@ -40,6 +40,11 @@ CONFIGS = {
     "cfg4": dict(n=1_000_000, w=1920, h=1080, views=8, kind="random", cfg_id=4,
                  workload="cfg4: DN-Splatter train step (render + backprop + Adam), 1M Gaussians 1920x1080, 8 views, "
                           "1 view/GPU/iter (the camera batch of 8 is sharded over the GPUs at N = 8)"),
+    # BASELINE.json configs[4]: camera batch 32 per iteration dealt over the GPUs (32 / N views per rank per iteration,
+    # rendered one after the other inside the one captured step, gradients accumulated, one Adam step), 8 distinct views
+    "cfg5": dict(n=3_000_000, w=3840, h=2160, views=8, kind="random", cfg_id=5, global_views=32,
+                 workload="cfg5: DN-Splatter train step, 3M Gaussians 3840x2160, camera batch 32 per iteration sharded "
+                          "over the GPUs (32 / N views per rank, 8 distinct views cycled), one Adam step per iteration"),
 }
 METRIC = "dn_splatter_train_iter_per_s"
 UNIT = "iter/s"
@@ -342,7 +347,8 @@ class Ctx:
             self.sampler.start()
 
 
-def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, detail: bool, literal_leg: bool):
+def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, detail: bool, literal_leg: bool,
+                 refine_leg: bool = False):
     """Time one configuration: resident-targets leg, end-to-end leg and (detail) the per-kernel roofline legs.
     Returns a dict on every rank (timings are max-over-ranks)."""
     import torch
@@ -355,11 +361,12 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
     world, rank, device = ctx.world, ctx.rank, ctx.device
     c = CONFIGS[cfg_name]
     n_views = c["views"]
+    vpi = max(1, c.get("global_views", world) // world)  # views per rank per iteration
     model = build_model(cfg_name, device)
     views = list(range(n_views))
     dev_targets = {v: model.render_targets(v) for v in views}
     host_targets = {v: {k: t.cpu().pin_memory() for k, t in d.items()} for v, d in dev_targets.items()}
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values())
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values()) * min(vpi, n_views)
     params = [model.gauss_params[k] for k in model.config.lrs]
     graph_mode = mode == "graph"
 
@@ -385,7 +392,7 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
                           file=sys.stderr)
                     ctx.exchange = "nccl (peer exchange unavailable)"
                     sync = allreduce_grads
-        runner = GraphedDNSplatterStep(model, dev_targets, grad_sync=sync, loss_scale=1.0 / world)
+        runner = GraphedDNSplatterStep(model, dev_targets, grad_sync=sync, loss_scale=1.0 / world, views_per_iter=vpi)
 
     def eager_step(m, i, batch):
         v = (i * world + rank) % n_views
@@ -416,14 +423,16 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
             if read_loss:
                 float(loss)
             return
-        v = (i * world + rank) % n_views
+        vs = [((i * vpi + j) * world + rank) % n_views for j in range(vpi)]
         if staged and i == 0:
-            runner.stage_async(v, host_targets[v])
-        runner.train_iteration(v)  # waits for this view's copy
+            for v in dict.fromkeys(vs):
+                runner.stage_async(v, host_targets[v])
+        runner.train_iteration(vs if vpi > 1 else vs[0])  # waits for its views' copies
         if staged and i + 1 < n_total:
-            # the next step's inputs travel while this step's kernels run (copy stream, pinned source)
-            vn = ((i + 1) * world + rank) % n_views
-            runner.stage_async(vn, host_targets[vn])
+            # the next step's inputs travel while this step's kernels run (copy stream, pinned source); a view that
+            # the running step reads as well is re-staged after it (stage_async orders the copy behind the reader)
+            for vn in dict.fromkeys(((i + 1) * vpi + j) * world + rank for j in range(vpi)):
+                runner.stage_async(vn % n_views, host_targets[vn % n_views])
         if read_loss:
             # 32-byte D2H read of [loss, overflow count, n_isects x2] per step; the host consumes step i - 1's
             # values here and the last step's after the loop (timed() drains the ring before the closing event)
@@ -500,9 +509,10 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
 
     ms_per_step = ms_total / steps
     out = {
-        "cfg": cfg_name, "value": world * 1e3 / ms_per_step, "ms_per_step": ms_per_step,
-        "optimizer_steps_per_s": 1e3 / ms_per_step, "views_per_s": world * 1e3 / ms_per_step,
-        "e2e": {"value": world * steps * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+        "cfg": cfg_name, "value": world * vpi * 1e3 / ms_per_step, "ms_per_step": ms_per_step,
+        "optimizer_steps_per_s": 1e3 / ms_per_step, "views_per_s": world * vpi * 1e3 / ms_per_step,
+        "views_per_iter_per_gpu": vpi,
+        "e2e": {"value": world * vpi * steps * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 32 if graph_mode else 4},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / steps, "clocks": clocks,
         "graph": graph_info, "warmup_actual": warmup + warm_extra, "fused_outputs": bool(model.config.fused_outputs),
@@ -524,6 +534,36 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
         pairs = ops.pair_probe.summary()
         out["roofline"] = _roofline(cfg_name, model, params, ktimes, pairs, clocks)
 
+    if refine_leg and runner is not None:
+        # densify / prune inside a timed run (dn_model.py:326-451 every refine_every = 100 iterations):
+        # 300 iterations from a step count at which the refine steps really densify, the (synchronised) refinement,
+        # the re-capture on the new Gaussian count and the capacity re-probe all inside the timed region
+        from fusionsense_b200 import dist as fdist
+
+        model.step = 3100
+        runner.graph = None
+        n_before = model.num_points
+        cap0, refines = runner.captures, []
+
+        def step_with_refine(i):
+            one_step(i, False, False)
+            if model.step % model.config.refine_every == 0:
+                runner.poll()
+                if world > 1:
+                    fdist.synchronised_refinement(model, model.optimizers, model.step, seed=7)
+                else:
+                    model.refinement_after()
+                refines.append(model.num_points)
+
+        n_ref = 300
+        ms_ref = timed(n_ref, step_with_refine, drain=lambda: runner.poll())
+        out["with_refinement"] = {"value": world * n_ref * 1e3 / ms_ref, "unit": UNIT, "steps": n_ref,
+                                  "ms_per_step": ms_ref / n_ref, "refine_every": model.config.refine_every,
+                                  "gaussians_before": n_before, "gaussians_after_each_refine": refines,
+                                  "recaptures": runner.captures - cap0,
+                                  "what": "300 captured iterations with refinement_after every 100 (densify + cull + "
+                                          "Adam-state rebuild, statistics all-reduced and a shared split RNG at N > 1), "
+                                          "re-captures included"}
     if literal_leg:
         out["shim_only_eager"] = _reference_model_leg(ctx, cfg_name, model, dev_targets, min(steps, 100), warmup, timed)
     del model, dev_targets, host_targets
@@ -635,7 +675,7 @@ def run_ours(args):
     if args.config != "cfg2" and not args.no_secondary:
         # the FusionSense-sized scene: long enough a region for stable numbers (1 ms steps)
         secondary = run_workload(ctx, "cfg2", max(args.steps, 200), args.warmup, args.mode, detail=False,
-                                 literal_leg=(world == 1))
+                                 literal_leg=(world == 1), refine_leg=True)
     ctx.sampler.stop()
     line = None
     if rank == 0:
@@ -648,7 +688,8 @@ def run_ours(args):
                         "renders one view per iteration and all ranks apply the same all-reduced update)",
             "optimizer_steps_per_s": main["optimizer_steps_per_s"], "views_per_s": main["views_per_s"],
             "config": {"workload": c["workload"], "gaussians": c["n"], "width": c["w"], "height": c["h"],
-                       "views": c["views"], "views_per_iter_per_gpu": 1, "global_views_per_iter": world,
+                       "views": c["views"], "views_per_iter_per_gpu": main["views_per_iter_per_gpu"],
+                       "global_views_per_iter": world * main["views_per_iter_per_gpu"],
                        "execution": ("one CUDA graph replay per iteration (static-capacity intersection lists, "
                                      "no host sync); every kernel of the eager step runs in every replay"
                                      if graph_mode else "eager launches"),
@@ -678,7 +719,8 @@ def run_ours(args):
                 "workload": CONFIGS["cfg2"]["workload"], "value": secondary["value"], "unit": UNIT,
                 "ms_per_step": secondary["ms_per_step"], "steps": max(args.steps, 200),
                 "optimizer_steps_per_s": secondary["optimizer_steps_per_s"], "e2e": secondary["e2e"],
-                "shim_only_eager": secondary.get("shim_only_eager"), "graph": secondary["graph"],
+                "shim_only_eager": secondary.get("shim_only_eager"), "with_refinement": secondary.get("with_refinement"),
+                "graph": secondary["graph"],
                 "clocks": secondary["clocks"], "gpu_launches_per_step": secondary["gpu_launches_per_step"],
             }
     if world > 1:
@@ -737,7 +779,9 @@ def main():
     line = run_ours(args)
     if line is None:
         return
-    if line["n_gpus"] == 1 and not args.no_cpu_baseline:
+    if args.config == "cfg5":
+        line["cpu_baseline"] = None  # the oracle needs ~10 min per bounded sample at 3M Gaussians: reported for cfg4 / cfg2
+    elif line["n_gpus"] == 1 and not args.no_cpu_baseline:
         sec, cores, sample = cpu_step_seconds(args.config, 1, warmup=0)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     else:

@@ -68,7 +68,7 @@ __device__ __forceinline__ Box tile_box(float mx, float my, int r, int tile_size
 // The order of one Gaussian's entries among themselves is free: their keys differ (different tiles), and entries with
 // equal keys (same tile, same depth, different Gaussians) keep the order of the offsets = Gaussian index, which is what
 // the stable sort preserves.
-constexpr int WIDE_TILES = 24;
+constexpr int WIDE_TILES = 24;  // <= 64: a narrow box's reach results fit the 64-bit hit mask
 constexpr int32_t LEGACY_FLAG = (int32_t)0x80000000;
 
 struct GaussTile {
@@ -101,7 +101,7 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
                    const float* __restrict__ opacities, const int64_t* __restrict__ offsets, int tile_size, int tile_w,
                    int tile_h, int tile_bits, int legacy_bbox, const int64_t* __restrict__ n_dev, int64_t capacity,
                    int32_t* __restrict__ overflow_flag, int32_t* __restrict__ counts, int64_t* __restrict__ isect_ids,
-                   int32_t* __restrict__ flatten_ids) {
+                   int32_t* __restrict__ flatten_ids, unsigned long long* __restrict__ hit_masks) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool in_range = idx < (int64_t)C * N;
@@ -134,14 +134,35 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
     const bool wide = n_box > WIDE_TILES;
     int n = 0;
     if (r > 0 && !wide) {
+        // hit_masks (optional, boxes of at most WIDE_TILES <= 64 tiles): the count pass leaves bit k = "tile k of the box,
+        // row-major, is reached"; the emit pass reads it instead of repeating the reach tests
         int64_t cur = g.cur;
-        for (int i = g.box.ay; i < g.box.by; ++i)
-            for (int j = g.box.ax; j < g.box.bx; ++j) {
-                const int hit = reach_one_tile<COUNT_ONLY>(g, i, j, tile_size, tile_w, flag_outer, limit, cur, isect_ids,
-                                                           flatten_ids);
-                cur += hit;
-                n += hit;
+        if (!COUNT_ONLY && hit_masks != nullptr) {
+            unsigned long long hm = hit_masks[idx];
+            while (hm) {
+                const int k = __ffsll((long long)hm) - 1;
+                hm &= hm - 1;
+                const int i = g.box.ay + k / bw, j = g.box.ax + k % bw;
+                if (cur < limit) {
+                    const bool outer = flag_outer && !(i >= g.inner.ay && i < g.inner.by && j >= g.inner.ax && j < g.inner.bx);
+                    isect_ids[cur] = g.cam_part | ((int64_t)(i * tile_w + j) << 32) | g.depth_part;
+                    flatten_ids[cur] = outer ? (g.idx | LEGACY_FLAG) : g.idx;
+                }
+                ++cur;
             }
+        } else {
+            unsigned long long hm = 0ull;
+            int k = 0;
+            for (int i = g.box.ay; i < g.box.by; ++i)
+                for (int j = g.box.ax; j < g.box.bx; ++j, ++k) {
+                    const int hit = reach_one_tile<COUNT_ONLY>(g, i, j, tile_size, tile_w, flag_outer, limit, cur,
+                                                               isect_ids, flatten_ids);
+                    cur += hit;
+                    n += hit;
+                    hm |= (unsigned long long)hit << k;
+                }
+            if (COUNT_ONLY && hit_masks != nullptr) hit_masks[idx] = hm;
+        }
     }
     // wide boxes: the warp takes them one at a time, 32 tiles per round
     unsigned todo = __ballot_sync(0xffffffffu, wide);
@@ -197,15 +218,16 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
 
 // counts[C*N] = tiles of the bounding box (legacy_bbox: 0.1.x rule) that the Gaussian can reach with alpha >= 1/255.
 // conics[C*N,3], opacities[C*N] as handed to the compositing kernels.
+// hit_masks (nullable, uint64[C*N]): scratch the count pass fills and the matching emit pass reads (same arguments).
 FSB_API int fsb_isect_count_reach(int C, int N, const float* means2d, const int32_t* radii, const float* conics,
                                   const float* opacities, int tile_size, int tile_w, int tile_h, int legacy_bbox,
-                                  int32_t* counts, void* stream) {
+                                  int32_t* counts, uint64_t* hit_masks, void* stream) {
     if (C <= 0 || N < 0 || tile_size <= 0 || !conics || !opacities || !counts) return FSB_E_ARG;
     if (N == 0) return 0;
     const int64_t total = (int64_t)C * N;
     isect_reach_kernel<true><<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
         C, N, means2d, radii, nullptr, conics, opacities, nullptr, tile_size, tile_w, tile_h, 0, legacy_bbox, nullptr, 0,
-        nullptr, counts, nullptr, nullptr);
+        nullptr, counts, nullptr, nullptr, (unsigned long long*)hit_masks);
     FSB_LAUNCH_CHECK();
     return 0;
 }
@@ -216,7 +238,7 @@ FSB_API int fsb_isect_emit_reach(int C, int N, const float* means2d, const int32
                                  const float* conics, const float* opacities, const int64_t* offsets, int tile_size,
                                  int tile_w, int tile_h, int tile_bits, int legacy_bbox, const int64_t* n_dev,
                                  int64_t capacity, int32_t* overflow_flag, int64_t* isect_ids, int32_t* flatten_ids,
-                                 void* stream) {
+                                 const uint64_t* hit_masks, void* stream) {
     if (C <= 0 || N < 0 || tile_size <= 0 || tile_bits < 0 || tile_bits > 30) return FSB_E_ARG;
     if (!conics || !opacities || !offsets || !isect_ids || !flatten_ids) return FSB_E_ARG;
     if (n_dev && capacity < 0) return FSB_E_ARG;
@@ -225,7 +247,7 @@ FSB_API int fsb_isect_emit_reach(int C, int N, const float* means2d, const int32
     const int64_t total = (int64_t)C * N;
     isect_reach_kernel<false><<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
         C, N, means2d, radii, depths, conics, opacities, offsets, tile_size, tile_w, tile_h, tile_bits, legacy_bbox, n_dev,
-        capacity, overflow_flag, nullptr, isect_ids, flatten_ids);
+        capacity, overflow_flag, nullptr, isect_ids, flatten_ids, (unsigned long long*)hit_masks);
     FSB_LAUNCH_CHECK();
     return 0;
 }

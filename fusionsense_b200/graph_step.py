@@ -33,12 +33,16 @@ from .optim import CapturedAdam
 
 class GraphedDNSplatterStep:
     def __init__(self, model: DNSplatterStep, targets: Dict[int, Dict[str, Tensor]], capacity: Optional[int] = None,
-                 margin: float = 1.3, grad_sync=None, loss_scale: float = 1.0):
+                 margin: float = 1.3, grad_sync=None, loss_scale: float = 1.0, views_per_iter: int = 1):
         """`targets[v]` = batch of view v (`image`, `sensor_depth`, `normal`, device tensors).  They are stacked
         into one resident tensor per key; `stage(v, host_batch)` overwrites a view's slot from host memory.
         `grad_sync(params, overflow_flag)`: optional hook run inside the captured step between backward and Adam
         (multi-GPU: the NCCL all-reduce of the parameter gradients and of the overflow flag); `loss_scale`
-        multiplies the loss before backward (1 / world_size keeps the mean over the global camera batch)."""
+        multiplies the loss before backward (1 / world_size keeps the mean over the global camera batch).
+        `views_per_iter` = V > 1: a camera batch per iteration (BASELINE.json configs[4]: 32 views per step, dealt over
+        the ranks): the V views are rendered and differentiated one after the other inside the one captured step,
+        their gradients accumulate (each loss scaled by 1 / V), the densification statistics take every view, and
+        Adam steps once.  `train_iteration` then takes V view indices."""
         if model.device.type != "cuda":
             raise RuntimeError("GraphedDNSplatterStep needs a CUDA model (no CPU fallback)")
         if not model._fused_optim:
@@ -50,8 +54,9 @@ class GraphedDNSplatterStep:
         self.targets = {k: torch.stack([targets[v][k] for v in views]).contiguous() for k in targets[views[0]]}
         self.margin = float(margin)
         self.capacity = int(capacity) if capacity else None
-        self.cam = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._cam_host = (ctypes.c_int64 * 1)()
+        self.views_per_iter = V = max(1, int(views_per_iter))
+        self.cam = torch.zeros(V, dtype=torch.int64, device=self.device)
+        self._cam_host = (ctypes.c_int64 * V)()
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         # [loss, overflowed steps so far, n_isects of the RGB+ED pass, n_isects of the legacy normals pass]
         self.result = torch.zeros(4, dtype=torch.float64, device=self.device)
@@ -128,26 +133,37 @@ class GraphedDNSplatterStep:
         else:
             self.overflow.zero_()
         with ops.static_capacity(self.capacity, self.overflow) as st:
-            # this view's targets are gathered on a side stream while the main one projects, bins and composites:
-            # three image-sized copies (8.6 MB at 640x480) that nothing needs before the losses
-            cur = torch.cuda.current_stream()
-            if getattr(self, "_select_stream", None) is None:
-                self._select_stream = torch.cuda.Stream(device=self.device)
-            sel = self._select_stream
-            sel.wait_stream(cur)
-            with torch.cuda.stream(sel):
-                batch = {k: t.index_select(0, self.cam)[0] for k, t in self.targets.items()}
-            outputs = m.get_outputs(self.cam)
-            cur.wait_stream(sel)
-            for t in batch.values():
-                t.record_stream(cur)
-            if m.config.step_metrics:
-                m.last_metrics = m.get_metrics_dict(outputs, batch)  # device tensors, rewritten by every replay
-            loss_dict = m.get_loss_dict(outputs, batch)
-            loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
-            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+            V = self.views_per_iter
+            total = None
+            for j in range(V):
+                cam_j = self.cam[j:j + 1]
+                # this view's targets are gathered on a side stream while the main one projects, bins and composites:
+                # three image-sized copies (8.6 MB at 640x480) that nothing needs before the losses
+                cur = torch.cuda.current_stream()
+                if getattr(self, "_select_stream", None) is None:
+                    self._select_stream = torch.cuda.Stream(device=self.device)
+                sel = self._select_stream
+                sel.wait_stream(cur)
+                with torch.cuda.stream(sel):
+                    batch = {k: t.index_select(0, cam_j)[0] for k, t in self.targets.items()}
+                outputs = m.get_outputs(cam_j)
+                cur.wait_stream(sel)
+                for t in batch.values():
+                    t.record_stream(cur)
+                if m.config.step_metrics:
+                    m.last_metrics = m.get_metrics_dict(outputs, batch)  # device tensors, rewritten by every replay
+                loss_dict = m.get_loss_dict(outputs, batch)
+                loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
+                scale = self.loss_scale / V
+                (loss * scale if scale != 1.0 else loss).backward()
+                total = loss.detach() if total is None else total + loss.detach()
+                if j < V - 1:
+                    # statistics of every view but the last here (they need this view's radii / absgrad); the last
+                    # view's follow the gradient exchange in _body_tail, where the overflow flag covers all ranks
+                    m.after_train(skip_flag=self.overflow)
+            loss = total / V if V > 1 else total
             counts = list(st.counts)
-        return loss.detach(), counts
+        return loss, counts
 
     def _body_tail(self, loss, counts, warmup: bool = False):
         """Adam (all groups, one launch) -> after_train statistics -> result vector."""
@@ -249,24 +265,31 @@ class GraphedDNSplatterStep:
         self.captures += 1
 
     # ---- per step ----------------------------------------------------------------------------
-    def train_iteration(self, cam_idx: int) -> Tensor:
-        """One training iteration on view `cam_idx`; returns the device-resident result vector
-        [loss, overflowed steps, n_isects, n_isects (normals pass)] (float64, overwritten by the next call)."""
+    def train_iteration(self, cam_idx) -> Tensor:
+        """One training iteration on view `cam_idx` (a sequence of `views_per_iter` views when that is > 1); returns
+        the device-resident result vector [loss, overflowed steps, n_isects, n_isects (normals pass)] (float64,
+        overwritten by the next call)."""
         m = self.model
+        cams = [int(cam_idx)] if self.views_per_iter == 1 and not isinstance(cam_idx, (list, tuple)) else [int(c) for c in cam_idx]
+        if len(cams) != self.views_per_iter:
+            raise ValueError(f"train_iteration takes {self.views_per_iter} view indices, got {len(cams)}")
         if self.graph is None or self.signature != self._signature():
             self.capture()
         m.optimizers["means"].param_groups[0]["lr"] = m._means_lr()
         self.adam.advance()
-        self._cam_host[0] = int(cam_idx)
-        check(lib.fsb_upload_small(self.cam.data_ptr(), ctypes.addressof(self._cam_host), 8, ops._stream()),
+        for j, c in enumerate(cams):
+            self._cam_host[j] = c
+        check(lib.fsb_upload_small(self.cam.data_ptr(), ctypes.addressof(self._cam_host), 8 * len(cams), ops._stream()),
               "fsb_upload_small")
-        staged = self._slot_staged.pop(int(cam_idx), None)
-        if staged is not None:
-            torch.cuda.current_stream().wait_event(staged)
+        for c in cams:
+            staged = self._slot_staged.pop(c, None)
+            if staged is not None:
+                torch.cuda.current_stream().wait_event(staged)
         self.graph.replay()
         self._ev_prev, self._ev_last = self._ev_last, torch.cuda.Event()
         self._ev_last.record()
-        self._slot_read[int(cam_idx)] = self._ev_last
+        for c in cams:
+            self._slot_read[c] = self._ev_last
         if self.graph_tail is not None:
             self._sync_grads()
             self.graph_tail.replay()

@@ -180,8 +180,11 @@ def isect_count_reach(means2d: Tensor, radii: Tensor, conics: Tensor, opacities:
     _req_cuda(means2d, radii, conics, opacities)
     C, N = radii.shape
     counts = torch.empty(radii.shape, dtype=torch.int32, device=radii.device)
+    hit_masks = torch.empty(radii.shape, dtype=torch.int64, device=radii.device)  # read back by isect_emit(reach=...)
     check(lib.fsb_isect_count_reach(C, N, ptr(means2d), ptr(radii), ptr(conics), ptr(opacities), tile_size, tile_w,
-                                    tile_h, int(legacy_bbox), ptr(counts), _stream()), "fsb_isect_count_reach")
+                                    tile_h, int(legacy_bbox), ptr(counts), ptr(hit_masks), _stream()),
+          "fsb_isect_count_reach")
+    counts.hit_masks = hit_masks
     return counts
 
 
@@ -218,7 +221,7 @@ def sort_end_bit(n_tiles: int, C: int) -> int:
 
 
 def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox, n_dev=None,
-               overflow=None, reach=None):
+               overflow=None, reach=None, hit_masks=None):
     """`n_dev` (device int64[1]) selects static-capacity mode: `n_isects` is then the capacity of the buffers.
     `reach` = (conics [C,N,3], opacities [C,N]): EXPERIMENTAL, emit only the reached tiles (`offsets` must then be
     the scan of `isect_count_reach`)."""
@@ -234,7 +237,7 @@ def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_
     else:
         check(lib.fsb_isect_emit_reach(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(reach[0]), ptr(reach[1]),
                                        ptr(offsets), tile_size, tile_w, tile_h, tb, int(legacy_bbox), ptr(n_dev),
-                                       n_isects, ptr(overflow), ptr(ids), ptr(flat), _stream()),
+                                       n_isects, ptr(overflow), ptr(ids), ptr(flat), ptr(hit_masks), _stream()),
               "fsb_isect_emit_reach")
     kernel_timer.stop(ev)
     return ids, flat
@@ -295,7 +298,8 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
         n_dev = totals[:1]
         st.counts.append(n_dev)
         ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h,
-                               legacy_bbox, n_dev=n_dev, overflow=st.overflow, reach=reach)
+                               legacy_bbox, n_dev=n_dev, overflow=st.overflow, reach=reach,
+                               hit_masks=getattr(list_counts, "hit_masks", None))
         if sort:
             end_bit = sort_end_bit(tile_w * tile_h, C)
             ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=n_dev)
@@ -307,7 +311,7 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
         totals.host = n_isects  # the values that came back with the one D2H read
         n_isects = n_isects[0]
     ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox,
-                           reach=reach)
+                           reach=reach, hit_masks=getattr(list_counts, "hit_masks", None))
     if sort:
         end_bit = sort_end_bit(tile_w * tile_h, C)
         ids, flat = radix_sort_pairs(ids, flat, end_bit)
@@ -342,7 +346,7 @@ def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h,
     gate = torch.empty(1, dtype=torch.int64, device=dev)
     check(lib.fsb_isect_share_gate(ptr(first_flat.n_dev), ptr(n_list), ptr(gate), _stream()), "fsb_isect_share_gate")
     ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h, True,
-                           n_dev=gate, overflow=st.overflow, reach=reach)
+                           n_dev=gate, overflow=st.overflow, reach=reach, hit_masks=getattr(counts, "hit_masks", None))
     end_bit = sort_end_bit(tile_w * tile_h, C)
     ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=gate)
     tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=gate)

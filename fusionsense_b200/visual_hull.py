@@ -130,14 +130,16 @@ class HullCarver:
         self.lut = torch.from_numpy(np.arange(256, dtype=np.uint8) / 255).to(self.device)
         self.V = self.nz * self.nx * self.ny
         self.votes = None
+        # binary masks (what Grounded-SAM-2 writes): a vote is an exact integer count, stored in one byte per voxel
+        self.votes_u8 = bool(M <= 255 and np.isin(masks_u8, (0, 255)).all())
 
     def vote(self) -> float:
         """Launch the vote kernel over this rank's slab; returns the slab's vote maximum (one 8-byte D2H)."""
-        self.votes = torch.empty((self.V,), dtype=torch.float64, device=self.device)
+        self.votes = torch.empty((self.V,), dtype=torch.uint8 if self.votes_u8 else torch.float64, device=self.device)
         max_bits = torch.zeros((1,), dtype=torch.int64, device=self.device)
         check(lib.fsb_vh_votes(self.M, self.H, self.W, ptr(self.masks), self.mats.ctypes.data, ptr(self.lut),
                                ptr(self.xs), self.nx, ptr(self.ys), self.ny, ptr(self.zs), self.nz, ptr(self.votes),
-                               ptr(max_bits), _stream()), "fsb_vh_votes")
+                               int(self.votes_u8), ptr(max_bits), _stream()), "fsb_vh_votes")
         return float(max_bits.view(torch.float64).item())
 
     def extract(self, iso: float, want_indices: bool = False):
@@ -148,12 +150,12 @@ class HullCarver:
         counts = torch.empty((max(nb, 1),), dtype=torch.int32, device=self.device)
         if self.V == 0:
             counts.zero_()
-        check(lib.fsb_vh_count(self.V, ptr(self.votes), iso, ptr(counts), _stream()), "fsb_vh_count")
+        check(lib.fsb_vh_count(self.V, ptr(self.votes), int(self.votes_u8), iso, ptr(counts), _stream()), "fsb_vh_count")
         offsets, n_occ = isect_scan(counts)
         points = torch.empty((n_occ, 3), dtype=torch.float64, device=self.device)
         idx = torch.empty((n_occ,), dtype=torch.int64, device=self.device) if want_indices else None
         if n_occ:
-            check(lib.fsb_vh_compact(self.V, ptr(self.votes), iso, ptr(offsets), ptr(self.xs), self.nx, ptr(self.ys),
+            check(lib.fsb_vh_compact(self.V, ptr(self.votes), int(self.votes_u8), iso, ptr(offsets), ptr(self.xs), self.nx, ptr(self.ys),
                                      self.ny, ptr(self.zs), ptr(points), ptr(idx), _stream()), "fsb_vh_compact")
         if want_indices:
             return points, idx + self.z0 * self.nx * self.ny

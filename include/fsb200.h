@@ -99,16 +99,18 @@ int fsb_isect_count(int64_t M, const float* means2d, const int32_t* radii, int t
  *   legacy_bbox: 0 / 1 as in fsb_isect_count; 2 = UNION list for fsb_raster_dn_*: the 0.1.x box (a superset of the 1.0
  *   box) with FSB_LEGACY_FLAG set in flatten_ids for the tiles that only the 0.1.x rule of rasterize_gaussians yields
  *   (dn_model.py:644-653), so ONE sorted list serves rasterization() and the legacy normals pass.
- *   emit: offsets = exclusive scan of the reach counts; static-capacity arguments as in fsb_isect_emit. */
+ *   emit: offsets = exclusive scan of the reach counts; static-capacity arguments as in fsb_isect_emit.
+ *   hit_masks (nullable, u64[C*N]): scratch; the count pass records the reached tiles of every narrow box there and the
+ *   emit pass called with the same arguments reads them instead of repeating the tests. */
 #define FSB_LEGACY_FLAG 0x80000000u
 int fsb_isect_count_reach(int C, int N, const float* means2d, const int32_t* radii, const float* conics,
                           const float* opacities, int tile_size, int tile_w, int tile_h, int legacy_bbox,
-                          int32_t* counts, void* stream);
+                          int32_t* counts, uint64_t* hit_masks, void* stream);
 int fsb_isect_emit_reach(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
                          const float* conics, const float* opacities, const int64_t* offsets, int tile_size,
                          int tile_w, int tile_h, int tile_bits, int legacy_bbox, const int64_t* n_dev,
                          int64_t capacity, int32_t* overflow_flag, int64_t* isect_ids, int32_t* flatten_ids,
-                         void* stream);
+                         const uint64_t* hit_masks, void* stream);
 
 /* exclusive int64 prefix sum of counts[M] (replaces torch.cumsum inside gsplat isect_tiles);
  * total_dev receives the grand total (= n_isects), a device scalar the caller copies back. */
@@ -258,19 +260,20 @@ int fsb_adam_multi_xchg(int n_tensors, float* const* p, float* const* m, float* 
  * Voxel l = (iz*nx + ix)*ny + iy, zs given in the reference's loop order (descending).
  *   masks[n_views,H,W] u8 (device), mats_host[n_views,12] f64 (HOST: K @ [R|t] rows), lut[256] f64 (device,
  *   value/255 as numpy computes it), xs/ys/zs f64 axis tables (device).
- *   votes[nz*nx*ny] f64 ; max_bits: device u64, zero-filled by the caller, gets bits of max(votes). */
+ *   votes[nz*nx*ny]: f64, or u8 when votes_u8 != 0 (binary 0 / 255 masks: a vote is an exact integer <= n_views, one
+ *   byte per voxel instead of eight) ; max_bits: device u64, zero-filled by the caller, gets bits of max(votes) as f64. */
 int fsb_vh_max_views(void);
 int fsb_vh_count_block(void);
 int fsb_vh_votes(int n_views, int H, int W, const uint8_t* masks, const double* mats_host, const double* lut,
-                 const double* xs, int nx, const double* ys, int ny, const double* zs, int nz, double* votes,
-                 uint64_t* max_bits, void* stream);
+                 const double* xs, int nx, const double* ys, int ny, const double* zs, int nz, void* votes,
+                 int votes_u8, uint64_t* max_bits, void* stream);
 /* block_counts[ceil(V / fsb_vh_count_block())] i32 = voxels with votes > iso per block of consecutive voxels */
-int fsb_vh_count(int64_t V, const double* votes, double iso, int32_t* block_counts, void* stream);
+int fsb_vh_count(int64_t V, const void* votes, int votes_u8, double iso, int32_t* block_counts, void* stream);
 /* order-preserving compaction: points[n_occ,3] f64 (x,y,z) and indices[n_occ] i64 (nullable) in voxel order;
  * block_offsets = exclusive scan of block_counts (fsb_isect_scan). */
-int fsb_vh_compact(int64_t V, const double* votes, double iso, const int64_t* block_offsets, const double* xs,
-                   int nx, const double* ys, int ny, const double* zs, double* points, int64_t* indices,
-                   void* stream);
+int fsb_vh_compact(int64_t V, const void* votes, int votes_u8, double iso, const int64_t* block_offsets,
+                   const double* xs, int nx, const double* ys, int ny, const double* zs, double* points,
+                   int64_t* indices, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a15: densify / prune bookkeeping.  replaces dn_splatter/dn_model.py:326-451 (refinement_after) and the

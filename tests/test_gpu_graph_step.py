@@ -290,3 +290,36 @@ def test_graph_step_survives_refine_steps_that_drop_the_statistics():
     graphed.refinement_after()
     runner.train_iteration(0)
     assert runner.captures == 3 and runner.poll()["overflowed_steps"] == 0
+
+
+def test_camera_batch_per_iteration_accumulates_like_separate_backwards():
+    """views_per_iter = 3: one captured iteration renders three views, accumulates their gradients (each loss / 3),
+    counts all three in the densification statistics and steps Adam once — compared with the eager model doing the
+    same by hand."""
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+    from fusionsense_b200.optim import fused_step
+
+    eager, graphed, targets = _pair()
+    runner = GraphedDNSplatterStep(graphed, targets, views_per_iter=3)
+    for views in ([0, 1, 2], [2, 0, 1]):
+        for opt in eager.optimizers.values():
+            opt.zero_grad(set_to_none=True)
+        losses = []
+        for v in views:
+            out = eager.get_outputs(v)
+            loss = eager.get_loss_dict(out, targets[v])["main_loss"]
+            (loss / 3).backward()
+            eager.after_train()
+            losses.append(float(loss))
+        eager.optimizers["means"].param_groups[0]["lr"] = eager._means_lr()
+        fused_step(eager.optimizers.values())
+        eager.step += 1
+        runner.train_iteration(views)
+        info = runner.poll()
+        assert info["loss"] == pytest.approx(sum(losses) / 3, rel=2e-5) and info["overflowed_steps"] == 0
+    assert runner.captures == 1 and graphed.step == eager.step
+    for k in eager.gauss_params:
+        assert_close(graphed.gauss_params[k].data, eager.gauss_params[k].data, f"graph3.param.{k}", tol=1e-5,
+                     outlier_frac=1e-4)
+    assert torch.equal(graphed.vis_counts, eager.vis_counts)
+    assert_close(graphed.xys_grad_norm, eager.xys_grad_norm, "graph3.xys_grad_norm", tol=1e-5, outlier_frac=1e-4)

@@ -5,8 +5,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 import bench
 
-model = bench.build_model(torch.device("cuda", 0))
-targets = {v: model.render_targets(v) for v in range(bench.N_VIEWS)}
+model = bench.build_model("cfg2", torch.device("cuda", 0))
+targets = {v: model.render_targets(v) for v in range(bench.CONFIGS["cfg2"]["views"])}
 for i in range(5):
     model.train_iteration(i % 9, targets[i % 9])
 torch.cuda.synchronize()

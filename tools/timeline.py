@@ -13,8 +13,8 @@ from torch.profiler import ProfilerActivity, profile
 import bench
 
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.json"
-model = bench.build_model(torch.device("cuda", 0))
-targets = {v: model.render_targets(v) for v in range(bench.N_VIEWS)}
+model = bench.build_model("cfg2", torch.device("cuda", 0))
+targets = {v: model.render_targets(v) for v in range(bench.CONFIGS["cfg2"]["views"])}
 for i in range(8):
     model.train_iteration(i % 9, targets[i % 9])
 torch.cuda.synchronize()
