@@ -7,6 +7,7 @@
 // HBM-bound streaming kernels: one thread per (camera, Gaussian) forward, one thread per Gaussian
 // looping over cameras backward (so the cross-camera sum is a register accumulation, no atomics).
 #include "common.cuh"
+#include <stdlib.h>
 #include "fs_math.cuh"
 
 namespace {
@@ -197,7 +198,10 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 // One thread per Gaussian, looping over cameras.  The SH rows (192 B per Gaussian at K = 16) are the bulk of the
 // traffic; a thread-per-row access pattern touches 32 sectors per request, so each warp moves its 32 rows
 // through a shared-memory tile with row-contiguous (coalesced) global loads and stores.
-__global__ void __launch_bounds__(PB_THREADS)
+// MINB = minimum resident CTAs per SM the register allocation targets: 4 -> 115 registers (round 1), 6 -> 80 registers
+// with 48 bytes of spills, 24 instead of 16 warps per SM for a kernel that is latency / HBM bound (20 % of HBM in r01).
+template <int MINB>
+__global__ void __launch_bounds__(PB_THREADS, MINB)
 project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float* __restrict__ quats,
                       const float* __restrict__ scales, const float* __restrict__ viewmats,
                       const float* __restrict__ Ks, int width, int height, float eps2d, int sh_degree, int K,
@@ -511,7 +515,7 @@ FSB_API int fsb_project_sh_bwd(int C, int N, const float* means, const float* qu
     if (sh_degree >= 0 && v_colors && (!coeffs || !v_coeffs)) return FSB_E_ARG;
     if (v_campos && !campos) return FSB_E_ARG;
     if (N == 0) return 0;
-    project_sh_bwd_kernel<<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(
+    project_sh_bwd_kernel<4><<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, coeffs, nullptr, 0, campos,
         color_stride, depth_channel, radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_means, v_quats, v_scales,
         v_coeffs, nullptr, v_viewmats, v_campos);
@@ -533,11 +537,18 @@ FSB_API int fsb_project_params_bwd(int C, int N, const float* means, const float
     if (!features_dc || !v_features_dc || !v_colors || K < 1 || K > 16) return FSB_E_ARG;
     if (K > 1 && (!features_rest || !v_features_rest)) return FSB_E_ARG;
     if (N == 0) return 0;
-    project_sh_bwd_kernel<<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(
-        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, features_dc,
-        K > 1 ? features_rest : nullptr, exp_scales ? ACT_EXP_SCALES : 0, nullptr, color_stride, depth_channel, radii,
-        v_means2d, v_depths, v_conics, nullptr, v_colors, v_means, v_quats, v_scales, v_features_dc,
-        K > 1 ? v_features_rest : nullptr, nullptr, nullptr);
+    // FSB_PROJ_BWD_MINB=6 selects the 80-register build (24 instead of 16 warps per SM); measured SLOWER on B200
+    // (r02i, cfg4: 0.304 ms against 0.276 ms: the spills and the longer dependent chains cost more than the extra
+    // warps hide), so the 115-register build stays the default
+    static const int minb = [] { const char* e = getenv("FSB_PROJ_BWD_MINB"); return e ? atoi(e) : 4; }();
+#define FSB_PBWD(MINB)                                                                                              \
+    project_sh_bwd_kernel<MINB><<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(                \
+        C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, features_dc,                  \
+        K > 1 ? features_rest : nullptr, exp_scales ? ACT_EXP_SCALES : 0, nullptr, color_stride, depth_channel,    \
+        radii, v_means2d, v_depths, v_conics, nullptr, v_colors, v_means, v_quats, v_scales, v_features_dc,         \
+        K > 1 ? v_features_rest : nullptr, nullptr, nullptr)
+    if (minb <= 4) FSB_PBWD(4); else FSB_PBWD(6);
+#undef FSB_PBWD
     FSB_LAUNCH_CHECK();
     return 0;
 }

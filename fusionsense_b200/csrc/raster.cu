@@ -494,8 +494,15 @@ raster_pack_kernel(int C, int64_t n_isects, const int64_t* __restrict__ n_dev, P
 #pragma unroll
         for (int k = 0; k < DP; ++k) row[k] = 0.f;
         const float* ca = in.colors_a + (size_t)g * DA;
+        if constexpr (DA == 4) {
+            // one 16-byte request per lane instead of four scalar ones: the gather is bound by L1 request slots
+            // (r02i ncu: lg_throttle on top, 82 M instructions but 252 us), not by bytes
+            const float4 c4 = *reinterpret_cast<const float4*>(ca);
+            row[0] = c4.x; row[1] = c4.y; row[2] = c4.z; row[3] = c4.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < DA; ++k) row[k] = ca[k];
+            for (int k = 0; k < DA; ++k) row[k] = ca[k];
+        }
         if constexpr (DB > 0) {
             const float* cb = in.colors_b + (size_t)g * DB;
 #pragma unroll
@@ -1023,10 +1030,13 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     if (cta_bin_final < unit_b) return;  // no pixel of the tile reaches into this unit
 
     float T_final = 1.f, v_ra = 0.f, T = 1.f;
+    // The colour accumulated BEHIND the current entry enters dL/dalpha only through its dot product with the pixel's
+    // cotangent, so one scalar per colour set replaces the D-vector gsplat carries:
+    //   dL/dalpha = T (c . v) - (1 / (1 - alpha)) S,   S <- S + alpha T (c . v)        (c . v = sum_k colour_k v_rc_k)
     float v_rc[D];
-    float buffer[D];
+    float S_a = 0.f, S_b = 0.f;
 #pragma unroll
-    for (int c = 0; c < D; ++c) { v_rc[c] = 0.f; buffer[c] = 0.f; }
+    for (int c = 0; c < D; ++c) v_rc[c] = 0.f;
     if (tg.inside) {
         const float alpha_out = in.render_alphas[pix];
         // state at the END of this unit, left behind by the forward pass
@@ -1057,7 +1067,10 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
         if (!ug.light) {
             const size_t lidx = (size_t)u_last * MAX_BLOCK + tg.tr;
 #pragma unroll
-            for (int c = 0; c < D; ++c) buffer[c] = ws.prefix_C[lidx * D + c] - ws.prefix_C[cidx * D + c];
+            for (int c = 0; c < D; ++c) {
+                const float behind = ws.prefix_C[lidx * D + c] - ws.prefix_C[cidx * D + c];
+                if (c < DA) S_a = fmaf(behind, v_rc[c], S_a); else S_b = fmaf(behind, v_rc[c], S_b);
+            }
         }
     }
     // out = acc + T_final bg  and  alpha_out = 1 - T_final:  dL/dT_final = bg . v_out - v_alpha_out, folded into K
@@ -1133,17 +1146,20 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
                 const float ra = fast_rcp(1.f - alpha);
                 T *= ra;
                 const float fac = alpha * T;
-                float va_a = K_a * ra, va_b = K_b * ra;  // dL/dalpha through group A / group B
                 const float* cp = scol + t * DP;
+                float cv_a = 0.f, cv_b = 0.f;  // colour . cotangent per colour set
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     const float ck = cp[k];
                     if constexpr (kTranspose) v[k] = fac * v_rc[k];
                     else v_colD[k] = fac * v_rc[k];
-                    const float term = (ck * T - buffer[k] * ra) * v_rc[k];
-                    if (k < DA) va_a += term; else va_b += term;
-                    buffer[k] += ck * fac;
+                    if (k < DA) cv_a = fmaf(ck, v_rc[k], cv_a); else cv_b = fmaf(ck, v_rc[k], cv_b);
                 }
+                // dL/dalpha through group A / group B
+                const float va_a = fmaf(T, cv_a, (K_a - S_a) * ra);
+                const float va_b = SPLIT ? fmaf(T, cv_b, (K_b - S_b) * ra) : 0.f;
+                S_a = fmaf(fac, cv_a, S_a);
+                if constexpr (SPLIT) S_b = fmaf(fac, cv_b, S_b);
                 if (au <= ALPHA_MAX) {
                     // au = opacity * vis.  v_sigma = -au v_alpha; the opacity gradient vis v_alpha = (au / opacity)
                     // v_alpha is reduced as au v_alpha and divided by the opacity once, by the lane that owns the total.
@@ -1245,7 +1261,7 @@ raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     const int32_t unit_b = ug.rb + ug.c0 * CH;
 
     Px2 P[2];
-    float v_rc[2][D], buffer[2][D];
+    float v_rc[2][D], S_a[2], S_b[2];  // S: colour behind the current entry . cotangent (see raster_bwd_kernel)
     size_t cidx[2];
     int64_t pix[2];
     int32_t warp_bin_final = -1;
@@ -1275,7 +1291,8 @@ raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
         float T_final = 1.f, v_ra = 0.f;
         P[h].T = 1.f;
 #pragma unroll
-        for (int c = 0; c < D; ++c) { v_rc[h][c] = 0.f; buffer[h][c] = 0.f; }
+        for (int c = 0; c < D; ++c) v_rc[h][c] = 0.f;
+        S_a[h] = S_b[h] = 0.f;
         if (P[h].inside) {
             const float alpha_out = in.render_alphas[pix[h]];
             P[h].T = fabsf(ws.chain_T[cidx[h]]);  // state at the END of this unit, left behind by the forward pass
@@ -1305,7 +1322,10 @@ raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
             if (!ug.light) {
                 const size_t lidx = (size_t)u_last * MAX_BLOCK + (cidx[h] - (size_t)u * MAX_BLOCK);
 #pragma unroll
-                for (int c = 0; c < D; ++c) buffer[h][c] = ws.prefix_C[lidx * D + c] - ws.prefix_C[cidx[h] * D + c];
+                for (int c = 0; c < D; ++c) {
+                    const float behind = ws.prefix_C[lidx * D + c] - ws.prefix_C[cidx[h] * D + c];
+                    if (c < DA) S_a[h] = fmaf(behind, v_rc[h][c], S_a[h]); else S_b[h] = fmaf(behind, v_rc[h][c], S_b[h]);
+                }
             }
         }
         float bg_dot_a = 0.f, bg_dot_b = 0.f;
@@ -1394,15 +1414,16 @@ raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
                     P[h].T *= ra;
                     const float T = P[h].T;
                     const float fac = alpha[h] * T;
-                    float va_a = P[h].K_a * ra, va_b = P[h].K_b * ra;
+                    float cv_a = 0.f, cv_b = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        const float ck = col[k];
                         v[k] = fmaf(fac, v_rc[h][k], v[k]);
-                        const float term = (ck * T - buffer[h][k] * ra) * v_rc[h][k];
-                        if (k < DA) va_a += term; else va_b += term;
-                        buffer[h][k] += ck * fac;
+                        if (k < DA) cv_a = fmaf(col[k], v_rc[h][k], cv_a); else cv_b = fmaf(col[k], v_rc[h][k], cv_b);
                     }
+                    const float va_a = fmaf(T, cv_a, (P[h].K_a - S_a[h]) * ra);
+                    const float va_b = SPLIT ? fmaf(T, cv_b, (P[h].K_b - S_b[h]) * ra) : 0.f;
+                    S_a[h] = fmaf(fac, cv_a, S_a[h]);
+                    if constexpr (SPLIT) S_b[h] = fmaf(fac, cv_b, S_b[h]);
                     if (au[h] <= ALPHA_MAX) {
                         const float nvs_a = au[h] * va_a;
                         const float nvs = SPLIT ? au[h] * (va_a + va_b) : nvs_a;

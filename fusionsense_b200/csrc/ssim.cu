@@ -13,8 +13,8 @@
 //   mu_x = w*x, mu_y = w*y, e_xx = w*x^2, e_yy = w*y^2, e_xy = w*xy          (w = separable gaussian)
 //   S = (2 mu_x mu_y + c1)(2 s_xy + c2) / ((mu_x^2 + mu_y^2 + c1)(s_x + s_y + c2)),  s_x = e_xx - mu_x^2, ...
 //
-// forward   one CTA per 16x16 block of interior pixels; per channel a 26x26 tile of x and y is staged in shared
-//           memory, 5 moments are convolved horizontally then vertically; S is block-reduced (fp32) and
+// forward   one CTA per 32x32 block of interior pixels; per channel a 42x42 tile of x and y is staged in shared
+//           memory, 5 moments are convolved horizontally then vertically (register-blocked, see below); S is block-reduced (fp32) and
 //           accumulated in fp64, the last CTA writes the mean.  The three partials dS/dmu_x, dS/de_xx, dS/de_xy
 //           are stored per interior pixel for the backward.
 // backward  dL/dx(p) = v * [ (w * dS/dmu_x)(p) + 2 x(p) (w * dS/de_xx)(p) + y(p) (w * dS/de_xy)(p) ] / count,
@@ -24,11 +24,18 @@
 
 namespace {
 
-constexpr int TS = 16;           // output tile edge
+// Round 2: register-blocked separable filter.  One CTA = 32 x 32 outputs, 256 threads; the horizontal pass gives every
+// thread eight adjacent outputs of one staged row (18 loads per image instead of 8 x 11), the vertical pass four
+// vertically adjacent outputs of one column (14 loads per moment instead of 4 x 11): ~30 shared-memory loads per output
+// and channel against ~90 for the one-output-per-thread form (r02b: 0.145 ms forward at 1080p, LSU bound).
+constexpr int TS = 32;           // output tile edge
 constexpr int KS = 11;           // gaussian taps
-constexpr int TL = TS + KS - 1;  // staged tile edge (26)
-constexpr int TLP = TL + 1;      // padded row length
-constexpr int S_THREADS = TS * TS;
+constexpr int TL = TS + KS - 1;  // staged tile edge (42)
+constexpr int TLP = TL + 1;      // padded row length (43: conflict-free for the 8-wide horizontal items)
+constexpr int HP = TS + 1;       // padded row length of the horizontally filtered rows
+constexpr int S_THREADS = 256;
+constexpr int HC = 8;            // horizontal outputs per work item
+constexpr int VR = 4;            // vertical outputs per thread
 
 struct SsimArgs {
     int H, W, C;
@@ -36,33 +43,53 @@ struct SsimArgs {
     float w[KS];
 };
 
-// horizontal then vertical 11-tap pass over NQ staged quantities; returns the NQ filtered values of this thread's
-// output pixel.  `src(q, r, i)` reads staged quantity q at tile row r, tile column i.
+// horizontal then vertical 11-tap pass over NQ staged quantities; out[v][q] = filtered quantity q of this thread's
+// v-th output pixel (tile row VR * (tid / 32) + v, tile column tid % 32).  `src(r, i, v)` reads the NQ staged
+// quantities at tile row r, tile column i.
 template <int NQ, typename Src>
-__device__ __forceinline__ void separable(const SsimArgs& a, Src src, float (*hbuf)[TL][TS], float (&out)[NQ]) {
-    for (int e = threadIdx.x; e < TL * TS; e += S_THREADS) {
-        const int r = e / TS, j = e - r * TS;
-        float acc[NQ];
+__device__ __forceinline__ void separable(const SsimArgs& a, Src src, float (*hbuf)[TL][HP], float (&out)[VR][NQ]) {
+    for (int e = threadIdx.x; e < TL * (TS / HC); e += S_THREADS) {
+        const int r = e / (TS / HC), j0 = (e - r * (TS / HC)) * HC;
+        float acc[HC][NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+        for (int o = 0; o < HC; ++o)
 #pragma unroll
-        for (int t = 0; t < KS; ++t) {
+            for (int q = 0; q < NQ; ++q) acc[o][q] = 0.f;
+#pragma unroll
+        for (int i = 0; i < HC + KS - 1; ++i) {
             float v[NQ];
-            src(r, j + t, v);
+            src(r, j0 + i, v);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) acc[q] += a.w[t] * v[q];
+            for (int o = 0; o < HC; ++o) {
+                const int t = i - o;  // tap index of input i for output o (compile-time after unrolling)
+                if (t >= 0 && t < KS) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) acc[o][q] = fmaf(a.w[t], v[q], acc[o][q]);
+                }
+            }
         }
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) hbuf[q][r][j] = acc[q];
+        for (int o = 0; o < HC; ++o)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) hbuf[q][r][j0 + o] = acc[o][q];
     }
     __syncthreads();
-    const int ty = threadIdx.x / TS, tx = threadIdx.x - ty * TS;
+    const int tx = threadIdx.x & 31, y0 = (threadIdx.x >> 5) * VR;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) out[q] = 0.f;
+    for (int v = 0; v < VR; ++v)
 #pragma unroll
-    for (int t = 0; t < KS; ++t) {
+        for (int q = 0; q < NQ; ++q) out[v][q] = 0.f;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) out[q] += a.w[t] * hbuf[q][ty + t][tx];
+    for (int i = 0; i < VR + KS - 1; ++i) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float h = hbuf[q][y0 + i][tx];
+#pragma unroll
+            for (int v = 0; v < VR; ++v) {
+                const int t = i - v;
+                if (t >= 0 && t < KS) out[v][q] = fmaf(a.w[t], h, out[v][q]);
+            }
+        }
     }
 }
 
@@ -70,14 +97,15 @@ __global__ void __launch_bounds__(S_THREADS)
 ssim_fwd_kernel(SsimArgs a, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ d_mu,
                 float* __restrict__ d_xx, float* __restrict__ d_xy, double* __restrict__ sum,
                 unsigned* __restrict__ ticket, float* __restrict__ out) {
-    __shared__ float sx[TL][TLP], sy[TL][TLP];
-    __shared__ float hbuf[5][TL][TS];
+    extern __shared__ __align__(16) unsigned char ssim_smem[];
+    float (*sx)[TLP] = reinterpret_cast<float (*)[TLP]>(ssim_smem);
+    float (*sy)[TLP] = reinterpret_cast<float (*)[TLP]>(ssim_smem + sizeof(float) * TL * TLP);
+    float (*hbuf)[TL][HP] = reinterpret_cast<float (*)[TL][HP]>(ssim_smem + 2 * sizeof(float) * TL * TLP);
     __shared__ float red[S_THREADS / 32];
     const int Hi = a.H - (KS - 1), Wi = a.W - (KS - 1);
     const int oy0 = blockIdx.y * TS, ox0 = blockIdx.x * TS;  // interior coordinates == image coordinates of the window start
-    const int ty = threadIdx.x / TS, tx = threadIdx.x - ty * TS;
-    const int qy = oy0 + ty, qx = ox0 + tx;
-    const bool live = (qy < Hi && qx < Wi);
+    const int tx = threadIdx.x & 31, y0 = (threadIdx.x >> 5) * VR;
+    const int qx = ox0 + tx;
     float local = 0.f;
     for (int c = 0; c < a.C; ++c) {
         __syncthreads();  // previous channel's hbuf / tiles are no longer read
@@ -94,26 +122,30 @@ ssim_fwd_kernel(SsimArgs a, const float* __restrict__ x, const float* __restrict
             sy[r][i] = vy;
         }
         __syncthreads();
-        float m[5];
+        float m[VR][5];
         separable<5>(a, [&](int r, int i, float (&v)[5]) {
             const float p = sx[r][i], t = sy[r][i];
             v[0] = p; v[1] = t; v[2] = p * p; v[3] = t * t; v[4] = p * t;
         }, hbuf, m);
-        if (live) {
-            const float mu_x = m[0], mu_y = m[1];
-            const float s_x = m[2] - mu_x * mu_x, s_y = m[3] - mu_y * mu_y, s_xy = m[4] - mu_x * mu_y;
-            const float num1 = 2.f * mu_x * mu_y + a.c1, num2 = 2.f * s_xy + a.c2;
-            const float den1 = mu_x * mu_x + mu_y * mu_y + a.c1, den2 = s_x + s_y + a.c2;
-            const float inv = 1.f / (den1 * den2);
-            const float S = num1 * num2 * inv;
-            local += S;
-            if (d_mu) {
-                const float dS_dnum1 = num2 * inv, dS_dnum2 = num1 * inv;
-                const float dS_dden1 = -S / den1, dS_dden2 = -S / den2;
-                const size_t o = ((size_t)qy * Wi + qx) * a.C + c;
-                d_mu[o] = 2.f * (mu_y * (dS_dnum1 - dS_dnum2) + mu_x * (dS_dden1 - dS_dden2));
-                d_xx[o] = dS_dden2;
-                d_xy[o] = 2.f * dS_dnum2;
+#pragma unroll
+        for (int v = 0; v < VR; ++v) {
+            const int qy = oy0 + y0 + v;
+            if (qy < Hi && qx < Wi) {
+                const float mu_x = m[v][0], mu_y = m[v][1];
+                const float s_x = m[v][2] - mu_x * mu_x, s_y = m[v][3] - mu_y * mu_y, s_xy = m[v][4] - mu_x * mu_y;
+                const float num1 = 2.f * mu_x * mu_y + a.c1, num2 = 2.f * s_xy + a.c2;
+                const float den1 = mu_x * mu_x + mu_y * mu_y + a.c1, den2 = s_x + s_y + a.c2;
+                const float inv = 1.f / (den1 * den2);
+                const float S = num1 * num2 * inv;
+                local += S;
+                if (d_mu) {
+                    const float dS_dnum1 = num2 * inv, dS_dnum2 = num1 * inv;
+                    const float dS_dden1 = -S / den1, dS_dden2 = -S / den2;
+                    const size_t o = ((size_t)qy * Wi + qx) * a.C + c;
+                    d_mu[o] = 2.f * (mu_y * (dS_dnum1 - dS_dnum2) + mu_x * (dS_dden1 - dS_dden2));
+                    d_xx[o] = dS_dden2;
+                    d_xy[o] = 2.f * dS_dnum2;
+                }
             }
         }
     }
@@ -140,13 +172,15 @@ __global__ void __launch_bounds__(S_THREADS)
 ssim_bwd_kernel(SsimArgs a, const float* __restrict__ x, const float* __restrict__ y,
                 const float* __restrict__ d_mu, const float* __restrict__ d_xx, const float* __restrict__ d_xy,
                 const float* __restrict__ v_out, float* __restrict__ v_x) {
-    __shared__ float s0[TL][TLP], s1[TL][TLP], s2[TL][TLP];
-    __shared__ float hbuf[3][TL][TS];
+    extern __shared__ __align__(16) unsigned char ssim_smem[];
+    float (*s0)[TLP] = reinterpret_cast<float (*)[TLP]>(ssim_smem);
+    float (*s1)[TLP] = reinterpret_cast<float (*)[TLP]>(ssim_smem + sizeof(float) * TL * TLP);
+    float (*s2)[TLP] = reinterpret_cast<float (*)[TLP]>(ssim_smem + 2 * sizeof(float) * TL * TLP);
+    float (*hbuf)[TL][HP] = reinterpret_cast<float (*)[TL][HP]>(ssim_smem + 3 * sizeof(float) * TL * TLP);
     const int Hi = a.H - (KS - 1), Wi = a.W - (KS - 1);
     const int py0 = blockIdx.y * TS, px0 = blockIdx.x * TS;
-    const int ty = threadIdx.x / TS, tx = threadIdx.x - ty * TS;
-    const int py = py0 + ty, px = px0 + tx;
-    const bool live = (py < a.H && px < a.W);
+    const int tx = threadIdx.x & 31, y0 = (threadIdx.x >> 5) * VR;
+    const int px = px0 + tx;
     const float scale = *v_out / ((float)Hi * (float)Wi * (float)a.C);
     for (int c = 0; c < a.C; ++c) {
         __syncthreads();
@@ -161,15 +195,22 @@ ssim_bwd_kernel(SsimArgs a, const float* __restrict__ x, const float* __restrict
             s0[r][i] = v0; s1[r][i] = v1; s2[r][i] = v2;
         }
         __syncthreads();
-        float g[3];
+        float g[VR][3];
         separable<3>(a, [&](int r, int i, float (&v)[3]) { v[0] = s0[r][i]; v[1] = s1[r][i]; v[2] = s2[r][i]; },
                      hbuf, g);
-        if (live) {
-            const size_t o = ((size_t)py * a.W + px) * a.C + c;
-            v_x[o] = scale * (g[0] + 2.f * x[o] * g[1] + y[o] * g[2]);
+#pragma unroll
+        for (int v = 0; v < VR; ++v) {
+            const int py = py0 + y0 + v;
+            if (py < a.H && px < a.W) {
+                const size_t o = ((size_t)py * a.W + px) * a.C + c;
+                v_x[o] = scale * (g[v][0] + 2.f * x[o] * g[v][1] + y[o] * g[v][2]);
+            }
         }
     }
 }
+
+constexpr size_t FWD_SMEM = sizeof(float) * (2 * TL * TLP + 5 * TL * HP);
+constexpr size_t BWD_SMEM = sizeof(float) * (3 * TL * TLP + 3 * TL * HP);
 
 int fill(SsimArgs& a, int H, int W, int C, float data_range, float k1, float k2, const float* taps) {
     if (H < KS || W < KS || C < 1 || C > 4 || !taps) return FSB_E_ARG;
@@ -201,7 +242,7 @@ FSB_API int fsb_ssim_fwd(int H, int W, int C, const float* x, const float* y, fl
     cudaStream_t st = (cudaStream_t)stream;
     FSB_CUDA(cudaMemsetAsync(workspace, 0, fsb_ssim_workspace(), st));
     dim3 grid(fsb_div_up(W - (KS - 1), TS), fsb_div_up(H - (KS - 1), TS));
-    ssim_fwd_kernel<<<grid, S_THREADS, 0, st>>>(a, x, y, d_mu, d_xx, d_xy, (double*)workspace,
+    ssim_fwd_kernel<<<grid, S_THREADS, FWD_SMEM, st>>>(a, x, y, d_mu, d_xx, d_xy, (double*)workspace,
                                                 (unsigned*)((char*)workspace + 8), ssim_out);
     FSB_LAUNCH_CHECK();
     return 0;
@@ -216,7 +257,7 @@ FSB_API int fsb_ssim_bwd(int H, int W, int C, const float* x, const float* y, fl
     if (rc) return rc;
     if (!x || !y || !d_mu || !d_xx || !d_xy || !v_out || !v_x) return FSB_E_ARG;
     dim3 grid(fsb_div_up(W, TS), fsb_div_up(H, TS));
-    ssim_bwd_kernel<<<grid, S_THREADS, 0, (cudaStream_t)stream>>>(a, x, y, d_mu, d_xx, d_xy, v_out, v_x);
+    ssim_bwd_kernel<<<grid, S_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(a, x, y, d_mu, d_xx, d_xy, v_out, v_x);
     FSB_LAUNCH_CHECK();
     return 0;
 }

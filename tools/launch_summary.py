@@ -17,6 +17,10 @@ def main(path, steps):
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += v
+    if steps is None:
+        # one Adam launch per training iteration: the list itself says how many iterations it holds (the round-1
+        # summary of a 3-iteration capture was printed with the default of 1, every us/step in it 3x too large)
+        steps = max(1, sum(a[0] for k, a in agg.items() if "adam_multi" in k))
     tot = sum(a[1] for a in agg.values())
     print(f"launches/step {len(rows) / steps:.1f}   sum of kernel durations {tot / steps:.1f} us/step ({steps} steps)")
     print(f"{'us/step':>10} {'share':>6} {'n/step':>6}  kernel")
@@ -25,4 +29,4 @@ def main(path, steps):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else None)
