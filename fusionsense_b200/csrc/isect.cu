@@ -45,13 +45,14 @@ __device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t* total, in
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_block_sums_kernel(int64_t M, const int32_t* __restrict__ counts, int64_t* __restrict__ block_sums) {
+scan_block_sums_kernel(int64_t M, const int32_t* __restrict__ counts, const int32_t* __restrict__ perm,
+                       int64_t* __restrict__ block_sums) {
     __shared__ int64_t sm[9];
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int64_t s = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < M) s += counts[base + i];
+        if (base + i < M) s += counts[perm ? perm[base + i] : base + i];
     int64_t total;
     block_excl_scan(s, &total, sm);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -75,15 +76,15 @@ scan_spine_kernel(int64_t n_blocks, int64_t* __restrict__ block_sums, int64_t* _
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_apply_kernel(int64_t M, const int32_t* __restrict__ counts, const int64_t* __restrict__ block_sums,
-                  int64_t* __restrict__ offsets) {
+scan_apply_kernel(int64_t M, const int32_t* __restrict__ counts, const int32_t* __restrict__ perm,
+                  const int64_t* __restrict__ block_sums, int64_t* __restrict__ offsets) {
     __shared__ int64_t sm[9];
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int32_t v[SCAN_ITEMS];
     int64_t s = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        v[i] = (base + i < M) ? counts[base + i] : 0;
+        v[i] = (base + i < M) ? counts[perm ? perm[base + i] : base + i] : 0;
         s += v[i];
     }
     int64_t total;
@@ -225,9 +226,9 @@ FSB_API size_t fsb_isect_scan_workspace(int64_t M) {
     return (size_t)n_blocks * sizeof(int64_t);
 }
 
-// offsets[i] = sum(counts[0..i)) as int64 ; *total_dev = sum of all counts (device scalar)
-FSB_API int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, int64_t* total_dev, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+// offsets[i] = sum(counts[perm[0..i)]) as int64 (perm nullable = identity); *total_dev = sum of all counts
+static int scan_launch(int64_t M, const int32_t* counts, const int32_t* perm, int64_t* offsets, int64_t* total_dev,
+                       void* workspace, size_t workspace_bytes, void* stream) {
     if (M < 0) return FSB_E_ARG;
     if (workspace_bytes < fsb_isect_scan_workspace(M)) return FSB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -237,13 +238,27 @@ FSB_API int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, i
     }
     int64_t n_blocks = (M + SCAN_TILE - 1) / SCAN_TILE;
     int64_t* sums = (int64_t*)workspace;
-    scan_block_sums_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, st>>>(M, counts, sums);
+    scan_block_sums_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, st>>>(M, counts, perm, sums);
     FSB_LAUNCH_CHECK();
     scan_spine_kernel<<<1, SCAN_THREADS, 0, st>>>(n_blocks, sums, total_dev);
     FSB_LAUNCH_CHECK();
-    scan_apply_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, st>>>(M, counts, sums, offsets);
+    scan_apply_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, st>>>(M, counts, perm, sums, offsets);
     FSB_LAUNCH_CHECK();
     return 0;
+}
+
+// offsets[i] = sum(counts[0..i)) as int64 ; *total_dev = sum of all counts (device scalar)
+FSB_API int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, int64_t* total_dev, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    return scan_launch(M, counts, nullptr, offsets, total_dev, workspace, workspace_bytes, stream);
+}
+
+// The same scan taken in the order `perm` (int32[M], a permutation of 0 .. M-1): offsets[i] = sum(counts[perm[0..i)]).
+// Two-level binning: perm = the Gaussians in depth order, offsets[i] = where the entries of the i-th nearest start.
+FSB_API int fsb_isect_scan_perm(int64_t M, const int32_t* counts, const int32_t* perm, int64_t* offsets,
+                                int64_t* total_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!perm) return FSB_E_ARG;
+    return scan_launch(M, counts, perm, offsets, total_dev, workspace, workspace_bytes, stream);
 }
 
 FSB_API int fsb_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,

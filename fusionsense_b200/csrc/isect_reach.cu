@@ -1,8 +1,7 @@
 // isect_reach.cu — tile intersection with an exact reach test: count / emit only the (Gaussian, tile) pairs whose
 // Gaussian can pass the alpha test (alpha >= 1/255) on at least one pixel centre of the tile.
 //
-// EXPERIMENTAL (round 1: compiled and declared, NOT yet exercised on a GPU; off by default, see
-// DNSplatterStepConfig.prune_lists).  The reference bins by the 3-sigma bounding box
+// On by default in the DN-Splatter step (DNSplatterStepConfig.prune_lists).  The reference bins by the 3-sigma bounding box
 // (gsplat isect_tiles, reached from /root/reference/dn_splatter/dn_model.py:570-591 and :644-653); projected
 // surfels are thin rotated ellipses whose box is mostly empty: 35 % of the binned pairs of the 300 k bench scene and
 // 49 % of cfg1's never reach a pixel (tools/raster_stats.py, profiles/r01_raster_stats_*.json, which also checks
@@ -78,18 +77,29 @@ struct GaussTile {
     int32_t idx;
 };
 
+// one list entry: key = (camera, tile) | depth bits with the value beside it, or (packed) key = (camera, tile) | value
+__device__ __forceinline__ void put_entry(int64_t* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids, int64_t at,
+                                          int64_t high, int64_t depth_part, int32_t val, int packed) {
+    if (packed) {
+        isect_ids[at] = high | (int64_t)(uint32_t)val;
+    } else {
+        isect_ids[at] = high | depth_part;
+        flatten_ids[at] = val;
+    }
+}
+
 template <bool COUNT_ONLY>
 __device__ __forceinline__ int reach_one_tile(const GaussTile& g, int i, int j, int tile_size, int tile_w, bool flag_outer,
                                               int64_t limit, int64_t cur, int64_t* __restrict__ isect_ids,
-                                              int32_t* __restrict__ flatten_ids) {
+                                              int32_t* __restrict__ flatten_ids, int packed) {
     // pixel centres of the tile; the part of an edge tile beyond the image only makes the test more generous
     const float px0 = (float)(j * tile_size) + 0.5f, py0 = (float)(i * tile_size) + 0.5f;
     if (!rect_reach(g.mx, g.my, g.o, g.a, g.b, g.c, px0, px0 + (float)(tile_size - 1), py0, py0 + (float)(tile_size - 1)))
         return 0;
     if (!COUNT_ONLY && cur < limit) {
         const bool outer = flag_outer && !(i >= g.inner.ay && i < g.inner.by && j >= g.inner.ax && j < g.inner.bx);
-        isect_ids[cur] = g.cam_part | ((int64_t)(i * tile_w + j) << 32) | g.depth_part;
-        flatten_ids[cur] = outer ? (g.idx | LEGACY_FLAG) : g.idx;
+        put_entry(isect_ids, flatten_ids, cur, g.cam_part | ((int64_t)(i * tile_w + j) << 32), g.depth_part,
+                  outer ? (g.idx | LEGACY_FLAG) : g.idx, packed);
     }
     return 1;
 }
@@ -101,10 +111,19 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
                    const float* __restrict__ opacities, const int64_t* __restrict__ offsets, int tile_size, int tile_w,
                    int tile_h, int tile_bits, int legacy_bbox, const int64_t* __restrict__ n_dev, int64_t capacity,
                    int32_t* __restrict__ overflow_flag, int32_t* __restrict__ counts, int64_t* __restrict__ isect_ids,
-                   int32_t* __restrict__ flatten_ids, unsigned long long* __restrict__ hit_masks) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                   int32_t* __restrict__ flatten_ids, unsigned long long* __restrict__ hit_masks,
+                   const int32_t* __restrict__ perm, int packed, unsigned long long* __restrict__ depth_keys,
+                   int32_t* __restrict__ depth_vals) {
+    // Two-level binning (ops.isect_tiles_depth_first):
+    //   count pass: depth_keys / depth_vals (nullable) receive (depth bits, index) of every (camera, Gaussian) for the
+    //               depth sort; a Gaussian without entries gets the largest key.
+    //   emit pass : thread `gid` handles Gaussian perm[gid] (perm = the depth order) and `offsets` is indexed by gid;
+    //               packed != 0: the low word of the key is the flatten id (flag included) instead of the depth bits and
+    //               flatten_ids is not written — a stable sort on the (camera, tile) bits then finishes the order.
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool in_range = idx < (int64_t)C * N;
+    const bool in_range = gid < (int64_t)C * N;
+    const int64_t idx = (in_range && perm != nullptr) ? (int64_t)perm[gid] : gid;
     if (!COUNT_ONLY) {
         if (idx == 0 && n_dev && overflow_flag && *n_dev > capacity) *overflow_flag = 1;
         if (n_dev && *n_dev == 0) return;
@@ -123,8 +142,8 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
         g.cam_part = g.depth_part = g.cur = 0;
         if (!COUNT_ONLY) {
             g.cam_part = (idx / N) << (32 + tile_bits);
-            g.depth_part = (int64_t)(uint32_t)__float_as_int(depths[idx]);
-            g.cur = offsets[idx];
+            g.depth_part = packed ? 0 : (int64_t)(uint32_t)__float_as_int(depths[idx]);
+            g.cur = offsets[gid];
         }
     }
     const int64_t limit = n_dev ? capacity : INT64_MAX;
@@ -145,8 +164,8 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
                 const int i = g.box.ay + k / bw, j = g.box.ax + k % bw;
                 if (cur < limit) {
                     const bool outer = flag_outer && !(i >= g.inner.ay && i < g.inner.by && j >= g.inner.ax && j < g.inner.bx);
-                    isect_ids[cur] = g.cam_part | ((int64_t)(i * tile_w + j) << 32) | g.depth_part;
-                    flatten_ids[cur] = outer ? (g.idx | LEGACY_FLAG) : g.idx;
+                    put_entry(isect_ids, flatten_ids, cur, g.cam_part | ((int64_t)(i * tile_w + j) << 32), g.depth_part,
+                              outer ? (g.idx | LEGACY_FLAG) : g.idx, packed);
                 }
                 ++cur;
             }
@@ -156,7 +175,7 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
             for (int i = g.box.ay; i < g.box.by; ++i)
                 for (int j = g.box.ax; j < g.box.bx; ++j, ++k) {
                     const int hit = reach_one_tile<COUNT_ONLY>(g, i, j, tile_size, tile_w, flag_outer, limit, cur,
-                                                               isect_ids, flatten_ids);
+                                                               isect_ids, flatten_ids, packed);
                     cur += hit;
                     n += hit;
                     hm |= (unsigned long long)hit << k;
@@ -201,8 +220,8 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
                 const int64_t at = cur + __popc(hits & ((1u << lane) - 1u));
                 if (at < limit) {
                     const bool outer = flag_outer && !(i >= w.inner.ay && i < w.inner.by && j >= w.inner.ax && j < w.inner.bx);
-                    isect_ids[at] = w.cam_part | ((int64_t)(i * tile_w + j) << 32) | w.depth_part;
-                    flatten_ids[at] = outer ? (w.idx | LEGACY_FLAG) : w.idx;
+                    put_entry(isect_ids, flatten_ids, at, w.cam_part | ((int64_t)(i * tile_w + j) << 32), w.depth_part,
+                              outer ? (w.idx | LEGACY_FLAG) : w.idx, packed);
                 }
             }
             (void)hit;
@@ -211,7 +230,13 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
         }
         if (lane == src) n = found;
     }
-    if (COUNT_ONLY && in_range) counts[idx] = n;
+    if (COUNT_ONLY && in_range) {
+        counts[idx] = n;
+        if (depth_keys != nullptr) {
+            depth_keys[idx] = n > 0 ? (unsigned long long)(uint32_t)__float_as_int(depths[idx]) : 0xffffffffull;
+            depth_vals[idx] = (int32_t)idx;
+        }
+    }
 }
 
 }  // namespace
@@ -219,35 +244,46 @@ isect_reach_kernel(int C, int N, const float* __restrict__ means2d, const int32_
 // counts[C*N] = tiles of the bounding box (legacy_bbox: 0.1.x rule) that the Gaussian can reach with alpha >= 1/255.
 // conics[C*N,3], opacities[C*N] as handed to the compositing kernels.
 // hit_masks (nullable, uint64[C*N]): scratch the count pass fills and the matching emit pass reads (same arguments).
+// depths + depth_keys (uint64[C*N]) + depth_vals (int32[C*N]), all three or none: input of the depth sort of the
+// two-level binning — key = the depth's float bits (0xffffffff for a Gaussian without entries), value = its index.
 FSB_API int fsb_isect_count_reach(int C, int N, const float* means2d, const int32_t* radii, const float* conics,
                                   const float* opacities, int tile_size, int tile_w, int tile_h, int legacy_bbox,
-                                  int32_t* counts, uint64_t* hit_masks, void* stream) {
+                                  int32_t* counts, uint64_t* hit_masks, const float* depths, uint64_t* depth_keys,
+                                  int32_t* depth_vals, void* stream) {
     if (C <= 0 || N < 0 || tile_size <= 0 || !conics || !opacities || !counts) return FSB_E_ARG;
+    if ((depth_keys != nullptr) != (depth_vals != nullptr) || (depth_keys != nullptr && depths == nullptr)) return FSB_E_ARG;
+    if ((int64_t)C * N > 0x7fffffffLL) return FSB_E_ARG;
     if (N == 0) return 0;
     const int64_t total = (int64_t)C * N;
     isect_reach_kernel<true><<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        C, N, means2d, radii, nullptr, conics, opacities, nullptr, tile_size, tile_w, tile_h, 0, legacy_bbox, nullptr, 0,
-        nullptr, counts, nullptr, nullptr, (unsigned long long*)hit_masks);
+        C, N, means2d, radii, depths, conics, opacities, nullptr, tile_size, tile_w, tile_h, 0, legacy_bbox, nullptr, 0,
+        nullptr, counts, nullptr, nullptr, (unsigned long long*)hit_masks, nullptr, 0,
+        (unsigned long long*)depth_keys, depth_vals);
     FSB_LAUNCH_CHECK();
     return 0;
 }
 
 // fsb_isect_emit restricted to the reached tiles; `offsets` = exclusive scan of fsb_isect_count_reach's counts.
 // Static-capacity mode (n_dev, capacity, overflow_flag) as in fsb_isect_emit.
+// perm (nullable, int32[C*N]): entry i of `offsets` belongs to Gaussian perm[i] (fsb_isect_scan_perm).
+// packed != 0: isect_ids[k] = (camera, tile) << 32 | flatten id (flag included), flatten_ids may be null and is not
+// written; feed the result to fsb_radix_sort_keys(begin_bit = 32).
 FSB_API int fsb_isect_emit_reach(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
                                  const float* conics, const float* opacities, const int64_t* offsets, int tile_size,
                                  int tile_w, int tile_h, int tile_bits, int legacy_bbox, const int64_t* n_dev,
                                  int64_t capacity, int32_t* overflow_flag, int64_t* isect_ids, int32_t* flatten_ids,
-                                 const uint64_t* hit_masks, void* stream) {
+                                 const uint64_t* hit_masks, const int32_t* perm, int packed, void* stream) {
     if (C <= 0 || N < 0 || tile_size <= 0 || tile_bits < 0 || tile_bits > 30) return FSB_E_ARG;
-    if (!conics || !opacities || !offsets || !isect_ids || !flatten_ids) return FSB_E_ARG;
+    if (!conics || !opacities || !offsets || !isect_ids || (!flatten_ids && !packed)) return FSB_E_ARG;
+    if (!packed && !depths) return FSB_E_ARG;
     if (n_dev && capacity < 0) return FSB_E_ARG;
     if ((int64_t)C * N > 0x7fffffffLL) return FSB_E_ARG;
     if (N == 0) return 0;
     const int64_t total = (int64_t)C * N;
     isect_reach_kernel<false><<<fsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
         C, N, means2d, radii, depths, conics, opacities, offsets, tile_size, tile_w, tile_h, tile_bits, legacy_bbox, n_dev,
-        capacity, overflow_flag, nullptr, isect_ids, flatten_ids, (unsigned long long*)hit_masks);
+        capacity, overflow_flag, nullptr, isect_ids, flatten_ids, (unsigned long long*)hit_masks, perm, packed, nullptr,
+        nullptr);
     FSB_LAUNCH_CHECK();
     return 0;
 }

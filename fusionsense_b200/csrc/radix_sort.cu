@@ -11,6 +11,11 @@
 //
 // HBM-bound: algorithmic traffic = n * 12 B * 2 per pass + one n * 8 B histogram read.  Pairs are reordered by digit
 // in shared memory before they are written, so every digit's run of a 4096-pair tile leaves as whole sectors.
+//
+// fsb_radix_sort_keys is the keys-only form on a bit window [begin_bit, end_bit): the second level of the two-level
+// binning (ops.isect_tiles_depth_first): the (camera, tile) id sits in the high word, the Gaussian id rides in the low
+// word, and because the entries were emitted in depth order a stable sort on the 11 .. 13 tile bits alone (2 passes,
+// 8 B per entry) gives the order the reference gets from sorting the full 64-bit (tile | depth) keys (5 passes, 12 B).
 #include "common.cuh"
 
 namespace {
@@ -27,17 +32,15 @@ constexpr uint32_t FLAG_INC = 2u << 30;
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VAL_MASK = ~FLAG_MASK;
 
-// digit of pass p: key bits [BITS p, min(BITS (p + 1), end_bit))
-template <int BITS>
-__device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, int end_bit) {
-    const int w = min(BITS, end_bit - shift);
-    return (uint32_t)((key >> shift) & ((1u << w) - 1u));
+// digit of a pass: key bits [shift, shift + width)
+__device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, int width) {
+    return (uint32_t)((key >> shift) & ((1u << width) - 1u));
 }
 
 template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ keys, int passes,
-                  int end_bit, uint32_t* __restrict__ hist) {
+                  int begin_bit, int digit_w, int end_bit, uint32_t* __restrict__ hist) {
     constexpr int RADIX = 1 << BITS;
     n = fsb_eff_n(n, n_dev);
     __shared__ uint32_t sh[MAX_PASSES][RADIX];
@@ -52,8 +55,9 @@ radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* 
         bool valid = i < n;
         uint64_t key = valid ? keys[i] : 0;
         for (int p = 0; p < passes; ++p) {
-            uint32_t d = valid ? digit_of<BITS>(key, BITS * p, end_bit) : 0xffffffffu;
-            if (BITS * (p + 1) <= 23) {
+            const int shift = begin_bit + digit_w * p;
+            uint32_t d = valid ? digit_of(key, shift, min(digit_w, end_bit - shift)) : 0xffffffffu;
+            if (shift + digit_w <= 23) {
                 // digit inside the mantissa of the depth: values are spread, same-address conflicts are rare, and a
                 // plain shared-memory atomic is cheaper than MATCH.ANY (the unit the ranking loop also leans on)
                 if (valid) atomicAdd(&sh[p][d], 1u);
@@ -71,20 +75,23 @@ radix_hist_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* 
     }
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS)
+// PAIRS: (key, value) pairs; else keys only, and `low32_out` (nullable, last pass) also receives the low word of every
+// key at its sorted position.
+template <int BITS, bool PAIRS>
+__global__ void __launch_bounds__(SORT_THREADS, PAIRS ? 2 : 3)
 onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ keys_in,
                      const int32_t* __restrict__ vals_in,
-                     uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
+                     uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int32_t* __restrict__ low32_out,
                      const uint32_t* __restrict__ pass_hist, volatile uint32_t* status, uint32_t* tile_counter,
-                     int shift, int end_bit) {
+                     int shift, int width) {
     constexpr int RADIX = 1 << BITS;
     constexpr int DPT = RADIX / SORT_THREADS;  // digits owned by a thread: DPT t .. DPT t + DPT - 1
     static_assert(DPT >= 1 && RADIX <= MAX_RADIX, "digit width");
     extern __shared__ __align__(16) unsigned char sort_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(sort_smem);                        // [SORT_TILE]
-    int32_t* s_vals = reinterpret_cast<int32_t*>(sort_smem + SORT_TILE * 8);          // [SORT_TILE]
-    uint32_t (*warp_hist)[RADIX] = reinterpret_cast<uint32_t (*)[RADIX]>(sort_smem + SORT_TILE * 12);  // [SORT_WARPS]
+    int32_t* s_vals = reinterpret_cast<int32_t*>(sort_smem + SORT_TILE * 8);          // [SORT_TILE], PAIRS only
+    uint32_t (*warp_hist)[RADIX] =
+        reinterpret_cast<uint32_t (*)[RADIX]>(sort_smem + SORT_TILE * (PAIRS ? 12 : 8));  // [SORT_WARPS]
     __shared__ uint32_t digit_base[RADIX];
     __shared__ uint32_t cta_total[RADIX];
     __shared__ uint32_t local_start[RADIX];
@@ -102,21 +109,21 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
     const int64_t tile_base = (int64_t)tile * SORT_TILE + (int64_t)warp * (32 * KPT);
 
     uint64_t key[KPT];
-    int32_t val[KPT];
+    int32_t val[PAIRS ? KPT : 1];
     uint32_t rank[KPT];
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
         int64_t i = tile_base + k * 32 + lane;
         bool valid = i < n;
         key[k] = valid ? keys_in[i] : ~0ull;
-        val[k] = valid ? vals_in[i] : 0;
+        if (PAIRS) val[k] = valid ? vals_in[i] : 0;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
         int64_t i = tile_base + k * 32 + lane;
         bool valid = i < n;
-        uint32_t d = digit_of<BITS>(key[k], shift, end_bit);
+        uint32_t d = digit_of(key[k], shift, width);
         uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
         int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
@@ -254,64 +261,85 @@ onesweep_pass_kernel(int64_t n, const int64_t* __restrict__ n_dev, const uint64_
     for (int k = 0; k < KPT; ++k) {
         int64_t i = tile_base + k * 32 + lane;
         if (i < n) {
-            uint32_t d = digit_of<BITS>(key[k], shift, end_bit);
+            uint32_t d = digit_of(key[k], shift, width);
             uint32_t slot = local_start[d] + warp_hist[warp][d] + rank[k];
             s_keys[slot] = key[k];
-            s_vals[slot] = val[k];
+            if (PAIRS) s_vals[slot] = val[k];
         }
     }
     __syncthreads();
     for (int slot = tid; slot < cta_n; slot += SORT_THREADS) {
         const uint64_t kk = s_keys[slot];
-        const uint32_t d = digit_of<BITS>(kk, shift, end_bit);
+        const uint32_t d = digit_of(kk, shift, width);
         const uint32_t pos = digit_base[d] + ((uint32_t)slot - local_start[d]);
         keys_out[pos] = kk;
-        vals_out[pos] = s_vals[slot];
+        if (PAIRS) vals_out[pos] = s_vals[slot];
+        else if (low32_out != nullptr) low32_out[pos] = (int32_t)(uint32_t)kk;
     }
 }
 
 }  // namespace
 
 static inline int64_t sort_num_tiles(int64_t n) { return n > 0 ? (n + SORT_TILE - 1) / SORT_TILE : 1; }
-// 9-bit digits when they save a pass (end_bit 41..45, 49..54, 57..63), else 8-bit
-static inline int sort_digit_bits(int end_bit) { return (end_bit + 8) / 9 < (end_bit + 7) / 8 ? 9 : 8; }
-static inline int sort_num_passes(int end_bit) {
-    const int b = sort_digit_bits(end_bit);
-    return (end_bit + b - 1) / b;
+
+// Pass plan of a window of `nbits` key bits: 9-bit digits when they save a pass (41..45, 49..54, 57..63 bits), else
+// 8-bit; the window is then split into equal digits (45 bits -> 5 x 9, 32 -> 4 x 8, 13 -> 2 x 7).
+struct SortPlan {
+    int radix_bits;  // kernel instantiation (table sizes)
+    int passes;
+    int digit_w;     // bits per pass (the last pass takes what is left)
+};
+static inline SortPlan sort_plan(int nbits) {
+    SortPlan pl;
+    pl.radix_bits = (nbits + 8) / 9 < (nbits + 7) / 8 ? 9 : 8;
+    pl.passes = (nbits + pl.radix_bits - 1) / pl.radix_bits;
+    pl.digit_w = (nbits + pl.passes - 1) / pl.passes;
+    return pl;
 }
 
-FSB_API size_t fsb_radix_sort_workspace(int64_t n, int end_bit) {
-    const int passes = sort_num_passes(end_bit);
-    const size_t radix = (size_t)1 << sort_digit_bits(end_bit);
-    size_t bytes = (size_t)passes * radix * sizeof(uint32_t);                  // histograms
-    bytes += fsb_align_up((size_t)passes * sizeof(uint32_t), 256);             // tile counters
-    bytes += (size_t)passes * (size_t)sort_num_tiles(n) * radix * sizeof(uint32_t);  // look-back status
+static size_t sort_workspace_bytes(int64_t n, int nbits) {
+    const SortPlan pl = sort_plan(nbits);
+    const size_t radix = (size_t)1 << pl.radix_bits;
+    size_t bytes = (size_t)pl.passes * radix * sizeof(uint32_t);                        // histograms
+    bytes += fsb_align_up((size_t)pl.passes * sizeof(uint32_t), 256);                   // tile counters
+    bytes += (size_t)pl.passes * (size_t)sort_num_tiles(n) * radix * sizeof(uint32_t);  // look-back status
     return fsb_align_up(bytes, 256);
 }
 
-template <int BITS>
-static int sort_launch(int64_t n, const int64_t* n_dev, int end_bit, int passes, uint64_t* keys_a, int32_t* vals_a,
-                       uint64_t* keys_b, int32_t* vals_b, void* workspace, cudaStream_t st) {
+FSB_API size_t fsb_radix_sort_workspace(int64_t n, int end_bit) { return sort_workspace_bytes(n, end_bit); }
+FSB_API size_t fsb_radix_sort_keys_workspace(int64_t n, int begin_bit, int end_bit) {
+    return sort_workspace_bytes(n, end_bit - begin_bit);
+}
+
+template <int BITS, bool PAIRS>
+static int sort_launch(int64_t n, const int64_t* n_dev, int begin_bit, int end_bit, SortPlan pl, uint64_t* keys_a,
+                       int32_t* vals_a, uint64_t* keys_b, int32_t* vals_b, int32_t* low32_out, void* workspace,
+                       cudaStream_t st) {
     constexpr int RADIX = 1 << BITS;
+    const int passes = pl.passes;
     int64_t tiles = sort_num_tiles(n);
     uint32_t* hist = (uint32_t*)workspace;
     uint32_t* counters = hist + (size_t)passes * RADIX;
     uint32_t* status = (uint32_t*)((char*)counters + fsb_align_up((size_t)passes * sizeof(uint32_t), 256));
     int hist_blocks = (int)(tiles < FSB_NUM_SMS * 8 ? tiles : FSB_NUM_SMS * 8);
-    radix_hist_kernel<BITS><<<hist_blocks, SORT_THREADS, 0, st>>>(n, n_dev, keys_a, passes, end_bit, hist);
+    radix_hist_kernel<BITS><<<hist_blocks, SORT_THREADS, 0, st>>>(n, n_dev, keys_a, passes, begin_bit, pl.digit_w, end_bit,
+                                                                  hist);
     FSB_LAUNCH_CHECK();
     uint64_t* kin = keys_a; int32_t* vin = vals_a;
     uint64_t* kout = keys_b; int32_t* vout = vals_b;
-    const size_t smem = (size_t)SORT_TILE * 12 + (size_t)SORT_WARPS * RADIX * 4;
+    const size_t smem = (size_t)SORT_TILE * (PAIRS ? 12 : 8) + (size_t)SORT_WARPS * RADIX * 4;
     static bool smem_opted_in = false;  // once per instantiation, outside any stream capture (the first call is eager)
     if (!smem_opted_in) {
-        FSB_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSB_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<BITS, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
         smem_opted_in = true;
     }
     for (int p = 0; p < passes; ++p) {
-        onesweep_pass_kernel<BITS><<<(unsigned)tiles, SORT_THREADS, smem, st>>>(
-            n, n_dev, kin, vin, kout, vout, hist + (size_t)p * RADIX, status + (size_t)p * tiles * RADIX, counters + p,
-            BITS * p, end_bit);
+        const int shift = begin_bit + pl.digit_w * p;
+        const int width = pl.digit_w < end_bit - shift ? pl.digit_w : end_bit - shift;
+        onesweep_pass_kernel<BITS, PAIRS><<<(unsigned)tiles, SORT_THREADS, smem, st>>>(
+            n, n_dev, kin, vin, kout, vout, p == passes - 1 ? low32_out : nullptr, hist + (size_t)p * RADIX,
+            status + (size_t)p * tiles * RADIX, counters + p, shift, width);
         FSB_LAUNCH_CHECK();
         uint64_t* tk = kin; kin = kout; kout = tk;
         int32_t* tv = vin; vin = vout; vout = tv;
@@ -326,14 +354,36 @@ FSB_API int fsb_radix_sort_pairs(int64_t n, const int64_t* n_dev, int end_bit, u
                                  uint64_t* keys_b, int32_t* vals_b, void* workspace, size_t workspace_bytes,
                                  int* result_in_b, void* stream) {
     if (n < 0 || n >= (1ll << 30) || end_bit < 1 || end_bit > 64) return FSB_E_ARG;
-    int passes = sort_num_passes(end_bit);
-    if (passes > MAX_PASSES) return FSB_E_ARG;
-    if (workspace_bytes < fsb_radix_sort_workspace(n, end_bit)) return FSB_E_ARG;
-    if (result_in_b) *result_in_b = passes & 1;
+    const SortPlan pl = sort_plan(end_bit);
+    if (pl.passes > MAX_PASSES) return FSB_E_ARG;
+    if (workspace_bytes < sort_workspace_bytes(n, end_bit)) return FSB_E_ARG;
+    if (result_in_b) *result_in_b = pl.passes & 1;
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    FSB_CUDA(cudaMemsetAsync(workspace, 0, fsb_radix_sort_workspace(n, end_bit), st));
-    if (sort_digit_bits(end_bit) == 9)
-        return sort_launch<9>(n, n_dev, end_bit, passes, keys_a, vals_a, keys_b, vals_b, workspace, st);
-    return sort_launch<8>(n, n_dev, end_bit, passes, keys_a, vals_a, keys_b, vals_b, workspace, st);
+    FSB_CUDA(cudaMemsetAsync(workspace, 0, sort_workspace_bytes(n, end_bit), st));
+    if (pl.radix_bits == 9)
+        return sort_launch<9, true>(n, n_dev, 0, end_bit, pl, keys_a, vals_a, keys_b, vals_b, nullptr, workspace, st);
+    return sort_launch<8, true>(n, n_dev, 0, end_bit, pl, keys_a, vals_a, keys_b, vals_b, nullptr, workspace, st);
+}
+
+// Stable sort of 64-bit keys on bits [begin_bit, end_bit) only (the other bits travel with the key).  Buffers A (input,
+// clobbered) and B ping-pong, *result_in_b as above.  low32_out (nullable, int32[n]): the low word of every key at its
+// sorted position, written by the last pass.  n_dev as above.
+FSB_API int fsb_radix_sort_keys(int64_t n, const int64_t* n_dev, int begin_bit, int end_bit, uint64_t* keys_a,
+                                uint64_t* keys_b, int32_t* low32_out, void* workspace, size_t workspace_bytes,
+                                int* result_in_b, void* stream) {
+    if (n < 0 || n >= (1ll << 30) || begin_bit < 0 || end_bit <= begin_bit || end_bit > 64) return FSB_E_ARG;
+    const int nbits = end_bit - begin_bit;
+    const SortPlan pl = sort_plan(nbits);
+    if (pl.passes > MAX_PASSES) return FSB_E_ARG;
+    if (workspace_bytes < sort_workspace_bytes(n, nbits)) return FSB_E_ARG;
+    if (result_in_b) *result_in_b = pl.passes & 1;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    FSB_CUDA(cudaMemsetAsync(workspace, 0, sort_workspace_bytes(n, nbits), st));
+    if (pl.radix_bits == 9)
+        return sort_launch<9, false>(n, n_dev, begin_bit, end_bit, pl, keys_a, nullptr, keys_b, nullptr, low32_out,
+                                     workspace, st);
+    return sort_launch<8, false>(n, n_dev, begin_bit, end_bit, pl, keys_a, nullptr, keys_b, nullptr, low32_out,
+                                 workspace, st);
 }

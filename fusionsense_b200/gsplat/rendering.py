@@ -100,6 +100,21 @@ def rasterization_from_params(
                                prune=prune_lists or colors_b is not None, colors_b=colors_b, backgrounds_b=backgrounds_b)
 
 
+class _Meta(dict):
+    """meta dict whose "isect_ids" is built on first access when the lists came from the two-level binning
+    (ops.PackedIsectIds): the render path itself never needs the gsplat key form."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, ops.PackedIsectIds):
+            v = v.materialize()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane, far_plane,
                         radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode, sparse_grad,
                         absgrad, rasterize_mode, channel_chunk, stored=None, prune=False, colors_b=None,
@@ -182,7 +197,8 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
     with torch.no_grad():
         _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(
             means2d, radii, depths, tile_size, tile_width, tile_height, tiles_per_gauss=tiles_per_gauss,
-            totals=totals, reach=(conics, opac) if prune else None, legacy_bbox=2 if colors_b is not None else False)
+            totals=totals, reach=(conics, opac) if prune else None, legacy_bbox=2 if colors_b is not None else False,
+            lazy_ids=True)
         n_dev = getattr(flatten_ids, "n_dev", None)  # static-capacity mode (ops.static_capacity): count on device
         lists_done = None
         if n_dev is not None:
@@ -248,7 +264,7 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
     else:
         render_colors, render_alphas = _raster(ras_colors, backgrounds, ed_normalize)
 
-    meta = {
+    meta = _Meta({
         "camera_ids": None,
         "gaussian_ids": None,
         "radii": radii,
@@ -266,7 +282,7 @@ def _rasterization_impl(means, quats, scales, opacities, colors, viewmats, Ks, w
         "height": height,
         "tile_size": tile_size,
         "n_cameras": C,
-    }
+    })
     if render_b is not None:
         meta["render_b"] = render_b  # extension: the second colour set (rasterization_from_params(colors_b=...))
     if proj_done is not None:

@@ -7,6 +7,7 @@ tensors and raises otherwise.
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 from typing import Optional, Tuple
 
@@ -174,22 +175,33 @@ def isect_count(means2d: Tensor, radii: Tensor, tile_size: int, tile_w: int, til
 
 
 def isect_count_reach(means2d: Tensor, radii: Tensor, conics: Tensor, opacities: Tensor, tile_size: int, tile_w: int,
-                      tile_h: int, legacy_bbox: bool):
-    """EXPERIMENTAL (csrc/isect_reach.cu): tiles of each Gaussian's bounding box on which it can pass the alpha test.
-    means2d [C,N,2], radii [C,N], conics [C,N,3], opacities [C,N] -> counts [C,N] int32."""
+                      tile_h: int, legacy_bbox: bool, depths: Optional[Tensor] = None):
+    """csrc/isect_reach.cu: tiles of each Gaussian's bounding box on which it can pass the alpha test.
+    means2d [C,N,2], radii [C,N], conics [C,N,3], opacities [C,N] -> counts [C,N] int32.
+    `depths` [C,N]: also write the (depth bits, index) pairs of the two-level binning's depth sort
+    (counts.depth_keys int64 [C*N], counts.depth_vals int32 [C*N])."""
     _req_cuda(means2d, radii, conics, opacities)
     C, N = radii.shape
-    counts = torch.empty(radii.shape, dtype=torch.int32, device=radii.device)
-    hit_masks = torch.empty(radii.shape, dtype=torch.int64, device=radii.device)  # read back by isect_emit(reach=...)
+    dev = radii.device
+    counts = torch.empty(radii.shape, dtype=torch.int32, device=dev)
+    hit_masks = torch.empty(radii.shape, dtype=torch.int64, device=dev)  # read back by isect_emit(reach=...)
+    depth_keys = depth_vals = None
+    if depths is not None:
+        _req_cuda(depths)
+        depth_keys = torch.empty((C * N,), dtype=torch.int64, device=dev)
+        depth_vals = torch.empty((C * N,), dtype=torch.int32, device=dev)
     check(lib.fsb_isect_count_reach(C, N, ptr(means2d), ptr(radii), ptr(conics), ptr(opacities), tile_size, tile_w,
-                                    tile_h, int(legacy_bbox), ptr(counts), ptr(hit_masks), _stream()),
+                                    tile_h, int(legacy_bbox), ptr(counts), ptr(hit_masks), ptr(depths), ptr(depth_keys),
+                                    ptr(depth_vals), _stream()),
           "fsb_isect_count_reach")
     counts.hit_masks = hit_masks
+    counts.depth_keys, counts.depth_vals = depth_keys, depth_vals
     return counts
 
 
-def isect_scan(counts: Tensor, totals: Optional[Tensor] = None, read_back: bool = True):
+def isect_scan(counts: Tensor, totals: Optional[Tensor] = None, read_back: bool = True, perm: Optional[Tensor] = None):
     """Exclusive int64 offsets of `counts` and the total (one small D2H read, like gsplat's).
+    `perm` (int32 [M]): the scan runs over counts[perm[i]] (two-level binning: the Gaussians in depth order).
 
     `totals`: optional int64 device tensor whose element 0 receives the total; the whole tensor comes back in the
     same read (rasterization() keeps the legacy-bbox mismatch counter in element 1), and the return value is then
@@ -200,8 +212,12 @@ def isect_scan(counts: Tensor, totals: Optional[Tensor] = None, read_back: bool 
     total = totals if totals is not None else torch.empty((1,), dtype=torch.int64, device=dev)
     ws_bytes = lib.fsb_isect_scan_workspace(M)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    check(lib.fsb_isect_scan(M, ptr(counts), ptr(offsets), ptr(total), ptr(ws), ws_bytes, _stream()),
-          "fsb_isect_scan")
+    if perm is None:
+        check(lib.fsb_isect_scan(M, ptr(counts), ptr(offsets), ptr(total), ptr(ws), ws_bytes, _stream()),
+              "fsb_isect_scan")
+    else:
+        check(lib.fsb_isect_scan_perm(M, ptr(counts), ptr(perm), ptr(offsets), ptr(total), ptr(ws), ws_bytes, _stream()),
+              "fsb_isect_scan_perm")
     if not read_back:
         return offsets, None
     if totals is not None:
@@ -221,13 +237,15 @@ def sort_end_bit(n_tiles: int, C: int) -> int:
 
 
 def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox, n_dev=None,
-               overflow=None, reach=None, hit_masks=None):
+               overflow=None, reach=None, hit_masks=None, perm=None, packed=False):
     """`n_dev` (device int64[1]) selects static-capacity mode: `n_isects` is then the capacity of the buffers.
-    `reach` = (conics [C,N,3], opacities [C,N]): EXPERIMENTAL, emit only the reached tiles (`offsets` must then be
-    the scan of `isect_count_reach`)."""
+    `reach` = (conics [C,N,3], opacities [C,N]): emit only the reached tiles (`offsets` must then be the scan of
+    `isect_count_reach`).  `perm` / `packed` (reach only): two-level binning, see include/fsb200.h; with `packed` the
+    second return value is None."""
     dev = means2d.device
     ids = torch.empty((n_isects,), dtype=torch.int64, device=dev)
-    flat = torch.empty((n_isects,), dtype=torch.int32, device=dev)
+    flat = None if packed else torch.empty((n_isects,), dtype=torch.int32, device=dev)
+    assert reach is not None or (perm is None and not packed)
     tb = tile_bits_for(tile_w * tile_h)
     ev = kernel_timer.start("isect_emit")
     if reach is None:
@@ -237,7 +255,8 @@ def isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_
     else:
         check(lib.fsb_isect_emit_reach(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(reach[0]), ptr(reach[1]),
                                        ptr(offsets), tile_size, tile_w, tile_h, tb, int(legacy_bbox), ptr(n_dev),
-                                       n_isects, ptr(overflow), ptr(ids), ptr(flat), ptr(hit_masks), _stream()),
+                                       n_isects, ptr(overflow), ptr(ids), ptr(flat), ptr(hit_masks), ptr(perm), int(packed),
+                                       _stream()),
               "fsb_isect_emit_reach")
     kernel_timer.stop(ev)
     return ids, flat
@@ -263,6 +282,26 @@ def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int, n_dev: Optional[T
     return (keys_b, vals_b) if in_b.value else (keys, vals)
 
 
+def radix_sort_keys(keys: Tensor, begin_bit: int, end_bit: int, n_dev: Optional[Tensor] = None,
+                    want_low32: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    """Stable sort of int64 keys on bits [begin_bit, end_bit); the input is clobbered.  Returns (sorted keys, int32 low
+    words of the sorted keys).  `n_dev` as in radix_sort_pairs."""
+    _req_cuda(keys)
+    n = keys.numel()
+    low = torch.empty((n,), dtype=torch.int32, device=keys.device) if want_low32 else None
+    if n == 0:
+        return keys, low
+    keys_b = torch.empty_like(keys)
+    ws_bytes = lib.fsb_radix_sort_keys_workspace(n, begin_bit, end_bit)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=keys.device)
+    in_b = ctypes.c_int(0)
+    ev = kernel_timer.start("radix_sort")
+    check(lib.fsb_radix_sort_keys(n, ptr(n_dev), begin_bit, end_bit, ptr(keys), ptr(keys_b), ptr(low), ptr(ws), ws_bytes,
+                                  ctypes.addressof(in_b), _stream()), "fsb_radix_sort_keys")
+    kernel_timer.stop(ev)
+    return (keys_b if in_b.value else keys), low
+
+
 def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int, n_dev: Optional[Tensor] = None) -> Tensor:
     n_tiles = tile_w * tile_h
     offsets = torch.empty((C, tile_h, tile_w), dtype=torch.int32, device=sorted_ids.device)
@@ -272,7 +311,7 @@ def isect_offsets(sorted_ids: Tensor, C: int, tile_w: int, tile_h: int, n_dev: O
 
 
 def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gauss=None, legacy_bbox=False,
-                sort=True, totals=None, reach=None):
+                sort=True, totals=None, reach=None, lazy_ids=False):
     """gsplat.isect_tiles + isect_offset_encode in one go (unpacked layout).
 
     means2d [C,N,2], radii [C,N] int32, depths [C,N] -> tiles_per_gauss [C,N], isect_ids [n_isects] int64 (sorted),
@@ -286,37 +325,72 @@ def isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h, tiles_per_gau
     # pass the alpha test somewhere in the tile (csrc/isect_reach.cu); `tiles_per_gauss` stays the bounding-box count
     # the API reports, the lists are built from the reach counts
     list_counts = tiles_per_gauss
+    # Two-level binning (pruned lists, sorted): Gaussians by depth first, entries emitted in that order, then a stable
+    # sort on the (camera, tile) bits alone — the same order as sorting the 64-bit (camera | tile | depth) keys, with
+    # 2 passes over 8-byte entries instead of 5 over 12-byte pairs (include/fsb200.h).
+    two_level = reach is not None and sort and TWO_LEVEL_BINNING
+    perm = None
     if reach is not None:
         reach = (_f32c(reach[0]), _f32c(reach[1]))
-        list_counts = isect_count_reach(means2d, radii, reach[0], reach[1], tile_size, tile_w, tile_h, legacy_bbox)
+        list_counts = isect_count_reach(means2d, radii, reach[0], reach[1], tile_size, tile_w, tile_h, legacy_bbox,
+                                        depths=depths if two_level else None)
+        if two_level:
+            _, perm = radix_sort_pairs(list_counts.depth_keys, list_counts.depth_vals, 32)
+    hit_masks = getattr(list_counts, "hit_masks", None)
+    hi_end = sort_end_bit(tile_w * tile_h, C)
     st = static_mode()
     if st is not None:
         # no host read: buffers for the capacity, the true count stays in totals[0] on the device
         if totals is None:
             totals = torch.zeros(1, dtype=torch.int64, device=radii.device)
-        offsets, _ = isect_scan(list_counts, totals, read_back=False)
+        offsets, _ = isect_scan(list_counts, totals, read_back=False, perm=perm)
         n_dev = totals[:1]
         st.counts.append(n_dev)
-        ids, flat = isect_emit(means2d, radii, depths, offsets, st.capacity, C, N, tile_size, tile_w, tile_h,
-                               legacy_bbox, n_dev=n_dev, overflow=st.overflow, reach=reach,
-                               hit_masks=getattr(list_counts, "hit_masks", None))
-        if sort:
-            end_bit = sort_end_bit(tile_w * tile_h, C)
-            ids, flat = radix_sort_pairs(ids, flat, end_bit, n_dev=n_dev)
-        tile_offsets = isect_offsets(ids, C, tile_w, tile_h, n_dev=n_dev)
+        capacity = st.capacity
+    else:
+        offsets, n_isects = isect_scan(list_counts, totals, perm=perm)
+        if totals is not None:
+            totals.host = n_isects  # the values that came back with the one D2H read
+            n_isects = n_isects[0]
+        n_dev, capacity = None, n_isects
+    ids, flat = isect_emit(means2d, radii, depths, offsets, capacity, C, N, tile_size, tile_w, tile_h, legacy_bbox,
+                           n_dev=n_dev, overflow=st.overflow if st is not None else None, reach=reach,
+                           hit_masks=hit_masks, perm=perm, packed=two_level)
+    if two_level:
+        ids, flat = radix_sort_keys(ids, 32, hi_end, n_dev=n_dev)
+        ids = PackedIsectIds(ids, flat, depths)  # `lazy_ids`: the caller may never ask for the gsplat key form
+    elif sort:
+        ids, flat = radix_sort_pairs(ids, flat, hi_end, n_dev=n_dev)
+    # the (camera, tile) id sits in the high word of either key format
+    tile_offsets = isect_offsets(ids.packed if two_level else ids, C, tile_w, tile_h, n_dev=n_dev)
+    if n_dev is not None:
         flat.n_dev = n_dev
-        return tiles_per_gauss, ids, flat, tile_offsets
-    offsets, n_isects = isect_scan(list_counts, totals)
-    if totals is not None:
-        totals.host = n_isects  # the values that came back with the one D2H read
-        n_isects = n_isects[0]
-    ids, flat = isect_emit(means2d, radii, depths, offsets, n_isects, C, N, tile_size, tile_w, tile_h, legacy_bbox,
-                           reach=reach, hit_masks=getattr(list_counts, "hit_masks", None))
-    if sort:
-        end_bit = sort_end_bit(tile_w * tile_h, C)
-        ids, flat = radix_sort_pairs(ids, flat, end_bit)
-    tile_offsets = isect_offsets(ids, C, tile_w, tile_h)
+    if two_level and not lazy_ids:
+        ids = ids.materialize()
     return tiles_per_gauss, ids, flat, tile_offsets
+
+
+TWO_LEVEL_BINNING = os.environ.get("FSB_TWO_LEVEL_BINNING", "1") != "0"
+
+
+class PackedIsectIds:
+    """`isect_ids` of the two-level binning: the sorted keys exist as (camera, tile) << 32 | flatten id; the gsplat form
+    (camera, tile) << 32 | depth bits is built on request (`.ids()`, `torch.as_tensor(...)`-style consumers call
+    `materialize`).  Only tests and debugging ask for it; the compositing kernels use flatten_ids and isect_offsets."""
+
+    def __init__(self, packed: Tensor, flatten_ids: Tensor, depths: Tensor):
+        self.packed, self._flat, self._depths = packed, flatten_ids, depths
+
+    def materialize(self) -> Tensor:
+        n_dev = getattr(self._flat, "n_dev", None)
+        flat = (self._flat & 0x7FFFFFFF).long()
+        if n_dev is not None:  # static-capacity mode: entries past the true count are uninitialised
+            flat = flat.clamp_(0, self._depths.numel() - 1)
+        depth_bits = self._depths.reshape(-1).view(torch.int32)[flat].long() & 0xFFFFFFFF
+        return (self.packed & ~0xFFFFFFFF) | depth_bits
+
+    def numel(self):
+        return self.packed.numel()
 
 
 def isect_tiles_legacy_shared(means2d, radii, depths, tile_size, tile_w, tile_h, first_flat, first_offsets,

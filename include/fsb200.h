@@ -105,16 +105,24 @@ int fsb_isect_count(int64_t M, const float* means2d, const int32_t* radii, int t
 #define FSB_LEGACY_FLAG 0x80000000u
 int fsb_isect_count_reach(int C, int N, const float* means2d, const int32_t* radii, const float* conics,
                           const float* opacities, int tile_size, int tile_w, int tile_h, int legacy_bbox,
-                          int32_t* counts, uint64_t* hit_masks, void* stream);
+                          int32_t* counts, uint64_t* hit_masks, const float* depths, uint64_t* depth_keys,
+                          int32_t* depth_vals, void* stream);
 int fsb_isect_emit_reach(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
                          const float* conics, const float* opacities, const int64_t* offsets, int tile_size,
                          int tile_w, int tile_h, int tile_bits, int legacy_bbox, const int64_t* n_dev,
                          int64_t capacity, int32_t* overflow_flag, int64_t* isect_ids, int32_t* flatten_ids,
-                         const uint64_t* hit_masks, void* stream);
+                         const uint64_t* hit_masks, const int32_t* perm, int packed, void* stream);
+/* Two-level binning (the default of the pruned path): the reference sorts 64-bit (camera | tile | depth bits) keys; the
+ * same order comes from (1) a sort of the C*N Gaussians by depth bits (fsb_isect_count_reach's depth_keys / depth_vals
+ * through fsb_radix_sort_pairs, end_bit 32), (2) emission in that order (fsb_isect_scan_perm + fsb_isect_emit_reach
+ * with perm, packed = 1) and (3) a stable sort of the entries on the (camera, tile) bits only
+ * (fsb_radix_sort_keys, begin_bit 32): 2 passes over 8-byte entries instead of 5 over 12-byte pairs at 1080p. */
 
 /* exclusive int64 prefix sum of counts[M] (replaces torch.cumsum inside gsplat isect_tiles);
  * total_dev receives the grand total (= n_isects), a device scalar the caller copies back. */
 size_t fsb_isect_scan_workspace(int64_t M);
+int fsb_isect_scan_perm(int64_t M, const int32_t* counts, const int32_t* perm, int64_t* offsets, int64_t* total_dev,
+                        void* workspace, size_t workspace_bytes, void* stream);
 int fsb_isect_scan(int64_t M, const int32_t* counts, int64_t* offsets, int64_t* total_dev, void* workspace,
                    size_t workspace_bytes, void* stream);
 
@@ -143,6 +151,12 @@ size_t fsb_radix_sort_workspace(int64_t n, int end_bit);
 int fsb_radix_sort_pairs(int64_t n, const int64_t* n_dev, int end_bit, uint64_t* keys_a, int32_t* vals_a,
                          uint64_t* keys_b, int32_t* vals_b, void* workspace, size_t workspace_bytes,
                          int* result_in_b, void* stream);
+/* keys only, on key bits [begin_bit, end_bit); low32_out (nullable, i32[n]) = low word of each key at its sorted
+ * position, written by the last pass. */
+size_t fsb_radix_sort_keys_workspace(int64_t n, int begin_bit, int end_bit);
+int fsb_radix_sort_keys(int64_t n, const int64_t* n_dev, int begin_bit, int end_bit, uint64_t* keys_a,
+                        uint64_t* keys_b, int32_t* low32_out, void* workspace, size_t workspace_bytes,
+                        int* result_in_b, void* stream);
 
 /* I3: offsets[C, n_tiles] i32 = first sorted position of each (camera, tile).
  * replaces gsplat isect_offset_encode / legacy get_tile_bin_edges. */

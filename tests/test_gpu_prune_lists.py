@@ -136,3 +136,71 @@ def test_step_eager_and_captured_agree_with_unpruned():
     for k in runs["on"][0].gauss_params:
         assert_close(runs["on"][0].gauss_params[k].data, runs["off"][0].gauss_params[k].data,
                      f"prune.graph.param.{k}", tol=1e-5, outlier_frac=1e-4)
+
+
+@pytest.mark.parametrize("begin,end,n", [(32, 45, 300000), (32, 43, 5000), (0, 32, 70000), (32, 51, 40000), (5, 6, 1000)])
+def test_radix_sort_keys_window_is_a_stable_sort_on_those_bits(begin, end, n):
+    """fsb_radix_sort_keys against torch's stable sort of the extracted bit window; the low words ride along."""
+    from fusionsense_b200 import ops
+
+    g = torch.Generator().manual_seed(begin * 64 + end)
+    keys = torch.randint(0, 2**62, (n,), generator=g, dtype=torch.int64)
+    # few distinct high digits and long runs of equal ones, as tile ids have
+    keys[: n // 2] &= ~(((1 << (end - begin)) - 1) << begin) | (0x15 << begin)
+    keys = keys.to(DEV)
+    window = (keys >> begin) & ((1 << (end - begin)) - 1)
+    order = torch.sort(window, stable=True).indices
+    want = keys[order]
+    got, low = ops.radix_sort_keys(keys.clone(), begin, end)
+    assert torch.equal(got, want)
+    assert torch.equal(low.long() & 0xFFFFFFFF, want & 0xFFFFFFFF)
+    # static-capacity form: only the first *n_dev keys are sorted
+    m = n // 3
+    n_dev = torch.tensor([m], dtype=torch.int64, device=DEV)
+    got2, low2 = ops.radix_sort_keys(keys.clone(), begin, end, n_dev=n_dev)
+    order2 = torch.sort(window[:m], stable=True).indices
+    assert torch.equal(got2[:m], keys[:m][order2])
+    assert torch.equal(low2[:m].long() & 0xFFFFFFFF, keys[:m][order2] & 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("legacy", [False, 2])
+@pytest.mark.parametrize("C", [1, 3])
+@pytest.mark.parametrize("static", [False, True])
+def test_two_level_binning_gives_the_order_of_the_64_bit_key_sort(legacy, C, static, monkeypatch):
+    """Depth sort of the Gaussians + emission in that order + stable sort on the (camera, tile) bits == one stable sort
+    of the (camera | tile | depth bits) keys: same flatten ids (flags included), same keys, same tile ranges.  Half of
+    the Gaussians are exact duplicates of the other half so equal depths inside a tile are common and the tie rule
+    (emission order = Gaussian index) is exercised."""
+    from fusionsense_b200 import ops
+
+    W, H = 320, 240
+    sc = make_scene(6000, W, H, n_views=3, cfg_id=72, kind="bunny", fx=300.0).to(DEV)
+    dup = lambda t: torch.cat([t, t], dim=0).contiguous()
+    coeffs = dup(torch.cat((sc.features_dc[:, None, :], sc.features_rest), dim=1))
+    q = dup(sc.quats / sc.quats.norm(dim=-1, keepdim=True))
+    radii, m2, dep, con, _, _, tiles = ops.project_sh_fwd(
+        dup(sc.means), q, dup(torch.exp(sc.scales)), sc.viewmats[:C].contiguous(), sc.Ks[:C].contiguous(), W, H, 0.3,
+        0.01, 1e10, 0.0, 16, 3, coeffs, None, 4, 3, False)
+    opac = dup(torch.sigmoid(sc.opacities[:, 0]))[None].expand(C, -1).contiguous()
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+
+    def run(two_level):
+        monkeypatch.setattr(ops, "TWO_LEVEL_BINNING", two_level)
+        if not static:
+            _, ids, flat, offs = ops.isect_tiles(m2, radii, dep, 16, tw, th, legacy_bbox=legacy, reach=(con, opac))
+            return ids, flat, offs
+        overflow = torch.zeros(1, dtype=torch.int32, device=DEV)
+        with ops.static_capacity(400000, overflow):
+            _, ids, flat, offs = ops.isect_tiles(m2, radii, dep, 16, tw, th, legacy_bbox=legacy, reach=(con, opac))
+        n = int(flat.n_dev.item())
+        assert int(overflow.item()) == 0 and 0 < n < 400000
+        return ids[:n], flat[:n], offs
+
+    ids1, flat1, offs1 = run(False)
+    ids2, flat2, offs2 = run(True)
+    assert ids1.numel() > 20000
+    assert torch.equal(flat1, flat2)
+    assert torch.equal(ids1, ids2)
+    assert torch.equal(offs1, offs2)
+    # ties exist: the same (tile, depth) key on neighbouring entries
+    assert int((ids1[1:] == ids1[:-1]).sum()) > 1000
