@@ -129,6 +129,7 @@ struct Workspace {
     float4* geo;           // [n_isects]  x, y, log2(opacity), reach mask
     float4* con;           // [n_isects]  -0.5 log2e a, -log2e b, -0.5 log2e c, id bits
     float* col;            // [n_isects, DP]
+    float4* rec;           // [C * N, 2 + DP / 4]  per Gaussian: (x, y, opacity, 0), (a, b, c, 0), colours (prepack)
 };
 
 // a flagged tile takes two unit slots (group A state, group B state), hence 2 * n_tiles
@@ -137,7 +138,7 @@ inline int64_t max_units(int64_t n_isects, int64_t n_tiles, int D) {
 }
 
 template <bool CARVE>
-inline size_t ws_layout(void* base, int64_t n_isects, int64_t n_tiles, int D, Workspace* w) {
+inline size_t ws_layout(void* base, int64_t n_isects, int64_t n_tiles, int64_t n_gauss, int D, Workspace* w) {
     const int64_t mu = max_units(n_isects, n_tiles, D);
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -161,6 +162,7 @@ inline size_t ws_layout(void* base, int64_t n_isects, int64_t n_tiles, int D, Wo
     p = take((size_t)(n_isects + 1) * 16); if (CARVE) w->geo = (float4*)p;
     p = take((size_t)(n_isects + 1) * 16); if (CARVE) w->con = (float4*)p;
     p = take((size_t)(n_isects + 1) * color_stride(D) * 4); if (CARVE) w->col = (float*)p;
+    p = take((size_t)n_gauss * (32 + color_stride(D) * 4)); if (CARVE) w->rec = (float4*)p;
     return off;
 }
 
@@ -464,12 +466,39 @@ struct PackIn {
     const int32_t* flatten_ids;
 };
 
+// Per (camera, Gaussian): the fields the pack gathers, side by side in one 32 + 4 DP byte record.  The pack runs once
+// per LIST ENTRY (7 per visible Gaussian at 1080p) and was bound by L1 request slots — ten scattered requests over
+// five arrays per entry (r02i / r02k ncu: lg_throttle + long_scoreboard, 236 us for 82 M instructions); with the
+// record it issues 2 + DP / 4 16-byte requests into two or three adjacent sectors.
+template <int D, int DA>
+__global__ void __launch_bounds__(256)
+raster_prepack_kernel(int64_t n_gauss, PackIn in, float4* __restrict__ rec) {
+    constexpr int DP = color_stride(D), DB = D - DA, RS = 2 + DP / 4;
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_gauss) return;
+    const float2 xy = in.means2d[g];
+    float4* r = rec + g * RS;
+    r[0] = make_float4(xy.x, xy.y, in.opacities[g], 0.f);
+    r[1] = make_float4(in.conics[3 * g], in.conics[3 * g + 1], in.conics[3 * g + 2], 0.f);
+    float row[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) row[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DA; ++k) row[k] = in.colors_a[g * DA + k];
+    if constexpr (DB > 0) {
+#pragma unroll
+        for (int k = 0; k < DB; ++k) row[DA + k] = in.colors_b[g * DB + k];
+    }
+#pragma unroll
+    for (int k = 0; k < DP / 4; ++k) r[2 + k] = make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+}
+
 template <int D, int DA>
 __global__ void __launch_bounds__(256)
 raster_pack_kernel(int C, int64_t n_isects, const int64_t* __restrict__ n_dev, PackIn in,
                    const uint8_t* __restrict__ masks, int tile_size, int tile_w, int tile_h, int light_chunks,
                    const int32_t* __restrict__ tile_offsets, Workspace ws) {
-    constexpr int CH = chunk_len(D), DP = color_stride(D), DB = D - DA;
+    constexpr int CH = chunk_len(D), DP = color_stride(D), DB = D - DA, RS = 2 + DP / 4;
     n_isects = fsb_eff_n(n_isects, n_dev);
     if ((int)blockIdx.x >= ws.hdr->total_units) return;
     const int u = ws.unit_order[blockIdx.x];
@@ -484,33 +513,15 @@ raster_pack_kernel(int C, int64_t n_isects, const int64_t* __restrict__ n_dev, P
     for (int32_t e = eb + (int32_t)threadIdx.x; e < ee; e += 256) {
         const int32_t raw = in.flatten_ids[e];
         const int32_t g = raw & ~LEGACY_FLAG;
-        const float2 xy = in.means2d[g];
-        const float o = in.opacities[g];
-        const float a = in.conics[3 * (size_t)g], b = in.conics[3 * (size_t)g + 1], c = in.conics[3 * (size_t)g + 2];
-        const uint32_t m = reach_mask(xy.x, xy.y, o, a, b, c, tx0, ty0, tile_size);
-        ws.geo[e] = make_float4(xy.x, xy.y, __log2f(o), __int_as_float((int)m));
+        const float4* r = ws.rec + (size_t)g * RS;
+        const float4 r0 = r[0], r1 = r[1];
+        const float o = r0.z, a = r1.x, b = r1.y, c = r1.z;
+        const uint32_t m = reach_mask(r0.x, r0.y, o, a, b, c, tx0, ty0, tile_size);
+        ws.geo[e] = make_float4(r0.x, r0.y, __log2f(o), __int_as_float((int)m));
         ws.con[e] = make_float4(-0.5f * LOG2E * a, -LOG2E * b, -0.5f * LOG2E * c, __int_as_float(raw));
-        float row[DP];
-#pragma unroll
-        for (int k = 0; k < DP; ++k) row[k] = 0.f;
-        const float* ca = in.colors_a + (size_t)g * DA;
-        if constexpr (DA == 4) {
-            // one 16-byte request per lane instead of four scalar ones: the gather is bound by L1 request slots
-            // (r02i ncu: lg_throttle on top, 82 M instructions but 252 us), not by bytes
-            const float4 c4 = *reinterpret_cast<const float4*>(ca);
-            row[0] = c4.x; row[1] = c4.y; row[2] = c4.z; row[3] = c4.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < DA; ++k) row[k] = ca[k];
-        }
-        if constexpr (DB > 0) {
-            const float* cb = in.colors_b + (size_t)g * DB;
-#pragma unroll
-            for (int k = 0; k < DB; ++k) row[DA + k] = cb[k];
-        }
         float4* dst = reinterpret_cast<float4*>(ws.col + (size_t)e * DP);
 #pragma unroll
-        for (int k = 0; k < DP / 4; ++k) dst[k] = make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+        for (int k = 0; k < DP / 4; ++k) dst[k] = r[2 + k];
     }
 }
 
@@ -967,6 +978,39 @@ __device__ __forceinline__ int slot_of_lane(int lane) {
     return n >= 1 ? base : -1;
 }
 
+// The same reduce-scatter through shared memory: every lane stores its N values (row k = value k, 32 columns), then
+// lanes 2k and 2k + 1 each add 16 columns of row k and exchange the halves, so BOTH hold the warp total of value k
+// (lanes >= 2 N hold 0).  N stores + four 16-byte loads + 17 adds + one shuffle per lane, against 16 shuffles + 30
+// selects + 18 adds of the butterfly at N = 15 — the butterfly was 43 % of the two-pixel backward's instructions
+// (profiles/r02j_misc_cfg4_ncu_summary.txt).  Columns are XOR-swizzled in groups of four by (k & 3) so that the eight
+// lanes of a 16-byte load phase hit eight different bank groups; `red` = this warp's N x 32 floats.
+template <int N>
+__device__ __forceinline__ float warp_smem_sum(const float (&v)[N], int lane, float* __restrict__ red) {
+    static_assert(N <= 16, "two lanes per value");
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[k * 32 + (lane ^ ((k & 3) << 2))] = v[k];
+    __syncwarp();
+    const int k = lane >> 1;
+    float tot = 0.f;
+    if (k < N) {
+        const int at = k * 32 + ((lane & 1) << 4) + ((k & 3) << 2);
+        const float4 q0 = *reinterpret_cast<const float4*>(red + at);
+        const float4 q1 = *reinterpret_cast<const float4*>(red + (at ^ 4));
+        const float4 q2 = *reinterpret_cast<const float4*>(red + (at ^ 8));
+        const float4 q3 = *reinterpret_cast<const float4*>(red + (at ^ 12));
+        tot = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
+              (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
+    }
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    __syncwarp();  // the next entry's stores must not overtake these loads
+    return tot;
+}
+
+// dynamic shared memory of the backward kernels: the Stage, then n_warps x NV x 32 floats of reduction scratch
+template <int D>
+__host__ __device__ constexpr size_t bwd_red_offset() { return (sizeof(Stage<D>) + 127) / 128 * 128; }
+__host__ __device__ constexpr size_t bwd_red_bytes(int nv, int n_warps) { return (size_t)n_warps * nv * 32 * sizeof(float); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1094,7 +1138,10 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     constexpr int NG = 4 + 2 * XYMODE;             // conic a b c, opacity (, xy (, |xy|))
     constexpr int NV = kTranspose ? D + NG : NG;   // values reduced by the transposing butterfly
     constexpr int B = kTranspose ? D : 0;          // first geometric slot
-    const int slot = slot_of_lane<NV>(tg.lane);
+    // narrow colour vectors: reduce-scatter through shared memory (warp_smem_sum), lane 2 k owns value k
+    const int slot = kTranspose ? (((tg.lane & 1) == 0 && (tg.lane >> 1) < NV) ? (tg.lane >> 1) : -1)
+                                : slot_of_lane<NV>(tg.lane);
+    float* const red = reinterpret_cast<float*>(smem_raw + bwd_red_offset<D>()) + tg.warp * (NV * 32);
     float* slot_base = nullptr;
     int slot_stride = 0;
     if (slot >= 0) {
@@ -1196,7 +1243,7 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
                     if (tg.lane == 0) atomicAdd(out.v_colors_a + (size_t)g * D + k, tot);
                 }
             }
-            float total = warp_transpose_sum(v, tg.lane);
+            float total = kTranspose ? warp_smem_sum(v, tg.lane, red) : warp_transpose_sum(v, tg.lane);
             if (opac_slot) total *= fast_ex2(-sgeo[t].z);  // 1 / opacity
             if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
         }
@@ -1224,14 +1271,16 @@ __device__ __forceinline__ int fwd_thread_of(int ti, int tj, int warps_x) {
     return ((wy * warps_x + wx) << 5) | (q << 3) | s_;
 }
 
-template <int D, int DA, int XYMODE>
+// SMEM_RED: warp_smem_sum instead of the butterfly; its scratch follows the Stage in dynamic shared memory.
+template <int D, int DA, int XYMODE, bool SMEM_RED>
 __global__ void __launch_bounds__(MAX_BLOCK / 2)
 raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     constexpr int CH = chunk_len(D), DP = color_stride(D), DB = D - DA;
     constexpr bool SPLIT = (DB > 0);
-    static_assert(D <= 8, "two-pixel backward: transposing butterfly only");
+    static_assert(D <= 8, "two-pixel backward: reduce-scatter forms only");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage<D>& s = *reinterpret_cast<Stage<D>*>(smem_raw);
+    float* const red_all = reinterpret_cast<float*>(smem_raw + bwd_red_offset<D>());
     __shared__ int32_t s_wmax[MAX_BLOCK / 64];
     const int64_t n_isects = fsb_eff_n(a.n_isects, a.n_dev);
     if ((int)blockIdx.x >= ws.hdr->total_units) return;
@@ -1348,7 +1397,9 @@ raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     constexpr int NG = 4 + 2 * XYMODE;
     constexpr int NV = D + NG;
     constexpr int B = D;
-    const int slot = slot_of_lane<NV>(lane);
+    // value index whose warp total this lane adds to global memory (-1: none)
+    const int slot = SMEM_RED ? (((lane & 1) == 0 && (lane >> 1) < NV) ? (lane >> 1) : -1) : slot_of_lane<NV>(lane);
+    float* const red = red_all + warp * (NV * 32);
     float* slot_base = nullptr;
     int slot_stride = 0;
     if (slot >= 0) {
@@ -1447,7 +1498,7 @@ raster_bwd2_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
                 }
             }
             const int32_t g = __float_as_int(con.w) & ~LEGACY_FLAG;
-            float total = warp_transpose_sum(v, lane);
+            float total = SMEM_RED ? warp_smem_sum(v, lane, red) : warp_transpose_sum(v, lane);
             if (opac_slot) total *= fast_ex2(-geo.z);  // 1 / opacity
             if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
         }
@@ -1476,7 +1527,7 @@ int launch_fwd(const FwdCall& f, cudaStream_t st) {
     const RasterArgs& a = f.a;
     const int64_t n_tiles = (int64_t)a.C * a.tile_w * a.tile_h;
     Workspace ws;
-    ws_layout<true>(f.workspace, a.n_isects, n_tiles, D, &ws);
+    ws_layout<true>(f.workspace, a.n_isects, n_tiles, (int64_t)a.C * a.N, D, &ws);
     constexpr bool SPLIT = (DA < D);
     if (SPLIT) {
         FSB_CUDA(cudaMemsetAsync(ws.tile_flag, 0, (size_t)n_tiles, st));
@@ -1493,6 +1544,9 @@ int launch_fwd(const FwdCall& f, cudaStream_t st) {
     FSB_LAUNCH_CHECK();
     const unsigned grid_units = (unsigned)max_units(a.n_isects, n_tiles, D);
     if (a.n_isects > 0) {
+        const int64_t n_gauss = (int64_t)a.C * a.N;
+        raster_prepack_kernel<D, DA><<<fsb_div_up(n_gauss, 256), 256, 0, st>>>(n_gauss, f.pack, ws.rec);
+        FSB_LAUNCH_CHECK();
         raster_pack_kernel<D, DA><<<grid_units, 256, 0, st>>>(a.C, a.n_isects, a.n_dev, f.pack, a.masks, a.tile_size,
                                                              a.tile_w, a.tile_h, a.light_chunks, a.tile_offsets, ws);
         FSB_LAUNCH_CHECK();
@@ -1536,7 +1590,7 @@ int launch_bwd(const BwdCall& f, cudaStream_t st) {
     const RasterArgs& a = f.a;
     const int64_t n_tiles = (int64_t)a.C * a.tile_w * a.tile_h;
     Workspace ws;
-    ws_layout<true>(f.workspace, a.n_isects, n_tiles, D, &ws);
+    ws_layout<true>(f.workspace, a.n_isects, n_tiles, (int64_t)a.C * a.N, D, &ws);
     dim3 block(a.tile_size, a.tile_size);
     const unsigned grid = (unsigned)max_units(a.n_isects, n_tiles, D);
     const size_t smem = sizeof(Stage<D>);
@@ -1546,20 +1600,30 @@ int launch_bwd(const BwdCall& f, cudaStream_t st) {
     // 0.23 ms.  FSB_RASTER_BWD_PX=1 / 2 forces a kernel (A/B runs).
     static const int forced_px = [] { const char* e = getenv("FSB_RASTER_BWD_PX"); return e ? atoi(e) : 0; }();
     const bool one_px = forced_px == 1 || (forced_px != 2 && n_tiles < 4 * FSB_NUM_SMS * 4);
+    // FSB_RASTER_BWD_REDUCE=shfl: the butterfly instead of the shared-memory reduce-scatter (A/B runs)
+    static const bool smem_red = [] { const char* e = getenv("FSB_RASTER_BWD_REDUCE"); return !(e && e[0] == 's' && e[1] == 'h'); }();
     dim3 block2(a.tile_size, a.tile_size / 2);
 #define FSB_BWD_LAUNCH(MODE)                                                   \
     do {                                                                       \
         if constexpr (D <= 8) {                                                \
+            if (!one_px && smem_red) {                                         \
+                auto k2 = raster_bwd2_kernel<D, DA, MODE, true>;               \
+                const size_t sm2 = bwd_red_offset<D>() + bwd_red_bytes(D + 4 + 2 * MODE, MAX_BLOCK / 64); \
+                int e2 = set_smem(k2, sm2); if (e2) return e2;                 \
+                k2<<<grid, block2, sm2, st>>>(a, ws, f.in, f.out);             \
+                break;                                                         \
+            }                                                                  \
             if (!one_px) {                                                     \
-                auto k2 = raster_bwd2_kernel<D, DA, MODE>;                     \
+                auto k2 = raster_bwd2_kernel<D, DA, MODE, false>;              \
                 int e2 = set_smem(k2, smem); if (e2) return e2;                \
                 k2<<<grid, block2, smem, st>>>(a, ws, f.in, f.out);            \
                 break;                                                         \
             }                                                                  \
         }                                                                      \
         auto k = raster_bwd_kernel<D, DA, MODE>;                               \
-        int e = set_smem(k, smem); if (e) return e;                            \
-        k<<<grid, block, smem, st>>>(a, ws, f.in, f.out);                      \
+        const size_t sm1 = D <= 8 ? bwd_red_offset<D>() + bwd_red_bytes(D + 4 + 2 * MODE, MAX_BLOCK / 32) : smem; \
+        int e = set_smem(k, sm1); if (e) return e;                             \
+        k<<<grid, block, sm1, st>>>(a, ws, f.in, f.out);                       \
     } while (0)
     if (f.out.v_means2d_abs) FSB_BWD_LAUNCH(2);
     else if (f.out.v_means2d) FSB_BWD_LAUNCH(1);
@@ -1660,12 +1724,12 @@ FSB_API int fsb_raster_supported_channels(int D) {
 
 // bytes of the per-call workspace: unit table, the per-(unit, pixel) state that the forward leaves for the backward and
 // the packed list records (n_tiles = C * tile_w * tile_h).  DB = 0: one colour set.
-FSB_API size_t fsb_raster_dn_workspace(int64_t n_isects, int64_t n_tiles, int DA, int DB) {
+FSB_API size_t fsb_raster_dn_workspace(int64_t n_isects, int64_t n_tiles, int64_t n_gauss, int DA, int DB) {
     if (n_isects < 0 || n_tiles <= 0 || DA <= 0 || DB < 0) return 0;
-    return ws_layout<false>(nullptr, n_isects, n_tiles, DA + DB, nullptr);
+    return ws_layout<false>(nullptr, n_isects, n_tiles, n_gauss, DA + DB, nullptr);
 }
-FSB_API size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D) {
-    return fsb_raster_dn_workspace(n_isects, n_tiles, D, 0);
+FSB_API size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int64_t n_gauss, int D) {
+    return fsb_raster_dn_workspace(n_isects, n_tiles, n_gauss, D, 0);
 }
 
 // Forward with two colour sets composited by one walk (see the file header).  DB = 0 (colors_b, backgrounds_b, out_b
@@ -1681,7 +1745,7 @@ FSB_API int fsb_raster_dn_fwd(int C, int N, int DA, int DB, int64_t n_isects, co
     if (bad_geometry(C, tile_size, n_isects)) return FSB_E_ARG;
     if (DB < 0 || (DB > 0 && (!colors_b || !out_b)) || ed_channel >= DA) return FSB_E_ARG;
     if (tile_w <= 0 || tile_h <= 0) return 0;
-    if (!workspace || workspace_bytes < fsb_raster_dn_workspace(n_isects, (int64_t)C * tile_w * tile_h, DA, DB))
+    if (!workspace || workspace_bytes < fsb_raster_dn_workspace(n_isects, (int64_t)C * tile_w * tile_h, (int64_t)C * N, DA, DB))
         return FSB_E_ARG;
     FwdCall f;
     f.a = RasterArgs{C, N, n_isects, n_isects_dev, masks, width, height, tile_size, tile_w, tile_h, tile_offsets,
@@ -1709,7 +1773,7 @@ FSB_API int fsb_raster_dn_bwd(int C, int N, int DA, int DB, int64_t n_isects, co
     if (v_means2d_abs && !v_means2d) return FSB_E_ARG;
     if (DB < 0 || (DB > 0 && (!v_render_b || !v_colors_b)) || ed_channel >= DA) return FSB_E_ARG;
     if (tile_w <= 0 || tile_h <= 0 || n_isects == 0) return 0;
-    if (!workspace || workspace_bytes < fsb_raster_dn_workspace(n_isects, (int64_t)C * tile_w * tile_h, DA, DB))
+    if (!workspace || workspace_bytes < fsb_raster_dn_workspace(n_isects, (int64_t)C * tile_w * tile_h, (int64_t)C * N, DA, DB))
         return FSB_E_ARG;
     BwdCall f;
     f.a = RasterArgs{C, N, n_isects, n_isects_dev, masks, width, height, tile_size, tile_w, tile_h, tile_offsets,

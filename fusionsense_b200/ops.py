@@ -455,7 +455,7 @@ def raster_dn_fwd(means2d, conics, colors_a, colors_b, opacities, backgrounds_a,
     out_b = torch.empty((C, height, width, DB), dtype=torch.float32, device=dev)
     alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
     last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
-    ws_bytes = lib.fsb_raster_dn_workspace(flatten_ids.numel(), C * tile_h * tile_w, DA, DB)
+    ws_bytes = lib.fsb_raster_dn_workspace(flatten_ids.numel(), C * tile_h * tile_w, C * N, DA, DB)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     ev = kernel_timer.start(f"raster_fwd_D{DA}+{DB}")
     check(lib.fsb_raster_dn_fwd(C, N, DA, DB, flatten_ids.numel(), ptr(n_dev), ptr(means2d), ptr(conics), ptr(colors_a),
@@ -508,7 +508,7 @@ def raster_fwd(means2d, conics, colors, opacities, backgrounds, masks, width, he
     out = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
     alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
     last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
-    ws_bytes = lib.fsb_raster_workspace(flatten_ids.numel(), C * tile_h * tile_w, D)
+    ws_bytes = lib.fsb_raster_workspace(flatten_ids.numel(), C * tile_h * tile_w, C * N, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     ev = kernel_timer.start(f"raster_fwd_D{D}")
     check(lib.fsb_raster_fwd(C, N, D, flatten_ids.numel(), ptr(n_dev), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),

@@ -183,7 +183,7 @@ int fsb_isect_share_copy(const int64_t* gate, const int64_t* n_list, int64_t cap
  * copies; it also leaves the per-unit state there that the backward consumes (csrc/raster.cu).
  * D must be one of fsb_raster_supported_channels(); tile_size 8 or 16. */
 int fsb_raster_supported_channels(int D);
-size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int D);
+size_t fsb_raster_workspace(int64_t n_isects, int64_t n_tiles, int64_t n_gauss, int D);  /* n_gauss = C*N */
 int fsb_raster_fwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isects_dev, const float* means2d, const float* conics,
                    const float* colors, const float* opacities, const float* backgrounds, const uint8_t* masks,
                    int width, int height, int tile_size, int tile_w, int tile_h, const int32_t* tile_offsets,
@@ -212,7 +212,7 @@ int fsb_raster_bwd(int C, int N, int D, int64_t n_isects, const int64_t* n_isect
  *   ed_channel: channel of set A divided by max(alpha, 1e-10) on output (-1: none).
  *   backward: the 2-D mean gradients take set A's dL/dalpha only (dn_model.py:638 detaches the means of the legacy
  *   pass); conics / opacities receive both.  Gradient outputs are ACCUMULATED; the caller zero-fills them. */
-size_t fsb_raster_dn_workspace(int64_t n_isects, int64_t n_tiles, int DA, int DB);
+size_t fsb_raster_dn_workspace(int64_t n_isects, int64_t n_tiles, int64_t n_gauss, int DA, int DB);
 int fsb_raster_dn_fwd(int C, int N, int DA, int DB, int64_t n_isects, const int64_t* n_isects_dev,
                       const float* means2d, const float* conics, const float* colors_a, const float* colors_b,
                       const float* opacities, const float* backgrounds_a, const float* backgrounds_b,

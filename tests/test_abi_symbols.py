@@ -36,7 +36,7 @@ def test_pure_host_entry_points_answer_without_a_gpu():
     assert lib.fsb_adam_max_tensors() == 8 and lib.fsb_vh_max_views() >= 9
     # argument validation happens before any CUDA call
     assert lib.fsb_radix_sort_pairs(-1, None, 44, None, None, None, None, None, 0, None, None) == 10001
-    ws = lib.fsb_raster_workspace(0, 1, 8)
+    ws = lib.fsb_raster_workspace(0, 1, 0, 8)
     assert ws > 0
     assert lib.fsb_raster_fwd(1, 1, 7, 0, None, None, None, None, None, None, None, 16, 16, 16, 1, 1, None, None, 0, 1, ws,
                               None, None, None, None) == 10001  # D = 7 is not an instantiated channel count

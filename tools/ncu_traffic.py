@@ -2,7 +2,7 @@
 per launch DRAM traffic, pipe utilisation, occupancy, stall reasons.  Writes profiles/raster_bwd_traffic.json
 (read by bench.py for `roofline.traffic`) and prints a short table for profiles/.
 
-  python tools/ncu_traffic.py gpurun_out/r01f_ncu_full_raster_bwd.csv [kernel-substring] [out.json]
+  python tools/ncu_traffic.py gpurun_out/r01f_ncu_full_raster_bwd.csv [kernel-substring] [out.json] [workload] [command]
 """
 import csv
 import json
@@ -45,7 +45,7 @@ def to_bytes(v, unit):
     return v
 
 
-def main(path, needle="raster_bwd_kernel<4", out=None):
+def main(path, needle="raster_bwd_kernel<4", out=None, workload="cfg2", command="bench.py --mode eager"):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rd = csv.reader(lines)
@@ -75,7 +75,7 @@ def main(path, needle="raster_bwd_kernel<4", out=None):
             "dram_bytes_read": d.get("dram__bytes_read.sum"),
             "dram_bytes_write": d.get("dram__bytes_write.sum"),
             "ncu_duration_us": d.get("gpu__time_duration.sum"),
-            "source": f"ncu --set full --clock-control none, launch id {d['id']} of `bench.py --mode eager` on cfg2 ({path.split('/')[-1]})",
+            "source": f"ncu --set full --clock-control none, launch id {d['id']} of `{command}` on {workload} ({path.split('/')[-1]})",
         }
         with open(out, "w") as f:
             json.dump(rec, f, indent=1)

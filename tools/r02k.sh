@@ -8,10 +8,11 @@ for tl in 1 0; do
 FSB_TWO_LEVEL_BINNING=$tl timeout 300 python tools/stage_bench.py cfg4 10 > $OUT/${TAG}_stage_cfg4_tl$tl.json 2> $OUT/${TAG}_stage_cfg4_tl$tl.err; cat $OUT/${TAG}_stage_cfg4_tl$tl.json; tail -2 $OUT/${TAG}_stage_cfg4_tl$tl.err
 FSB_TWO_LEVEL_BINNING=$tl timeout 300 python tools/stage_bench.py cfg2 20 > $OUT/${TAG}_stage_cfg2_tl$tl.json 2> $OUT/${TAG}_stage_cfg2_tl$tl.err; cat $OUT/${TAG}_stage_cfg2_tl$tl.json
 done
+FSB_RASTER_BWD_REDUCE=shfl timeout 300 python tools/stage_bench.py cfg4 10 > $OUT/${TAG}_stage_cfg4_shfl.json 2> $OUT/${TAG}_stage_cfg4_shfl.err; cat $OUT/${TAG}_stage_cfg4_shfl.json; tail -2 $OUT/${TAG}_stage_cfg4_shfl.err
 echo "t=${SECONDS}s"
 timeout 900 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err; head -c 400 $OUT/${TAG}_bench_default.json; echo; tail -3 $OUT/${TAG}_bench_default.err | cut -c1-300
 echo "t=${SECONDS}s"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'onesweep|radix_hist|isect_reach|scan_|isect_offsets|raster_pack|unit_table|tile_flag' --launch-skip 80 -c 24 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'onesweep|radix_hist|isect_reach|scan_|isect_offsets|raster_pack|unit_table|tile_flag|raster_bwd2' --launch-skip 90 -c 27 \
    -o $OUT/${TAG}_binning_cfg4 -f python tools/stage_bench.py cfg4 2 > $OUT/${TAG}_ncu.log 2>&1
 tail -3 $OUT/${TAG}_ncu.log | cut -c1-300
 echo "elapsed ${SECONDS}s"
