@@ -642,10 +642,16 @@ def _roofline(cfg_name, model, params, ktimes, pairs, clocks):
     N, K, C = c["n"], 16, 1
     tiles = ((c["w"] + 15) // 16) * ((c["h"] + 15) // 16)
     key_bytes = -(-(32 + max(1, (tiles - 1).bit_length())) // 8)
+    from fusionsense_b200 import ops as _ops
+
+    two_level = bool(model.config.prune_lists) and _ops.TWO_LEVEL_BINNING
+    # two-level binning: C N (key 8 B + value 4 B) pairs sorted on 32 depth bits (histogram read + 4 passes of read +
+    # write), then the I 8-byte entries on the tile bits (histogram read + 2 passes + the 4-byte flatten ids)
+    sort_bytes = (C * N * (8 + 4 * 24) + I * (8 + 2 * 16 + 4)) if two_level else (I * 8 + I * 24 * key_bytes)
     stage_bytes = {
         "project_sh_fwd": C * N * 68 + Nv * (12 * K + 12),
         "project_sh_bwd": C * N * 4 + Nv * (76 + 12 * K) + N * (40 + 12 * K),
-        "radix_sort": I * 8 + I * 24 * key_bytes,
+        "radix_sort": sort_bytes,
         "adam_multi": sum(p.numel() for p in params) * 28,
         "raster_fwd_D4": I * (28 + 16) + P * (16 + 8), "raster_fwd_D3": I * (28 + 12) + P * (12 + 8),
         "raster_bwd_D4": I * (28 + 16) + P * (16 + 12) + Nv * (32 + 16),
@@ -662,7 +668,8 @@ def _roofline(cfg_name, model, params, ktimes, pairs, clocks):
                             "bound": "fp32" if name.startswith("raster") else "hbm"}
     fwd_ms = ktimes.get(f"raster_fwd_{key}", (0, 0))[0]
     return {
-        "kernel": ("raster_bwd_kernel<7,4,2> (RGB + expected depth + normals in one walk)" if fused
+        "kernel": (("raster_bwd2_kernel<7,4,2> (two pixels per lane; " if tiles * C >= 4 * 148 * 4 else
+                    "raster_bwd_kernel<7,4,2> (") + "RGB + expected depth + normals in one walk)" if fused
                    else "raster_bwd_kernel<4,4,2> (RGB+ED pass)"), "bound": "hbm", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
         "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "kernel_ms": bwd_ms,

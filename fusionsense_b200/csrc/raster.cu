@@ -307,36 +307,32 @@ unit_table_kernel(int n_tiles, int64_t n_isects, const int64_t* __restrict__ n_d
         return (int)(r.e - r.b);
     };
     auto flagged = [&](int t) { return split && ws.tile_flag[t] != 0; };
-    for (int base = 0; base < n_tiles; base += 1024) {
-        const int t = base + tid;
-        int nu = 0;
-        bool heavy = false;
-        if (t < n_tiles) {
-            const UnitShape s = unit_shape(tile_len(t), CH, flagged(t), light_chunks);
-            nu = s.n_units;
-            heavy = !s.light;
-        }
-        int inc = nu;
+    // every thread takes TPT consecutive tiles: its loads are issued together, and the whole table needs one block scan
+    // (a 1024-tile stripe per iteration was 8 dependent rounds of global loads + three barriers each at 1080p: this
+    // single-CTA kernel sits on the forward's critical path, r02k: 44 us)
+    const int TPT = (n_tiles + 1023) / 1024;
+    const int t0 = tid * TPT, t1 = min(n_tiles, t0 + TPT);
+    int nu_sum = 0;
+    for (int t = t0; t < t1; ++t) nu_sum += unit_shape(tile_len(t), CH, flagged(t), light_chunks).n_units;
+    int inc = nu_sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += s_warp[w];
-        const int carry = s_carry;
-        const int excl = carry + wbase + inc - nu;
-        if (t < n_tiles) {
-            ws.unit_start[t] = excl;
-            for (int k = 0; k < nu; ++k) ws.unit_tile[excl + k] = t;
-            if (heavy) ws.heavy_tiles[atomicAdd(&s_heavy, 1)] = t;
-        }
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + wbase + inc;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
     }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int excl = inc - nu_sum;
+    for (int w = 0; w < warp; ++w) excl += s_warp[w];
+    if (tid == 1023) s_carry = excl + nu_sum;
+    for (int t = t0; t < t1; ++t) {
+        const UnitShape sh = unit_shape(tile_len(t), CH, flagged(t), light_chunks);
+        ws.unit_start[t] = excl;
+        for (int k = 0; k < sh.n_units; ++k) ws.unit_tile[excl + k] = t;
+        if (!sh.light) ws.heavy_tiles[atomicAdd(&s_heavy, 1)] = t;
+        excl += sh.n_units;
+    }
+    __syncthreads();
     const int total = s_carry;
     if (tid == 0) {
         ws.unit_start[n_tiles] = total;
@@ -493,7 +489,8 @@ raster_prepack_kernel(int64_t n_gauss, PackIn in, float4* __restrict__ rec) {
     for (int k = 0; k < DP / 4; ++k) r[2 + k] = make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
 }
 
-template <int D, int DA>
+// REC: gather from the prepack records (lists with several entries per Gaussian), else from the five arrays.
+template <int D, int DA, bool REC>
 __global__ void __launch_bounds__(256)
 raster_pack_kernel(int C, int64_t n_isects, const int64_t* __restrict__ n_dev, PackIn in,
                    const uint8_t* __restrict__ masks, int tile_size, int tile_w, int tile_h, int light_chunks,
@@ -513,15 +510,40 @@ raster_pack_kernel(int C, int64_t n_isects, const int64_t* __restrict__ n_dev, P
     for (int32_t e = eb + (int32_t)threadIdx.x; e < ee; e += 256) {
         const int32_t raw = in.flatten_ids[e];
         const int32_t g = raw & ~LEGACY_FLAG;
-        const float4* r = ws.rec + (size_t)g * RS;
-        const float4 r0 = r[0], r1 = r[1];
-        const float o = r0.z, a = r1.x, b = r1.y, c = r1.z;
-        const uint32_t m = reach_mask(r0.x, r0.y, o, a, b, c, tx0, ty0, tile_size);
-        ws.geo[e] = make_float4(r0.x, r0.y, __log2f(o), __int_as_float((int)m));
-        ws.con[e] = make_float4(-0.5f * LOG2E * a, -LOG2E * b, -0.5f * LOG2E * c, __int_as_float(raw));
         float4* dst = reinterpret_cast<float4*>(ws.col + (size_t)e * DP);
+        float x, y, o, a, b, c;
+        if constexpr (REC) {
+            const float4* r = ws.rec + (size_t)g * RS;
+            const float4 r0 = r[0], r1 = r[1];
+            x = r0.x; y = r0.y; o = r0.z; a = r1.x; b = r1.y; c = r1.z;
 #pragma unroll
-        for (int k = 0; k < DP / 4; ++k) dst[k] = r[2 + k];
+            for (int k = 0; k < DP / 4; ++k) dst[k] = r[2 + k];
+        } else {
+            const float2 xy = in.means2d[g];
+            x = xy.x; y = xy.y; o = in.opacities[g];
+            a = in.conics[3 * (size_t)g]; b = in.conics[3 * (size_t)g + 1]; c = in.conics[3 * (size_t)g + 2];
+            float row[DP];
+#pragma unroll
+            for (int k = 0; k < DP; ++k) row[k] = 0.f;
+            const float* ca = in.colors_a + (size_t)g * DA;
+            if constexpr (DA == 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(ca);
+                row[0] = c4.x; row[1] = c4.y; row[2] = c4.z; row[3] = c4.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < DA; ++k) row[k] = ca[k];
+            }
+            if constexpr (DB > 0) {
+                const float* cb = in.colors_b + (size_t)g * DB;
+#pragma unroll
+                for (int k = 0; k < DB; ++k) row[DA + k] = cb[k];
+            }
+#pragma unroll
+            for (int k = 0; k < DP / 4; ++k) dst[k] = make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+        }
+        const uint32_t m = reach_mask(x, y, o, a, b, c, tx0, ty0, tile_size);
+        ws.geo[e] = make_float4(x, y, __log2f(o), __int_as_float((int)m));
+        ws.con[e] = make_float4(-0.5f * LOG2E * a, -LOG2E * b, -0.5f * LOG2E * c, __int_as_float(raw));
     }
 }
 
@@ -1138,10 +1160,9 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
     constexpr int NG = 4 + 2 * XYMODE;             // conic a b c, opacity (, xy (, |xy|))
     constexpr int NV = kTranspose ? D + NG : NG;   // values reduced by the transposing butterfly
     constexpr int B = kTranspose ? D : 0;          // first geometric slot
-    // narrow colour vectors: reduce-scatter through shared memory (warp_smem_sum), lane 2 k owns value k
-    const int slot = kTranspose ? (((tg.lane & 1) == 0 && (tg.lane >> 1) < NV) ? (tg.lane >> 1) : -1)
-                                : slot_of_lane<NV>(tg.lane);
-    float* const red = reinterpret_cast<float*>(smem_raw + bwd_red_offset<D>()) + tg.warp * (NV * 32);
+    // (the shared-memory reduce-scatter of the two-pixel kernel loses here: 0.216 against 0.198 ms at cfg2, r02l — half
+    // the values per visit are live and eight warps' scratch costs occupancy)
+    const int slot = slot_of_lane<NV>(tg.lane);
     float* slot_base = nullptr;
     int slot_stride = 0;
     if (slot >= 0) {
@@ -1243,7 +1264,7 @@ raster_bwd_kernel(RasterArgs a, Workspace ws, BwdIn in, BwdOut out) {
                     if (tg.lane == 0) atomicAdd(out.v_colors_a + (size_t)g * D + k, tot);
                 }
             }
-            float total = kTranspose ? warp_smem_sum(v, tg.lane, red) : warp_transpose_sum(v, tg.lane);
+            float total = warp_transpose_sum(v, tg.lane);
             if (opac_slot) total *= fast_ex2(-sgeo[t].z);  // 1 / opacity
             if (slot_base != nullptr && total != 0.f) atomicAdd(slot_base + (size_t)g * slot_stride, total);
         }
@@ -1544,11 +1565,21 @@ int launch_fwd(const FwdCall& f, cudaStream_t st) {
     FSB_LAUNCH_CHECK();
     const unsigned grid_units = (unsigned)max_units(a.n_isects, n_tiles, D);
     if (a.n_isects > 0) {
+        // records pay when a Gaussian has several list entries (7 at 1080p / 1M: pack 236 -> 164 + 23 us); with about
+        // one entry per Gaussian (cfg2's object scene) the extra pass only costs.  In static-capacity mode n_isects is
+        // the capacity, ~1.4 x the count.
         const int64_t n_gauss = (int64_t)a.C * a.N;
-        raster_prepack_kernel<D, DA><<<fsb_div_up(n_gauss, 256), 256, 0, st>>>(n_gauss, f.pack, ws.rec);
-        FSB_LAUNCH_CHECK();
-        raster_pack_kernel<D, DA><<<grid_units, 256, 0, st>>>(a.C, a.n_isects, a.n_dev, f.pack, a.masks, a.tile_size,
-                                                             a.tile_w, a.tile_h, a.light_chunks, a.tile_offsets, ws);
+        if (a.n_isects >= 3 * n_gauss) {
+            raster_prepack_kernel<D, DA><<<fsb_div_up(n_gauss, 256), 256, 0, st>>>(n_gauss, f.pack, ws.rec);
+            FSB_LAUNCH_CHECK();
+            raster_pack_kernel<D, DA, true><<<grid_units, 256, 0, st>>>(a.C, a.n_isects, a.n_dev, f.pack, a.masks,
+                                                                       a.tile_size, a.tile_w, a.tile_h, a.light_chunks,
+                                                                       a.tile_offsets, ws);
+        } else {
+            raster_pack_kernel<D, DA, false><<<grid_units, 256, 0, st>>>(a.C, a.n_isects, a.n_dev, f.pack, a.masks,
+                                                                        a.tile_size, a.tile_w, a.tile_h, a.light_chunks,
+                                                                        a.tile_offsets, ws);
+        }
         FSB_LAUNCH_CHECK();
     }
     dim3 block(a.tile_size, a.tile_size);
@@ -1621,9 +1652,8 @@ int launch_bwd(const BwdCall& f, cudaStream_t st) {
             }                                                                  \
         }                                                                      \
         auto k = raster_bwd_kernel<D, DA, MODE>;                               \
-        const size_t sm1 = D <= 8 ? bwd_red_offset<D>() + bwd_red_bytes(D + 4 + 2 * MODE, MAX_BLOCK / 32) : smem; \
-        int e = set_smem(k, sm1); if (e) return e;                             \
-        k<<<grid, block, sm1, st>>>(a, ws, f.in, f.out);                       \
+        int e = set_smem(k, smem); if (e) return e;                            \
+        k<<<grid, block, smem, st>>>(a, ws, f.in, f.out);                      \
     } while (0)
     if (f.out.v_means2d_abs) FSB_BWD_LAUNCH(2);
     else if (f.out.v_means2d) FSB_BWD_LAUNCH(1);
