@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(L_THREADS)
 dn_loss_fwd_kernel(LossArgs a, double* __restrict__ sums, unsigned* __restrict__ ticket, float* __restrict__ loss) {
     __shared__ float red[S_COUNT][L_THREADS / 32];
     const int64_t P = (int64_t)a.H * a.W;
-    const int64_t p = (int64_t)blockIdx.x * L_THREADS + threadIdx.x;
     float s[S_COUNT];
 #pragma unroll
     for (int k = 0; k < S_COUNT; ++k) s[k] = 0.f;
-    if (p < P) {
+    // grid-stride: a CTA per 256 pixels made 8100 CTAs x 10 fp64 atomics on the same ten addresses at 1080p
+    for (int64_t p = (int64_t)blockIdx.x * L_THREADS + threadIdx.x; p < P; p += (int64_t)gridDim.x * L_THREADS) {
         const int i = (int)(p / a.W), j = (int)(p - (int64_t)i * a.W);
         const bool hx = j < a.W - 1, hy = i < a.H - 1;
         const float d = a.depth[p];
@@ -56,13 +56,13 @@ dn_loss_fwd_kernel(LossArgs a, double* __restrict__ sums, unsigned* __restrict__
             const float g = a.sensor[p];
             if (g > a.depth_tol) {
                 const float ll = logf(1.f + fabsf(d - g));
-                if (hx) { s[S_EAX] = edge_weight(a.edge_rgb, p, p + 1, a.rgb_clamp_min) * ll; s[S_CNTX] = 1.f; }
-                if (hy) { s[S_EAY] = edge_weight(a.edge_rgb, p, p + a.W, a.rgb_clamp_min) * ll; s[S_CNTY] = 1.f; }
+                if (hx) { s[S_EAX] += edge_weight(a.edge_rgb, p, p + 1, a.rgb_clamp_min) * ll; s[S_CNTX] += 1.f; }
+                if (hy) { s[S_EAY] += edge_weight(a.edge_rgb, p, p + a.W, a.rgb_clamp_min) * ll; s[S_CNTY] += 1.f; }
             }
         }
         if (a.l_smooth != 0.f) {
-            if (hx) s[S_TVX] = fabsf(d - a.depth[p + 1]);
-            if (hy) s[S_TVY] = fabsf(d - a.depth[p + a.W]);
+            if (hx) s[S_TVX] += fabsf(d - a.depth[p + 1]);
+            if (hy) s[S_TVY] += fabsf(d - a.depth[p + a.W]);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -203,7 +203,9 @@ FSB_API int fsb_dn_loss_fwd(int H, int W, const float* depth, const float* senso
     FSB_CUDA(cudaMemsetAsync(workspace, 0, fsb_dn_loss_workspace(), st));
     double* sums = (double*)workspace;
     unsigned* ticket = (unsigned*)(sums + 12);
-    dn_loss_fwd_kernel<<<fsb_div_up((int64_t)H * W, L_THREADS), L_THREADS, 0, st>>>(a, sums, ticket, loss_out);
+    int blocks = fsb_div_up((int64_t)H * W, L_THREADS);
+    if (blocks > FSB_NUM_SMS * 8) blocks = FSB_NUM_SMS * 8;
+    dn_loss_fwd_kernel<<<blocks, L_THREADS, 0, st>>>(a, sums, ticket, loss_out);
     FSB_LAUNCH_CHECK();
     return 0;
 }

@@ -263,6 +263,10 @@ int fsb_xchg_pack(int n_tensors, const float* const* src, const int64_t* n, cons
                   int64_t total, void* stream);
 int fsb_xchg_reduce_scatter(int world, int rank, const float* const* grads, const float* grads_mc, int64_t S,
                             float* out, void* stream);
+/* in-place all-reduce of the flat gradient buffers: this rank reduces slice [rank S, (rank+1) S) and writes the sum
+ * into every rank's buffer (NVSwitch multimem.ld_reduce + multimem.st when grads_mc is given, else peer loads and
+ * stores).  Between two fsb_xchg_barrier's; afterwards the optimizer reads its own buffer. */
+int fsb_xchg_allreduce(int world, int rank, float* const* grads, float* grads_mc, int64_t S, void* stream);
 int fsb_adam_multi_xchg(int n_tensors, float* const* p, float* const* m, float* const* v, const int64_t* n,
                         const int64_t* off, int world, const float* const* reduced, int64_t S,
                         const float* hyper_dev, int hyper_stride, const int32_t* skip_flag, double beta1,

@@ -38,7 +38,7 @@ def main():
 
     pa, oa, adam_a = make()
     pb, ob, adam_b = make()
-    ex = PeerGradExchange(multicast=os.environ.get("FSB_XCHG_MULTICAST") == "1")
+    ex = PeerGradExchange()  # FSB_XCHG_MULTICAST / FSB_XCHG_MODE from the environment
     overflow = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def set_grads(step):
@@ -71,6 +71,7 @@ def main():
     overflow.zero_()
     # 2) eager steps against NCCL + plain Adam
     worst = 0.0
+    worst_grad = 0.0
     for s in range(1, 4):
         set_grads(s)
         adam_a.advance(); adam_b.advance()
@@ -79,10 +80,12 @@ def main():
         flat_ref = torch.cat([pb[k].grad.reshape(-1) for k in shapes])
         red = ex.reduced_flat()
         got = torch.cat([red[ex.off[i]:ex.off[i] + ex.ns[i]] for i in range(len(ex.ns))])
-        worst = max(worst, float((got - flat_ref).abs().max() / flat_ref.abs().max()))
+        worst_grad = max(worst_grad, float((got - flat_ref).abs().max() / flat_ref.abs().max()))
         for k in shapes:
             worst = max(worst, float((pa[k] - pb[k]).abs().max() / pb[k].abs().max()))
     out["eager_worst_rel_diff"] = worst
+    out["reduced_gradient_worst_rel_diff"] = worst_grad
+    out["mode"] = ex.mode
     out["g_mc_used"] = ex.g_mc is not None
     # 3) captured in a graph, replayed
     set_grads(10)
@@ -133,10 +136,17 @@ def main():
     for _ in range(3):
         gr.replay(); nccl_flat()
     out["ms_ours_graph"] = timed(gr.replay)
+    grads_a = [pa[k].grad for k in shapes]
+    out["ms_ours_exchange_only"] = timed(lambda: ex.exchange(grads_a, overflow))
     out["ms_nccl_pack_allreduce_adam"] = timed(nccl_flat)
     out["payload_mb"] = ex.total * 4 / 1e6
-    ok = (out["overflow_seen_everywhere"] and out["skipped_step_is_noop"] and out["eager_worst_rel_diff"] < 1e-6
-          and out["graph_worst_rel_diff"] < 1e-6 and out["replicas_bit_identical"])
+    # two ranks: a + b is the same bit pattern whoever adds.  More: NCCL's ring / tree / switch order differs from ours,
+    # the sums differ in the last bits, and Adam (eps 1e-15) turns a sign flip of a near-zero sum into a +-lr step:
+    # the reduced gradient has to agree to rounding, the parameters to a few learning-rate steps, and — the actual
+    # requirement — the replicas among themselves bit for bit.
+    tol_g, tol_p = (1e-6, 1e-6) if world == 2 else (2e-6, 1e-3)
+    ok = (out["overflow_seen_everywhere"] and out["skipped_step_is_noop"] and out["reduced_gradient_worst_rel_diff"] < tol_g
+          and out["eager_worst_rel_diff"] < tol_p and out["graph_worst_rel_diff"] < tol_p and out["replicas_bit_identical"])
     out["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(out), flush=True)
