@@ -323,6 +323,37 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+_FULL_AFFINITY = None  # the affinity the process started with (the CPU-baseline leg runs on all of it)
+
+
+def _bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's threads to the CPUs NVML names as closest to its GPU, BEFORE any pinned host buffer is
+    allocated: the end-to-end leg copies 58 MB of targets per step from pinned memory, and with 8 ranks on a two-socket
+    host half of those copies otherwise cross the socket interconnect (r02m, 8 GPUs: e2e 1200 views/s against a
+    device-resident 1980).  Returns the number of CPUs in the mask, or None when NVML cannot say."""
+    global _FULL_AFFINITY
+    if os.environ.get("FSB_BIND_NUMA", "1") == "0":
+        return None
+    try:
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001 - no NVML, a container without the topology: leave the affinity alone
+        return None
+    return None
+
+
 class Ctx:
     """Process-wide state of one bench run (one rank)."""
 
@@ -337,6 +368,7 @@ class Ctx:
             raise SystemExit("bench.py (impl=ours) needs a CUDA device: fusionsense_b200 has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         self.device = torch.device("cuda", self.local_rank)
+        self.cpu_affinity = _bind_to_gpu_numa_node(self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.device)
         # N > 1 gradient exchange: "peer" = this library's kernels over NVLink peer memory (default), "nccl" = one flat
@@ -733,6 +765,7 @@ def run_ours(args):
             "gpu_launches": main["gpu_launches"],
             "gpu_launches_per_step": main["gpu_launches_per_step"],
             "clocks": main["clocks"],
+            "host": {"cpus_bound_to_gpu_numa_node": ctx.cpu_affinity},
             "roofline": main.get("roofline"),
         }
         if secondary is not None:
@@ -803,6 +836,8 @@ def main():
     if args.config == "cfg5":
         line["cpu_baseline"] = None  # the oracle needs ~10 min per bounded sample at 3M Gaussians: reported for cfg4 / cfg2
     elif line["n_gpus"] == 1 and not args.no_cpu_baseline:
+        if _FULL_AFFINITY:
+            os.sched_setaffinity(0, _FULL_AFFINITY)  # the GPU legs ran bound to the GPU's NUMA node
         sec, cores, sample = cpu_step_seconds(args.config, 1, warmup=0)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     else:

@@ -339,8 +339,8 @@ FSB_API int fsb_xchg_allreduce(int world, int rank, float* const* grads, float* 
     if (world < 1 || world > FSB_XCHG_MAX_WORLD || rank < 0 || rank >= world || !grads || S < 0 || (S & 3))
         return FSB_E_ARG;
     if (S == 0) return 0;
-    int blocks = fsb_div_up(S / 4, AR_THREADS * AR_UNROLL);
-    if (blocks > FSB_NUM_SMS * 2) blocks = FSB_NUM_SMS * 2;
+    int blocks = fsb_div_up(S / 4, AR_THREADS * (grads_mc != nullptr ? AR_UNROLL : 1));
+    if (blocks > FSB_NUM_SMS * 4) blocks = FSB_NUM_SMS * 4;
     if (grads_mc != nullptr) {
         xchg_allreduce_mc_kernel<<<blocks, AR_THREADS, 0, (cudaStream_t)stream>>>(rank, grads_mc, S);
     } else {

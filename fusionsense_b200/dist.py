@@ -120,7 +120,9 @@ class PeerGradExchange:
             env = os.environ.get("FSB_XCHG_MULTICAST")
             multicast = (env == "1") if env is not None else self.world > 2
         self.want_multicast = bool(multicast)
-        self.mode = os.environ.get("FSB_XCHG_MODE", "inplace")
+        # two GPUs: reduce-scatter + Adam gathering the other half wins (r02n: 0.60 ms against 0.71 ms in place and
+        # 0.79 ms for NCCL); more replicas: the in-place all-reduce through the switch
+        self.mode = os.environ.get("FSB_XCHG_MODE", "inplace" if self.world > 2 else "gather")
         if self.mode not in ("inplace", "gather"):
             raise ValueError(f"FSB_XCHG_MODE={self.mode}: inplace or gather")
         self._layout = None

@@ -8,8 +8,8 @@ chk() { name=$1; shift
 run() { name=$1; shift
   env "$@" timeout 300 $TR bench.py --gpus $N --steps 100 --warmup 5 --no-cpu-baseline --no-secondary > $OUT/${TAG}_bench_n${N}_${name}.json 2> $OUT/${TAG}_bench_n${N}_${name}.err
   echo "rc=$? $name t=${SECONDS}s"; head -c 330 $OUT/${TAG}_bench_n${N}_${name}.json; echo; grep -v "^\s*$" $OUT/${TAG}_bench_n${N}_${name}.err | tail -2 | cut -c1-300; }
-chk inplace_mc FSB_XCHG_MULTICAST=1
-chk inplace_peer FSB_XCHG_MULTICAST=0
+chk inplace_mc FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=1
+chk inplace_peer FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0
 if [ "$N" = "2" ]; then chk gather_peer FSB_XCHG_MODE=gather FSB_XCHG_MULTICAST=0; fi
 run peer FSB_EXCHANGE=peer
 if [ "$N" != "8" ]; then run nccl FSB_EXCHANGE=nccl; fi
