@@ -339,8 +339,11 @@ FSB_API int fsb_xchg_allreduce(int world, int rank, float* const* grads, float* 
     if (world < 1 || world > FSB_XCHG_MAX_WORLD || rank < 0 || rank >= world || !grads || S < 0 || (S & 3))
         return FSB_E_ARG;
     if (S == 0) return 0;
+    // two 512-thread CTAs per SM keep ~10 MB on the wire (the links need about 3) and leave half of every SM to the
+    // Adam launch of the previous chunk that runs beside this kernel (dist.PeerGradExchange.exchange_and_adam)
+    static const int per_sm = [] { const char* e = getenv("FSB_XCHG_AR_CTAS_PER_SM"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
     int blocks = fsb_div_up(S / 4, AR_THREADS * (grads_mc != nullptr ? AR_UNROLL : 1));
-    if (blocks > FSB_NUM_SMS * 4) blocks = FSB_NUM_SMS * 4;
+    if (blocks > FSB_NUM_SMS * per_sm) blocks = FSB_NUM_SMS * per_sm;
     if (grads_mc != nullptr) {
         xchg_allreduce_mc_kernel<<<blocks, AR_THREADS, 0, (cudaStream_t)stream>>>(rank, grads_mc, S);
     } else {

@@ -87,6 +87,7 @@ __device__ __forceinline__ float sh_load(const float* __restrict__ coeffs, const
 }
 
 // act_flags: the parameters arrive as the model stores them and the activation is applied here
+constexpr int ACT_VEC4_ROWS = 2;   // backward: the warp's run of features_rest rows moves as 16-byte requests
 constexpr int ACT_EXP_SCALES = 1;  // scales are log-scales: s = exp(raw)  (dn_model.py:573)
 
 __global__ void __launch_bounds__(256)
@@ -259,10 +260,47 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 const int LR = L - 3;
                 const int total = min(32, N - n0) * LR;
                 const float* base = coeffs_rest + (size_t)n0 * LR;
+                int e_done = 0;  // floats [0, e_done) of the run are in the tile
+                if ((act_flags & ACT_VEC4_ROWS) && ((((uintptr_t)base) & 15) == 0)) {
+                    // 16-byte requests, four per lane in flight: at 16 warps per SM the 4-byte version keeps 16 KB per
+                    // SM on the wire, about a third of what the HBM latency needs (r02l: 268 us for 0.5 GB)
+                    constexpr int UB4 = 4;
+                    const int total4 = total >> 2;
+                    const float4* base4 = reinterpret_cast<const float4*>(base);
+                    int r = 0, col = 4 * lane;  // (row, column) of the first float of this lane's current float4
+                    while (col >= LR) { col -= LR; ++r; }
+                    for (int e0 = lane; e0 < total4; e0 += 32 * UB4) {
+                        float4 v[UB4];
+                        int rr[UB4], cc[UB4];
+#pragma unroll
+                        for (int u = 0; u < UB4; ++u) {
+                            const int e = e0 + 32 * u;
+                            rr[u] = r; cc[u] = col;
+                            const int r_last = (col + 3 >= LR) ? r + 1 : r;
+                            const bool ok = e < total4 && (((vmask >> r) | (vmask >> min(r_last, 31))) & 1u);
+                            v[u] = ok ? base4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (!ok) rr[u] = -1;
+                            col += 128;
+                            while (col >= LR) { col -= LR; ++r; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB4; ++u) {
+                            if (rr[u] < 0) continue;
+                            const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                int rk = rr[u], ck = cc[u] + k;
+                                if (ck >= LR) { ck -= LR; ++rk; }
+                                if (rk < 32) tile[rk][3 + ck] = f[k];
+                            }
+                        }
+                    }
+                    e_done = total4 << 2;
+                }
                 constexpr int UB = 8;
-                int r = 0, col = lane;          // element e = lane + 32 it  ->  (row r, column col) of the run
+                int r = 0, col = e_done + lane;          // element e = e_done + lane + 32 it  ->  (row r, column col) of the run
                 while (col >= LR) { col -= LR; ++r; }
-                for (int e0 = lane; e0 < total; e0 += 32 * UB) {
+                for (int e0 = e_done + lane; e0 < total; e0 += 32 * UB) {
                     float v[UB];
                     int rr[UB], cc[UB];
 #pragma unroll
@@ -413,10 +451,31 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 const int LR = L - 3;
                 const int total = rows * LR;
                 float* base = v_coeffs_rest + (size_t)n0 * LR;
-                int r = 0, col = lane;
+                int e_done = 0;
+                if ((act_flags & ACT_VEC4_ROWS) && ((((uintptr_t)base) & 15) == 0)) {
+                    const int total4 = total >> 2;
+                    float4* base4 = reinterpret_cast<float4*>(base);
+                    int r = 0, col = 4 * lane;
+                    while (col >= LR) { col -= LR; ++r; }
+#pragma unroll 2
+                    for (int e = lane; e < total4; e += 32) {
+                        float f[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            int rk = r, ck = col + k;
+                            if (ck >= LR) { ck -= LR; ++rk; }
+                            f[k] = tile[min(rk, 31)][3 + ck];
+                        }
+                        base4[e] = make_float4(f[0], f[1], f[2], f[3]);
+                        col += 128;
+                        while (col >= LR) { col -= LR; ++r; }
+                    }
+                    e_done = total4 << 2;
+                }
+                int r = 0, col = e_done + lane;
                 while (col >= LR) { col -= LR; ++r; }
 #pragma unroll 4
-                for (int e = lane; e < total; e += 32) {
+                for (int e = e_done + lane; e < total; e += 32) {
                     base[e] = tile[r][3 + col];
                     col += 32;
                     while (col >= LR) { col -= LR; ++r; }
@@ -541,10 +600,12 @@ FSB_API int fsb_project_params_bwd(int C, int N, const float* means, const float
     // (r02i, cfg4: 0.304 ms against 0.276 ms: the spills and the longer dependent chains cost more than the extra
     // warps hide), so the 115-register build stays the default
     static const int minb = [] { const char* e = getenv("FSB_PROJ_BWD_MINB"); return e ? atoi(e) : 4; }();
+    // FSB_PROJ_BWD_VEC4=0: 4-byte requests for the SH rows (A/B runs)
+    static const int vec4 = [] { const char* e = getenv("FSB_PROJ_BWD_VEC4"); return (e && e[0] == '0') ? 0 : ACT_VEC4_ROWS; }();
 #define FSB_PBWD(MINB)                                                                                              \
     project_sh_bwd_kernel<MINB><<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(                \
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, features_dc,                  \
-        K > 1 ? features_rest : nullptr, exp_scales ? ACT_EXP_SCALES : 0, nullptr, color_stride, depth_channel,    \
+        K > 1 ? features_rest : nullptr, (exp_scales ? ACT_EXP_SCALES : 0) | vec4, nullptr, color_stride, depth_channel, \
         radii, v_means2d, v_depths, v_conics, nullptr, v_colors, v_means, v_quats, v_scales, v_features_dc,         \
         K > 1 ? v_features_rest : nullptr, nullptr, nullptr)
     if (minb <= 4) FSB_PBWD(4); else FSB_PBWD(6);

@@ -104,7 +104,8 @@ class PeerGradExchange:
     Every element is reduced once, by its owner, so all replicas apply bit-identical updates."""
 
     capturable = True
-    N_SLOTS = 4
+    MAX_CHUNKS = 8
+    N_SLOTS = 2 + MAX_CHUNKS
 
     def __init__(self, group=None, multicast: Optional[bool] = None):
         import os
@@ -125,6 +126,10 @@ class PeerGradExchange:
         self.mode = os.environ.get("FSB_XCHG_MODE", "inplace" if self.world > 2 else "gather")
         if self.mode not in ("inplace", "gather"):
             raise ValueError(f"FSB_XCHG_MODE={self.mode}: inplace or gather")
+        # in place: the flat buffer is all-reduced in `chunks` pieces and the Adam launch of piece k runs on a second
+        # stream beside the all-reduce of piece k + 1 (one is NVLink-bound, the other HBM-bound)
+        self.chunks = max(1, min(self.MAX_CHUNKS, int(os.environ.get("FSB_XCHG_CHUNKS", "4")))) if self.mode == "inplace" else 1
+        self._side = None
         self._layout = None
 
     def _setup(self, grads: List[Tensor]) -> None:
@@ -137,8 +142,10 @@ class PeerGradExchange:
         off = [0]
         for n in ns:
             off.append(off[-1] + (n + 3) // 4 * 4)
-        per = -(-off[-1] // self.world)
-        self.S = (per + 3) // 4 * 4
+        # per = floats of one rank's share of one chunk; S = one rank's slice of the whole buffer when it is exchanged
+        # in one piece (gather mode, or exchange() in place)
+        self.per = -(-off[-1] // (self.world * self.chunks * 4)) * 4
+        self.S = self.per * self.chunks
         self.total = self.S * self.world
         self.ns, self.off = ns, off
         self.G = symm_mem.empty(self.total, dtype=torch.float32, device=dev)
@@ -197,6 +204,59 @@ class PeerGradExchange:
         # step, which a rank enters only after its Adam has read them.
         check(lib.fsb_xchg_barrier(self.world, self.rank, ctypes.addressof(self._pad_ptrs), 1, self.epoch.data_ptr(),
                                    None, st), "fsb_xchg_barrier")
+
+    def exchange_and_adam(self, grads: List[Tensor], overflow: Optional[Tensor], adam) -> None:
+        """In-place mode, pipelined: pack, barrier, then per chunk k { all-reduce of chunk k; barrier } on the current
+        stream with `adam.launch_range(chunk k)` on a second stream beside the all-reduce of chunk k + 1; the streams
+        are joined before returning.  Same result as exchange() + adam.launch_xchg()."""
+        import ctypes
+
+        from ._abi import check, lib
+        from .ops import _stream
+
+        if self.mode != "inplace" or self.chunks == 1:
+            self.exchange(grads, overflow)
+            adam.launch_xchg(self, skip_flag=overflow)
+            return
+        grads = [g.contiguous() for g in grads]
+        if self._layout != (tuple(g.numel() for g in grads), grads[0].device):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PeerGradExchange: the gradient layout changed inside a capture; run one eager "
+                                   "step first (symmetric buffers cannot be created while capturing)")
+            self._setup(grads)
+        n = len(grads)
+        st = _stream()
+        src = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads])
+        ns = (ctypes.c_int64 * n)(*self.ns)
+        off = (ctypes.c_int64 * (n + 1))(*self.off)
+        check(lib.fsb_xchg_pack(n, ctypes.addressof(src), ctypes.addressof(ns), ctypes.addressof(off), self.G.data_ptr(),
+                                self.total, st), "fsb_xchg_pack")
+        self._keep = grads
+        flag = None if overflow is None else overflow.data_ptr()
+        check(lib.fsb_xchg_barrier(self.world, self.rank, ctypes.addressof(self._pad_ptrs), 0, self.epoch.data_ptr(),
+                                   flag, st), "fsb_xchg_barrier")
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=grads[0].device)
+        side = self._side
+        W = self.world
+        chunk = self.per * W  # floats per chunk
+        for k in range(self.chunks):
+            shift = k * chunk * 4  # bytes
+            ptrs = (ctypes.c_void_p * W)(*[int(p) + shift for p in self._g_ptrs])
+            mc = None if self.g_mc is None else self.g_mc + shift
+            check(lib.fsb_xchg_allreduce(W, self.rank, ctypes.addressof(ptrs), mc, self.per, st), "fsb_xchg_allreduce")
+            check(lib.fsb_xchg_barrier(W, self.rank, ctypes.addressof(self._pad_ptrs), 2 + k, self.epoch.data_ptr(),
+                                       None, st), "fsb_xchg_barrier")
+            if k == self.chunks - 1:
+                adam.launch_range(self, k * chunk, (k + 1) * chunk, skip_flag=overflow)
+            else:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    adam.launch_range(self, k * chunk, (k + 1) * chunk, skip_flag=overflow)
+        main.wait_stream(side)
 
     def probe(self, device) -> None:
         """Collective: establish a tiny symmetric buffer, so that a box without peer-memory support fails here (before

@@ -171,8 +171,7 @@ class GraphedDNSplatterStep:
         if self._peer:
             # gradients of the Adam entries, in its order, through our own NVLink exchange; Adam gathers the result
             grads = [p.grad for _, _, p in self.adam.entries]
-            self.grad_sync.exchange(grads, self.overflow)
-            self.adam.launch_xchg(self.grad_sync, skip_flag=self.overflow)
+            self.grad_sync.exchange_and_adam(grads, self.overflow, self.adam)
         else:
             self.adam.launch(skip_flag=self.overflow)
         m.after_train(skip_flag=self.overflow)

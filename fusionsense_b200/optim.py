@@ -149,6 +149,36 @@ class CapturedAdam:
                                       self.betas[1], self.eps, _stream()), "fsb_adam_multi_xchg")
 
     @torch.no_grad()
+    def launch_range(self, exchange, flat_begin: int, flat_end: int, skip_flag=None) -> None:
+        """The update of the elements whose index in the exchange's flat gradient buffer lies in [flat_begin, flat_end)
+        (multiples of 4), the gradient read from this rank's own, all-reduced buffer: one piece of
+        PeerGradExchange.exchange_and_adam's pipeline.  Tensors outside the range ride along with n = 0, so every
+        tensor keeps its slot in the hyper-parameter table."""
+        n = len(self.entries)
+        off = exchange.off
+        VP = ctypes.c_void_p * n
+        ps, ms, vs, ns, offs = [], [], [], [], []
+        for i, (opt, group, p) in enumerate(self.entries):
+            st = opt.state[p]
+            if p.numel() != exchange.ns[i]:
+                raise RuntimeError("CapturedAdam.launch_range: the exchange was run on a different tensor list")
+            lo = min(max(0, flat_begin - off[i]), p.numel())
+            hi = min(p.numel(), max(0, flat_end - off[i]))
+            cnt = max(0, hi - lo)
+            ps.append(p.data_ptr() + 4 * lo); ms.append(st["exp_avg"].data_ptr() + 4 * lo)
+            vs.append(st["exp_avg_sq"].data_ptr() + 4 * lo)
+            ns.append(cnt); offs.append(off[i] + lo)
+        p_, m_, v_ = VP(*ps), VP(*ms), VP(*vs)
+        numel = (ctypes.c_int64 * n)(*ns)
+        offs_ = (ctypes.c_int64 * n)(*offs)
+        g_self = (ctypes.c_void_p * 1)(int(exchange.G.data_ptr()))
+        check(lib.fsb_adam_multi_xchg(n, ctypes.addressof(p_), ctypes.addressof(m_), ctypes.addressof(v_),
+                                      ctypes.addressof(numel), ctypes.addressof(offs_), 1, ctypes.addressof(g_self),
+                                      exchange.total, self.hyper.data_ptr(), self.maxt,
+                                      None if skip_flag is None else skip_flag.data_ptr(), self.betas[0],
+                                      self.betas[1], self.eps, _stream()), "fsb_adam_multi_xchg")
+
+    @torch.no_grad()
     def launch(self, skip_flag=None) -> None:
         """Inside the capture, after backward(): one launch for all tensors, scalars read from `self.hyper`."""
         n = len(self.entries)

@@ -49,8 +49,8 @@ def main():
             pb[k].grad = gr.clone()
 
     def step_a():
-        ex.exchange([p.grad for _, _, p in adam_a.entries], overflow)
-        adam_a.launch_xchg(ex, skip_flag=overflow)
+        # in place: all-reduce by chunks with Adam of chunk k beside the all-reduce of chunk k + 1; gather: RS + Adam
+        ex.exchange_and_adam([p.grad for _, _, p in adam_a.entries], overflow, adam_a)
 
     def step_b():
         for k in shapes:
@@ -86,6 +86,7 @@ def main():
     out["eager_worst_rel_diff"] = worst
     out["reduced_gradient_worst_rel_diff"] = worst_grad
     out["mode"] = ex.mode
+    out["chunks"] = ex.chunks
     out["g_mc_used"] = ex.g_mc is not None
     # 3) captured in a graph, replayed
     set_grads(10)

@@ -8,9 +8,17 @@ chk() { name=$1; shift
 run() { name=$1; shift
   env "$@" timeout 300 $TR bench.py --gpus $N --steps 100 --warmup 5 --no-cpu-baseline --no-secondary > $OUT/${TAG}_bench_n${N}_${name}.json 2> $OUT/${TAG}_bench_n${N}_${name}.err
   echo "rc=$? $name t=${SECONDS}s"; head -c 330 $OUT/${TAG}_bench_n${N}_${name}.json; echo; grep -v "^\s*$" $OUT/${TAG}_bench_n${N}_${name}.err | tail -2 | cut -c1-300; }
-chk inplace_mc FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=1
-chk inplace_peer FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0
-if [ "$N" = "2" ]; then chk gather_peer FSB_XCHG_MODE=gather FSB_XCHG_MULTICAST=0; fi
-run peer FSB_EXCHANGE=peer
-if [ "$N" != "8" ]; then run nccl FSB_EXCHANGE=nccl; fi
+if [ "$N" = "2" ]; then
+  chk inplace_peer_k4 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0 FSB_XCHG_CHUNKS=4
+  chk inplace_mc_k4 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=1 FSB_XCHG_CHUNKS=4
+  chk inplace_peer_k1 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0 FSB_XCHG_CHUNKS=1
+  run peer_inplace_k4 FSB_EXCHANGE=peer FSB_XCHG_MODE=inplace
+  timeout 600 python -m pytest tests/test_gpu_graph_step.py -m gpu -q -x > $OUT/${TAG}_pytest_graph.log 2>&1; tail -3 $OUT/${TAG}_pytest_graph.log
+else
+  chk inplace_mc_k4 FSB_XCHG_CHUNKS=4
+  chk inplace_mc_k2 FSB_XCHG_CHUNKS=2
+  chk inplace_mc_k1 FSB_XCHG_CHUNKS=1
+  run peer_k4 FSB_EXCHANGE=peer FSB_XCHG_CHUNKS=4
+  if [ "$N" != "8" ]; then run nccl FSB_EXCHANGE=nccl; fi
+fi
 echo "elapsed ${SECONDS}s"
