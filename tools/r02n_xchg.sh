@@ -11,9 +11,9 @@ run() { name=$1; shift
 if [ "$N" = "2" ]; then
   chk inplace_peer_k4 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0 FSB_XCHG_CHUNKS=4
   chk inplace_mc_k4 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=1 FSB_XCHG_CHUNKS=4
+  chk inplace_peer_k2 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0 FSB_XCHG_CHUNKS=2
   chk inplace_peer_k1 FSB_XCHG_MODE=inplace FSB_XCHG_MULTICAST=0 FSB_XCHG_CHUNKS=1
   run peer_inplace_k4 FSB_EXCHANGE=peer FSB_XCHG_MODE=inplace
-  timeout 600 python -m pytest tests/test_gpu_graph_step.py -m gpu -q -x > $OUT/${TAG}_pytest_graph.log 2>&1; tail -3 $OUT/${TAG}_pytest_graph.log
 else
   chk inplace_mc_k4 FSB_XCHG_CHUNKS=4
   chk inplace_mc_k2 FSB_XCHG_CHUNKS=2
