@@ -16,9 +16,9 @@ if [ "$N" = "2" ]; then
   run peer_inplace_k4 FSB_EXCHANGE=peer FSB_XCHG_MODE=inplace
 else
   chk inplace_mc_k4 FSB_XCHG_CHUNKS=4
-  chk inplace_mc_k2 FSB_XCHG_CHUNKS=2
-  chk inplace_mc_k1 FSB_XCHG_CHUNKS=1
+  chk inplace_mc_k8 FSB_XCHG_CHUNKS=8
   run peer_k4 FSB_EXCHANGE=peer FSB_XCHG_CHUNKS=4
+  run peer_k8 FSB_EXCHANGE=peer FSB_XCHG_CHUNKS=8
   if [ "$N" != "8" ]; then run nccl FSB_EXCHANGE=nccl; fi
 fi
 echo "elapsed ${SECONDS}s"
