@@ -396,8 +396,20 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
     vpi = max(1, c.get("global_views", world) // world)  # views per rank per iteration
     model = build_model(cfg_name, device)
     views = list(range(n_views))
-    dev_targets = {v: model.render_targets(v) for v in views}
-    host_targets = {v: {k: t.cpu().pin_memory() for k, t in d.items()} for v, d in dev_targets.items()}
+    # RGB and normal targets hold 8-bit values, as the PNGs of a FusionSense dataset do (images/rgb_i.png,
+    # normals_from_pretrain/*.png); the host side of the e2e leg keeps them as uint8 (nerfstudio caches uint8 images)
+    # and the float32 `x / 255.0` of splatfacto's get_gt_img / dn_dataset.py:205 happens on the device after the copy
+    # (fsb_u8_to_unit_float, identical bits): 20.7 MB per 1080p view cross PCIe instead of 58 MB.  Depth is float32.
+    dev_targets = {v: model.render_targets(v, eight_bit=True) for v in views}
+
+    def to_host(k, t):
+        if k in ("image", "normal"):
+            q = torch.round(t * 255.0).to(torch.uint8)
+            assert torch.equal(q.float() / 255.0, t), f"{k}: 8-bit host copy does not reproduce the resident target"
+            t = q
+        return t.cpu().pin_memory()
+
+    host_targets = {v: {k: to_host(k, t) for k, t in d.items()} for v, d in dev_targets.items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values()) * min(vpi, n_views)
     params = [model.gauss_params[k] for k in model.config.lrs]
     graph_mode = mode == "graph"
@@ -445,7 +457,10 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
         return dev_targets[v]
 
     def from_host(v):
-        return {k: t.to(device, non_blocking=True) for k, t in host_targets[v].items()}
+        from fusionsense_b200.compose import u8_to_unit_float
+
+        out = {k: t.to(device, non_blocking=True) for k, t in host_targets[v].items()}
+        return {k: u8_to_unit_float(t) if t.dtype == torch.uint8 else t for k, t in out.items()}
 
     def one_step(i, staged, read_loss, n_total=1 << 30):
         """One training iteration; `staged`: this step's targets come from pinned host memory; `read_loss`: the

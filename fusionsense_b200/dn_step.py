@@ -523,8 +523,10 @@ class DNSplatterStep:
                 opt.step()
 
     @torch.no_grad()
-    def render_targets(self, cam_idx: int, perturb: float = 0.02, seed: int = 0) -> Dict[str, Tensor]:
-        """Ground truth for a synthetic view: a render of a perturbed copy of the scene."""
+    def render_targets(self, cam_idx: int, perturb: float = 0.02, seed: int = 0, eight_bit: bool = False) -> Dict[str, Tensor]:
+        """Ground truth for a synthetic view: a render of a perturbed copy of the scene.
+        `eight_bit`: RGB and normal targets take the values an 8-bit PNG holds (`round(x * 255) / 255`), as the
+        reference's datasets do (images/rgb_i.png, normals_from_pretrain/*.png; depth stays float32)."""
         g = torch.Generator(device="cpu").manual_seed(seed + cam_idx)
         saved = {k: v.data.clone() for k, v in self.gauss_params.items()}
         for k, v in self.gauss_params.items():
@@ -536,4 +538,8 @@ class DNSplatterStep:
         for k, v in self.gauss_params.items():
             v.data.copy_(saved[k])
         depth = torch.where(out["accumulation"] > 0.5, out["depth"], torch.zeros_like(out["depth"]))
-        return {"image": out["rgb"].contiguous(), "sensor_depth": depth.contiguous(), "normal": out["normal"].contiguous()}
+        rgb, normal = out["rgb"].contiguous(), out["normal"].contiguous()
+        if eight_bit:
+            rgb = torch.round(rgb.clamp(0, 1) * 255.0) / 255.0
+            normal = torch.round(normal.clamp(0, 1) * 255.0) / 255.0
+        return {"image": rgb, "sensor_depth": depth.contiguous(), "normal": normal}

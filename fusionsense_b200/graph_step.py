@@ -317,8 +317,7 @@ class GraphedDNSplatterStep:
         n = 0
         with torch.cuda.stream(cs):
             for k, t in host_batch.items():
-                self.targets[k][cam_idx].copy_(t, non_blocking=True)
-                n += t.numel() * t.element_size()
+                n += self._copy_target(k, cam_idx, t)
             done = torch.cuda.Event()
             done.record(cs)
         self._slot_staged[cam_idx] = done
@@ -350,9 +349,30 @@ class GraphedDNSplatterStep:
         """Copy a view's targets from (pinned) host memory into its resident slot; returns the bytes moved."""
         n = 0
         for k, t in host_batch.items():
-            self.targets[k][cam_idx].copy_(t, non_blocking=True)
-            n += t.numel() * t.element_size()
+            n += self._copy_target(k, cam_idx, t)
         return n
+
+    def _copy_target(self, key: str, cam_idx: int, t: Tensor) -> int:
+        """Host tensor -> resident slot on the current stream; returns the bytes that crossed PCIe.  uint8 sources
+        (the 8-bit RGB / normal images as they are on disk) travel as bytes into a device staging buffer and are
+        turned into the slot's float32 by `fsb_u8_to_unit_float` on the same stream — what the reference does with
+        `image.float() / 255.0` after its own H2D copy (splatfacto get_gt_img; dn_dataset.py:205 for normals)."""
+        slot = self.targets[key][cam_idx]
+        if t.dtype == torch.uint8 and slot.dtype == torch.float32:
+            from .compose import u8_to_unit_float
+
+            if getattr(self, "_u8_stage", None) is None:
+                self._u8_stage: Dict[tuple, Tensor] = {}
+            sk = (key, torch.cuda.current_stream().cuda_stream)
+            buf = self._u8_stage.get(sk)
+            if buf is None or buf.numel() != t.numel():
+                # one buffer per (key, stream): copies and conversions of successive views are ordered by the stream
+                buf = self._u8_stage[sk] = torch.empty(t.numel(), dtype=torch.uint8, device=self.device)
+            buf.copy_(t.reshape(-1), non_blocking=True)
+            u8_to_unit_float(buf, slot)
+        else:
+            slot.copy_(t, non_blocking=True)
+        return t.numel() * t.element_size()
 
     def _check_async(self) -> None:
         self._last_check = self.replays

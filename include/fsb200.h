@@ -415,6 +415,9 @@ int fsb_compose_rgbd_bwd(int64_t P, const float* render, const float* alpha, con
                          const float* v_rgb, const float* v_depth, float* v_render, float* v_alpha, void* stream);
 int fsb_normal_map_fwd(int64_t P, const float* normals_raw, float* out, void* stream);
 int fsb_normal_map_bwd(int64_t P, const float* normals_raw, const float* v_out, float* v_normals_raw, void* stream);
+/* 8-bit image targets -> float32 on the device: dst[i] = float(src[i]) / 255.0f — splatfacto get_gt_img's
+ * `image.float() / 255.0` for uint8 batches and dn_dataset.py:205 for the normal maps, IEEE division. */
+int fsb_u8_to_unit_float(int64_t n, const uint8_t* src, float* dst, void* stream);
 
 /* Flatness regulariser ("two_d_gaussians").  replaces dn_splatter/dn_model.py:817-819:
  *   out = mean_i min_k exp(log_scales[i,k])     (device scalar; workspace: 16 bytes)

@@ -323,3 +323,47 @@ def test_camera_batch_per_iteration_accumulates_like_separate_backwards():
                      outlier_frac=1e-4)
     assert torch.equal(graphed.vis_counts, eager.vis_counts)
     assert_close(graphed.xys_grad_norm, eager.xys_grad_norm, "graph3.xys_grad_norm", tol=1e-5, outlier_frac=1e-4)
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 4099, 3 * 640 * 480 + 5])
+def test_u8_targets_convert_to_torch_bits(n):
+    """fsb_u8_to_unit_float == `image.float() / 255.0` (splatfacto get_gt_img, dn_dataset.py:205), bit for bit,
+    on aligned and unaligned starts and ragged tails."""
+    from fusionsense_b200.compose import u8_to_unit_float
+
+    g = torch.Generator().manual_seed(n)
+    base = torch.randint(0, 256, (n + 3,), dtype=torch.uint8, generator=g).to(DEV)
+    for off in (0, 1, 3):
+        src = base[off:off + n]
+        if n > 256:
+            src[:256] = torch.arange(256, dtype=torch.uint8, device=DEV)  # every byte value at least once
+        src = src.contiguous() if off == 0 else src  # a slice of a 1-D tensor is contiguous but unaligned
+        out = u8_to_unit_float(src)
+        assert torch.equal(out, src.float() / 255.0)
+
+
+def test_staged_u8_targets_equal_resident_float_targets():
+    """8-bit host targets staged through stage_async / stage land in the resident slots as the float32 values the
+    reference computes after its own copy; a replay on them gives the loss of the float32 targets."""
+    from fusionsense_b200.graph_step import GraphedDNSplatterStep
+
+    eager, graphed, _ = _pair()
+    targets = {v: eager.render_targets(v, eight_bit=True) for v in range(3)}
+    runner = GraphedDNSplatterStep(graphed, targets)
+    host = {v: {k: (torch.round(t * 255.0).to(torch.uint8) if k != "sensor_depth" else t).cpu().pin_memory()
+                for k, t in d.items()} for v, d in targets.items()}
+    want = {k: t.clone() for k, t in runner.targets.items()}
+    for t in runner.targets.values():
+        t.zero_()
+    moved = runner.stage_async(0, host[0]) + runner.stage(1, host[1])
+    runner.stage_async(2, host[2])
+    px = 256 * 192
+    assert moved == 2 * px * (3 + 3 + 4)
+    runner.train_iteration(0)
+    runner.train_iteration(2)
+    loss = runner.poll()["loss"]
+    torch.cuda.synchronize()
+    for k in want:
+        assert torch.equal(runner.targets[k], want[k]), k
+    eager.train_iteration(0, targets[0])
+    assert loss == pytest.approx(float(eager.train_iteration(2, targets[2])), rel=2e-4)
