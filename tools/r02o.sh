@@ -12,7 +12,10 @@ timeout 900 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench_default.json 2
 echo "t=${SECONDS}s"
 timeout 300 python tools/glue_profile.py cfg4 > $OUT/${TAG}_glue_cfg4.txt 2> $OUT/${TAG}_glue_cfg4.err; head -30 $OUT/${TAG}_glue_cfg4.txt | cut -c1-200; tail -2 $OUT/${TAG}_glue_cfg4.err | cut -c1-300
 echo "t=${SECONDS}s"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'project_sh_bwd|adam_multi|dn_loss|raster_bwd2|ssim_fwd|densify_stats|normals_bwd' --launch-skip 24 -c 16 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'project_sh_bwd|adam_multi|dn_loss|raster_bwd2|ssim_fwd|ssim_bwd|densify_stats|normals_bwd|radix_hist' --launch-skip 24 -c 16 \
    -o $OUT/${TAG}_bwdside_cfg4 -f python tools/stage_bench.py cfg4 2 > $OUT/${TAG}_ncu.log 2>&1
 tail -3 $OUT/${TAG}_ncu.log | cut -c1-300
+echo "elapsed ${SECONDS}s"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'vh_' -c 6 -o $OUT/${TAG}_hull -f python tools/hull_bench.py 512 1 > $OUT/${TAG}_ncu_hull.log 2>&1
+tail -3 $OUT/${TAG}_ncu_hull.log | cut -c1-300
 echo "elapsed ${SECONDS}s"
