@@ -402,10 +402,13 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
     # (fsb_u8_to_unit_float, identical bits): 20.7 MB per 1080p view cross PCIe instead of 58 MB.  Depth is float32.
     dev_targets = {v: model.render_targets(v, eight_bit=True) for v in views}
 
+    from fusionsense_b200.compose import u8_to_unit_float
+
     def to_host(k, t):
         if k in ("image", "normal"):
             q = torch.round(t * 255.0).to(torch.uint8)
-            assert torch.equal(q.float() / 255.0, t), f"{k}: 8-bit host copy does not reproduce the resident target"
+            back = u8_to_unit_float(q.contiguous().view(-1), recip=(k == "image")).view(t.shape)
+            assert torch.equal(back, t), f"{k}: 8-bit host copy does not reproduce the resident target"
             t = q
         return t.cpu().pin_memory()
 
@@ -457,10 +460,8 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
         return dev_targets[v]
 
     def from_host(v):
-        from fusionsense_b200.compose import u8_to_unit_float
-
         out = {k: t.to(device, non_blocking=True) for k, t in host_targets[v].items()}
-        return {k: u8_to_unit_float(t) if t.dtype == torch.uint8 else t for k, t in out.items()}
+        return {k: u8_to_unit_float(t, recip=(k == "image")) if t.dtype == torch.uint8 else t for k, t in out.items()}
 
     def one_step(i, staged, read_loss, n_total=1 << 30):
         """One training iteration; `staged`: this step's targets come from pinned host memory; `read_loss`: the

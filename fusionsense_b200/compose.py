@@ -141,14 +141,16 @@ def combine_losses(ssim, reg, flat, ssim_lambda: float, flat_lambda: float) -> T
     return _LossCombine.apply(ssim, reg, flat, ssim_lambda, flat_lambda)
 
 
-def u8_to_unit_float(src: Tensor, out: Tensor = None) -> Tensor:
-    """`src.float() / 255.0` for a uint8 CUDA tensor, written into `out` (float32, same element count) — splatfacto's
-    `get_gt_img` for uint8 image batches and `dn_dataset.py:205` for the 8-bit normal maps, so the
-    step's RGB / normal targets can cross PCIe as bytes.  IEEE division: the same bits as torch."""
+def u8_to_unit_float(src: Tensor, out: Tensor = None, recip: bool = True) -> Tensor:
+    """uint8 CUDA tensor -> float32 in [0, 1], written into `out` (same element count), so the step's RGB / normal
+    targets can cross PCIe as bytes.  `recip=True`: `src * (1.0f / 255.0f)`, the bits of `image.float() / 255.0` on a
+    CUDA tensor (splatfacto's get_gt_img, SURVEY.md A.7: torch divides by a Python scalar through the fp32 reciprocal);
+    `recip=False`: IEEE division, the bits of numpy's `normal_map.astype("float32") / 255.0` (dn_dataset.py:205)."""
     _req_cuda(src)
     assert src.dtype == torch.uint8 and src.is_contiguous(), (src.dtype, src.is_contiguous())
     if out is None:
         out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
     assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == src.numel() and out.is_cuda
-    check(lib.fsb_u8_to_unit_float(src.numel(), ptr(src), ptr(out), _stream()), "fsb_u8_to_unit_float")
+    check(lib.fsb_u8_to_unit_float(src.numel(), ptr(src), ptr(out), 1 if recip else 0, _stream()),
+          "fsb_u8_to_unit_float")
     return out

@@ -273,11 +273,19 @@ FSB_API int fsb_loss_combine_bwd(const float* v_out, float w_ssim, float w_flat,
 }
 
 // ---- 8-bit targets -> float32 in [0, 1] on the device --------------------------------------------------------------
-// splatfacto's get_gt_img (`image.float() / 255.0` for uint8 batches) and dn_dataset.py:205
-// (`normal_map.astype("float32") / 255.0`) on the device, so a step's RGB and normal targets cross PCIe as the 8-bit
-// images they are on disk: 20.7 MB instead of 58 MB per 1080p view (8 ranks feeding float32 targets are bound by the
-// host).  IEEE division, the same bits as torch / numpy.
+// The step's RGB and normal targets cross PCIe as the 8-bit images they are on disk (20.7 MB instead of 58 MB per 1080p
+// view; 8 ranks feeding float32 targets are bound by the host) and become float32 here, with the bits the
+// reference produces:
+//   recip = 1: x * (1.0f / 255.0f) — what `image.float() / 255.0` evaluates to ON THE DEVICE (splatfacto get_gt_img,
+//              torch's CUDA division by a Python scalar multiplies by the fp32 reciprocal);
+//   recip = 0: IEEE x / 255.0f — numpy / torch-CPU division (dn_dataset.py:205 `normal_map.astype("float32") / 255.0`).
 namespace {
+template <bool RECIP>
+__device__ __forceinline__ float unit_of(uint32_t b) {
+    return RECIP ? (float)b * (1.0f / 255.0f) : __fdiv_rn((float)b, 255.0f);
+}
+
+template <bool RECIP>
 __global__ void __launch_bounds__(256)
 u8_to_unit_float_kernel(int64_t n, const uint8_t* __restrict__ src, float* __restrict__ dst) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
@@ -288,26 +296,29 @@ u8_to_unit_float_kernel(int64_t n, const uint8_t* __restrict__ src, float* __res
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float4 f;
-                f.x = (float)(w[k] & 0xffu) / 255.0f;
-                f.y = (float)((w[k] >> 8) & 0xffu) / 255.0f;
-                f.z = (float)((w[k] >> 16) & 0xffu) / 255.0f;
-                f.w = (float)(w[k] >> 24) / 255.0f;
+                f.x = unit_of<RECIP>(w[k] & 0xffu);
+                f.y = unit_of<RECIP>((w[k] >> 8) & 0xffu);
+                f.z = unit_of<RECIP>((w[k] >> 16) & 0xffu);
+                f.w = unit_of<RECIP>(w[k] >> 24);
                 *reinterpret_cast<float4*>(dst + i + 4 * k) = f;
             }
         } else {
-            for (int64_t j = i; j < n && j < i + 16; ++j) dst[j] = (float)src[j] / 255.0f;
+            for (int64_t j = i; j < n && j < i + 16; ++j) dst[j] = unit_of<RECIP>(src[j]);
         }
     }
 }
 }  // namespace
 
-// dst[i] = float(src[i]) / 255.0f, i in [0, n)
-FSB_API int fsb_u8_to_unit_float(int64_t n, const uint8_t* src, float* dst, void* stream) {
+// dst[i] = float(src[i]) * (1.0f / 255.0f)  (recip != 0)  or  float(src[i]) / 255.0f  (recip == 0), i in [0, n)
+FSB_API int fsb_u8_to_unit_float(int64_t n, const uint8_t* src, float* dst, int recip, void* stream) {
     if (n < 0 || (n > 0 && (!src || !dst))) return FSB_E_ARG;
     if (n == 0) return 0;
     int blocks = fsb_div_up(n, 256 * 16);
     if (blocks > FSB_NUM_SMS * 8) blocks = FSB_NUM_SMS * 8;
-    u8_to_unit_float_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, src, dst);
+    if (recip)
+        u8_to_unit_float_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, src, dst);
+    else
+        u8_to_unit_float_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, src, dst);
     FSB_LAUNCH_CHECK();
     return 0;
 }

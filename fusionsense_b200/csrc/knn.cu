@@ -1,0 +1,422 @@
+// knn.cu — exact k nearest neighbours of 3-D points on a quantile grid, and the local-density field built on it.
+//
+// Replaces, on the mesh-export / SDF path of the reference:
+//   * dn_splatter/utils/knn.py:29-43  knn_sk(x, y, k): sklearn NearestNeighbors(k + 1).fit(x).kneighbors(y)[:, 1:]
+//     on the CPU (every call copies both clouds to the host and the indices back);
+//   * dn_splatter/dn_model.py:1575-1635  get_density: ~15 torch launches over [S, K, 3, 3] temporaries.
+//
+// Structure: a g x g x g grid whose cell boundaries along each axis are the i/g QUANTILES of that coordinate (from a
+// strided sample sorted by the library's radix sort), so a dense object inside a sparse room — the shape of a
+// FusionSense scene — gets fine cells where the points are and coarse ones elsewhere; border cells are open-ended.
+// Points are sorted by cell, and each query walks Chebyshev rings of cells around its own cell until the k-th best
+// distance is provably smaller than the distance to the nearest unvisited slab boundary.  Queries that would need
+// more than `max_rings` rings (outliers in empty space) go to a list that a brute-force kernel finishes, so
+// the result is exact for every query.  Distances are fp64 of the fp32 coordinates — the differences and
+// squares are exact, like the KD-tree sklearn picks for 3-D data — and ties are ordered by index.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_MAX_G = 320;  // cells per axis (320^3 = 32.8 M cells)
+
+struct KnnGrid {
+    int g;                 // cells per axis
+    const float* edges;    // [3][g + 1]: cell c of axis a covers [edges[a][c], edges[a][c + 1]); [0] and [g] are the
+                           // sample's extremes, never used as boundaries (the border cells are open-ended)
+};
+
+__device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
+
+// monotone map float -> uint32 (NaN / inf never get here)
+__device__ __forceinline__ uint32_t ordered_bits(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// cell of coordinate p: the number of interior edges e[1 .. g-1] that are <= p (pure comparisons: a point and a query
+// with the same coordinate always land in the same cell, and p in cell c  <=>  e[c] <= p < e[c + 1] away from the borders)
+__device__ __forceinline__ int cell_of(const float* __restrict__ e, int g, float p) {
+    int lo = 0, hi = g - 1;  // answer in [0, g - 1]
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (e[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---- per-axis quantile edges --------------------------------------------------------------------------------
+// keys[a * S + i] = (a << 32) | ordered bits of coordinate a of sample i (point i * stride); non-finite points sort
+// to the end of their axis segment
+__global__ void __launch_bounds__(256)
+knn_axis_keys_kernel(int64_t S, int64_t stride, const float* __restrict__ pts, uint64_t* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const float* p = pts + 3 * (i * stride);
+    const bool fin = finite3(p[0], p[1], p[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        keys[(int64_t)a * S + i] = ((uint64_t)a << 32) | (fin ? ordered_bits(p[a]) : 0xffffffffu);
+}
+
+__global__ void __launch_bounds__(256)
+knn_edges_kernel(int64_t S, const uint64_t* __restrict__ sorted_keys, int g, float* __restrict__ edges) {
+    const int a = blockIdx.x;
+    const uint64_t* k = sorted_keys + (int64_t)a * S;
+    // number of finite samples of this axis: first position whose low word is the non-finite marker
+    int64_t lo = 0, hi = S;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((uint32_t)k[mid] == 0xffffffffu) hi = mid; else lo = mid + 1;
+    }
+    const int64_t n_fin = lo;
+    for (int c = threadIdx.x; c <= g; c += blockDim.x) {
+        float e = 0.f;
+        if (n_fin > 0) {
+            int64_t r = ((int64_t)c * n_fin) / g;  // c <= 320, n_fin < 2^31
+            if (r >= n_fin) r = n_fin - 1;
+            e = from_ordered_bits((uint32_t)k[r]);
+        }
+        edges[a * (g + 1) + c] = e;
+    }
+}
+
+// ---- binning ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_cells_kernel(int64_t N, const float* __restrict__ pts, KnnGrid gr, uint64_t* __restrict__ keys,
+                 int32_t* __restrict__ vals, int32_t* __restrict__ n_nonfinite) {
+    extern __shared__ float s_edges[];
+    for (int i = threadIdx.x; i < 3 * (gr.g + 1); i += blockDim.x) s_edges[i] = gr.edges[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const int g = gr.g;
+    uint64_t key = (uint64_t)g * g * g;  // the cell after the grid: never visited
+    if (finite3(x, y, z)) {
+        const int cx = cell_of(s_edges, g, x);
+        const int cy = cell_of(s_edges + (g + 1), g, y);
+        const int cz = cell_of(s_edges + 2 * (g + 1), g, z);
+        key = ((uint64_t)cz * g + cy) * g + cx;
+    } else if (n_nonfinite) {
+        atomicAdd(n_nonfinite, 1);
+    }
+    keys[i] = key;
+    vals[i] = (int32_t)i;
+}
+
+// cell_start[c] = first sorted position whose key is >= c, c in [0, n_cells]
+__global__ void __launch_bounds__(256)
+knn_cell_start_kernel(int64_t N, const uint64_t* __restrict__ keys, int64_t n_cells, int32_t* __restrict__ cell_start) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    int64_t lo = 0, hi = N;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < (uint64_t)c) lo = mid + 1; else hi = mid;
+    }
+    cell_start[c] = (int32_t)lo;
+}
+
+// sorted_pts[i] = point vals[i] with its index in .w
+__global__ void __launch_bounds__(256)
+knn_gather_kernel(int64_t N, const int32_t* __restrict__ vals, const float* __restrict__ pts,
+                  float4* __restrict__ sorted_pts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int32_t v = vals[i];
+    sorted_pts[i] = make_float4(pts[3 * (size_t)v], pts[3 * (size_t)v + 1], pts[3 * (size_t)v + 2], __int_as_float(v));
+}
+
+// ---- query --------------------------------------------------------------------------------------------------
+// sorted candidate list of the K best (distance^2, index), lexicographic order
+template <int KCAP>
+struct Best {
+    double d[KCAP];
+    int32_t id[KCAP];
+    int n;
+    __device__ __forceinline__ void offer(double dd, int32_t ii, int K) {
+        if (n == K) {
+            if (dd > d[K - 1] || (dd == d[K - 1] && ii > id[K - 1])) return;
+        }
+        int j = n < K ? n : K - 1;
+        while (j > 0 && (d[j - 1] > dd || (d[j - 1] == dd && id[j - 1] > ii))) {
+            d[j] = d[j - 1]; id[j] = id[j - 1];
+            --j;
+        }
+        d[j] = dd; id[j] = ii;
+        if (n < K) ++n;
+    }
+};
+
+template <int KCAP>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_query_kernel(int64_t Ny, const float* __restrict__ y, const int32_t* __restrict__ order, KnnGrid gr,
+                 const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted_pts, int K, int drop_first,
+                 int max_rings, int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                 int32_t* __restrict__ unresolved, int32_t* __restrict__ n_unresolved) {
+    extern __shared__ float s_edges[];
+    const int g = gr.g;
+    for (int i = threadIdx.x; i < 3 * (g + 1); i += blockDim.x) s_edges[i] = gr.edges[i];
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Ny) return;
+    const int64_t qi = order ? order[t] : t;
+    const float qxf = y[3 * qi], qyf = y[3 * qi + 1], qzf = y[3 * qi + 2];
+    const int KO = K - drop_first;
+    if (!finite3(qxf, qyf, qzf)) {  // sklearn refuses NaN input; the caller nan_to_num's (dn_model.py:180)
+        for (int k = 0; k < KO; ++k) {
+            out_idx[qi * KO + k] = -1;
+            if (out_dist) out_dist[qi * KO + k] = NAN;
+        }
+        return;
+    }
+    const float* ex = s_edges;
+    const float* ey = s_edges + (g + 1);
+    const float* ez = s_edges + 2 * (g + 1);
+    const double qx = qxf, qy = qyf, qz = qzf;
+    const int cx = cell_of(ex, g, qxf), cy = cell_of(ey, g, qyf), cz = cell_of(ez, g, qzf);
+    Best<KCAP> best;
+    best.n = 0;
+    bool done = false;
+    for (int r = 0; r <= max_rings; ++r) {
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, g - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, g - 1);
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, g - 1);
+        for (int zz = z0; zz <= z1; ++zz) {
+            const bool zface = (zz == cz - r) || (zz == cz + r);
+            for (int yy = y0; yy <= y1; ++yy) {
+                const bool face = zface || (yy == cy - r) || (yy == cy + r);
+                const int64_t row = ((int64_t)zz * g + yy) * g;
+                // a row on a face of the ring's shell is a run of consecutive cells (consecutive in the sorted order
+                // too); inside the shell only the two end cells of the row belong to ring r
+                const int n_runs = face ? 1 : 2;
+                for (int run = 0; run < n_runs; ++run) {
+                    int xa, xb;
+                    if (face) { xa = x0; xb = x1; }
+                    else { xa = xb = run ? cx + r : cx - r; if (xa < 0 || xa >= g) continue; }
+                    const int b = cell_start[row + xa], e = cell_start[row + xb + 1];
+                    for (int i = b; i < e; ++i) {
+                        const float4 p = sorted_pts[i];
+                        const double dx = qx - (double)p.x, dy = qy - (double)p.y, dz = qz - (double)p.z;
+                        best.offer(dx * dx + dy * dy + dz * dz, __float_as_int(p.w), K);
+                    }
+                }
+            }
+        }
+        // Every unvisited point sits in a cell more than r away (in cells) along some axis, i.e. beyond one of the six
+        // slab boundaries below; border cells are open-ended, so a side whose slab reaches the border holds nothing more.
+        double reach = INFINITY;
+        if (cx - r >= 1) reach = fmin(reach, qx - (double)ex[cx - r]);
+        if (cx + r + 1 <= g - 1) reach = fmin(reach, (double)ex[cx + r + 1] - qx);
+        if (cy - r >= 1) reach = fmin(reach, qy - (double)ey[cy - r]);
+        if (cy + r + 1 <= g - 1) reach = fmin(reach, (double)ey[cy + r + 1] - qy);
+        if (cz - r >= 1) reach = fmin(reach, qz - (double)ez[cz - r]);
+        if (cz + r + 1 <= g - 1) reach = fmin(reach, (double)ez[cz + r + 1] - qz);
+        if (reach == INFINITY) { done = true; break; }  // the whole grid has been visited
+        // strict: an unvisited point at exactly the k-th distance could still win the tie on its index
+        if (best.n == K && reach > 0.0 && best.d[K - 1] < reach * reach) { done = true; break; }
+    }
+    if (!done) {
+        const int slot = atomicAdd(n_unresolved, 1);
+        unresolved[slot] = (int32_t)qi;
+        return;
+    }
+    for (int k = 0; k < KO; ++k) {
+        const int s = k + drop_first;
+        out_idx[qi * KO + k] = s < best.n ? (int64_t)best.id[s] : -1;
+        if (out_dist) out_dist[qi * KO + k] = s < best.n ? sqrt(best.d[s]) : INFINITY;
+    }
+}
+
+// Queries the grid walk gave up on: one CTA per query, K rounds of "smallest (distance, index) above the previous pick"
+// over all points.  O(K N) per query, for the handful of outliers only.
+__global__ void __launch_bounds__(256)
+knn_brute_kernel(int64_t Nx, const float* __restrict__ x, const float* __restrict__ y,
+                 const int32_t* __restrict__ unresolved, const int32_t* __restrict__ n_unresolved, int K, int drop_first,
+                 int64_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    __shared__ double sd[256];
+    __shared__ int32_t si[256];
+    const int KO = K - drop_first;
+    const int total = *n_unresolved;
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        const int64_t qi = unresolved[u];
+        const double qx = y[3 * qi], qy = y[3 * qi + 1], qz = y[3 * qi + 2];
+        double pd = -1.0;
+        int32_t pi = -1;
+        for (int k = 0; k < K; ++k) {
+            double bd = INFINITY;
+            int32_t bi = 0x7fffffff;
+            for (int64_t i = threadIdx.x; i < Nx; i += blockDim.x) {
+                const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
+                if (!finite3(px, py, pz)) continue;
+                const double dx = qx - (double)px, dy = qy - (double)py, dz = qz - (double)pz;
+                const double d = dx * dx + dy * dy + dz * dz;
+                const int32_t ii = (int32_t)i;
+                const bool after_prev = d > pd || (d == pd && ii > pi);
+                if (after_prev && (d < bd || (d == bd && ii < bi))) { bd = d; bi = ii; }
+            }
+            sd[threadIdx.x] = bd; si[threadIdx.x] = bi;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if ((int)threadIdx.x < o) {
+                    const double od = sd[threadIdx.x + o];
+                    const int32_t oi = si[threadIdx.x + o];
+                    if (od < sd[threadIdx.x] || (od == sd[threadIdx.x] && oi < si[threadIdx.x])) {
+                        sd[threadIdx.x] = od; si[threadIdx.x] = oi;
+                    }
+                }
+                __syncthreads();
+            }
+            pd = sd[0]; pi = si[0];
+            const bool found = pi != 0x7fffffff;
+            if (threadIdx.x == 0 && k >= drop_first) {
+                out_idx[qi * KO + (k - drop_first)] = found ? (int64_t)pi : -1;
+                if (out_dist) out_dist[qi * KO + (k - drop_first)] = found ? sqrt(pd) : INFINITY;
+            }
+            __syncthreads();
+            if (!found) { pd = INFINITY; pi = 0x7fffffff; }
+        }
+    }
+}
+
+// ---- density ------------------------------------------------------------------------------------------------
+// dn_model.py:1596-1634 with scale_rot_to_inv_cov3d (:2141-2150, return_sqrt=True) and gsplat's quat_to_rotmat
+// (normalised wxyz) folded in: one thread per sample, K gathered Gaussians.
+__global__ void __launch_bounds__(256)
+gaussian_density_kernel(int64_t S, const float* __restrict__ samples, int K, const int64_t* __restrict__ knn,
+                        const float* __restrict__ means, const float* __restrict__ log_scales,
+                        const float* __restrict__ quats, const float* __restrict__ opacity_logits,
+                        float* __restrict__ out) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const float sx = samples[3 * s], sy = samples[3 * s + 1], sz = samples[3 * s + 2];
+    float dens = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const int64_t g = knn[s * K + k];
+        const float dx = sx - means[3 * g], dy = sy - means[3 * g + 1], dz = sz - means[3 * g + 2];
+        const float i0 = 1.0f / fmaxf(expf(log_scales[3 * g]), 1e-3f);
+        const float i1 = 1.0f / fmaxf(expf(log_scales[3 * g + 1]), 1e-3f);
+        const float i2 = 1.0f / fmaxf(expf(log_scales[3 * g + 2]), 1e-3f);
+        float w = quats[4 * g], x = quats[4 * g + 1], y = quats[4 * g + 2], z = quats[4 * g + 3];
+        const float qn = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-12f);  // F.normalize's eps
+        w /= qn; x /= qn; y /= qn; z /= qn;
+        const float r00 = 1.f - 2.f * (y * y + z * z), r01 = 2.f * (x * y - w * z), r02 = 2.f * (x * z + w * y);
+        const float r10 = 2.f * (x * y + w * z), r11 = 1.f - 2.f * (x * x + z * z), r12 = 2.f * (y * z - w * x);
+        const float r20 = 2.f * (x * z - w * y), r21 = 2.f * (y * z + w * x), r22 = 1.f - 2.f * (x * x + y * y);
+        // (M^T d)_j = inv_scale_j * sum_i R[i][j] d_i
+        const float m0 = (r00 * i0) * dx + (r10 * i0) * dy + (r20 * i0) * dz;
+        const float m1 = (r01 * i1) * dx + (r11 * i1) * dy + (r21 * i1) * dz;
+        const float m2 = (r02 * i2) * dx + (r12 * i2) * dy + (r22 * i2) * dz;
+        const float maha = fminf(fmaxf(m0 * m0 + m1 * m1 + m2 * m2, 0.f), 1e8f);
+        const float op = 1.f / (1.f + expf(-opacity_logits[g]));
+        dens += op * expf(-0.5f * maha);
+    }
+    if (dens >= 1.0f) dens = dens / (dens + 1e-5f);
+    out[s] = fmaxf(dens, 1e-4f);
+}
+
+}  // namespace
+
+static int knn_g_ok(int g) { return g >= 1 && g <= KNN_MAX_G; }
+
+// Per-axis quantile edges from a strided sample of the cloud (S = number of samples, point i * stride each):
+//   fsb_knn_axis_keys: keys[3 S] u64 = (axis << 32) | order-preserving bits of the coordinate; sort them on bits [0, 34)
+//   fsb_knn_edges    : edges[3][g + 1] f32 = the i/g quantiles of each axis (i = 0 .. g) from the sorted keys
+FSB_API int fsb_knn_axis_keys(int64_t S, int64_t stride, const float* pts, uint64_t* keys, void* stream) {
+    if (S <= 0 || stride < 1 || !pts || !keys) return FSB_E_ARG;
+    knn_axis_keys_kernel<<<fsb_div_up(S, 256), 256, 0, (cudaStream_t)stream>>>(S, stride, pts, keys);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+FSB_API int fsb_knn_edges(int64_t S, const uint64_t* sorted_keys, int g, float* edges, void* stream) {
+    if (S <= 0 || !knn_g_ok(g) || !sorted_keys || !edges) return FSB_E_ARG;
+    knn_edges_kernel<<<3, 256, 0, (cudaStream_t)stream>>>(S, sorted_keys, g, edges);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// keys[i] = linear cell ((cz g + cy) g + cx) of point i in the g^3 grid of `edges` (non-finite points -> g^3 and counted
+// into n_nonfinite, nullable i32, not zeroed here), vals[i] = i; sort the pairs with fsb_radix_sort_pairs
+FSB_API int fsb_knn_cells(int64_t N, const float* pts, int g, const float* edges, uint64_t* keys, int32_t* vals,
+                          int32_t* n_nonfinite, void* stream) {
+    if (N < 0 || N > 0x7fffffff || !knn_g_ok(g) || !edges || (N > 0 && (!pts || !keys || !vals))) return FSB_E_ARG;
+    if (N == 0) return 0;
+    KnnGrid gr{g, edges};
+    knn_cells_kernel<<<fsb_div_up(N, 256), 256, 3 * (g + 1) * sizeof(float), (cudaStream_t)stream>>>(N, pts, gr, keys,
+                                                                                                    vals, n_nonfinite);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// from the pairs sorted by key: cell_start[g^3 + 1] and the points in sorted order (xyz + index bits)
+FSB_API int fsb_knn_build(int64_t N, const uint64_t* sorted_keys, const int32_t* sorted_vals, const float* pts, int g,
+                          int32_t* cell_start, float* sorted_pts, void* stream) {
+    if (N <= 0 || N > 0x7fffffff || !knn_g_ok(g) || !sorted_keys || !sorted_vals || !pts || !cell_start || !sorted_pts)
+        return FSB_E_ARG;
+    const int64_t n_cells = (int64_t)g * g * g;
+    knn_cell_start_kernel<<<fsb_div_up(n_cells + 1, 256), 256, 0, (cudaStream_t)stream>>>(N, sorted_keys, n_cells,
+                                                                                        cell_start);
+    FSB_LAUNCH_CHECK();
+    knn_gather_kernel<<<fsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(N, sorted_vals, pts, (float4*)sorted_pts);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// The K nearest points of every query, nearest first, ties by index; the first `drop_first` of them are not written
+// (knn_sk drops the nearest one: the query itself when y is x).  out_idx [Ny, K - drop_first] i64, out_dist (nullable)
+// f64 distances.  order (nullable): the sequence in which queries are processed (sorted by cell for locality).
+// unresolved i32[Ny] + n_unresolved i32[1] (zeroed here): queries left to fsb_knn_brute.
+FSB_API int fsb_knn_query(int64_t Ny, const float* y, const int32_t* order, int g, const float* edges,
+                          const int32_t* cell_start, const float* sorted_pts, int K, int drop_first, int max_rings,
+                          int64_t* out_idx, double* out_dist, int32_t* unresolved, int32_t* n_unresolved,
+                          void* stream) {
+    if (Ny < 0 || Ny > 0x7fffffff || !knn_g_ok(g) || K < 1 || K > 33 || drop_first < 0 || drop_first >= K ||
+        max_rings < 0 || !n_unresolved)
+        return FSB_E_ARG;
+    FSB_CUDA(cudaMemsetAsync(n_unresolved, 0, sizeof(int32_t), (cudaStream_t)stream));
+    if (Ny == 0) return 0;
+    if (!y || !edges || !cell_start || !sorted_pts || !out_idx || !unresolved) return FSB_E_ARG;
+    KnnGrid gr{g, edges};
+    const int blocks = fsb_div_up(Ny, KNN_THREADS);
+    const size_t sh = 3 * (g + 1) * sizeof(float);
+    if (K <= 17)
+        knn_query_kernel<17><<<blocks, KNN_THREADS, sh, (cudaStream_t)stream>>>(
+            Ny, y, order, gr, cell_start, (const float4*)sorted_pts, K, drop_first, max_rings, out_idx, out_dist,
+            unresolved, n_unresolved);
+    else
+        knn_query_kernel<33><<<blocks, KNN_THREADS, sh, (cudaStream_t)stream>>>(
+            Ny, y, order, gr, cell_start, (const float4*)sorted_pts, K, drop_first, max_rings, out_idx, out_dist,
+            unresolved, n_unresolved);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+FSB_API int fsb_knn_brute(int64_t Nx, const float* x, const float* y, const int32_t* unresolved,
+                          const int32_t* n_unresolved, int K, int drop_first, int64_t* out_idx, double* out_dist,
+                          void* stream) {
+    if (Nx <= 0 || Nx > 0x7fffffff || !x || !y || !unresolved || !n_unresolved || K < 1 || drop_first < 0 ||
+        drop_first >= K || !out_idx)
+        return FSB_E_ARG;
+    knn_brute_kernel<<<FSB_NUM_SMS * 2, 256, 0, (cudaStream_t)stream>>>(Nx, x, y, unresolved, n_unresolved, K,
+                                                                       drop_first, out_idx, out_dist);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// out[s] = clamp_min(normalised sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (sample - mean_g)|^2), 1e-4), g = knn[s, k]
+FSB_API int fsb_gaussian_density(int64_t S, const float* samples, int K, const int64_t* knn, const float* means,
+                                 const float* log_scales, const float* quats, const float* opacity_logits, float* out,
+                                 void* stream) {
+    if (S < 0 || K < 1) return FSB_E_ARG;
+    if (S == 0) return 0;
+    if (!samples || !knn || !means || !log_scales || !quats || !opacity_logits || !out) return FSB_E_ARG;
+    gaussian_density_kernel<<<fsb_div_up(S, 256), 256, 0, (cudaStream_t)stream>>>(S, samples, K, knn, means, log_scales,
+                                                                                 quats, opacity_logits, out);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}

@@ -88,6 +88,7 @@ __device__ __forceinline__ float sh_load(const float* __restrict__ coeffs, const
 
 // act_flags: the parameters arrive as the model stores them and the activation is applied here
 constexpr int ACT_VEC4_ROWS = 2;   // backward: the warp's run of features_rest rows moves as 16-byte requests
+constexpr int ACT_FLAT_ROWS = 4;   // backward: that run keeps its global layout in shared memory (no row/column arithmetic)
 constexpr int ACT_EXP_SCALES = 1;  // scales are log-scales: s = exp(raw)  (dn_model.py:573)
 
 __global__ void __launch_bounds__(256)
@@ -215,7 +216,7 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                       float* __restrict__ v_coeffs, float* __restrict__ v_coeffs_rest, float* __restrict__ v_viewmats,
                       float* __restrict__ v_campos) {
     __shared__ float red[PB_WARPS];
-    __shared__ float tiles[PB_WARPS][32][SH_ROW_MAX + 1];
+    __shared__ __align__(16) float tiles[PB_WARPS][32][SH_ROW_MAX + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float (*tile)[SH_ROW_MAX + 1] = tiles[warp];
     int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,6 +234,16 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
         if (act_flags & ACT_EXP_SCALES) { sx = expf(sx); sy = expf(sy); sz = expf(sz); }
     }
     const bool split = (coeffs_rest != nullptr);  // the host entry point guarantees `staged` in this case
+    // Flat rows (split layout): the warp's 32 rows of features_rest are ONE contiguous run of 32 (L - 3) floats in
+    // global memory; shared memory keeps exactly that layout, so moving it in and out is a plain 16-byte copy with no
+    // (row, column) bookkeeping — that bookkeeping was ~40 % of the kernel's instructions (r02o source page) — and
+    // lane l's row starts at float l (L - 3): conflict-free whenever L - 3 is odd (45 at K = 16).  Band 0
+    // (features_dc) stays in registers.
+    const int LR = L - 3;
+    const bool flat = split && staged && (act_flags & ACT_FLAT_ROWS);
+    float* const flat_buf = &tiles[warp][0][0];  // 32 * 49 floats >= 32 * LR, 16-byte aligned
+    float* const frow = flat_buf + lane * LR;
+    float c0[3] = {0, 0, 0}, g0[3] = {0, 0, 0};  // band-0 coefficients / gradient (flat mode)
     float am[3] = {0, 0, 0}, aq[4] = {0, 0, 0, 0}, as[3] = {0, 0, 0};
     int nb = sh_degree >= 0 ? (sh_degree + 1) * (sh_degree + 1) : 0;
     bool any_sh = false;
@@ -240,14 +251,49 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
     // coefficients themselves (coalesced load), with several they are read straight from global memory
     const bool coeffs_in_tile = staged && C == 1;
     if (staged && !coeffs_in_tile) {
-        for (int k = 0; k < L; ++k) tile[lane][k] = 0.f;
+        if (flat) { for (int k = 0; k < LR; ++k) frow[k] = 0.f; }
+        else { for (int k = 0; k < L; ++k) tile[lane][k] = 0.f; }
     }
     for (int c = 0; c < C; ++c) {
         size_t idx = (size_t)c * N + n;
         bool vis = live && radii[idx] > 0;
         if (coeffs_in_tile) {
             const unsigned vmask = __ballot_sync(0xffffffffu, vis);
-            if (split) {
+            if (flat) {
+                if (vis) {
+                    c0[0] = coeffs[3 * (size_t)n + 0]; c0[1] = coeffs[3 * (size_t)n + 1]; c0[2] = coeffs[3 * (size_t)n + 2];
+                }
+                const int total = min(32, N - n0) * LR;
+                const float* base = coeffs_rest + (size_t)n0 * LR;
+                int e_done = 0;
+                if ((((uintptr_t)base) & 15) == 0) {
+                    constexpr int UB4 = 4;  // independent 16-byte requests per lane in flight
+                    const int total4 = total >> 2;
+                    const float4* base4 = reinterpret_cast<const float4*>(base);
+                    float4* flat4 = reinterpret_cast<float4*>(flat_buf);
+                    const float inv_lr = 1.0f / (float)LR;
+                    for (int e0 = lane; e0 < total4; e0 += 32 * UB4) {
+                        float4 v[UB4];
+#pragma unroll
+                        for (int u = 0; u < UB4; ++u) {
+                            const int e = e0 + 32 * u;
+                            // rows the four floats belong to ((a + 0.5) / LR is >= 0.5 / LR away from an integer: the
+                            // float quotient floors exactly); rows of culled Gaussians are not fetched
+                            const int r_a = (int)(((float)(4 * e) + 0.5f) * inv_lr);
+                            const int r_b = min((int)(((float)(4 * e + 3) + 0.5f) * inv_lr), 31);
+                            const bool ok = e < total4 && (((vmask >> r_a) | (vmask >> r_b)) & 1u);
+                            v[u] = ok ? base4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB4; ++u) {
+                            const int e = e0 + 32 * u;
+                            if (e < total4) flat4[e] = v[u];
+                        }
+                    }
+                    e_done = total4 << 2;
+                }
+                for (int e = e_done + lane; e < total; e += 32) flat_buf[e] = base[e];
+            } else if (split) {
                 // The warp's 32 rows of features_rest are one contiguous run of 32 (L - 3) floats: copy it flat,
                 // lane-contiguous (every request is a full 128-B line), and in batches of independent loads — a
                 // row-at-a-time loop waits for each row's data before it asks for the next (first split version:
@@ -350,11 +396,22 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 float ux = dx * inorm, uy = dy * inorm, uz = dz * inorm;
                 float basis[16];
                 fs::sh_basis(sh_degree, ux, uy, uz, basis);
-                auto cf = [&](int j) -> float {
-                    return coeffs_in_tile ? tile[lane][j] : sh_load(coeffs, coeffs_rest, n, L, j);
-                };
-                float r = 0.f, g = 0.f, b = 0.f;
-                for (int k = 0; k < nb; ++k) {
+                // coefficient (band k >= 1, channel ch) = crow[3 k + ch]; band 0 = cb[ch]
+                const float* crow;
+                float cb[3];
+                if (coeffs_in_tile) {
+                    if (flat) { crow = frow - 3; cb[0] = c0[0]; cb[1] = c0[1]; cb[2] = c0[2]; }
+                    else { crow = &tile[lane][0]; cb[0] = crow[0]; cb[1] = crow[1]; cb[2] = crow[2]; }
+                } else if (split) {
+                    crow = coeffs_rest + (size_t)n * LR - 3;
+                    cb[0] = coeffs[3 * (size_t)n + 0]; cb[1] = coeffs[3 * (size_t)n + 1]; cb[2] = coeffs[3 * (size_t)n + 2];
+                } else {
+                    crow = coeffs + (size_t)n * L;
+                    cb[0] = crow[0]; cb[1] = crow[1]; cb[2] = crow[2];
+                }
+                auto cf = [&](int j) -> float { return crow[j]; };  // j >= 3
+                float r = basis[0] * cb[0], g = basis[0] * cb[1], b = basis[0] * cb[2];
+                for (int k = 1; k < nb; ++k) {
                     r += basis[k] * cf(3 * k + 0);
                     g += basis[k] * cf(3 * k + 1);
                     b += basis[k] * cf(3 * k + 2);
@@ -375,16 +432,20 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
                 // the coefficients of this row are not needed any more: the tile row now takes the gradient
                 if (do_sh) {
                     if (staged) {
-                        float* vrow = &tile[lane][0];
+                        float* vrow = flat ? frow - 3 : &tile[lane][0];  // band k >= 1 at vrow[3 k + ch]
                         if (coeffs_in_tile) {
-                            for (int k = 0; k < nb; ++k) {
+                            if (flat) { g0[0] = basis[0] * vr; g0[1] = basis[0] * vg; g0[2] = basis[0] * vb; }
+                            else { vrow[0] = basis[0] * vr; vrow[1] = basis[0] * vg; vrow[2] = basis[0] * vb; }
+                            for (int k = 1; k < nb; ++k) {
                                 vrow[3 * k + 0] = basis[k] * vr;
                                 vrow[3 * k + 1] = basis[k] * vg;
                                 vrow[3 * k + 2] = basis[k] * vb;
                             }
                             for (int k = nb * 3; k < L; ++k) vrow[k] = 0.f;
                         } else {
-                            for (int k = 0; k < nb; ++k) {
+                            if (flat) { g0[0] += basis[0] * vr; g0[1] += basis[0] * vg; g0[2] += basis[0] * vb; }
+                            else { vrow[0] += basis[0] * vr; vrow[1] += basis[0] * vg; vrow[2] += basis[0] * vb; }
+                            for (int k = 1; k < nb; ++k) {
                                 vrow[3 * k + 0] += basis[k] * vr;
                                 vrow[3 * k + 1] += basis[k] * vg;
                                 vrow[3 * k + 2] += basis[k] * vb;
@@ -438,11 +499,30 @@ project_sh_bwd_kernel(int C, int N, const float* __restrict__ means, const float
         if (staged) {
             // rows of Gaussians that were never visible (or hold stale coefficients) are zero
             if (!any_sh) {
-                for (int k = 0; k < L; ++k) tile[lane][k] = 0.f;
+                if (flat) { for (int k = 0; k < LR; ++k) frow[k] = 0.f; }
+                else { for (int k = 0; k < L; ++k) tile[lane][k] = 0.f; }
             }
             __syncwarp();
             const int rows = min(32, N - n0);
-            if (split) {
+            if (flat) {
+                if (live) {
+                    v_coeffs[3 * (size_t)n + 0] = any_sh ? g0[0] : 0.f;
+                    v_coeffs[3 * (size_t)n + 1] = any_sh ? g0[1] : 0.f;
+                    v_coeffs[3 * (size_t)n + 2] = any_sh ? g0[2] : 0.f;
+                }
+                const int total = rows * LR;
+                float* base = v_coeffs_rest + (size_t)n0 * LR;
+                int e_done = 0;
+                if ((((uintptr_t)base) & 15) == 0) {
+                    const int total4 = total >> 2;
+                    float4* base4 = reinterpret_cast<float4*>(base);
+                    const float4* flat4 = reinterpret_cast<const float4*>(flat_buf);
+#pragma unroll 4
+                    for (int e = lane; e < total4; e += 32) base4[e] = flat4[e];
+                    e_done = total4 << 2;
+                }
+                for (int e = e_done + lane; e < total; e += 32) base[e] = flat_buf[e];
+            } else if (split) {
                 if (live) {
                     v_coeffs[3 * (size_t)n + 0] = tile[lane][0];
                     v_coeffs[3 * (size_t)n + 1] = tile[lane][1];
@@ -601,7 +681,11 @@ FSB_API int fsb_project_params_bwd(int C, int N, const float* means, const float
     // warps hide), so the 115-register build stays the default
     static const int minb = [] { const char* e = getenv("FSB_PROJ_BWD_MINB"); return e ? atoi(e) : 4; }();
     // FSB_PROJ_BWD_VEC4=0: 4-byte requests for the SH rows (A/B runs)
-    static const int vec4 = [] { const char* e = getenv("FSB_PROJ_BWD_VEC4"); return (e && e[0] == '0') ? 0 : ACT_VEC4_ROWS; }();
+    static const int vec4 = [] {
+        const char* e = getenv("FSB_PROJ_BWD_VEC4");
+        const char* f = getenv("FSB_PROJ_BWD_FLAT");  // =0: the row-tile staging of r02l (A/B runs)
+        return ((e && e[0] == '0') ? 0 : ACT_VEC4_ROWS) | ((f && f[0] == '0') ? 0 : ACT_FLAT_ROWS);
+    }();
 #define FSB_PBWD(MINB)                                                                                              \
     project_sh_bwd_kernel<MINB><<<fsb_div_up(N, PB_THREADS), PB_THREADS, 0, (cudaStream_t)stream>>>(                \
         C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, sh_degree, K, features_dc,                  \

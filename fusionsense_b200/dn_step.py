@@ -540,6 +540,9 @@ class DNSplatterStep:
         depth = torch.where(out["accumulation"] > 0.5, out["depth"], torch.zeros_like(out["depth"]))
         rgb, normal = out["rgb"].contiguous(), out["normal"].contiguous()
         if eight_bit:
+            # the float32 values the reference's loaders make of the bytes: `image.float() / 255.0` on the device
+            # (get_gt_img; torch's CUDA division by a scalar multiplies by the fp32 reciprocal) and numpy's IEEE
+            # division for the normal maps (dn_dataset.py:205)
             rgb = torch.round(rgb.clamp(0, 1) * 255.0) / 255.0
-            normal = torch.round(normal.clamp(0, 1) * 255.0) / 255.0
+            normal = torch.div(torch.round(normal.clamp(0, 1) * 255.0), torch.full((), 255.0, device=normal.device))
         return {"image": rgb, "sensor_depth": depth.contiguous(), "normal": normal}

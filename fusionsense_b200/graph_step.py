@@ -369,7 +369,7 @@ class GraphedDNSplatterStep:
                 # one buffer per (key, stream): copies and conversions of successive views are ordered by the stream
                 buf = self._u8_stage[sk] = torch.empty(t.numel(), dtype=torch.uint8, device=self.device)
             buf.copy_(t.reshape(-1), non_blocking=True)
-            u8_to_unit_float(buf, slot)
+            u8_to_unit_float(buf, slot, recip=(key != "normal"))  # normals: numpy's division (dn_dataset.py:205)
         else:
             slot.copy_(t, non_blocking=True)
         return t.numel() * t.element_size()

@@ -415,9 +415,10 @@ int fsb_compose_rgbd_bwd(int64_t P, const float* render, const float* alpha, con
                          const float* v_rgb, const float* v_depth, float* v_render, float* v_alpha, void* stream);
 int fsb_normal_map_fwd(int64_t P, const float* normals_raw, float* out, void* stream);
 int fsb_normal_map_bwd(int64_t P, const float* normals_raw, const float* v_out, float* v_normals_raw, void* stream);
-/* 8-bit image targets -> float32 on the device: dst[i] = float(src[i]) / 255.0f — splatfacto get_gt_img's
- * `image.float() / 255.0` for uint8 batches and dn_dataset.py:205 for the normal maps, IEEE division. */
-int fsb_u8_to_unit_float(int64_t n, const uint8_t* src, float* dst, void* stream);
+/* 8-bit image targets -> float32 on the device, with the reference's bits: recip = 1: src * (1.0f / 255.0f) — what
+ * splatfacto get_gt_img's `image.float() / 255.0` evaluates to on the device (torch's CUDA division by a Python scalar
+ * multiplies by the fp32 reciprocal); recip = 0: IEEE src / 255.0f — numpy's division in dn_dataset.py:205. */
+int fsb_u8_to_unit_float(int64_t n, const uint8_t* src, float* dst, int recip, void* stream);
 
 /* Flatness regulariser ("two_d_gaussians").  replaces dn_splatter/dn_model.py:817-819:
  *   out = mean_i min_k exp(log_scales[i,k])     (device scalar; workspace: 16 bytes)
@@ -462,6 +463,39 @@ int fsb_densify_stats(int N, const int32_t* radii, const float* grads2d, float m
  *   normals[H,W,3] = normalize((right - left) x (top - bottom)), the one-pixel border is zero. */
 int fsb_normal_from_depth(int H, int W, const float* depth, const float* xyz, float fx, float fy, float cx,
                           float cy, const float* rot_inv, const float* trans, float* normals, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * f2: exact k nearest neighbours of 3-D points and the local density field of the mesh-export /
+ * SDF path.  replaces knn_sk (dn_splatter/utils/knn.py:29-43: sklearn NearestNeighbors(k + 1) on the CPU, first
+ * neighbour dropped; call sites dn_splatter/dn_model.py:183-189, :306-310, :1562-1572) and get_density
+ * (dn_model.py:1575-1635 with scale_rot_to_inv_cov3d, :2141-2150).
+ *   fsb_knn_axis_keys : keys[3 S] u64 = (axis << 32) | order-preserving bits of coordinate `axis` of the S sampled
+ *                    points (point i * stride); sort them with fsb_radix_sort_keys on bits [0, 34)
+ *   fsb_knn_edges  : edges[3][g + 1] f32 = the i/g quantiles of every axis: a g^3 grid that is fine where the points are
+ *   fsb_knn_cells  : keys[i] = linear cell ((cz g + cy) g + cx) of point i (border cells open-ended, non-finite points
+ *                    -> g^3 and counted into n_nonfinite, nullable), vals[i] = i; sort with fsb_radix_sort_pairs
+ *   fsb_knn_build  : cell_start[g^3 + 1] i32 and sorted_pts[N,4] (xyz + index bits) from the sorted pairs
+ *   fsb_knn_query  : the K <= 33 nearest points of every y, nearest first, ties by index (distances in fp64 of the fp32
+ *                    coordinates); the first drop_first are not written.  out_idx [Ny, K - drop_first] i64, out_dist
+ *                    (nullable) f64.  order (nullable) = processing order.  Queries needing more than max_rings rings
+ *                    of cells are appended to unresolved[Ny] / n_unresolved[1] and finished by
+ *   fsb_knn_brute  : K selection rounds over all points, one CTA per unresolved query.
+ *   fsb_gaussian_density : out[s] = clamp_min(norm(sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (x_s - mu_g)|^2)), 1e-4),
+ *                    g = knn[s,k], M = R(quat) diag(1 / clamp_min(exp(log_scales), 1e-3)), norm(d) = d / (d + 1e-5) if d >= 1 */
+int fsb_knn_axis_keys(int64_t S, int64_t stride, const float* pts, uint64_t* keys, void* stream);
+int fsb_knn_edges(int64_t S, const uint64_t* sorted_keys, int g, float* edges, void* stream);
+int fsb_knn_cells(int64_t N, const float* pts, int g, const float* edges, uint64_t* keys, int32_t* vals,
+                  int32_t* n_nonfinite, void* stream);
+int fsb_knn_build(int64_t N, const uint64_t* sorted_keys, const int32_t* sorted_vals, const float* pts, int g,
+                  int32_t* cell_start, float* sorted_pts, void* stream);
+int fsb_knn_query(int64_t Ny, const float* y, const int32_t* order, int g, const float* edges,
+                  const int32_t* cell_start, const float* sorted_pts, int K, int drop_first, int max_rings,
+                  int64_t* out_idx, double* out_dist, int32_t* unresolved, int32_t* n_unresolved, void* stream);
+int fsb_knn_brute(int64_t Nx, const float* x, const float* y, const int32_t* unresolved, const int32_t* n_unresolved,
+                  int K, int drop_first, int64_t* out_idx, double* out_dist, void* stream);
+int fsb_gaussian_density(int64_t S, const float* samples, int K, const int64_t* knn, const float* means,
+                         const float* log_scales, const float* quats, const float* opacity_logits, float* out,
+                         void* stream);
 
 /* library bookkeeping: kernels launched by libfsb200 since load (monotone), ABI revision */
 uint64_t fsb_launch_count(void);

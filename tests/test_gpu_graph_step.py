@@ -327,8 +327,8 @@ def test_camera_batch_per_iteration_accumulates_like_separate_backwards():
 
 @pytest.mark.parametrize("n", [0, 1, 15, 16, 4099, 3 * 640 * 480 + 5])
 def test_u8_targets_convert_to_torch_bits(n):
-    """fsb_u8_to_unit_float == `image.float() / 255.0` (splatfacto get_gt_img, dn_dataset.py:205), bit for bit,
-    on aligned and unaligned starts and ragged tails."""
+    """fsb_u8_to_unit_float == `image.float() / 255.0` on the device (splatfacto get_gt_img) and numpy's
+    `x.astype("float32") / 255.0` (dn_dataset.py:205), bit for bit, on aligned and unaligned starts and ragged tails."""
     from fusionsense_b200.compose import u8_to_unit_float
 
     g = torch.Generator().manual_seed(n)
@@ -338,8 +338,11 @@ def test_u8_targets_convert_to_torch_bits(n):
         if n > 256:
             src[:256] = torch.arange(256, dtype=torch.uint8, device=DEV)  # every byte value at least once
         src = src.contiguous() if off == 0 else src  # a slice of a 1-D tensor is contiguous but unaligned
-        out = u8_to_unit_float(src)
-        assert torch.equal(out, src.float() / 255.0)
+        # on the device torch divides by a Python scalar through the fp32 reciprocal (get_gt_img runs there) ...
+        assert torch.equal(u8_to_unit_float(src), src.float() / 255.0)
+        # ... numpy divides (dn_dataset.py:205)
+        want = torch.from_numpy(src.cpu().numpy().astype("float32") / 255.0).to(DEV)
+        assert torch.equal(u8_to_unit_float(src, recip=False), want)
 
 
 def test_staged_u8_targets_equal_resident_float_targets():
