@@ -295,7 +295,7 @@ class DNSplatterStep:
             self.conics = info["conics"]
             self.num_tiles_hit = info["tiles_per_gauss"]
             rgb, depth_im = compose_rgbd(render, alpha, self.background)
-            normals_im = normal_map(info["render_b"][0])
+            normals_im = normal_map(info["render_b"].squeeze(0))  # squeeze: a view in backward too (select is not)
             return {"rgb": rgb, "depth": depth_im, "normal": normals_im, "accumulation": alpha.squeeze(0),
                     "background": self.background}
         render, alpha, info = self._rasterization_from_params(

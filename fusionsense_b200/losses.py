@@ -160,7 +160,9 @@ class FusedSSIM(nn.Module):
         if t.dim() == 4:
             if t.shape[0] != 1:
                 raise ValueError("FusedSSIM handles one image per call (the reference trains one camera per step)")
-            return t[0].permute(1, 2, 0)  # a view; contiguous again when it came from an [H,W,C] image
+            # squeeze, not t[0]: select's backward materialises a zero [1,C,H,W] tensor and copies into it (two 25 MB
+            # launches per 1080p step); squeeze's backward is a view.  Contiguous again when it came from an [H,W,C] image
+            return t.squeeze(0).permute(1, 2, 0)
         return t
 
     def forward(self, preds: Tensor, target: Tensor) -> Tensor:

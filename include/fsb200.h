@@ -497,6 +497,31 @@ int fsb_gaussian_density(int64_t S, const float* samples, int K, const int64_t* 
                          const float* log_scales, const float* quats, const float* opacity_logits, float* out,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * f3: the seed point cloud of Module 1.  replaces get_pointcloud (utils/generate_pcd.py:15-48:
+ * meshgrid, (x - CX) / FX, [3,3] @ [3,P] matmul, colour permute, two boolean-mask gathers per view) and open3d's
+ * voxel_down_sample(0.02) on the CPU (utils/generate_pcd.py:98-101), i.e. what init_pcd_generate (scripts/train.py:95)
+ * writes to merged_pcd.ply.
+ *   fsb_backproject_flags : flags[i] i32 = lo < depth[i] < hi; scan them with fsb_isect_scan -> offsets, count
+ *   fsb_backproject_emit  : out[offsets[i], 0:6] = (R p_cam + T, r, g, b) for every kept pixel, in pixel order;
+ *                           c2w_rot (9, row-major) / c2w_trans (3) are HOST pointers, color_chw the [3,H,W] image
+ *   fsb_voxel_keys        : open3d's voxel = floor((p - (min_bound - voxel / 2)) / voxel) in fp64 as a 63-bit key (21 bits
+ *                           per axis, x high); min_bound[3] f64 (device) is computed here; *overflow (device i32, not
+ *                           zeroed here) is set when an index leaves [0, 2^21); sort with fsb_radix_sort_pairs(63)
+ *   fsb_voxel_heads       : heads[i] i32 = sorted position i starts a voxel; scan with fsb_isect_scan
+ *   fsb_voxel_mean        : out[n_voxels, width] f64 = mean of each voxel's rows pts[., 0:width] (fp64 sums in input
+ *                           order, like open3d's AccumulatedPoint), voxels in ascending key order */
+int fsb_backproject_flags(int64_t P, const float* depth, float lo, float hi, int32_t* flags, void* stream);
+int fsb_backproject_emit(int H, int W, const float* depth, const float* color_chw, const float* c2w_rot,
+                         const float* c2w_trans, float fx, float fy, float cx, float cy, float lo, float hi,
+                         const int64_t* offsets, float* out, void* stream);
+size_t fsb_voxel_workspace(void);
+int fsb_voxel_keys(int64_t N, const float* pts, int stride, double voxel, double* min_bound, uint64_t* keys,
+                   int32_t* vals, int32_t* overflow, void* workspace, size_t workspace_bytes, void* stream);
+int fsb_voxel_heads(int64_t N, const uint64_t* sorted_keys, int32_t* heads, void* stream);
+int fsb_voxel_mean(int64_t N, const uint64_t* sorted_keys, const int32_t* sorted_vals, const int32_t* heads,
+                   const int64_t* offsets, const float* pts, int stride, int width, double* out, void* stream);
+
 /* library bookkeeping: kernels launched by libfsb200 since load (monotone), ABI revision */
 uint64_t fsb_launch_count(void);
 int fsb_abi_version(void);
