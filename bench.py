@@ -399,20 +399,14 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
     # RGB and normal targets hold 8-bit values, as the PNGs of a FusionSense dataset do (images/rgb_i.png,
     # normals_from_pretrain/*.png); the host side of the e2e leg keeps them as uint8 (nerfstudio caches uint8 images)
     # and the float32 `x / 255.0` of splatfacto's get_gt_img / dn_dataset.py:205 happens on the device after the copy
-    # (fsb_u8_to_unit_float, identical bits): 20.7 MB per 1080p view cross PCIe instead of 58 MB.  Depth is float32.
-    dev_targets = {v: model.render_targets(v, eight_bit=True) for v in views}
-
+    # (fsb_u8_to_unit_float, the reference's bits): 20.7 MB per 1080p view cross PCIe instead of 58 MB.  Depth is
+    # float32.  The resident leg trains on the very same float32 values (graph_step.eight_bit_targets).
     from fusionsense_b200.compose import u8_to_unit_float
+    from fusionsense_b200.graph_step import eight_bit_targets
 
-    def to_host(k, t):
-        if k in ("image", "normal"):
-            q = torch.round(t * 255.0).to(torch.uint8)
-            back = u8_to_unit_float(q.contiguous().view(-1), recip=(k == "image")).view(t.shape)
-            assert torch.equal(back, t), f"{k}: 8-bit host copy does not reproduce the resident target"
-            t = q
-        return t.cpu().pin_memory()
-
-    host_targets = {v: {k: to_host(k, t) for k, t in d.items()} for v, d in dev_targets.items()}
+    dev_targets, host_targets = {}, {}
+    for v in views:
+        dev_targets[v], host_targets[v] = eight_bit_targets(model.render_targets(v))
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values()) * min(vpi, n_views)
     params = [model.gauss_params[k] for k in model.config.lrs]
     graph_mode = mode == "graph"

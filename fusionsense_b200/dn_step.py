@@ -523,10 +523,8 @@ class DNSplatterStep:
                 opt.step()
 
     @torch.no_grad()
-    def render_targets(self, cam_idx: int, perturb: float = 0.02, seed: int = 0, eight_bit: bool = False) -> Dict[str, Tensor]:
-        """Ground truth for a synthetic view: a render of a perturbed copy of the scene.
-        `eight_bit`: RGB and normal targets take the values an 8-bit PNG holds (`round(x * 255) / 255`), as the
-        reference's datasets do (images/rgb_i.png, normals_from_pretrain/*.png; depth stays float32)."""
+    def render_targets(self, cam_idx: int, perturb: float = 0.02, seed: int = 0) -> Dict[str, Tensor]:
+        """Ground truth for a synthetic view: a render of a perturbed copy of the scene."""
         g = torch.Generator(device="cpu").manual_seed(seed + cam_idx)
         saved = {k: v.data.clone() for k, v in self.gauss_params.items()}
         for k, v in self.gauss_params.items():
@@ -538,11 +536,4 @@ class DNSplatterStep:
         for k, v in self.gauss_params.items():
             v.data.copy_(saved[k])
         depth = torch.where(out["accumulation"] > 0.5, out["depth"], torch.zeros_like(out["depth"]))
-        rgb, normal = out["rgb"].contiguous(), out["normal"].contiguous()
-        if eight_bit:
-            # the float32 values the reference's loaders make of the bytes: `image.float() / 255.0` on the device
-            # (get_gt_img; torch's CUDA division by a scalar multiplies by the fp32 reciprocal) and numpy's IEEE
-            # division for the normal maps (dn_dataset.py:205)
-            rgb = torch.round(rgb.clamp(0, 1) * 255.0) / 255.0
-            normal = torch.div(torch.round(normal.clamp(0, 1) * 255.0), torch.full((), 255.0, device=normal.device))
-        return {"image": rgb, "sensor_depth": depth.contiguous(), "normal": normal}
+        return {"image": out["rgb"].contiguous(), "sensor_depth": depth.contiguous(), "normal": out["normal"].contiguous()}

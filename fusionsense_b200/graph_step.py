@@ -20,7 +20,7 @@ the host notices through `poll()`, grows the capacity and re-runs).
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional
+from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -29,6 +29,30 @@ from . import ops
 from ._abi import check, lib
 from .dn_step import DNSplatterStep
 from .optim import CapturedAdam
+
+
+U8_TARGET_KEYS = ("image", "normal")
+
+
+def eight_bit_targets(batch: Dict[str, Tensor]) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+    """A view's targets as a FusionSense dataset holds them: RGB and normal map as 8-bit images (images/rgb_i.png,
+    normals_from_pretrain/*.png), depth as float32.  Returns (resident, host): `host` keeps the two images as pinned
+    uint8 (what nerfstudio's image cache holds and what crosses PCIe), `resident` is what the reference's loaders make
+    of those bytes on the device — `image.float() / 255.0` (splatfacto get_gt_img) and numpy's
+    `normal_map.astype("float32") / 255.0` (dn_dataset.py:205) — computed by the same kernel `stage_async` runs after
+    the copy, so a staged view and a resident one are bit-identical."""
+    from .compose import u8_to_unit_float
+
+    resident, host = {}, {}
+    for k, t in batch.items():
+        if k in U8_TARGET_KEYS:
+            q = torch.round(t.detach().clamp(0, 1) * 255.0).to(torch.uint8).contiguous()
+            resident[k] = u8_to_unit_float(q.view(-1), recip=(k != "normal")).view(t.shape)
+            host[k] = q.cpu().pin_memory()
+        else:
+            resident[k] = t
+            host[k] = t.detach().cpu().pin_memory()
+    return resident, host
 
 
 class GraphedDNSplatterStep:

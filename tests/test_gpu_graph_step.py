@@ -350,11 +350,18 @@ def test_staged_u8_targets_equal_resident_float_targets():
     reference computes after its own copy; a replay on them gives the loss of the float32 targets."""
     from fusionsense_b200.graph_step import GraphedDNSplatterStep
 
-    eager, graphed, _ = _pair()
-    targets = {v: eager.render_targets(v, eight_bit=True) for v in range(3)}
+    from fusionsense_b200.graph_step import eight_bit_targets
+
+    eager, graphed, raw = _pair()
+    both = {v: eight_bit_targets(raw[v]) for v in range(3)}
+    targets = {v: both[v][0] for v in range(3)}
+    host = {v: both[v][1] for v in range(3)}
+    assert host[0]["image"].dtype == torch.uint8 and host[0]["normal"].dtype == torch.uint8
+    assert host[0]["sensor_depth"].dtype == torch.float32 and host[0]["image"].is_pinned()
+    # the resident float32 targets are what the reference's loaders make of the bytes
+    assert torch.equal(targets[1]["image"], host[1]["image"].to(DEV).float() / 255.0)
+    assert torch.equal(targets[1]["normal"].cpu(), torch.from_numpy(host[1]["normal"].numpy().astype("float32") / 255.0))
     runner = GraphedDNSplatterStep(graphed, targets)
-    host = {v: {k: (torch.round(t * 255.0).to(torch.uint8) if k != "sensor_depth" else t).cpu().pin_memory()
-                for k, t in d.items()} for v, d in targets.items()}
     want = {k: t.clone() for k, t in runner.targets.items()}
     for t in runner.targets.values():
         t.zero_()
