@@ -407,6 +407,8 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
     dev_targets, host_targets = {}, {}
     for v in views:
         dev_targets[v], host_targets[v] = eight_bit_targets(model.render_targets(v))
+    if os.environ.get("FSB_U8_TARGETS", "1") == "0":  # A/B: the same values cross PCIe as float32 (58 MB per 1080p view)
+        host_targets = {v: {k: t.cpu().pin_memory() for k, t in d.items()} for v, d in dev_targets.items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_targets[0].values()) * min(vpi, n_views)
     params = [model.gauss_params[k] for k in model.config.lrs]
     graph_mode = mode == "graph"
@@ -573,6 +575,7 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / steps, "clocks": clocks,
         "graph": graph_info, "warmup_actual": warmup + warm_extra, "fused_outputs": bool(model.config.fused_outputs),
         "prune_lists": bool(model.config.prune_lists), "step_metrics": bool(model.config.step_metrics),
+        "host_targets": {k: str(t.dtype).replace("torch.", "") for k, t in host_targets[0].items()},
     }
 
     if detail:
@@ -763,9 +766,13 @@ def run_ours(args):
                        # FSB_STEP_METRICS=1: get_metrics_dict (PSNR / SSIM / depth metrics, fused, no host sync) runs
                        # inside every iteration as under nerfstudio's Trainer
                        "step_metrics": main["step_metrics"],
+                       # what the e2e leg copies per view: the 8-bit RGB / normal images as a dataset holds them (the
+                       # x / 255.0 of get_gt_img / dn_dataset.py:205 runs on the device), float32 depth
+                       "host_targets": main["host_targets"],
                        "grad_exchange": (None if world == 1 else
-                                         ("own kernels over NVLink peer memory (pack, barrier, reduce-scatter, barrier, "
-                                          "Adam gathering the reduced slices), captured in the step's graph"
+                                         ("own kernels over NVLink peer memory (pack, barrier, in-place all-reduce in chunks "
+                                          "on a high-priority stream, Adam of chunk k beside the all-reduce of chunk "
+                                          "k + 1), captured in the step's graph"
                                           if ctx.exchange == "peer" else
                                           "one flat NCCL all-reduce captured in the step's graph")),
                        "l2": "per-step working set (parameters, Adam state, gradients, intersection lists, images: "

@@ -8,9 +8,9 @@
 // Structure: a g x g x g grid whose cell boundaries along each axis are the i/g QUANTILES of that coordinate (from a
 // strided sample sorted by the library's radix sort), so a dense object inside a sparse room — the shape of a
 // FusionSense scene — gets fine cells where the points are and coarse ones elsewhere; border cells are open-ended.
-// Points are sorted by cell, and each query walks Chebyshev rings of cells around its own cell until the k-th best
-// distance is provably smaller than the distance to the nearest unvisited slab boundary.  Queries that would need
-// more than `max_rings` rings (outliers in empty space) go to a list that a brute-force kernel finishes, so
+// Points are sorted by cell, and each query grows a box of cells around its own cell, always on the face nearest to
+// it, until the k-th best distance is provably smaller than the distance to the nearest face.  Queries that would need
+// more than `max_steps` growth steps (outliers in empty space) go to a list that a brute-force kernel finishes, so
 // the result is exact for every query.  Distances are fp64 of the fp32 coordinates — the differences and
 // squares are exact, like the KD-tree sklearn picks for 3-D data — and ties are ordered by index.
 #include "common.cuh"
@@ -156,7 +156,7 @@ template <int KCAP>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_query_kernel(int64_t Ny, const float* __restrict__ y, const int32_t* __restrict__ order, KnnGrid gr,
                  const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted_pts, int K, int drop_first,
-                 int max_rings, int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                 int max_steps, int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
                  int32_t* __restrict__ unresolved, int32_t* __restrict__ n_unresolved) {
     extern __shared__ float s_edges[];
     const int g = gr.g;
@@ -181,44 +181,64 @@ knn_query_kernel(int64_t Ny, const float* __restrict__ y, const int32_t* __restr
     const int cx = cell_of(ex, g, qxf), cy = cell_of(ey, g, qyf), cz = cell_of(ez, g, qzf);
     Best<KCAP> best;
     best.n = 0;
+    auto scan = [&](int b, int e) {
+        for (int i = b; i < e; ++i) {
+            const float4 p = sorted_pts[i];
+            const double dx = qx - (double)p.x, dy = qy - (double)p.y, dz = qz - (double)p.z;
+            // every product and sum rounded on its own (no FMA): the bits numpy and sklearn's KD-tree compute
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            best.offer(d2, __float_as_int(p.w), K);
+        }
+    };
+    // The visited set is a box of cells [lo, hi] per axis, grown one slab at a time on the face that is NEAREST to the
+    // query (cells are as wide as the local quantiles make them — a few millimetres across a dense object, decimetres in
+    // the room around it — so growing all six faces in step would crawl along the thin axes).  Every unvisited point lies
+    // beyond one of the six faces; border cells are open-ended, so a face on the border has nothing behind it.
+    int lo[3] = {cx, cy, cz}, hi[3] = {cx, cy, cz};
+    {
+        const int64_t c = ((int64_t)cz * g + cy) * g + cx;
+        scan(cell_start[c], cell_start[c + 1]);
+    }
+    const double q3[3] = {qx, qy, qz};
+    const float* e3[3] = {ex, ey, ez};
     bool done = false;
-    for (int r = 0; r <= max_rings; ++r) {
-        const int z0 = max(cz - r, 0), z1 = min(cz + r, g - 1);
-        const int y0 = max(cy - r, 0), y1 = min(cy + r, g - 1);
-        const int x0 = max(cx - r, 0), x1 = min(cx + r, g - 1);
-        for (int zz = z0; zz <= z1; ++zz) {
-            const bool zface = (zz == cz - r) || (zz == cz + r);
-            for (int yy = y0; yy <= y1; ++yy) {
-                const bool face = zface || (yy == cy - r) || (yy == cy + r);
-                const int64_t row = ((int64_t)zz * g + yy) * g;
-                // a row on a face of the ring's shell is a run of consecutive cells (consecutive in the sorted order
-                // too); inside the shell only the two end cells of the row belong to ring r
-                const int n_runs = face ? 1 : 2;
-                for (int run = 0; run < n_runs; ++run) {
-                    int xa, xb;
-                    if (face) { xa = x0; xb = x1; }
-                    else { xa = xb = run ? cx + r : cx - r; if (xa < 0 || xa >= g) continue; }
-                    const int b = cell_start[row + xa], e = cell_start[row + xb + 1];
-                    for (int i = b; i < e; ++i) {
-                        const float4 p = sorted_pts[i];
-                        const double dx = qx - (double)p.x, dy = qy - (double)p.y, dz = qz - (double)p.z;
-                        best.offer(dx * dx + dy * dy + dz * dz, __float_as_int(p.w), K);
-                    }
-                }
+    for (int step = 0; step <= max_steps; ++step) {
+        double reach = INFINITY;
+        int face = -1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (lo[a] >= 1) {
+                const double d = q3[a] - (double)e3[a][lo[a]];
+                if (d < reach) { reach = d; face = 2 * a; }
+            }
+            if (hi[a] + 1 <= g - 1) {
+                const double d = (double)e3[a][hi[a] + 1] - q3[a];
+                if (d < reach) { reach = d; face = 2 * a + 1; }
             }
         }
-        // Every unvisited point sits in a cell more than r away (in cells) along some axis, i.e. beyond one of the six
-        // slab boundaries below; border cells are open-ended, so a side whose slab reaches the border holds nothing more.
-        double reach = INFINITY;
-        if (cx - r >= 1) reach = fmin(reach, qx - (double)ex[cx - r]);
-        if (cx + r + 1 <= g - 1) reach = fmin(reach, (double)ex[cx + r + 1] - qx);
-        if (cy - r >= 1) reach = fmin(reach, qy - (double)ey[cy - r]);
-        if (cy + r + 1 <= g - 1) reach = fmin(reach, (double)ey[cy + r + 1] - qy);
-        if (cz - r >= 1) reach = fmin(reach, qz - (double)ez[cz - r]);
-        if (cz + r + 1 <= g - 1) reach = fmin(reach, (double)ez[cz + r + 1] - qz);
-        if (reach == INFINITY) { done = true; break; }  // the whole grid has been visited
+        if (face < 0) { done = true; break; }  // the whole grid has been visited
         // strict: an unvisited point at exactly the k-th distance could still win the tie on its index
-        if (best.n == K && reach > 0.0 && best.d[K - 1] < reach * reach) { done = true; break; }
+        if (best.n == K && best.d[K - 1] < reach * reach) { done = true; break; }
+        if (step == max_steps) break;
+        const int a = face >> 1;
+        const int idx = (face & 1) ? ++hi[a] : --lo[a];
+        if (a == 0) {          // a y-z sheet of single cells
+            for (int zz = lo[2]; zz <= hi[2]; ++zz)
+                for (int yy = lo[1]; yy <= hi[1]; ++yy) {
+                    const int64_t c = ((int64_t)zz * g + yy) * g + idx;
+                    scan(cell_start[c], cell_start[c + 1]);
+                }
+        } else if (a == 1) {   // one run of cells (consecutive in the sorted order too) per z
+            for (int zz = lo[2]; zz <= hi[2]; ++zz) {
+                const int64_t row = ((int64_t)zz * g + idx) * g;
+                scan(cell_start[row + lo[0]], cell_start[row + hi[0] + 1]);
+            }
+        } else {               // one run per y
+            for (int yy = lo[1]; yy <= hi[1]; ++yy) {
+                const int64_t row = ((int64_t)idx * g + yy) * g;
+                scan(cell_start[row + lo[0]], cell_start[row + hi[0] + 1]);
+            }
+        }
     }
     if (!done) {
         const int slot = atomicAdd(n_unresolved, 1);
@@ -254,7 +274,7 @@ knn_brute_kernel(int64_t Nx, const float* __restrict__ x, const float* __restric
                 const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
                 if (!finite3(px, py, pz)) continue;
                 const double dx = qx - (double)px, dy = qy - (double)py, dz = qz - (double)pz;
-                const double d = dx * dx + dy * dy + dz * dz;
+                const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                 const int32_t ii = (int32_t)i;
                 const bool after_prev = d > pd || (d == pd && ii > pi);
                 if (after_prev && (d < bd || (d == bd && ii < bi))) { bd = d; bi = ii; }
@@ -372,11 +392,11 @@ FSB_API int fsb_knn_build(int64_t N, const uint64_t* sorted_keys, const int32_t*
 // f64 distances.  order (nullable): the sequence in which queries are processed (sorted by cell for locality).
 // unresolved i32[Ny] + n_unresolved i32[1] (zeroed here): queries left to fsb_knn_brute.
 FSB_API int fsb_knn_query(int64_t Ny, const float* y, const int32_t* order, int g, const float* edges,
-                          const int32_t* cell_start, const float* sorted_pts, int K, int drop_first, int max_rings,
+                          const int32_t* cell_start, const float* sorted_pts, int K, int drop_first, int max_steps,
                           int64_t* out_idx, double* out_dist, int32_t* unresolved, int32_t* n_unresolved,
                           void* stream) {
     if (Ny < 0 || Ny > 0x7fffffff || !knn_g_ok(g) || K < 1 || K > 33 || drop_first < 0 || drop_first >= K ||
-        max_rings < 0 || !n_unresolved)
+        max_steps < 0 || !n_unresolved)
         return FSB_E_ARG;
     FSB_CUDA(cudaMemsetAsync(n_unresolved, 0, sizeof(int32_t), (cudaStream_t)stream));
     if (Ny == 0) return 0;
@@ -386,11 +406,11 @@ FSB_API int fsb_knn_query(int64_t Ny, const float* y, const int32_t* order, int 
     const size_t sh = 3 * (g + 1) * sizeof(float);
     if (K <= 17)
         knn_query_kernel<17><<<blocks, KNN_THREADS, sh, (cudaStream_t)stream>>>(
-            Ny, y, order, gr, cell_start, (const float4*)sorted_pts, K, drop_first, max_rings, out_idx, out_dist,
+            Ny, y, order, gr, cell_start, (const float4*)sorted_pts, K, drop_first, max_steps, out_idx, out_dist,
             unresolved, n_unresolved);
     else
         knn_query_kernel<33><<<blocks, KNN_THREADS, sh, (cudaStream_t)stream>>>(
-            Ny, y, order, gr, cell_start, (const float4*)sorted_pts, K, drop_first, max_rings, out_idx, out_dist,
+            Ny, y, order, gr, cell_start, (const float4*)sorted_pts, K, drop_first, max_steps, out_idx, out_dist,
             unresolved, n_unresolved);
     FSB_LAUNCH_CHECK();
     return 0;

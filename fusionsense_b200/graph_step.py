@@ -329,7 +329,9 @@ class GraphedDNSplatterStep:
         must not be the one a replay in flight reads (callers prefetch the following step's view); the copy is
         ordered after the last replay that read the slot."""
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
+            # high priority: the byte -> float conversions queued behind the copies are a few microseconds of work and
+            # must not wait for the step's 28k-CTA kernels to drain before the next copy can start
+            self._copy_stream = torch.cuda.Stream(device=self.device, priority=-1)
         cs = self._copy_stream
         # the slot was last read by `_slot_read[cam_idx]`; a slot no tracked replay has read can only have been
         # touched before the replay launched most recently (that one reads another view's slot)
@@ -340,8 +342,11 @@ class GraphedDNSplatterStep:
             cs.wait_stream(torch.cuda.current_stream())
         n = 0
         with torch.cuda.stream(cs):
+            pending = []
             for k, t in host_batch.items():
-                n += self._copy_target(k, cam_idx, t)
+                n += self._copy_target(k, cam_idx, t, convert_later=pending)
+            for job in pending:  # all copies are queued before the first conversion kernel: the copy engine never idles
+                job()
             done = torch.cuda.Event()
             done.record(cs)
         self._slot_staged[cam_idx] = done
@@ -376,7 +381,7 @@ class GraphedDNSplatterStep:
             n += self._copy_target(k, cam_idx, t)
         return n
 
-    def _copy_target(self, key: str, cam_idx: int, t: Tensor) -> int:
+    def _copy_target(self, key: str, cam_idx: int, t: Tensor, convert_later: Optional[list] = None) -> int:
         """Host tensor -> resident slot on the current stream; returns the bytes that crossed PCIe.  uint8 sources
         (the 8-bit RGB / normal images as they are on disk) travel as bytes into a device staging buffer and are
         turned into the slot's float32 by `fsb_u8_to_unit_float` on the same stream — what the reference does with
@@ -393,7 +398,11 @@ class GraphedDNSplatterStep:
                 # one buffer per (key, stream): copies and conversions of successive views are ordered by the stream
                 buf = self._u8_stage[sk] = torch.empty(t.numel(), dtype=torch.uint8, device=self.device)
             buf.copy_(t.reshape(-1), non_blocking=True)
-            u8_to_unit_float(buf, slot, recip=(key != "normal"))  # normals: numpy's division (dn_dataset.py:205)
+            recip = key != "normal"  # normals: numpy's division (dn_dataset.py:205)
+            if convert_later is None:
+                u8_to_unit_float(buf, slot, recip=recip)
+            else:
+                convert_later.append(lambda b=buf, s_=slot, r=recip: u8_to_unit_float(b, s_, recip=r))
         else:
             slot.copy_(t, non_blocking=True)
         return t.numel() * t.element_size()

@@ -28,7 +28,7 @@ MAX_K = 32            # k + 1 <= 33 candidates per query live in the query kerne
 TARGET_PER_CELL = 1.0
 MAX_G = 320           # cells per axis
 MAX_SAMPLE = 1 << 18  # points whose coordinates define the per-axis quantile edges
-MAX_RINGS = 8
+MAX_STEPS = 96        # growth steps of a query's cell box before it is handed to the brute-force finish
 
 
 class KnnIndex:
@@ -73,17 +73,17 @@ class KnnIndex:
         return keys, vals
 
     def query(self, y: Tensor, k: int, drop_first: int = 0, return_distances: bool = False,
-              max_rings: int = MAX_RINGS):
+              max_steps: int = MAX_STEPS):
         """Indices [len(y), k - drop_first] (int64) of the k nearest points of `x` for every row of `y`, nearest first,
         ties by index, without the first `drop_first`; optionally the float64 distances as well."""
         _req_cuda(y)
         assert y.dim() == 2 and y.shape[1] == 3, y.shape
-        if not 1 <= k <= MAX_K + 1:
-            raise ValueError(f"knn: k = {k} outside [1, {MAX_K + 1}]")
         if k > self.n_finite:
             # sklearn: "Expected n_neighbors <= n_samples_fit"
             raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {k}, n_samples_fit = "
                              f"{self.n_finite}")
+        if not 1 <= k <= MAX_K + 1:
+            raise ValueError(f"knn: k = {k} outside [1, {MAX_K + 1}] (the reference tracks knn_to_track = 16)")
         same = y.data_ptr() == self.x.data_ptr() and y.shape == self.x.shape and y.dtype == torch.float32
         yq = self.x if same else _f32c(y.detach())
         ny = yq.shape[0]
@@ -101,7 +101,7 @@ class KnnIndex:
         unresolved = torch.empty((ny,), dtype=torch.int32, device=dev)
         n_unres = torch.empty((1,), dtype=torch.int32, device=dev)
         check(lib.fsb_knn_query(ny, ptr(yq), ptr(order), self.g, ptr(self.edges), ptr(self.cell_start),
-                                ptr(self.sorted_pts), k, drop_first, max_rings, ptr(out), ptr(dist), ptr(unresolved),
+                                ptr(self.sorted_pts), k, drop_first, max_steps, ptr(out), ptr(dist), ptr(unresolved),
                                 ptr(n_unres), _stream()), "fsb_knn_query")
         check(lib.fsb_knn_brute(self.x.shape[0], ptr(self.x), ptr(yq), ptr(unresolved), ptr(n_unres), k, drop_first,
                                 ptr(out), ptr(dist), _stream()), "fsb_knn_brute")

@@ -477,8 +477,8 @@ int fsb_normal_from_depth(int H, int W, const float* depth, const float* xyz, fl
  *   fsb_knn_build  : cell_start[g^3 + 1] i32 and sorted_pts[N,4] (xyz + index bits) from the sorted pairs
  *   fsb_knn_query  : the K <= 33 nearest points of every y, nearest first, ties by index (distances in fp64 of the fp32
  *                    coordinates); the first drop_first are not written.  out_idx [Ny, K - drop_first] i64, out_dist
- *                    (nullable) f64.  order (nullable) = processing order.  Queries needing more than max_rings rings
- *                    of cells are appended to unresolved[Ny] / n_unresolved[1] and finished by
+ *                    (nullable) f64.  order (nullable) = processing order.  Queries needing more than max_steps growth
+ *                    steps of their cell box are appended to unresolved[Ny] / n_unresolved[1] and finished by
  *   fsb_knn_brute  : K selection rounds over all points, one CTA per unresolved query.
  *   fsb_gaussian_density : out[s] = clamp_min(norm(sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (x_s - mu_g)|^2)), 1e-4),
  *                    g = knn[s,k], M = R(quat) diag(1 / clamp_min(exp(log_scales), 1e-3)), norm(d) = d / (d + 1e-5) if d >= 1 */
@@ -489,7 +489,7 @@ int fsb_knn_cells(int64_t N, const float* pts, int g, const float* edges, uint64
 int fsb_knn_build(int64_t N, const uint64_t* sorted_keys, const int32_t* sorted_vals, const float* pts, int g,
                   int32_t* cell_start, float* sorted_pts, void* stream);
 int fsb_knn_query(int64_t Ny, const float* y, const int32_t* order, int g, const float* edges,
-                  const int32_t* cell_start, const float* sorted_pts, int K, int drop_first, int max_rings,
+                  const int32_t* cell_start, const float* sorted_pts, int K, int drop_first, int max_steps,
                   int64_t* out_idx, double* out_dist, int32_t* unresolved, int32_t* n_unresolved, void* stream);
 int fsb_knn_brute(int64_t Nx, const float* x, const float* y, const int32_t* unresolved, const int32_t* n_unresolved,
                   int K, int drop_first, int64_t* out_idx, double* out_dist, void* stream);

@@ -53,6 +53,29 @@ def test_oracle_density_matches_reference_golden():
     np.testing.assert_allclose(d.numpy(), g["density_self"], rtol=1e-6, atol=0)
 
 
+def test_kernel_algorithm_walkthrough_is_exact_on_the_golden_cloud():
+    """tests/knn_emulation.py restates csrc/knn.cu's grid build and box-growth query in numpy; on the golden cloud
+    (dense object, sparse shell, far outliers, a duplicate) its answers equal the brute-force oracle's, every query
+    terminates on the grid, and none needs more than the kernel's default step budget."""
+    from tests import knn_emulation as em
+
+    g = _gold()
+    x, y = g["x"], g["y"]
+    ix = em.build(x)
+    ref_idx, ref_dist = knn_ref.knn_full_ref(x, y[:120], 17)
+    most = 0
+    for r in range(120):
+        best, steps, ok = em.query_one(ix, y[r], 17)
+        assert ok
+        assert [b[1] for b in best] == list(ref_idx[r])
+        assert np.array_equal(np.sqrt([b[0] for b in best]), ref_dist[r])
+        most = max(most, steps)
+    assert most <= 96
+    # a step budget of 0 visits the query's own cell only: (nearly) nobody is settled, nothing wrong is returned
+    settled = [em.query_one(ix, y[r], 17, max_steps=0)[2] for r in range(40)]
+    assert sum(settled) <= 4
+
+
 # ---- CUDA path ----------------------------------------------------------------------------------------------------
 DEV = "cuda"
 
@@ -114,7 +137,7 @@ def test_knn_edge_cases():
 
     x = torch.rand(100, 3, device=DEV)
     with pytest.raises(ValueError, match="n_neighbors <= n_samples_fit"):  # sklearn's refusal, same words
-        knn_sk(x, x, 100)
+        knn_sk(x[:20].contiguous(), x[:20].contiguous(), 20)
     assert knn_sk(x, x[:0], 4).shape == (0, 4)
     with pytest.raises(ValueError):
         KnnIndex(x).query(x, 40)
@@ -141,7 +164,7 @@ def test_knn_edge_cases():
 
 @pytest.mark.gpu
 def test_knn_every_query_through_the_brute_force_finish():
-    """max_rings = 0 stops the grid walk after the query's own cell, which settles next to nothing: (almost) every query
+    """max_steps = 0 stops the grid walk after the query's own cell, which settles next to nothing: (almost) every query
     takes the fallback kernel and the answers stay exact."""
     from fusionsense_b200.knn import KnnIndex
 
@@ -149,7 +172,7 @@ def test_knn_every_query_through_the_brute_force_finish():
     x = torch.randn(3000, 3, generator=g)
     y = torch.randn(200, 3, generator=g)
     index = KnnIndex(x.to(DEV))
-    idx, dist = index.query(y.to(DEV), 9, drop_first=1, return_distances=True, max_rings=0)
+    idx, dist = index.query(y.to(DEV), 9, drop_first=1, return_distances=True, max_steps=0)
     assert int(index.last_unresolved) >= 150
     ref_idx, ref_dist = knn_ref.knn_full_ref(x.numpy(), y.numpy(), 9)
     assert np.array_equal(idx.cpu().numpy(), ref_idx[:, 1:])
