@@ -604,15 +604,20 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
         n_before = model.num_points
         cap0, refines = runner.captures, []
 
+        host_s = {"refinement": 0.0}
+        cap_s0 = runner.capture_seconds
+
         def step_with_refine(i):
             one_step(i, False, False)
             if model.step % model.config.refine_every == 0:
+                t0 = time.perf_counter()
                 runner.poll()
                 if world > 1:
                     fdist.synchronised_refinement(model, model.optimizers, model.step, seed=7)
                 else:
                     model.refinement_after()
                 refines.append(model.num_points)
+                host_s["refinement"] += time.perf_counter() - t0
 
         n_ref = 300
         ms_ref = timed(n_ref, step_with_refine, drain=lambda: runner.poll())
@@ -620,6 +625,10 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
                                   "ms_per_step": ms_ref / n_ref, "refine_every": model.config.refine_every,
                                   "gaussians_before": n_before, "gaussians_after_each_refine": refines,
                                   "recaptures": runner.captures - cap0,
+                                  # host wall time inside the timed region that is not graph replay: where a slow leg
+                                  # spent its time (poll + refinement_after incl. its device sync; warm-up + capture)
+                                  "host_seconds": {"refinement": round(host_s["refinement"], 4),
+                                                   "capture": round(runner.capture_seconds - cap_s0, 4)},
                                   "what": "300 captured iterations with refinement_after every 100 (densify + cull + "
                                           "Adam-state rebuild, statistics all-reduced and a shared split RNG at N > 1), "
                                           "re-captures included"}

@@ -20,6 +20,8 @@ the host notices through `poll()`, grows the capacity and re-runs).
 from __future__ import annotations
 
 import ctypes
+import os
+import time
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -91,6 +93,8 @@ class GraphedDNSplatterStep:
         self.signature = None
         self.adam: Optional[CapturedAdam] = None
         self.captures = 0
+        self.capture_seconds = 0.0  # host wall time spent inside capture() (warm-up iteration + capture), cumulative
+        self._pool = None
         self.replays = 0
         self.grad_sync = grad_sync
         # N > 1: capture the gradient exchange inside the one graph (True) or launch it eagerly between two graphs
@@ -228,7 +232,12 @@ class GraphedDNSplatterStep:
         if m.max_2Dsize is None:
             m.max_2Dsize = torch.zeros(m.num_points, device=self.device, dtype=torch.float32)
         self.adam = CapturedAdam(m.optimizers.values())
+        # the previous graph goes first and the new one is captured into the SAME private pool: its blocks are reused
+        # instead of a cudaFree / cudaMalloc round per re-capture (refinement re-captures every 100 steps)
         self.graph = self.graph_tail = None
+        self._keep = None
+        if self._pool is None and os.environ.get("FSB_GRAPH_SHARED_POOL", "1") != "0":
+            self._pool = torch.cuda.graph_pool_handle()
         params = [p for p in m.gauss_params.values()]
         side = self._side = getattr(self, "_side", None) or torch.cuda.Stream()  # warm-up and capture share it
         side.wait_stream(torch.cuda.current_stream())
@@ -248,13 +257,13 @@ class GraphedDNSplatterStep:
         g = torch.cuda.CUDAGraph()
         n0 = lib.fsb_launch_count()
         if self._peer:
-            with torch.cuda.graph(g, stream=side):
+            with torch.cuda.graph(g, stream=side, pool=self._pool):
                 loss, counts = self._body_main()
                 self._body_tail(loss, counts)
             tail = None
         elif self.grad_sync is not None and self.capture_collective:
             # ONE graph: the gradient exchange is captured between backward and Adam
-            with torch.cuda.graph(g, stream=side):
+            with torch.cuda.graph(g, stream=side, pool=self._pool):
                 loss, counts = self._body_main()
                 live = [p for p in params if p.grad is not None]
                 self._grad_src = [p.grad for p in live]
@@ -263,12 +272,12 @@ class GraphedDNSplatterStep:
                 self._body_tail(loss, counts)
             tail = None
         elif self.grad_sync is None:
-            with torch.cuda.graph(g, stream=side):
+            with torch.cuda.graph(g, stream=side, pool=self._pool):
                 loss, counts = self._body_main()
                 self._body_tail(loss, counts)
             tail = None
         else:
-            with torch.cuda.graph(g, stream=side):
+            with torch.cuda.graph(g, stream=side, pool=self._pool):
                 loss, counts = self._body_main()
             live = [p for p in params if p.grad is not None]
             self._grad_src = [p.grad for p in live]  # address-stable: rewritten by every replay of `g`
@@ -278,7 +287,7 @@ class GraphedDNSplatterStep:
                 p.grad = v
             torch.cuda.synchronize()
             tail = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(tail, stream=side, pool=g.pool()):
+            with torch.cuda.graph(tail, stream=side, pool=self._pool or g.pool()):
                 self._body_tail(loss, counts)
             self._keep = (loss, counts)  # read by the tail graph: keep the main graph's buffers alive
         self.launches_per_replay = int(lib.fsb_launch_count() - n0)
@@ -297,7 +306,9 @@ class GraphedDNSplatterStep:
         if len(cams) != self.views_per_iter:
             raise ValueError(f"train_iteration takes {self.views_per_iter} view indices, got {len(cams)}")
         if self.graph is None or self.signature != self._signature():
+            t0 = time.perf_counter()
             self.capture()
+            self.capture_seconds += time.perf_counter() - t0
         m.optimizers["means"].param_groups[0]["lr"] = m._means_lr()
         self.adam.advance()
         for j, c in enumerate(cams):

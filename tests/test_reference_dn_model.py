@@ -170,3 +170,49 @@ def test_reference_train_iterations_track_the_fused_step(fused_adam):
         assert_close(fused.gauss_params[name], model.gauss_params[name], f"ref_dn_model.train3.{name}", tol=1e-4,
                      outlier_frac=2e-3)
     assert_close(fused.xys_grad_norm, model.xys_grad_norm, "ref_dn_model.train3.xys_grad_norm", tol=1e-3, outlier_frac=5e-3)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_level_surface_search_with_the_gpu_knn_drop_in():
+    """f2: the reference's own `compute_level_surface_points` (dn_model.py:1705-1946: render,
+    back-project, `knn_sk(self.means, points, 16)`, 21 density samples per ray, level crossings) run twice on the same
+    model and camera — with the reference's sklearn `knn_sk` and with `fusionsense_b200.knn.knn_sk` bound in its place
+    (the one-line patch of INTEGRATION.md).  Exact neighbours -> every output tensor is bit-identical."""
+    import random
+
+    ref_model = _import_reference()
+    from fusionsense_b200 import knn as fsb_knn
+    from tests.stubs.harness import build_reference_model, camera_for
+
+    dev = "cuda"
+    scene = _gl_scene(n=20000, W=160, H=120)
+    _, model = build_reference_model(scene, 3001, dev)
+    g = torch.Generator().manual_seed(3)
+    model.gauss_params["normals"] = torch.nn.Parameter(
+        torch.nn.functional.normalize(torch.randn(scene.N, 3, generator=g), dim=-1).to(dev))
+    camera = camera_for(scene, 1, dev)
+    sklearn_knn = ref_model.knn_sk
+    assert sklearn_knn.__module__ == "dn_splatter.utils.knn"
+    calls = []
+
+    def ours(x, y, k):
+        calls.append((tuple(x.shape), tuple(y.shape), k))
+        return fsb_knn.knn_sk(x, y, k)
+
+    random.seed(11)
+    want = model.compute_level_surface_points(camera, num_samples=4000)
+    try:
+        ref_model.knn_sk = ours
+        random.seed(11)
+        got = model.compute_level_surface_points(camera, num_samples=4000)
+    finally:
+        ref_model.knn_sk = sklearn_knn
+    assert len(calls) == 1 and calls[0][0] == (scene.N, 3) and calls[0][2] == 16 and calls[0][1][0] > 1000
+    assert set(got) == set(want) == {0.1, 0.3, 0.5}
+    n_pts = 0
+    for level in want:
+        for key in ("points", "normals", "colors"):
+            assert torch.equal(got[level][key], want[level][key]), (level, key)
+        n_pts += want[level]["points"].shape[0]
+    assert n_pts > 1000  # the search found surfaces: the comparison is not vacuous

@@ -42,17 +42,16 @@ def main():
     x = x_cpu.cuda()
     knn_sk(x, x, k)  # warm-up (library load, allocator)
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    ev[0].record()
-    index = KnnIndex(x)
-    ev[1].record()
-    idx, dist = index.query(index.x, k + 1, drop_first=1, return_distances=True)
-    ev[2].record()
     g = torch.Generator().manual_seed(1)
     ls = torch.log(0.004 * torch.exp(0.5 * torch.randn(n, 3, generator=g))).cuda()
     q = torch.randn(n, 4, generator=g).cuda()
     op = torch.randn(n, 1, generator=g).cuda()
     torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    index = KnnIndex(x)
+    ev[1].record()
+    idx, dist = index.query(index.x, k + 1, drop_first=1, return_distances=True)
     ev[2].record()
     dens = gaussian_density(index.x, idx, index.x, ls, q, op)
     ev[3].record()
