@@ -557,6 +557,14 @@ def run_workload(ctx: Ctx, cfg_name: str, steps: int, warmup: int, mode: str, de
                       "graph_launches_per_step": 1 if runner.graph_tail is None else 2}
     clocks = ctx.sampler.window(t_region0, t_region1) if rank == 0 else None
     captures_before_e2e = runner.captures if runner is not None else 0
+    # the staged path has first-use costs of its own (copy stream, staging buffers, the pinned result ring's
+    # cudaHostAlloc, the conversion kernel's lazy load: tens to hundreds of ms on some boxes — r02s measured the 200-step
+    # cfg2 e2e leg anywhere between 366 and 1166 it/s because of them): warm it up like the resident leg
+    for i in range(max(3, min(warmup, 10))):
+        one_step(i, True, True, 1 << 30)
+    if runner is not None:
+        runner.poll()
+    torch.cuda.synchronize()
     model.step = BENCH_STEP
     ms_e2e = timed(steps, lambda i: one_step(i, True, True, steps),
                    drain=(lambda: runner.poll()) if runner is not None else None)

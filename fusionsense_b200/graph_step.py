@@ -94,7 +94,6 @@ class GraphedDNSplatterStep:
         self.adam: Optional[CapturedAdam] = None
         self.captures = 0
         self.capture_seconds = 0.0  # host wall time spent inside capture() (warm-up iteration + capture), cumulative
-        self._pool = None
         self.replays = 0
         self.grad_sync = grad_sync
         # N > 1: capture the gradient exchange inside the one graph (True) or launch it eagerly between two graphs
@@ -232,12 +231,11 @@ class GraphedDNSplatterStep:
         if m.max_2Dsize is None:
             m.max_2Dsize = torch.zeros(m.num_points, device=self.device, dtype=torch.float32)
         self.adam = CapturedAdam(m.optimizers.values())
-        # the previous graph goes first and the new one is captured into the SAME private pool: its blocks are reused
-        # instead of a cudaFree / cudaMalloc round per re-capture (refinement re-captures every 100 steps)
+        # (A private pool shared across re-captures does not work: dropping the only graph of a pool releases the pool,
+        # and capturing into the stale handle trips an allocator assert — r02s.  Each capture takes a fresh pool; the
+        # cost of a re-capture, ~0.18 s at cfg2, is reported by bench.py as `with_refinement.host_seconds`.)
         self.graph = self.graph_tail = None
         self._keep = None
-        if self._pool is None and os.environ.get("FSB_GRAPH_SHARED_POOL", "1") != "0":
-            self._pool = torch.cuda.graph_pool_handle()
         params = [p for p in m.gauss_params.values()]
         side = self._side = getattr(self, "_side", None) or torch.cuda.Stream()  # warm-up and capture share it
         side.wait_stream(torch.cuda.current_stream())
@@ -257,13 +255,13 @@ class GraphedDNSplatterStep:
         g = torch.cuda.CUDAGraph()
         n0 = lib.fsb_launch_count()
         if self._peer:
-            with torch.cuda.graph(g, stream=side, pool=self._pool):
+            with torch.cuda.graph(g, stream=side):
                 loss, counts = self._body_main()
                 self._body_tail(loss, counts)
             tail = None
         elif self.grad_sync is not None and self.capture_collective:
             # ONE graph: the gradient exchange is captured between backward and Adam
-            with torch.cuda.graph(g, stream=side, pool=self._pool):
+            with torch.cuda.graph(g, stream=side):
                 loss, counts = self._body_main()
                 live = [p for p in params if p.grad is not None]
                 self._grad_src = [p.grad for p in live]
@@ -272,12 +270,12 @@ class GraphedDNSplatterStep:
                 self._body_tail(loss, counts)
             tail = None
         elif self.grad_sync is None:
-            with torch.cuda.graph(g, stream=side, pool=self._pool):
+            with torch.cuda.graph(g, stream=side):
                 loss, counts = self._body_main()
                 self._body_tail(loss, counts)
             tail = None
         else:
-            with torch.cuda.graph(g, stream=side, pool=self._pool):
+            with torch.cuda.graph(g, stream=side):
                 loss, counts = self._body_main()
             live = [p for p in params if p.grad is not None]
             self._grad_src = [p.grad for p in live]  # address-stable: rewritten by every replay of `g`
@@ -287,7 +285,7 @@ class GraphedDNSplatterStep:
                 p.grad = v
             torch.cuda.synchronize()
             tail = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(tail, stream=side, pool=self._pool or g.pool()):
+            with torch.cuda.graph(tail, stream=side, pool=g.pool()):
                 self._body_tail(loss, counts)
             self._keep = (loss, counts)  # read by the tail graph: keep the main graph's buffers alive
         self.launches_per_replay = int(lib.fsb_launch_count() - n0)
