@@ -192,10 +192,8 @@ def cpu_step_seconds(cfg_name: str, steps: int, warmup: int):
     """Time the oracle-driven train step on the host cores -> (seconds per FULL step, cores, sample text).
 
     cfg2 runs whole steps (~6 s each).  cfg4 (1M Gaussians, 1080p) would take minutes per step, so its sample is
-    bounded: the same 1M-Gaussian scene rendered and differentiated through two centred sub-windows of the image
-    (1/16 and 1/32 of the pixels: every Gaussian is still projected, binned and culled), and the full-step time is
-    the linear extrapolation t(P) = a + b P of the two to the full pixel count — a is the per-Gaussian work
-    (projection, SH, Adam), b the per-pixel work (compositing, losses)."""
+    bounded: the same 1M-Gaussian scene rendered and differentiated through small sub-windows spread over the image
+    (every Gaussian is still projected, binned and culled), see below."""
     import torch
 
     cores = os.cpu_count() or 1
@@ -206,21 +204,29 @@ def cpu_step_seconds(cfg_name: str, steps: int, warmup: int):
         sample = (f"{steps} full train step(s) (RGB+ED pass, normals pass, losses, backward, torch Adam) of the same "
                   f"300k-Gaussian 640x480 scene through oracle/gsplat_ref.py, torch CPU fp32, {cores} threads")
         return sec, cores, sample
+    # Stratified sample: the image is cut into a 3 x 2 grid of cells and the step is run through a 160 x 96 window in
+    # the middle of every cell (all 1M Gaussians are projected, binned and culled each time), plus once through a
+    # 16 x 16 corner window whose time is the per-Gaussian part t0 (projection, SH, Adam).  Full step =
+    # t0 + sum_cells (t_cell - t0) * cell area / window area.  (Two centred windows and a linear fit, the first version,
+    # extrapolated the densest part of the frame to all of it: 248 s on the box where this form gives less.)
     W, H = c["w"], c["h"]
-    wa, ha = W // 4, (H // 4) // 16 * 16 + 16 if (H // 4) % 16 else H // 4
-    wb, hb = W // 4, max(16, (ha // 2) // 16 * 16)
-    crop_a = ((W - wa) // 2, (H - ha) // 2, wa, ha)
-    crop_b = ((W - wb) // 2, (H - hb) // 2, wb, hb)
-    ta = _cpu_step_once(cfg_name, crop_a, 1, 0)
-    tb = _cpu_step_once(cfg_name, crop_b, 1, 0)
-    pa, pb, pf = wa * ha, wb * hb, W * H
-    slope = max(0.0, (ta - tb) / (pa - pb))
-    base = max(0.0, tb - slope * pb)
-    sec = base + slope * pf
-    sample = (f"two train steps of the same {c['n']}-Gaussian scene through centred sub-windows {wa}x{ha} "
-              f"({ta:.1f} s) and {wb}x{hb} ({tb:.1f} s) of the {W}x{H} image, all Gaussians projected; full step = "
-              f"linear extrapolation in the pixel count ({base:.1f} s + {slope * pf:.1f} s); oracle/gsplat_ref.py, "
-              f"torch CPU fp32, {cores} threads")
+    gx, gy, ww, wh = 3, 2, 160, 96
+    t0 = _cpu_step_once(cfg_name, (0, 0, 16, 16), 1, 0)
+    cell_w, cell_h = W // gx, H // gy
+    times, per_px = [], 0.0
+    for j in range(gy):
+        for i in range(gx):
+            x0 = i * cell_w + (cell_w - ww) // 2
+            y0 = j * cell_h + (cell_h - wh) // 2
+            t = _cpu_step_once(cfg_name, (x0 // 16 * 16, y0 // 16 * 16, ww, wh), 1, 0)
+            times.append(t)
+            per_px += max(0.0, t - t0) / (ww * wh) * (cell_w * cell_h)
+    sec = t0 + per_px
+    sample = (f"{gx * gy + 1} train steps of the same {c['n']}-Gaussian scene, all Gaussians projected each time: one "
+              f"through a 16x16 corner window ({t0:.1f} s = the per-Gaussian part) and one through a {ww}x{wh} window in "
+              f"the middle of every cell of a {gx}x{gy} grid over the {W}x{H} image ("
+              + ", ".join(f"{t:.1f}" for t in times) + f" s); full step = {t0:.1f} s + sum over cells of (t - {t0:.1f} s) "
+              f"x cell area / window area = {sec:.1f} s; oracle/gsplat_ref.py, torch CPU fp32, {cores} threads")
     return sec, cores, sample
 
 
