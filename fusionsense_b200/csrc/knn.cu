@@ -309,7 +309,7 @@ knn_brute_kernel(int64_t Nx, const float* __restrict__ x, const float* __restric
 __global__ void __launch_bounds__(256)
 gaussian_density_kernel(int64_t S, const float* __restrict__ samples, int K, const int64_t* __restrict__ knn,
                         const float* __restrict__ means, const float* __restrict__ log_scales,
-                        const float* __restrict__ quats, const float* __restrict__ opacity_logits,
+                        const float* __restrict__ quats, const float* __restrict__ opacity_logits, float clamp_min,
                         float* __restrict__ out) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
@@ -336,7 +336,125 @@ gaussian_density_kernel(int64_t S, const float* __restrict__ samples, int K, con
         dens += op * expf(-0.5f * maha);
     }
     if (dens >= 1.0f) dens = dens / (dens + 1e-5f);
-    out[s] = fmaxf(dens, 1e-4f);
+    out[s] = fmaxf(dens, clamp_min);
+}
+
+
+// ---- level-set search along camera rays -----------------------------------------------------------------------
+// dn_model.py:1766-1870 (compute_level_surface_points) for one back-projected point per thread: the first neighbour's
+// standard deviation along the ray, 21 samples at linspace(-3, 3, 21) * std around the point, the density of the K
+// neighbours at every sample (the inlined get_density of :1806-1840: normalised above 1, NOT clamped below), and per
+// surface level the first sample above it with the linear interpolation of :1858-1880.  Every neighbour's M = R diag(1/s)
+// is built once and used for the 21 samples; nothing of the reference's [P*21, K, 3, 3] temporaries exists.
+constexpr int LS_SAMPLES = 21;
+constexpr int LS_MAX_LEVELS = 4;
+
+struct LevelArgs {
+    float cam[3];
+    float lin[LS_SAMPLES];        // torch.linspace(-3, 3, 21), from the host
+    float levels[LS_MAX_LEVELS];
+    int n_levels;
+};
+
+__device__ __forceinline__ void quat_rot(float w, float x, float y, float z, float (&r)[9]) {
+    const float qn = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-12f);  // F.normalize inside quat_to_rotmat
+    w /= qn; x /= qn; y /= qn; z /= qn;
+    r[0] = 1.f - 2.f * (y * y + z * z); r[1] = 2.f * (x * y - w * z); r[2] = 2.f * (x * z + w * y);
+    r[3] = 2.f * (x * y + w * z); r[4] = 1.f - 2.f * (x * x + z * z); r[5] = 2.f * (y * z - w * x);
+    r[6] = 2.f * (x * z - w * y); r[7] = 2.f * (y * z + w * x); r[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+__global__ void __launch_bounds__(128)
+level_crossings_kernel(int64_t P, const float* __restrict__ points, int K, const int64_t* __restrict__ knn,
+                       const float* __restrict__ means, const float* __restrict__ log_scales,
+                       const float* __restrict__ quats, const float* __restrict__ opacity_logits, LevelArgs a,
+                       float* __restrict__ t_out, uint8_t* __restrict__ valid_out, float* __restrict__ dens_out,
+                       float* __restrict__ std_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float px = points[3 * i], py = points[3 * i + 1], pz = points[3 * i + 2];
+    // camera_to_samples = F.normalize(points - cam)  (:1790-1792)
+    float dx = px - a.cam[0], dy = py - a.cam[1], dz = pz - a.cam[2];
+    {
+        const float n = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+        dx /= n; dy /= n; dz /= n;
+    }
+    // std of the FIRST neighbour along its own view direction (:1766-1776): |exp(s) * (R^T v)|, v = (cam - mu) / |cam - mu|,
+    // R from the normalised quaternion (quat_to_rotmat(invert_quaternion(q / |q|)) = R^T)
+    float std;
+    {
+        const int64_t g = knn[i * K];
+        float w = quats[4 * g], x = quats[4 * g + 1], y = quats[4 * g + 2], z = quats[4 * g + 3];
+        const float qn = sqrtf(w * w + x * x + y * y + z * z);
+        w /= qn; x /= qn; y /= qn; z /= qn;
+        float r[9];
+        quat_rot(w, x, y, z, r);
+        float vx = a.cam[0] - means[3 * g], vy = a.cam[1] - means[3 * g + 1], vz = a.cam[2] - means[3 * g + 2];
+        const float vn = sqrtf(vx * vx + vy * vy + vz * vz);
+        vx /= vn; vy /= vn; vz /= vn;
+        const float e0 = expf(log_scales[3 * g]) * (r[0] * vx + r[3] * vy + r[6] * vz);
+        const float e1 = expf(log_scales[3 * g + 1]) * (r[1] * vx + r[4] * vy + r[7] * vz);
+        const float e2 = expf(log_scales[3 * g + 2]) * (r[2] * vx + r[5] * vy + r[8] * vz);
+        std = sqrtf(e0 * e0 + e1 * e1 + e2 * e2);
+    }
+    if (std_out) std_out[i] = std;
+    float dens[LS_SAMPLES];
+#pragma unroll
+    for (int s = 0; s < LS_SAMPLES; ++s) dens[s] = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const int64_t g = knn[i * K + k];
+        const float mx = means[3 * g], my = means[3 * g + 1], mz = means[3 * g + 2];
+        const float i0 = 1.0f / fmaxf(expf(log_scales[3 * g]), 1e-3f);
+        const float i1 = 1.0f / fmaxf(expf(log_scales[3 * g + 1]), 1e-3f);
+        const float i2 = 1.0f / fmaxf(expf(log_scales[3 * g + 2]), 1e-3f);
+        float r[9];
+        quat_rot(quats[4 * g], quats[4 * g + 1], quats[4 * g + 2], quats[4 * g + 3], r);
+        const float op = 1.f / (1.f + expf(-opacity_logits[g]));
+        const float m00 = r[0] * i0, m10 = r[3] * i0, m20 = r[6] * i0;
+        const float m01 = r[1] * i1, m11 = r[4] * i1, m21 = r[7] * i1;
+        const float m02 = r[2] * i2, m12 = r[5] * i2, m22 = r[8] * i2;
+#pragma unroll
+        for (int s = 0; s < LS_SAMPLES; ++s) {
+            const float t = __fmul_rn(a.lin[s], std);
+            // samples = points + points_range * camera_to_samples: product and sum rounded separately, like torch
+            const float sx = __fadd_rn(px, __fmul_rn(t, dx)) - mx;
+            const float sy = __fadd_rn(py, __fmul_rn(t, dy)) - my;
+            const float sz = __fadd_rn(pz, __fmul_rn(t, dz)) - mz;
+            const float a0 = m00 * sx + m10 * sy + m20 * sz;
+            const float a1 = m01 * sx + m11 * sy + m21 * sz;
+            const float a2 = m02 * sx + m12 * sy + m22 * sz;
+            const float maha = fminf(fmaxf(a0 * a0 + a1 * a1 + a2 * a2, 0.f), 1e8f);
+            dens[s] += op * expf(-0.5f * maha);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < LS_SAMPLES; ++s) {
+        if (dens[s] >= 1.0f) dens[s] = dens[s] / (dens[s] + 1e-5f);
+        if (dens_out) dens_out[i * LS_SAMPLES + s] = dens[s];
+    }
+    for (int l = 0; l < a.n_levels; ++l) {
+        const float L = a.levels[l];
+        // first sample above the level (:1848-1850); a ray is empty when its first sample is not under the level or no
+        // sample is above it
+        int first = 0;
+#pragma unroll
+        for (int s = LS_SAMPLES - 1; s >= 1; --s)
+            if (dens[s] - L > 0.f) first = s;
+        const bool first_under = (dens[0] - L < 0.f);
+        const bool ok = first_under && first > 0;
+        float t = 0.f;
+        if (ok) {
+            float v1 = 0.f, v0 = 0.f;
+#pragma unroll
+            for (int s = 1; s < LS_SAMPLES; ++s)
+                if (s == first) { v1 = dens[s]; v0 = dens[s - 1]; }
+            const float t1 = __fmul_rn(a.lin[first], std), t0 = __fmul_rn(a.lin[first - 1], std);
+            // (L - v0) / (v1 - v0) * (t1 - t0) + t0   (:1873-1875)
+            t = __fadd_rn(__fmul_rn(__fdiv_rn(L - v0, v1 - v0), t1 - t0), t0);
+        }
+        t_out[(int64_t)l * P + i] = t;
+        valid_out[(int64_t)l * P + i] = ok ? 1 : 0;
+    }
 }
 
 }  // namespace
@@ -428,15 +546,39 @@ FSB_API int fsb_knn_brute(int64_t Nx, const float* x, const float* y, const int3
     return 0;
 }
 
-// out[s] = clamp_min(normalised sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (sample - mean_g)|^2), 1e-4), g = knn[s, k]
+// out[s] = max(normalised sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (sample - mean_g)|^2), clamp_min), g = knn[s, k]
+// (get_density clamps at 1e-4; the copy of it inlined in compute_level_surface_points does not: clamp_min = 0)
 FSB_API int fsb_gaussian_density(int64_t S, const float* samples, int K, const int64_t* knn, const float* means,
-                                 const float* log_scales, const float* quats, const float* opacity_logits, float* out,
-                                 void* stream) {
+                                 const float* log_scales, const float* quats, const float* opacity_logits,
+                                 float clamp_min, float* out, void* stream) {
     if (S < 0 || K < 1) return FSB_E_ARG;
     if (S == 0) return 0;
     if (!samples || !knn || !means || !log_scales || !quats || !opacity_logits || !out) return FSB_E_ARG;
     gaussian_density_kernel<<<fsb_div_up(S, 256), 256, 0, (cudaStream_t)stream>>>(S, samples, K, knn, means, log_scales,
-                                                                                 quats, opacity_logits, out);
+                                                                                 quats, opacity_logits, clamp_min, out);
+    FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Level-set search along the camera rays of P back-projected points (dn_model.py:1766-1880): per point 21 samples at
+// lin[s] * std (lin = torch.linspace(-3, 3, 21) from the host, std = the first neighbour's extent along its view
+// direction), densities from the K neighbours knn[P, K], and for each of n_levels <= 4 surface levels the first crossing:
+// t_out[l, p] (ray parameter of the intersection, 0 where none) and valid_out[l, p] (u8).  dens_out (nullable) [P, 21],
+// std_out (nullable) [P].  cam, lin, levels are HOST pointers.
+FSB_API int fsb_level_crossings(int64_t P, const float* points, const float* cam, int K, const int64_t* knn,
+                                const float* means, const float* log_scales, const float* quats,
+                                const float* opacity_logits, const float* lin, int n_levels, const float* levels,
+                                float* t_out, uint8_t* valid_out, float* dens_out, float* std_out, void* stream) {
+    if (P < 0 || K < 1 || n_levels < 1 || n_levels > LS_MAX_LEVELS || !cam || !lin || !levels) return FSB_E_ARG;
+    if (P == 0) return 0;
+    if (!points || !knn || !means || !log_scales || !quats || !opacity_logits || !t_out || !valid_out) return FSB_E_ARG;
+    LevelArgs a;
+    for (int i = 0; i < 3; ++i) a.cam[i] = cam[i];
+    for (int i = 0; i < LS_SAMPLES; ++i) a.lin[i] = lin[i];
+    for (int i = 0; i < LS_MAX_LEVELS; ++i) a.levels[i] = i < n_levels ? levels[i] : 0.f;
+    a.n_levels = n_levels;
+    level_crossings_kernel<<<fsb_div_up(P, 128), 128, 0, (cudaStream_t)stream>>>(
+        P, points, K, knn, means, log_scales, quats, opacity_logits, a, t_out, valid_out, dens_out, std_out);
     FSB_LAUNCH_CHECK();
     return 0;
 }

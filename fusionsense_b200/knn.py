@@ -121,9 +121,10 @@ def fast_knn(x: Tensor, y: Tensor, k: int = 2) -> Tensor:
 
 
 def gaussian_density(samples: Tensor, closest_gaussians: Tensor, means: Tensor, scales: Tensor, quats: Tensor,
-                     opacities: Tensor) -> Tensor:
+                     opacities: Tensor, clamp_min: float = 1e-4) -> Tensor:
     """`DNSplatterModel.get_density` (dn_model.py:1596-1634) for given neighbours: samples [S,3], closest_gaussians
     [S,K] int64, the model's raw parameters (log-scales, wxyz quats, opacity logits [N,1]) -> clamped densities [S].
+    `clamp_min=0` gives the unclamped copy inlined in compute_level_surface_points (dn_model.py:1806-1840).
     Forward only (the mesh-export path runs under no_grad)."""
     _req_cuda(samples, closest_gaussians, means, scales, quats, opacities)
     assert closest_gaussians.dtype == torch.int64 and closest_gaussians.dim() == 2
@@ -132,5 +133,6 @@ def gaussian_density(samples: Tensor, closest_gaussians: Tensor, means: Tensor, 
     out = torch.empty((S,), dtype=torch.float32, device=samples.device)
     check(lib.fsb_gaussian_density(S, ptr(_f32c(samples.detach())), K, ptr(closest_gaussians.contiguous()),
                                    ptr(_f32c(means.detach())), ptr(_f32c(scales.detach())), ptr(_f32c(quats.detach())),
-                                   ptr(_f32c(opacities.detach())), ptr(out), _stream()), "fsb_gaussian_density")
+                                   ptr(_f32c(opacities.detach())), float(clamp_min), ptr(out), _stream()),
+          "fsb_gaussian_density")
     return out

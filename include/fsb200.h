@@ -480,7 +480,7 @@ int fsb_normal_from_depth(int H, int W, const float* depth, const float* xyz, fl
  *                    (nullable) f64.  order (nullable) = processing order.  Queries needing more than max_steps growth
  *                    steps of their cell box are appended to unresolved[Ny] / n_unresolved[1] and finished by
  *   fsb_knn_brute  : K selection rounds over all points, one CTA per unresolved query.
- *   fsb_gaussian_density : out[s] = clamp_min(norm(sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (x_s - mu_g)|^2)), 1e-4),
+ *   fsb_gaussian_density : out[s] = max(norm(sum_k sigmoid(opacity[g]) exp(-0.5 |M_g^T (x_s - mu_g)|^2)), clamp_min = 1e-4),
  *                    g = knn[s,k], M = R(quat) diag(1 / clamp_min(exp(log_scales), 1e-3)), norm(d) = d / (d + 1e-5) if d >= 1 */
 int fsb_knn_axis_keys(int64_t S, int64_t stride, const float* pts, uint64_t* keys, void* stream);
 int fsb_knn_edges(int64_t S, const uint64_t* sorted_keys, int g, float* edges, void* stream);
@@ -494,8 +494,19 @@ int fsb_knn_query(int64_t Ny, const float* y, const int32_t* order, int g, const
 int fsb_knn_brute(int64_t Nx, const float* x, const float* y, const int32_t* unresolved, const int32_t* n_unresolved,
                   int K, int drop_first, int64_t* out_idx, double* out_dist, void* stream);
 int fsb_gaussian_density(int64_t S, const float* samples, int K, const int64_t* knn, const float* means,
-                         const float* log_scales, const float* quats, const float* opacity_logits, float* out,
-                         void* stream);
+                         const float* log_scales, const float* quats, const float* opacity_logits, float clamp_min,
+                         float* out, void* stream);
+/* Level-set search along the camera rays of P back-projected points.  replaces dn_splatter/dn_model.py:1766-1880 of
+ * compute_level_surface_points: per point the first neighbour's standard deviation along its view direction, 21 samples
+ * at lin[s] * std (lin = torch.linspace(-3, 3, 21), HOST) around the point, the density of the K neighbours knn[P,K] at
+ * every sample (the inlined get_density, normalised above 1, not clamped) and, for each of n_levels <= 4 surface levels
+ * (HOST), the first sample above the level with the linear interpolation of :1858-1880.  cam = camera position (HOST, 3).
+ *   t_out[l,p] f32 = ray parameter of the crossing (0 where none), valid_out[l,p] u8; dens_out (nullable) [P,21],
+ *   std_out (nullable) [P].  The reference materialises [P*21, K, 3, 3] temporaries in passes of 2M samples. */
+int fsb_level_crossings(int64_t P, const float* points, const float* cam, int K, const int64_t* knn, const float* means,
+                        const float* log_scales, const float* quats, const float* opacity_logits, const float* lin,
+                        int n_levels, const float* levels, float* t_out, uint8_t* valid_out, float* dens_out,
+                        float* std_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * f3: the seed point cloud of Module 1.  replaces get_pointcloud (utils/generate_pcd.py:15-48:
