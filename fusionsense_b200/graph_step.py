@@ -401,7 +401,7 @@ class GraphedDNSplatterStep:
 
             if getattr(self, "_u8_stage", None) is None:
                 self._u8_stage: Dict[tuple, Tensor] = {}
-            sk = (key, torch.cuda.current_stream().cuda_stream)
+            sk = (key, ops._stream())  # raw handle of the current stream (no Stream object per call)
             buf = self._u8_stage.get(sk)
             if buf is None or buf.numel() != t.numel():
                 # one buffer per (key, stream): copies and conversions of successive views are ordered by the stream
