@@ -131,3 +131,27 @@ def test_every_call_site_passes_the_declared_number_of_arguments():
                 f"{f.name}:{node.lineno}: {name} called with {len(node.args)} arguments, header declares "
                 f"{len(protos[name][1])}")
     assert seen > 40
+
+
+def test_integration_md_stub_matches_the_header():
+    """The hand-written ctypes stub shown in INTEGRATION.md §3 has as many argtypes as the header's prototype has
+    parameters, pointer for pointer (a maintainer copying it must not get a drifted signature)."""
+    import ctypes
+    import re
+    from pathlib import Path
+
+    from fusionsense_b200 import _abi
+
+    text = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    block = text[text.index("lib.fsb_raster_fwd.argtypes"):]
+    block = block[:block.index("\ndef raster_fwd")]
+    expr = block.split("=", 1)[1].replace("\\\n", " ")
+    P = ctypes.c_void_p
+    argtypes = eval(expr, {"ctypes": ctypes, "P": P})  # noqa: S307 — our own document
+    _, want, _ = _abi.parse_header()["fsb_raster_fwd"]
+    assert len(argtypes) == len(want)
+    assert [a is P for a in argtypes] == [w is ctypes.c_void_p for w in want]
+    call = text[text.index("rc = lib.fsb_raster_fwd("):]
+    call = call[:call.index("if rc:")]
+    n_args = len(re.sub(r"\([^()]*\)", "", call[call.index("(") + 1:call.rindex(")")]).split(","))
+    assert n_args == len(want)
