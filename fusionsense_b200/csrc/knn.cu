@@ -317,6 +317,7 @@ gaussian_density_kernel(int64_t S, const float* __restrict__ samples, int K, con
     float dens = 0.f;
     for (int k = 0; k < K; ++k) {
         const int64_t g = knn[s * K + k];
+        if (g < 0) continue;  // a neighbour slot the search left empty (non-finite query)
         const float dx = sx - means[3 * g], dy = sy - means[3 * g + 1], dz = sz - means[3 * g + 2];
         const float i0 = 1.0f / fmaxf(expf(log_scales[3 * g]), 1e-3f);
         const float i1 = 1.0f / fmaxf(expf(log_scales[3 * g + 1]), 1e-3f);
@@ -381,8 +382,8 @@ level_crossings_kernel(int64_t P, const float* __restrict__ points, int K, const
     }
     // std of the FIRST neighbour along its own view direction (:1766-1776): |exp(s) * (R^T v)|, v = (cam - mu) / |cam - mu|,
     // R from the normalised quaternion (quat_to_rotmat(invert_quaternion(q / |q|)) = R^T)
-    float std;
-    {
+    float std = 0.f;
+    if (knn[i * K] >= 0) {
         const int64_t g = knn[i * K];
         float w = quats[4 * g], x = quats[4 * g + 1], y = quats[4 * g + 2], z = quats[4 * g + 3];
         const float qn = sqrtf(w * w + x * x + y * y + z * z);
@@ -403,6 +404,7 @@ level_crossings_kernel(int64_t P, const float* __restrict__ points, int K, const
     for (int s = 0; s < LS_SAMPLES; ++s) dens[s] = 0.f;
     for (int k = 0; k < K; ++k) {
         const int64_t g = knn[i * K + k];
+        if (g < 0) continue;
         const float mx = means[3 * g], my = means[3 * g + 1], mz = means[3 * g + 2];
         const float i0 = 1.0f / fmaxf(expf(log_scales[3 * g]), 1e-3f);
         const float i1 = 1.0f / fmaxf(expf(log_scales[3 * g + 1]), 1e-3f);
