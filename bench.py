@@ -60,14 +60,15 @@ def _peaks():
 
 def _ncu_traffic(cfg_name: str):
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the roofline kernel on this
-    workload, from the committed `ncu --set full` capture (profiles/raster_bwd_traffic_<cfg>.json, written by
+    workload (+ its source text and the issue-slot / pipe figures of the same launch), from the committed
+    `ncu --set full` capture (profiles/raster_bwd_traffic_<cfg>.json, written by
     tools/ncu_traffic.py from the raw page); None when no capture is committed for this configuration."""
     for name in (f"raster_bwd_traffic_{cfg_name}.json",) + (("raster_bwd_traffic.json",) if cfg_name == "cfg2" else ()):
         p = ROOT / "profiles" / name
         if p.exists():
             d = json.loads(p.read_text())
-            return d.get("dram_bytes_per_launch"), d.get("source")
-    return None, None
+            return d.get("dram_bytes_per_launch"), d.get("source"), d.get("issue")
+    return None, None, None
 
 
 def _fp32_roofline(pairs, ktimes, D, clocks, key=None):
@@ -706,7 +707,7 @@ def _roofline(cfg_name, model, params, ktimes, pairs, clocks):
     bwd_bytes = I * (28 + 4 * D) + P * (4 * D + 12) + Nv * (32 + 4 * D)
     peak, peak_src = _peaks()
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms == bwd_ms and bwd_ms > 0 else None
-    traffic, traffic_src = _ncu_traffic(cfg_name)
+    traffic, traffic_src, issue = _ncu_traffic(cfg_name)
     N, K, C = c["n"], 16, 1
     tiles = ((c["w"] + 15) // 16) * ((c["h"] + 15) // 16)
     key_bytes = -(-(32 + max(1, (tiles - 1).bit_length())) // 8)
@@ -741,6 +742,8 @@ def _roofline(cfg_name, model, params, ktimes, pairs, clocks):
                    else "raster_bwd_kernel<4,4,2> (RGB+ED pass)"), "bound": "hbm", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
         "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": bwd_bytes, "kernel_ms": bwd_ms,
+        # the resource that does bind this kernel (issue slots / pipes of the same ncu launch the traffic comes from)
+        "issue": issue,
         "n_isects": I, "n_visible": Nv,
         "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md §8d); the HBM fraction is reported as "
                 "BASELINE.json asks, the pipe utilisation is in profiles/",

@@ -75,6 +75,18 @@ def main(path, needle="raster_bwd_kernel<4", out=None, workload="cfg2", command=
             "dram_bytes_read": d.get("dram__bytes_read.sum"),
             "dram_bytes_write": d.get("dram__bytes_write.sum"),
             "ncu_duration_us": d.get("gpu__time_duration.sum"),
+            # what binds a kernel that is not HBM-bound: issue slots and pipes, from the same launch
+            "issue": {
+                "warp_instructions": d.get("smsp__inst_executed.sum"),
+                "issue_active_pct": d.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fma_pipe_pct": d.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "alu_pipe_pct": d.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "xu_pipe_pct": d.get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                "lsu_pipe_pct": d.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                "warps_active_pct": d.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "registers_per_thread": d.get("launch__registers_per_thread"),
+                "top_stalls_per_issue": d.get("stalls_per_issue"),
+            },
             "source": f"ncu --set full --clock-control none, launch id {d['id']} of `{command}` on {workload} ({path.split('/')[-1]})",
         }
         with open(out, "w") as f:
