@@ -155,3 +155,38 @@ def test_integration_md_stub_matches_the_header():
     call = call[:call.index("if rc:")]
     n_args = len(re.sub(r"\([^()]*\)", "", call[call.index("(") + 1:call.rindex(")")]).split(","))
     assert n_args == len(want)
+
+
+def test_round2_host_mirrors_refuse_cpu_tensors_and_bad_arguments():
+    """No CPU path behind the mirrors added in round 2 (KNN, density, level set, seed cloud, 8-bit targets), and the
+    library refuses malformed arguments before any CUDA call."""
+    import torch
+
+    from fusionsense_b200 import knn, level_set, seed_points
+    from fusionsense_b200._abi import lib
+    from fusionsense_b200.compose import u8_to_unit_float
+
+    x = torch.rand(50, 3)
+    for call in (lambda: knn.knn_sk(x, x, 3),
+                 lambda: knn.gaussian_density(x, torch.zeros(50, 4, dtype=torch.int64), x, x, torch.rand(50, 4),
+                                              torch.rand(50, 1)),
+                 lambda: level_set.level_crossings(x, [0.0, 0.0, 1.0], torch.zeros(50, 4, dtype=torch.int64), x, x,
+                                                   torch.rand(50, 4), torch.rand(50, 1), [0.1, 0.3]),
+                 lambda: seed_points.get_pointcloud(torch.rand(3, 4, 5), torch.rand(4, 5), torch.eye(4), 1.0, 1.0, 2.0, 2.0),
+                 lambda: seed_points.voxel_down_sample(torch.rand(10, 6), 0.02),
+                 lambda: u8_to_unit_float(torch.zeros(16, dtype=torch.uint8))):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+    E = 10001  # FSB_E_ARG
+    assert lib.fsb_knn_cells(10, None, 0, None, None, None, None, None) == E        # g = 0
+    assert lib.fsb_knn_cells(10, None, 321, None, None, None, None, None) == E      # more cells per axis than the cap
+    assert lib.fsb_knn_query(10, None, None, 4, None, None, None, 34, 0, 8, None, None, None, None, None) == E  # K > 33
+    assert lib.fsb_knn_query(10, None, None, 4, None, None, None, 5, 5, 8, None, None, None, None, None) == E   # drops all
+    assert lib.fsb_gaussian_density(-1, None, 4, None, None, None, None, None, 0.0, None, None) == E
+    assert lib.fsb_gaussian_density(0, None, 4, None, None, None, None, None, 0.0, None, None) == 0            # empty: no-op
+    assert lib.fsb_level_crossings(10, None, None, 16, None, None, None, None, None, None, 5, None, None, None, None,
+                                   None, None) == E                                                          # 5 levels
+    assert lib.fsb_voxel_keys(10, None, 6, 0.0, None, None, None, None, None, 0, None) == E                    # voxel <= 0
+    assert lib.fsb_voxel_mean(10, None, None, None, None, None, 6, 10, None, None) == E                        # width > 9
+    assert lib.fsb_u8_to_unit_float(-1, None, None, 1, None) == E and lib.fsb_u8_to_unit_float(0, None, None, 1, None) == 0
+    assert lib.fsb_backproject_emit(0, 4, None, None, None, None, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, None, None, None) == E
