@@ -210,3 +210,31 @@ def test_knn_full_size_properties():
     ref_idx, ref_dist = knn_ref.knn_full_ref(x.cpu().numpy(), x[sub.to(DEV)].cpu().numpy(), 17, block=8)
     assert np.array_equal(idx[sub.to(DEV)].cpu().numpy(), ref_idx[:, 1:])
     assert np.array_equal(dist[sub.to(DEV)].cpu().numpy(), ref_dist[:, 1:])
+
+
+@pytest.mark.parametrize("case", ["coincident", "slab", "line", "tiny"])
+def test_kernel_algorithm_walkthrough_on_degenerate_clouds(case):
+    """Quantile edges repeat when many points share a coordinate (empty zero-width cells); the box growth must still
+    terminate with the exact answer (numpy walk-through of the kernel's algorithm, tests/knn_emulation.py)."""
+    from tests import knn_emulation as em
+
+    rng = np.random.default_rng(3)
+    if case == "coincident":
+        x = np.ones((60, 3), dtype=np.float32)
+    elif case == "slab":
+        x = rng.standard_normal((800, 3)).astype(np.float32)
+        x[:500, 2] = 0.25
+    elif case == "line":
+        x = np.zeros((300, 3), dtype=np.float32)
+        x[:, 0] = np.linspace(-1, 1, 300, dtype=np.float32)
+    else:
+        x = rng.standard_normal((5, 3)).astype(np.float32)
+    k = min(5, len(x))
+    ix = em.build(x)
+    queries = np.concatenate([x[:25], rng.standard_normal((10, 3)).astype(np.float32) * 3])
+    ref_idx, ref_dist = knn_ref.knn_full_ref(x, queries, k)
+    for r, q in enumerate(queries):
+        best, _, ok = em.query_one(ix, q, k, max_steps=10_000)
+        assert ok
+        assert [b[1] for b in best] == list(ref_idx[r]), (case, r)
+        assert np.array_equal(np.sqrt([b[0] for b in best]), ref_dist[r])
